@@ -1,0 +1,181 @@
+/* odise_b200 C ABI — the drop-in boundary for the ODISE per-image inference hot path on B200 (sm_100a).
+ *
+ * Plain pointers and sizes only; the caller owns every buffer; every entry point is asynchronous on the CUDA
+ * stream it is given (cudaStream_t passed as void*) and returns 0 or an error code (ODISE_ERR_* or a cudaError_t).
+ *
+ * The ONLY native surface of the reference is the pybind11 module "MultiScaleDeformableAttention"
+ * (third_party/Mask2Former/mask2former/modeling/pixel_decoder/ops/src/vision.cpp:18-21); odise_msda_forward_f32
+ * replaces ms_deform_attn_forward (.../src/ms_deform_attn.h:26-44 -> cuda/ms_deform_attn_cuda.cu:25-85).
+ * The remaining entry points are the kernel families of SURVEY.md §2.4 that the reference executes as individual
+ * ATen ops (cuDNN conv / GroupNorm / nn.MultiheadAttention / einsum); each one names the reference call site it
+ * replaces.  INTEGRATION.md shows the ctypes binding a reference maintainer would add.
+ *
+ * Operand convention for tensor-core GEMMs: fp32 values travel as a (hi, lo) pair of bf16 planes with
+ * hi = bf16(x), lo = bf16(x - hi); "nmma = 3" issues hi*hi + hi*lo + lo*hi (fp32-grade, the parity mode),
+ * "nmma = 1" uses the hi planes only (plain bf16).
+ */
+#ifndef ODISE_B200_H_
+#define ODISE_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ODISE_OK 0
+#define ODISE_ERR_ARG 10001       /* null / inconsistent argument */
+#define ODISE_ERR_ALIGN 10002     /* leading dimension / pointer alignment not supported */
+#define ODISE_ERR_DRIVER 10003    /* cuTensorMapEncodeTiled entry point not available */
+#define ODISE_ERR_TENSORMAP 10004 /* tensor-map encoding rejected */
+#define ODISE_ERR_WORKSPACE 10005 /* workspace missing / too small */
+#define ODISE_ERR_UNSUPPORTED 10006
+
+#define ODISE_ACT_NONE 0
+#define ODISE_ACT_RELU 1
+#define ODISE_ACT_SILU 2
+#define ODISE_ACT_GELU 3
+
+int odise_version(void);
+/* number of kernels launched through this library since load (bench.py "gpu_launches") */
+long long odise_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Multi-scale deformable attention forward (fp32).  Replaces MSDA.ms_deform_attn_forward
+ * (ops/src/cuda/ms_deform_attn_cuda.cu:25-85, kernel ops/src/cuda/ms_deform_im2col_cuda.cuh:242-304).
+ *   value          [N, S, M, D]      contiguous
+ *   spatial_shapes [L, 2] int64 (H_l, W_l), level_start [L] int64            (device pointers)
+ *   loc            [N, Lq, M, L, P, 2] (x, y) in [0,1];  attn [N, Lq, M, L, P]
+ *   out            [N, Lq, M*D]   (fully overwritten; the reference allocates at::zeros)
+ * D must be a multiple of 4 and <= 128 (ODISE: D = 32). */
+int odise_msda_forward_f32(const float* value, const int64_t* spatial_shapes, const int64_t* level_start,
+                           const float* loc, const float* attn, float* out, int N, int S, int M, int D, int L,
+                           int Lq, int P, void* stream);
+
+/* Fused front of MSDeformAttn.forward (ops/modules/ms_deform_attn.py:98-113): takes the raw outputs of the
+ * sampling_offsets / attention_weights linears, applies the softmax over L*P and loc = ref + off / (W_l, H_l)
+ * in registers, then samples.  offs [N, Lq, M, L, P, 2], logits [N, Lq, M, L*P], ref [N, Lq, L, 2]. */
+int odise_msda_fused_f32(const float* value, const int64_t* spatial_shapes, const int64_t* level_start,
+                         const float* ref, const float* offs, const float* logits, float* out,
+                         void* out_hi, void* out_lo, int N, int S, int M, int D, int L, int Lq, int P, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * tcgen05 GEMM / implicit-GEMM 3x3 convolution:  out[z][m][n] = epi(alpha * sum_k A[z][m][k] * B[z][n][k]).
+ * Replaces F.conv2d / F.linear / torch.einsum call sites of the path (ldm ResBlock & attention linears via
+ * odise/modeling/meta_arch/ldm.py:469-491; M2F linears; odise.py:746 mask einsum; odise.py:955-959 pooling;
+ * odise.py:192-205 CLIP match).
+ *   epi(v) = act(v + bias[n] + rowbias[(z*M+m)/rows_per_group][n]) + residual[z][m][n]
+ * conv3x3 = 1: A is an NHWC activation [B, H, W, C] (pixel stride lda elements), M = B*H*W, K = 9*C with
+ *   k = (kh*3 + kw)*C + c, padding 1, stride 1; C % 64 == 0 and tiles must cover whole rows (W | 128 or 128 | W).
+ * All bf16 leading dimensions are multiples of 8 elements, fp32 ones multiples of 4; base pointers 16-byte aligned. */
+typedef struct odise_gemm_desc {
+  int M, N, K, batch;
+  int nmma;     /* 1 = bf16, 3 = bf16x3 */
+  int conv3x3;  /* 0 plain, 1 implicit 3x3 conv */
+  int conv_C, conv_H, conv_W;
+  const void* a_hi; const void* a_lo; long long lda; long long a_batch_stride; /* 0 = shared across batch */
+  const void* b_hi; const void* b_lo; long long ldb; long long b_batch_stride;
+  float alpha;
+  const float* bias;                 /* [N] or NULL */
+  const float* rowbias; int rows_per_group; long long rowbias_ld; /* [groups, N] or NULL */
+  int act;
+  const float* residual; long long ld_residual; long long residual_batch_stride;
+  float* out_f32; long long ld_out; long long out_batch_stride;
+  void* out_hi; void* out_lo; long long ld_out_bf16; long long out_bf16_batch_stride;
+  int split_k; void* workspace; long long workspace_bytes;
+  int force_bn;                      /* 0 = heuristic; 64/128/160/256 */
+} odise_gemm_desc;
+int odise_gemm_bf16(const odise_gemm_desc* desc, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Elementwise / normalisation passes (HBM-bound).  Every one of them also produces the (hi, lo) bf16 operand
+ * planes the next GEMM consumes, so the fp32 -> bf16x2 split never costs an extra pass.  NHWC / token-major. */
+
+/* fp32 -> (hi, lo); rows x cols with leading dims (elements). out_lo may be NULL. */
+int odise_split_f32(const float* x, long long ldx, void* hi, void* lo, long long ldo, long long rows, int cols,
+                    void* stream);
+/* GroupNorm statistics over NHWC x[B, HW, C] (pixel stride ldx): mean/rstd [B, G].
+ * (torch.nn.GroupNorm in ldm ResBlock / SpatialTransformer / d2 BottleneckBlock / M2F input_proj) */
+int odise_groupnorm_stats_f32(const float* x, long long ldx, float* mean, float* rstd, int B, int HW, int C, int G,
+                              float eps, void* stream);
+/* y = act(gn(x) * gamma + beta): writes fp32 (optional) and (hi, lo) planes (optional). act: NONE/SILU/RELU */
+int odise_groupnorm_apply_f32(const float* x, long long ldx, const float* mean, const float* rstd,
+                              const float* gamma, const float* beta, int act, float* y, long long ldy, void* hi,
+                              void* lo, long long ldo, int B, int HW, int C, int G, void* stream);
+/* LayerNorm over the last dim (cols <= 4096): optional fp32 output, optional residual add BEFORE the norm
+ * (post-norm transformer: y = LN(x + res)), optional `post_add` AFTER the norm written only to the bf16 planes
+ * (query_pos / pos added to the GEMM operand, M2F with_pos_embed). */
+int odise_layernorm_f32(const float* x, long long ldx, const float* res, long long ldres, const float* gamma,
+                        const float* beta, float eps, float* y, long long ldy, const float* post_add,
+                        long long ldpa, void* hi, void* lo, long long ldo, long long rows, int cols, void* stream);
+/* GEGLU: y[m, j] = x[m, j] * gelu(x[m, j + cols]) for x [rows, 2*cols] -> (hi, lo) [rows, cols]
+ * (ldm attention.GEGLU) */
+int odise_geglu_f32(const float* x, long long ldx, void* hi, void* lo, long long ldo, long long rows, int cols,
+                    void* stream);
+/* y = a + b (optional b, optional fp32 y) -> (hi, lo); b_rows > 0 broadcasts b over rows modulo b_rows */
+int odise_add_split_f32(const float* a, long long lda, const float* b, long long ldb, long long b_rows, float* y,
+                        long long ldy, void* hi, void* lo, long long ldo, long long rows, int cols, void* stream);
+/* nearest 2x upsample of NHWC x[B,H,W,C] -> (hi, lo) [B,2H,2W,C] (ldm Upsample before its conv3x3) */
+int odise_upsample2x_split_f32(const float* x, long long ldx, void* hi, void* lo, long long ldo, int B, int H,
+                               int W, int C, void* stream);
+/* materialised im2col for the few convs the implicit path does not cover (C % 64 != 0, stride 2):
+ * x NHWC [B,H,W,C] -> (hi, lo) [B*Ho*Wo, Kpad] with k = (kh*3+kw)*C + c, zero padded to Kpad.
+ * pad_lo/pad_hi: zero padding before / after along both H and W (ldm Downsample: 1/1; VAE Downsample: 0/1). */
+int odise_im2col3x3_split_f32(const float* x, long long ldx, void* hi, void* lo, int Kpad, int B, int H, int W,
+                              int C, int stride, int pad_lo, int pad_hi, void* stream);
+/* strided 2-D fp32 copy (skip-concat into a channel slice, crop paste) with optional scale and accumulate */
+int odise_copy2d_f32(const float* src, long long lds, float* dst, long long ldd, long long rows, int cols,
+                     float scale, int accumulate, void* stream);
+/* bilinear (align_corners=False) / nearest resize of NHWC fp32, optional accumulate into dst (FPN top-down add,
+ * msdeformattn.py:349; F.interpolate nearest in feature_extractor.py:165) */
+int odise_resize_nhwc_f32(const float* src, long long lds, float* dst, long long ldd, int B, int Hs, int Ws, int Hd,
+                          int Wd, int C, int bilinear, int accumulate, void* stream);
+/* NHWC <-> NCHW transposes at the plugin boundary */
+int odise_nchw_to_nhwc_f32(const float* src, float* dst, long long ldd, int B, int C, int HW, void* stream);
+int odise_nhwc_to_nchw_f32(const float* src, long long lds, float* dst, int B, int C, int HW, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Attention.  q [B, Tq, heads*d] / k,v [B, Tk, heads*d] as (hi, lo) planes; softmax(q k^T * scale) v.
+ * UNet self / cross attention (ldm CrossAttention) — tcgen05 flash kernel. */
+int odise_attention_tc(const void* q_hi, const void* q_lo, long long ldq, const void* k_hi, const void* k_lo,
+                       long long ldk, const void* vt_hi, const void* vt_lo, long long ldvt, long long vt_bs,
+                       float* out, void* out_hi, void* out_lo, long long ldo, int B, int heads, int d, int Tq,
+                       int Tk, float scale, int nmma, void* stream);
+
+/* Masked cross-attention of the Mask2Former decoder (odise.py:683-692 + 760-774,
+ * mask2former_transformer_decoder.py:98-110).  The boolean attn_mask [B*8, Q, HW] of the reference is replaced by
+ * 1 bit per (b, q, key), shared by the 8 heads: bit = !(sigmoid(bilinear(mask_logits -> (Hl, Wl))) < 0.5), and
+ * row_any[b, q] = "some key allowed"; rows with row_any == 0 attend everywhere (the odise.py:683 fix-up).
+ *   mask_logits [B, Q, Hm, Wm] fp32; bits [B, Q, ceil(Hl*Wl/32)] uint32; row_any [B, Q] int32. */
+int odise_attn_mask_bits_f32(const float* mask_logits, uint32_t* bits, int32_t* row_any, int B, int Q, int Hm,
+                             int Wm, int Hl, int Wl, void* stream);
+/* Multi-head attention for head_dim 32 (nn.MultiheadAttention(256, 8) core of the decoder's cross- and
+ * self-attention layers): q [B, Tq, heads*32], k, v [B, Tk, heads*32] already projected, fp32;
+ * out = softmax(scale * q k^T  (+ -inf where bit == 0 and row_any != 0)) v, written as fp32 and/or (hi, lo).
+ * bits / row_any may be NULL (unmasked self-attention). */
+int odise_mha_d32_f32(const float* q, const float* k, const float* v, const uint32_t* bits, const int32_t* row_any,
+                      float* out, void* out_hi, void* out_lo, int B, int Tq, int Tk, int heads, float scale,
+                      void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Mask head helpers (odise.py:937-963 MaskPooling, odise.py:746 einsum) */
+/* mask_logits [B, Q, HW] fp32 -> binary (logit > 0) as bf16 plane [B, Q, HWpad] + counts [B, Q] */
+int odise_mask_binarize_f32(const float* logits, void* bin_bf16, long long ld_bin, float* counts, int B, int Q,
+                            int HW, void* stream);
+/* pooled[b,q,c] = sums[b,q,c] / (counts[b,q] + 1e-8) */
+int odise_pool_normalize_f32(const float* sums, const float* counts, float* pooled, int B, int Q, int C,
+                             void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * CLIP match tail (odise.py:181-207 cal_pred_logits + helper.py:79-109 ensemble max):
+ *   sims [BQ, Kp] = logit_scale * <normalize(mask_embed), normalize(text_embed)>  (GEMM above on normalised rows)
+ *   out [BQ, Kc+1]: per-class max over its synonym columns (group_start [Kc+1] int32 prefix) + null column. */
+int odise_l2_normalize_split_f32(const float* x, long long ldx, void* hi, void* lo, long long ldo, long long rows,
+                                 int cols, void* stream);
+int odise_class_max_f32(const float* sims, long long ld_sims, const int32_t* group_start, const float* null_sim,
+                        float* out, long long rows, int n_classes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ODISE_B200_H_ */

@@ -1,0 +1,616 @@
+// HBM-bound elementwise / normalisation passes of the ODISE hot path (sm_100a).  Activations are NHWC /
+// token-major fp32; every pass that feeds a GEMM also writes the (hi, lo) bf16 operand planes, so the
+// fp32 -> bf16x2 split is never a pass of its own.  Reference ops replaced (all individual ATen kernels in
+// the reference, SURVEY.md §2.4 "Fused ops: none"): nn.GroupNorm + SiLU (ldm ResBlock / Normalize),
+// nn.LayerNorm (+ residual, + with_pos_embed: mask2former_transformer_decoder.py:40-50,98-110,163-167),
+// ldm GEGLU, ldm Upsample (nearest x2), F.interpolate (feature_extractor.py:165, msdeformattn.py:349),
+// torch.cat skip concat (ldm.py:485), crop paste (feature_extractor.py:243-248), F.normalize + per-class max
+// (odise.py:181-207, helper.py:96-100), MaskPooling threshold / normalise (odise.py:945-959).
+#include "ptx.cuh"
+#include "odise_b200.h"
+#include "launch_count.h"
+#include <atomic>
+
+namespace ob {
+
+static std::atomic<long long> g_launches{0};
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+static inline int grid_for(long long work, int threads, int max_blocks = 148 * 16) {
+  long long b = (work + threads - 1) / threads;
+  if (b < 1) b = 1;
+  if (b > max_blocks) b = max_blocks;
+  return (int)b;
+}
+
+__device__ __forceinline__ float act_apply(float v, int act) {
+  if (act == ODISE_ACT_RELU) return fmaxf(v, 0.f);
+  if (act == ODISE_ACT_SILU) return v / (1.f + expf(-v));
+  if (act == ODISE_ACT_GELU) return 0.5f * v * (1.f + erff(v * 0.70710678118654752f));
+  return v;
+}
+
+__device__ __forceinline__ void store_split4(__nv_bfloat16* hi, __nv_bfloat16* lo, float4 v) {
+  __align__(8) __nv_bfloat16 h[4];
+  __align__(8) __nv_bfloat16 l[4];
+  split_bf16(v.x, h[0], l[0]); split_bf16(v.y, h[1], l[1]); split_bf16(v.z, h[2], l[2]); split_bf16(v.w, h[3], l[3]);
+  *reinterpret_cast<uint2*>(hi) = *reinterpret_cast<const uint2*>(h);
+  if (lo) *reinterpret_cast<uint2*>(lo) = *reinterpret_cast<const uint2*>(l);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// ---------------------------------------------------------------------------------------------- split / add
+// generic rows x cols with 4-wide vectors (cols % 4 == 0 required by all callers; checked on the host)
+__global__ void add_split_kernel(const float* __restrict__ a, long long lda, const float* __restrict__ b,
+                                 long long ldb, long long b_rows, float* __restrict__ y, long long ldy,
+                                 __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, long long ldo,
+                                 long long rows, int cols4) {
+  const long long total = rows * cols4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / cols4;
+    const int c = (int)(i - r * cols4) * 4;
+    float4 v = *reinterpret_cast<const float4*>(a + r * lda + c);
+    if (b) {
+      const long long rb = b_rows > 0 ? r % b_rows : r;
+      const float4 w = *reinterpret_cast<const float4*>(b + rb * ldb + c);
+      v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
+    }
+    if (y) *reinterpret_cast<float4*>(y + r * ldy + c) = v;
+    if (hi) store_split4(hi + r * ldo + c, lo ? lo + r * ldo + c : nullptr, v);
+  }
+}
+
+__global__ void copy2d_kernel(const float* __restrict__ src, long long lds, float* __restrict__ dst, long long ldd,
+                              long long rows, int cols4, float scale, int accumulate) {
+  const long long total = rows * cols4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / cols4;
+    const int c = (int)(i - r * cols4) * 4;
+    float4 v = *reinterpret_cast<const float4*>(src + r * lds + c);
+    v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
+    float4* d = reinterpret_cast<float4*>(dst + r * ldd + c);
+    if (accumulate) { const float4 o = *d; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+    *d = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- GroupNorm
+// one block per (image, group): two-pass mean / variance in fp32 with double block reduction (matches
+// torch.nn.GroupNorm's fp32 statistics to ~1e-7 relative).
+__global__ void __launch_bounds__(256)
+gn_stats_kernel(const float* __restrict__ x, long long ldx, float* __restrict__ mean, float* __restrict__ rstd,
+                int HW, int C, int G, float eps) {
+  const int b = blockIdx.x / G, g = blockIdx.x % G;
+  const int cpg = C / G;
+  const float* xb = x + (long long)b * HW * ldx + g * cpg;
+  const long long n = (long long)HW * cpg;
+  __shared__ double red[8];
+  __shared__ double s_mean;
+  double acc = 0.0;
+  {
+    float part = 0.f;
+    int cnt = 0;
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+      const long long pix = i / cpg;
+      const int c = (int)(i - pix * cpg);
+      part += xb[pix * ldx + c];
+      if (++cnt == 64) { acc += part; part = 0.f; cnt = 0; }
+    }
+    acc += part;
+  }
+  acc = warp_sum_d(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0;
+    for (int i = 0; i < (blockDim.x >> 5); ++i) t += red[i];
+    s_mean = t / (double)n;
+  }
+  __syncthreads();
+  const float mu = (float)s_mean;
+  acc = 0.0;
+  {
+    float part = 0.f;
+    int cnt = 0;
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+      const long long pix = i / cpg;
+      const int c = (int)(i - pix * cpg);
+      const float d = xb[pix * ldx + c] - mu;
+      part = fmaf(d, d, part);
+      if (++cnt == 64) { acc += part; part = 0.f; cnt = 0; }
+    }
+    acc += part;
+  }
+  acc = warp_sum_d(acc);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0;
+    for (int i = 0; i < (blockDim.x >> 5); ++i) t += red[i];
+    const double var = t / (double)n;
+    mean[blockIdx.x] = mu;
+    rstd[blockIdx.x] = (float)(1.0 / sqrt(var + (double)eps));
+  }
+}
+
+__global__ void gn_apply_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ mean,
+                                const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                const float* __restrict__ beta, int act, float* __restrict__ y, long long ldy,
+                                __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, long long ldo,
+                                long long rows, int HW, int C, int G) {
+  const int c4n = C / 4;
+  const int cpg = C / G;
+  const long long total = rows * c4n;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / c4n;
+    const int c = (int)(i - r * c4n) * 4;
+    const int b = (int)(r / HW);
+    const float4 v = *reinterpret_cast<const float4*>(x + r * ldx + c);
+    const float in[4] = {v.x, v.y, v.z, v.w};
+    float o[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int g = (c + t) / cpg;
+      const float mu = __ldg(mean + b * G + g), rs = __ldg(rstd + b * G + g);
+      // torch: (x - mean) * rstd * gamma + beta
+      float u = (in[t] - mu) * rs;
+      u = fmaf(u, __ldg(gamma + c + t), __ldg(beta + c + t));
+      o[t] = act_apply(u, act);
+    }
+    const float4 ov = make_float4(o[0], o[1], o[2], o[3]);
+    if (y) *reinterpret_cast<float4*>(y + r * ldy + c) = ov;
+    if (hi) store_split4(hi + r * ldo + c, lo ? lo + r * ldo + c : nullptr, ov);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- LayerNorm
+// one warp per row, row cached in registers (cols <= 4096)
+template <int MAXV>
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ res, long long ldres,
+                 const float* __restrict__ gamma, const float* __restrict__ beta, float eps, float* __restrict__ y,
+                 long long ldy, const float* __restrict__ post_add, long long ldpa, __nv_bfloat16* __restrict__ hi,
+                 __nv_bfloat16* __restrict__ lo, long long ldo, long long rows, int cols) {
+  const long long row = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const int nv = cols / 4;
+  float4 v[MAXV];
+  float sum = 0.f;
+#pragma unroll
+  for (int k = 0; k < MAXV; ++k) {
+    const int idx = lane + k * 32;
+    if (idx < nv) {
+      v[k] = *reinterpret_cast<const float4*>(x + row * ldx + idx * 4);
+      if (res) {
+        const float4 r = *reinterpret_cast<const float4*>(res + row * ldres + idx * 4);
+        v[k].x += r.x; v[k].y += r.y; v[k].z += r.z; v[k].w += r.w;
+      }
+      sum += (v[k].x + v[k].y) + (v[k].z + v[k].w);
+    }
+  }
+  const float mu = warp_sum(sum) / (float)cols;
+  float sq = 0.f;
+#pragma unroll
+  for (int k = 0; k < MAXV; ++k) {
+    const int idx = lane + k * 32;
+    if (idx < nv) {
+      const float a = v[k].x - mu, b = v[k].y - mu, c = v[k].z - mu, d = v[k].w - mu;
+      sq += (a * a + b * b) + (c * c + d * d);
+    }
+  }
+  const float rs = rsqrtf(warp_sum(sq) / (float)cols + eps);
+#pragma unroll
+  for (int k = 0; k < MAXV; ++k) {
+    const int idx = lane + k * 32;
+    if (idx < nv) {
+      const int c = idx * 4;
+      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
+      const float4 bt = __ldg(reinterpret_cast<const float4*>(beta + c));
+      float4 o;
+      o.x = fmaf((v[k].x - mu) * rs, g.x, bt.x);
+      o.y = fmaf((v[k].y - mu) * rs, g.y, bt.y);
+      o.z = fmaf((v[k].z - mu) * rs, g.z, bt.z);
+      o.w = fmaf((v[k].w - mu) * rs, g.w, bt.w);
+      if (y) *reinterpret_cast<float4*>(y + row * ldy + c) = o;
+      if (hi) {
+        if (post_add) {
+          const float4 pa = *reinterpret_cast<const float4*>(post_add + row * ldpa + c);
+          o.x += pa.x; o.y += pa.y; o.z += pa.z; o.w += pa.w;
+        }
+        store_split4(hi + row * ldo + c, lo ? lo + row * ldo + c : nullptr, o);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- GEGLU
+__global__ void geglu_kernel(const float* __restrict__ x, long long ldx, __nv_bfloat16* __restrict__ hi,
+                             __nv_bfloat16* __restrict__ lo, long long ldo, long long rows, int cols) {
+  const int c4n = cols / 4;
+  const long long total = rows * c4n;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / c4n;
+    const int c = (int)(i - r * c4n) * 4;
+    const float4 a = *reinterpret_cast<const float4*>(x + r * ldx + c);
+    const float4 g = *reinterpret_cast<const float4*>(x + r * ldx + cols + c);
+    float4 o;
+    o.x = a.x * act_apply(g.x, ODISE_ACT_GELU);
+    o.y = a.y * act_apply(g.y, ODISE_ACT_GELU);
+    o.z = a.z * act_apply(g.z, ODISE_ACT_GELU);
+    o.w = a.w * act_apply(g.w, ODISE_ACT_GELU);
+    store_split4(hi + r * ldo + c, lo ? lo + r * ldo + c : nullptr, o);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- resampling
+__global__ void upsample2x_split_kernel(const float* __restrict__ x, long long ldx, __nv_bfloat16* __restrict__ hi,
+                                        __nv_bfloat16* __restrict__ lo, long long ldo, int B, int H, int W, int C) {
+  const int c4n = C / 4;
+  const long long total = (long long)B * 4 * H * W * c4n;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % c4n) * 4;
+    long long p = i / c4n;
+    const int ox = (int)(p % (2 * W)); p /= 2 * W;
+    const int oy = (int)(p % (2 * H));
+    const int b = (int)(p / (2 * H));
+    const long long src = ((long long)b * H + (oy >> 1)) * W + (ox >> 1);
+    const long long dst = ((long long)b * 2 * H + oy) * 2 * W + ox;
+    const float4 v = *reinterpret_cast<const float4*>(x + src * ldx + c);
+    store_split4(hi + dst * ldo + c, lo ? lo + dst * ldo + c : nullptr, v);
+  }
+}
+
+__global__ void im2col3x3_split_kernel(const float* __restrict__ x, long long ldx, __nv_bfloat16* __restrict__ hi,
+                                       __nv_bfloat16* __restrict__ lo, int Kpad, int B, int H, int W, int C,
+                                       int stride, int pad_lo, int Ho, int Wo) {
+  const long long total = (long long)B * Ho * Wo * Kpad;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(i % Kpad);
+    long long p = i / Kpad;
+    const int ox = (int)(p % Wo); p /= Wo;
+    const int oy = (int)(p % Ho);
+    const int b = (int)(p / Ho);
+    float v = 0.f;
+    if (k < 9 * C) {
+      const int tap = k / C, c = k - tap * C;
+      const int iy = oy * stride + tap / 3 - pad_lo, ix = ox * stride + tap % 3 - pad_lo;
+      if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = x[(((long long)b * H + iy) * W + ix) * ldx + c];
+    }
+    __nv_bfloat16 h, l;
+    split_bf16(v, h, l);
+    hi[i] = h;
+    if (lo) lo[i] = l;
+  }
+}
+
+// F.interpolate(mode="bilinear", align_corners=False) / mode="nearest" on NHWC
+__global__ void resize_nhwc_kernel(const float* __restrict__ src, long long lds, float* __restrict__ dst,
+                                   long long ldd, int B, int Hs, int Ws, int Hd, int Wd, int C, int bilinear,
+                                   int accumulate) {
+  const int c4n = C / 4;
+  const long long total = (long long)B * Hd * Wd * c4n;
+  const float sy = (float)Hs / (float)Hd, sx = (float)Ws / (float)Wd;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % c4n) * 4;
+    long long p = i / c4n;
+    const int ox = (int)(p % Wd); p /= Wd;
+    const int oy = (int)(p % Hd);
+    const int b = (int)(p / Hd);
+    const float* sb = src + (long long)b * Hs * Ws * lds + c;
+    float4 v;
+    if (bilinear) {
+      // ATen area_pixel_compute_source_index(align_corners=False): max(0, (dst + 0.5) * scale - 0.5)
+      float fy = fmaxf((oy + 0.5f) * sy - 0.5f, 0.f), fx = fmaxf((ox + 0.5f) * sx - 0.5f, 0.f);
+      const int y0 = (int)fy, x0 = (int)fx;
+      const int y1 = y0 + (y0 < Hs - 1 ? 1 : 0), x1 = x0 + (x0 < Ws - 1 ? 1 : 0);
+      const float ly = fy - y0, lx = fx - x0, hy = 1.f - ly, hx = 1.f - lx;
+      const float4 a = *reinterpret_cast<const float4*>(sb + ((long long)y0 * Ws + x0) * lds);
+      const float4 bq = *reinterpret_cast<const float4*>(sb + ((long long)y0 * Ws + x1) * lds);
+      const float4 cq = *reinterpret_cast<const float4*>(sb + ((long long)y1 * Ws + x0) * lds);
+      const float4 d = *reinterpret_cast<const float4*>(sb + ((long long)y1 * Ws + x1) * lds);
+      v.x = hy * (hx * a.x + lx * bq.x) + ly * (hx * cq.x + lx * d.x);
+      v.y = hy * (hx * a.y + lx * bq.y) + ly * (hx * cq.y + lx * d.y);
+      v.z = hy * (hx * a.z + lx * bq.z) + ly * (hx * cq.z + lx * d.z);
+      v.w = hy * (hx * a.w + lx * bq.w) + ly * (hx * cq.w + lx * d.w);
+    } else {
+      const int y0 = min((int)floorf(oy * sy), Hs - 1), x0 = min((int)floorf(ox * sx), Ws - 1);
+      v = *reinterpret_cast<const float4*>(sb + ((long long)y0 * Ws + x0) * lds);
+    }
+    float4* dp = reinterpret_cast<float4*>(dst + (((long long)b * Hd + oy) * Wd + ox) * ldd + c);
+    if (accumulate) { const float4 o = *dp; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+    *dp = v;
+  }
+}
+
+// tiled transposes: NCHW [B, C, HW] <-> NHWC [B, HW, C(ld)]
+__global__ void transpose_kernel(const float* __restrict__ src, long long src_bs, long long lds,
+                                 float* __restrict__ dst, long long dst_bs, long long ldd, int R, int Cc) {
+  // src [R rows, Cc cols] (ld lds) -> dst [Cc rows, R cols] (ld ldd), per batch blockIdx.z
+  __shared__ float tile[32][33];
+  const float* s = src + blockIdx.z * src_bs;
+  float* d = dst + blockIdx.z * dst_bs;
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int r = r0 + j, c = c0 + threadIdx.x;
+    if (r < R && c < Cc) tile[j][threadIdx.x] = s[(long long)r * lds + c];
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int c = c0 + j, r = r0 + threadIdx.x;
+    if (r < R && c < Cc) d[(long long)c * ldd + r] = tile[threadIdx.x][j];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- CLIP-match tail
+__global__ void l2norm_split_kernel(const float* __restrict__ x, long long ldx, __nv_bfloat16* __restrict__ hi,
+                                    __nv_bfloat16* __restrict__ lo, long long ldo, long long rows, int cols) {
+  const long long row = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  float sq = 0.f;
+  for (int c = lane; c < cols; c += 32) { const float v = x[row * ldx + c]; sq = fmaf(v, v, sq); }
+  // F.normalize: x / max(||x||_2, 1e-12)
+  const float nrm = fmaxf(sqrtf(warp_sum(sq)), 1e-12f);
+  for (int c = lane; c < cols; c += 32) {
+    __nv_bfloat16 h, l;
+    split_bf16(x[row * ldx + c] / nrm, h, l);
+    hi[row * ldo + c] = h;
+    if (lo) lo[row * ldo + c] = l;
+  }
+}
+
+__global__ void class_max_kernel(const float* __restrict__ sims, long long ld, const int32_t* __restrict__ gs,
+                                 const float* __restrict__ null_sim, float* __restrict__ out, long long rows,
+                                 int K) {
+  const long long total = rows * (K + 1);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / (K + 1);
+    const int k = (int)(i - r * (K + 1));
+    float v;
+    if (k == K) {
+      v = null_sim[r];
+    } else {
+      v = -INFINITY;
+      for (int j = gs[k]; j < gs[k + 1]; ++j) v = fmaxf(v, sims[r * ld + j]);
+    }
+    out[i] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- mask pooling
+// one warp per (b, q) row: binary mask (sigmoid(x) > 0.5  <=>  x > 0) as bf16 0/1 + count
+__global__ void mask_binarize_kernel(const float* __restrict__ logits, __nv_bfloat16* __restrict__ bin,
+                                     long long ld_bin, float* __restrict__ counts, long long rows, int HW) {
+  const long long row = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const float* src = logits + row * HW;
+  __nv_bfloat16* dst = bin + row * ld_bin;
+  float cnt = 0.f;
+  for (int c = lane * 4; c < HW; c += 128) {
+    const float4 v = *reinterpret_cast<const float4*>(src + c);
+    __align__(8) __nv_bfloat16 o[4];
+    // MaskPooling: (sigmoid(mask) > 0.5).  sigmoid is monotone with sigmoid(0) = 0.5, and torch's fp32 sigmoid of a
+    // tiny positive x rounds to exactly 0.5 for |x| < ~6e-8; use the same predicate on the sigmoid value.
+    const float s0 = 1.f / (1.f + expf(-v.x)), s1 = 1.f / (1.f + expf(-v.y));
+    const float s2 = 1.f / (1.f + expf(-v.z)), s3 = 1.f / (1.f + expf(-v.w));
+    const float b0 = s0 > 0.5f, b1 = s1 > 0.5f, b2 = s2 > 0.5f, b3 = s3 > 0.5f;
+    o[0] = __float2bfloat16_rn(b0); o[1] = __float2bfloat16_rn(b1);
+    o[2] = __float2bfloat16_rn(b2); o[3] = __float2bfloat16_rn(b3);
+    cnt += (b0 + b1) + (b2 + b3);
+    *reinterpret_cast<uint2*>(dst + c) = *reinterpret_cast<const uint2*>(o);
+  }
+  cnt = warp_sum(cnt);
+  if (lane == 0) counts[row] = cnt;
+}
+
+__global__ void pool_normalize_kernel(const float* __restrict__ sums, const float* __restrict__ counts,
+                                      float* __restrict__ pooled, long long rows, int C) {
+  const long long total = rows * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / C;
+    // einsum(x, mask / (count + 1e-8)): the 0/1 mask makes this sum / (count + 1e-8) up to fp32 rounding order
+    pooled[i] = sums[i] / (counts[r] + 1e-8f);
+  }
+}
+
+}  // namespace ob
+
+using namespace ob;
+#define STREAM(s) reinterpret_cast<cudaStream_t>(s)
+#define BF(p) reinterpret_cast<__nv_bfloat16*>(p)
+
+extern "C" int odise_version(void) { return 100; }
+extern "C" long long odise_launch_count(void) { return g_launches.load(); }
+
+extern "C" int odise_split_f32(const float* x, long long ldx, void* hi, void* lo, long long ldo, long long rows,
+                               int cols, void* stream) {
+  return odise_add_split_f32(x, ldx, nullptr, 0, 0, nullptr, 0, hi, lo, ldo, rows, cols, stream);
+}
+
+extern "C" int odise_add_split_f32(const float* a, long long lda, const float* b, long long ldb, long long b_rows,
+                                   float* y, long long ldy, void* hi, void* lo, long long ldo, long long rows,
+                                   int cols, void* stream) {
+  if (!a || rows <= 0 || cols <= 0 || (!y && !hi)) return ODISE_ERR_ARG;
+  if (cols % 4 || lda % 4 || (b && ldb % 4) || (y && ldy % 4) || (hi && ldo % 4)) return ODISE_ERR_ALIGN;
+  add_split_kernel<<<grid_for(rows * (cols / 4), 256), 256, 0, STREAM(stream)>>>(a, lda, b, ldb, b_rows, y, ldy,
+                                                                               BF(hi), BF(lo), ldo, rows, cols / 4);
+  count_launch(1);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int odise_copy2d_f32(const float* src, long long lds, float* dst, long long ldd, long long rows, int cols,
+                                float scale, int accumulate, void* stream) {
+  if (!src || !dst || rows <= 0 || cols <= 0) return ODISE_ERR_ARG;
+  if (cols % 4 || lds % 4 || ldd % 4) return ODISE_ERR_ALIGN;
+  copy2d_kernel<<<grid_for(rows * (cols / 4), 256), 256, 0, STREAM(stream)>>>(src, lds, dst, ldd, rows, cols / 4,
+                                                                            scale, accumulate);
+  count_launch(1);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int odise_groupnorm_stats_f32(const float* x, long long ldx, float* mean, float* rstd, int B, int HW,
+                                         int C, int G, float eps, void* stream) {
+  if (!x || !mean || !rstd || B <= 0 || HW <= 0 || C <= 0 || G <= 0 || C % G) return ODISE_ERR_ARG;
+  gn_stats_kernel<<<B * G, 256, 0, STREAM(stream)>>>(x, ldx, mean, rstd, HW, C, G, eps);
+  count_launch(1);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int odise_groupnorm_apply_f32(const float* x, long long ldx, const float* mean, const float* rstd,
+                                         const float* gamma, const float* beta, int act, float* y, long long ldy,
+                                         void* hi, void* lo, long long ldo, int B, int HW, int C, int G,
+                                         void* stream) {
+  if (!x || !mean || !rstd || !gamma || !beta || (!y && !hi) || C % G) return ODISE_ERR_ARG;
+  if (C % 4 || ldx % 4 || (y && ldy % 4) || (hi && ldo % 4)) return ODISE_ERR_ALIGN;
+  const long long rows = (long long)B * HW;
+  gn_apply_kernel<<<grid_for(rows * (C / 4), 256), 256, 0, STREAM(stream)>>>(x, ldx, mean, rstd, gamma, beta, act, y,
+                                                                           ldy, BF(hi), BF(lo), ldo, rows, HW, C, G);
+  count_launch(1);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int odise_layernorm_f32(const float* x, long long ldx, const float* res, long long ldres,
+                                   const float* gamma, const float* beta, float eps, float* y, long long ldy,
+                                   const float* post_add, long long ldpa, void* hi, void* lo, long long ldo,
+                                   long long rows, int cols, void* stream) {
+  if (!x || !gamma || !beta || (!y && !hi) || rows <= 0 || cols <= 0 || cols > 4096) return ODISE_ERR_ARG;
+  if (cols % 4 || ldx % 4 || (res && ldres % 4) || (y && ldy % 4) || (hi && ldo % 4) || (post_add && ldpa % 4))
+    return ODISE_ERR_ALIGN;
+  const int wpb = 8;
+  const int blocks = (int)((rows + wpb - 1) / wpb);
+  const int nv = cols / 4;
+#define LN_LAUNCH(MV)                                                                                              \
+  layernorm_kernel<MV><<<blocks, wpb * 32, 0, STREAM(stream)>>>(x, ldx, res, ldres, gamma, beta, eps, y, ldy,       \
+                                                               post_add, ldpa, BF(hi), BF(lo), ldo, rows, cols)
+  if (nv <= 64) LN_LAUNCH(2);
+  else if (nv <= 128) LN_LAUNCH(4);
+  else if (nv <= 320) LN_LAUNCH(10);
+  else LN_LAUNCH(32);
+#undef LN_LAUNCH
+  count_launch(1);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int odise_geglu_f32(const float* x, long long ldx, void* hi, void* lo, long long ldo, long long rows,
+                               int cols, void* stream) {
+  if (!x || !hi || rows <= 0 || cols <= 0) return ODISE_ERR_ARG;
+  if (cols % 4 || ldx % 4 || ldo % 4) return ODISE_ERR_ALIGN;
+  geglu_kernel<<<grid_for(rows * (cols / 4), 256), 256, 0, STREAM(stream)>>>(x, ldx, BF(hi), BF(lo), ldo, rows, cols);
+  count_launch(1);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int odise_upsample2x_split_f32(const float* x, long long ldx, void* hi, void* lo, long long ldo, int B,
+                                          int H, int W, int C, void* stream) {
+  if (!x || !hi || B <= 0 || H <= 0 || W <= 0 || C <= 0) return ODISE_ERR_ARG;
+  if (C % 4 || ldx % 4 || ldo % 4) return ODISE_ERR_ALIGN;
+  upsample2x_split_kernel<<<grid_for((long long)B * 4 * H * W * (C / 4), 256), 256, 0, STREAM(stream)>>>(
+      x, ldx, BF(hi), BF(lo), ldo, B, H, W, C);
+  count_launch(1);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int odise_im2col3x3_split_f32(const float* x, long long ldx, void* hi, void* lo, int Kpad, int B, int H,
+                                         int W, int C, int stride, int pad_lo, int pad_hi, void* stream) {
+  if (!x || !hi || B <= 0 || H <= 0 || W <= 0 || C <= 0 || stride <= 0 || Kpad < 9 * C || Kpad % 8)
+    return ODISE_ERR_ARG;
+  const int Ho = (H + pad_lo + pad_hi - 3) / stride + 1, Wo = (W + pad_lo + pad_hi - 3) / stride + 1;
+  im2col3x3_split_kernel<<<grid_for((long long)B * Ho * Wo * Kpad, 256), 256, 0, STREAM(stream)>>>(
+      x, ldx, BF(hi), BF(lo), Kpad, B, H, W, C, stride, pad_lo, Ho, Wo);
+  count_launch(1);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int odise_resize_nhwc_f32(const float* src, long long lds, float* dst, long long ldd, int B, int Hs,
+                                     int Ws, int Hd, int Wd, int C, int bilinear, int accumulate, void* stream) {
+  if (!src || !dst || B <= 0 || Hs <= 0 || Ws <= 0 || Hd <= 0 || Wd <= 0 || C <= 0) return ODISE_ERR_ARG;
+  if (C % 4 || lds % 4 || ldd % 4) return ODISE_ERR_ALIGN;
+  resize_nhwc_kernel<<<grid_for((long long)B * Hd * Wd * (C / 4), 256), 256, 0, STREAM(stream)>>>(
+      src, lds, dst, ldd, B, Hs, Ws, Hd, Wd, C, bilinear, accumulate);
+  count_launch(1);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int odise_nchw_to_nhwc_f32(const float* src, float* dst, long long ldd, int B, int C, int HW,
+                                      void* stream) {
+  if (!src || !dst || B <= 0 || C <= 0 || HW <= 0) return ODISE_ERR_ARG;
+  dim3 grid((HW + 31) / 32, (C + 31) / 32, B), block(32, 8);
+  transpose_kernel<<<grid, block, 0, STREAM(stream)>>>(src, (long long)C * HW, HW, dst, (long long)HW * ldd, ldd, C,
+                                                       HW);
+  count_launch(1);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int odise_nhwc_to_nchw_f32(const float* src, long long lds, float* dst, int B, int C, int HW,
+                                      void* stream) {
+  if (!src || !dst || B <= 0 || C <= 0 || HW <= 0) return ODISE_ERR_ARG;
+  dim3 grid((C + 31) / 32, (HW + 31) / 32, B), block(32, 8);
+  transpose_kernel<<<grid, block, 0, STREAM(stream)>>>(src, (long long)HW * lds, lds, dst, (long long)C * HW, HW, HW,
+                                                       C);
+  count_launch(1);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int odise_l2_normalize_split_f32(const float* x, long long ldx, void* hi, void* lo, long long ldo,
+                                            long long rows, int cols, void* stream) {
+  if (!x || !hi || rows <= 0 || cols <= 0) return ODISE_ERR_ARG;
+  l2norm_split_kernel<<<(int)((rows + 7) / 8), 256, 0, STREAM(stream)>>>(x, ldx, BF(hi), BF(lo), ldo, rows, cols);
+  count_launch(1);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int odise_class_max_f32(const float* sims, long long ld_sims, const int32_t* group_start,
+                                   const float* null_sim, float* out, long long rows, int n_classes, void* stream) {
+  if (!sims || !group_start || !null_sim || !out || rows <= 0 || n_classes <= 0) return ODISE_ERR_ARG;
+  class_max_kernel<<<grid_for(rows * (n_classes + 1), 256), 256, 0, STREAM(stream)>>>(sims, ld_sims, group_start,
+                                                                                    null_sim, out, rows, n_classes);
+  count_launch(1);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int odise_mask_binarize_f32(const float* logits, void* bin_bf16, long long ld_bin, float* counts, int B,
+                                       int Q, int HW, void* stream) {
+  if (!logits || !bin_bf16 || !counts || B <= 0 || Q <= 0 || HW <= 0) return ODISE_ERR_ARG;
+  if (HW % 4 || ld_bin % 4) return ODISE_ERR_ALIGN;
+  const long long rows = (long long)B * Q;
+  mask_binarize_kernel<<<(int)((rows + 7) / 8), 256, 0, STREAM(stream)>>>(logits, BF(bin_bf16), ld_bin, counts, rows,
+                                                                         HW);
+  count_launch(1);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int odise_pool_normalize_f32(const float* sums, const float* counts, float* pooled, int B, int Q, int C,
+                                        void* stream) {
+  if (!sums || !counts || !pooled || B <= 0 || Q <= 0 || C <= 0) return ODISE_ERR_ARG;
+  const long long rows = (long long)B * Q;
+  pool_normalize_kernel<<<grid_for(rows * C, 256), 256, 0, STREAM(stream)>>>(sums, counts, pooled, rows, C);
+  count_launch(1);
+  return (int)cudaGetLastError();
+}

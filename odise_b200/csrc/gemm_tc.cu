@@ -1,0 +1,545 @@
+// tcgen05 / TMEM / TMA GEMM for sm_100a: the tensor-core workhorse behind every dense contraction on the ODISE
+// inference hot path (SURVEY.md §8a rows a7.1 ResBlock convs, a7.2 transformer linears, a3 projections,
+// b2-b4 pixel-decoder linears, b8-b10 decoder linears / mask einsum / pooling, b12 CLIP match).
+//
+//   D[z][m][n] = epi( alpha * sum_k A[z][m][k] * B[z][n][k] )        (both operands K-major, bf16)
+//
+// * A is either a row-major matrix (3-D tensor map {K, M, batch}) or, in conv mode, an NHWC activation read
+//   through a 4-D tensor map {C, W, H, B}: the 3x3 / pad-1 / stride-1 convolution is an implicit GEMM whose
+//   K loop walks (kh, kw, c-chunk) and lets TMA's out-of-bounds zero fill implement the padding.
+//   (reference op: F.conv2d inside ldm ResBlock, call sites odise/modeling/meta_arch/ldm.py:481-489)
+// * precision: NMMA=1 plain bf16, NMMA=3 "bf16x3": operands carry a (hi, lo) bf16 pair per fp32 value and the
+//   kernel issues hi*hi + hi*lo + lo*hi into the same fp32 TMEM accumulator (~16 mantissa bits, the mode that
+//   meets the 1e-3 fp32 parity bar of BASELINE.json).
+// * persistent, warp-specialised: warp0 = TMA producer, warp1 = single-thread tcgen05.mma issuer, warps 2-5 =
+//   epilogue (tcgen05.ld -> bias / per-image row bias / residual / activation -> fp32 and/or (hi,lo) bf16 stores).
+//   Two TMEM accumulator stages let the epilogue of tile i overlap the main loop of tile i+1.
+#include "ptx.cuh"
+#include "odise_b200.h"
+#include "launch_count.h"
+#include <cudaTypedefs.h>
+#include <mutex>
+
+namespace ob {
+
+struct GemmParams {
+  int M, N, K, batch;
+  int a_batched, b_batched;
+  int conv, C, H, W, bw, bh, bb;
+  int tiles_m, tiles_n, splits, kblocks;
+  float alpha;
+  const float* bias;
+  const float* rowbias;
+  int rows_per_group;
+  long long rowbias_ld;
+  const float* res;
+  long long ldres, res_bs;
+  float* D;
+  long long ldd, d_bs;
+  __nv_bfloat16* Dh;
+  __nv_bfloat16* Dl;
+  long long ldh, h_bs;
+  int act;
+  float* partial;  // [splits][batch][M][N] when splits > 1
+};
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  if (act == ODISE_ACT_RELU) return fmaxf(v, 0.f);
+  if (act == ODISE_ACT_SILU) return v / (1.f + __expf(-v));
+  if (act == ODISE_ACT_GELU) return 0.5f * v * (1.f + erff(v * 0.70710678118654752f));
+  return v;
+}
+
+// epilogue for one row segment of `cnt` (<=32) consecutive columns starting at n, values in acc[]
+__device__ __forceinline__ void epilogue_row(const GemmParams& p, int z, int m, int n, int cnt, float* acc) {
+  const bool vec = (cnt == 32);
+  if (p.alpha != 1.f) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc[j] *= p.alpha;
+  }
+  if (p.bias) {
+    if (vec) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n + j));
+        acc[j] += b.x; acc[j + 1] += b.y; acc[j + 2] += b.z; acc[j + 3] += b.w;
+      }
+    } else {
+      _Pragma("unroll") for (int j = 0; j < 32; ++j) if (j < cnt) acc[j] += __ldg(p.bias + n + j);
+    }
+  }
+  if (p.rowbias) {
+    const float* rb = p.rowbias + (long long)(((long long)z * p.M + m) / p.rows_per_group) * p.rowbias_ld + n;
+    if (vec) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        float4 b = __ldg(reinterpret_cast<const float4*>(rb + j));
+        acc[j] += b.x; acc[j + 1] += b.y; acc[j + 2] += b.z; acc[j + 3] += b.w;
+      }
+    } else {
+      _Pragma("unroll") for (int j = 0; j < 32; ++j) if (j < cnt) acc[j] += __ldg(rb + j);
+    }
+  }
+  if (p.act != ODISE_ACT_NONE) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc[j] = apply_act(acc[j], p.act);
+  }
+  if (p.res) {
+    const float* r = p.res + (long long)z * p.res_bs + (long long)m * p.ldres + n;
+    if (vec) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        float4 b = *reinterpret_cast<const float4*>(r + j);
+        acc[j] += b.x; acc[j + 1] += b.y; acc[j + 2] += b.z; acc[j + 3] += b.w;
+      }
+    } else {
+      _Pragma("unroll") for (int j = 0; j < 32; ++j) if (j < cnt) acc[j] += r[j];
+    }
+  }
+  if (p.D) {
+    float* d = p.D + (long long)z * p.d_bs + (long long)m * p.ldd + n;
+    if (vec) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4)
+        *reinterpret_cast<float4*>(d + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+    } else {
+      _Pragma("unroll") for (int j = 0; j < 32; ++j) if (j < cnt) d[j] = acc[j];
+    }
+  }
+  if (p.Dh) {
+    __nv_bfloat16* dh = p.Dh + (long long)z * p.h_bs + (long long)m * p.ldh + n;
+    __nv_bfloat16* dl = p.Dl ? p.Dl + (long long)z * p.h_bs + (long long)m * p.ldh + n : nullptr;
+    if (vec) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        __align__(16) __nv_bfloat16 h[8];
+        __align__(16) __nv_bfloat16 l[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) split_bf16(acc[j + t], h[t], l[t]);
+        *reinterpret_cast<uint4*>(dh + j) = *reinterpret_cast<const uint4*>(h);
+        if (dl) *reinterpret_cast<uint4*>(dl + j) = *reinterpret_cast<const uint4*>(l);
+      }
+    } else {
+      _Pragma("unroll") for (int j = 0; j < 32; ++j) if (j < cnt) {
+        __nv_bfloat16 h, l;
+        split_bf16(acc[j], h, l);
+        dh[j] = h;
+        if (dl) dl[j] = l;
+      }
+    }
+  }
+}
+
+template <int BN, int NMMA>
+struct GemmCfg {
+  static constexpr int BM = 128, BK = 64;
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int PLANES = (NMMA == 3) ? 2 : 1;
+  static constexpr int STAGE_BYTES = PLANES * (A_BYTES + B_BYTES);
+  static constexpr int STAGES_RAW = (220 * 1024) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  static constexpr int ACC_STRIDE = (BN <= 64) ? 64 : (BN <= 128 ? 128 : 256);  // TMEM columns per accumulator
+  static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BN, int NMMA>
+__global__ void __launch_bounds__(192, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
+               const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
+               const GemmParams p) {
+  using Cfg = GemmCfg<BN, NMMA>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full = bars;                       // [STAGES]
+  uint64_t* empty = bars + Cfg::STAGES;        // [STAGES]
+  uint64_t* tfull = bars + 2 * Cfg::STAGES;    // [2]
+  uint64_t* tempty = bars + 2 * Cfg::STAGES + 2;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmAh);
+    tma_prefetch_desc(&tmBh);
+    if (NMMA == 3) {
+      tma_prefetch_desc(&tmAl);
+      tma_prefetch_desc(&tmBl);
+    }
+    for (int s = 0; s < Cfg::STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull[s], 1);
+      mbar_init(&tempty[s], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int tiles_per_z = p.tiles_m * p.tiles_n * p.splits;
+  const int total_tiles = tiles_per_z * p.batch;
+  const int kb_per_split = (p.kblocks + p.splits - 1) / p.splits;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ------------------------------------------------------------ TMA producer
+      int stage = 0;
+      uint32_t phase = 0;
+      const int cpk = p.conv ? (p.C / 64) : 1;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int z = tile / tiles_per_z;
+        int r = tile - z * tiles_per_z;
+        const int sp = r / (p.tiles_m * p.tiles_n);
+        r -= sp * (p.tiles_m * p.tiles_n);
+        const int mt = r / p.tiles_n, nt = r - mt * p.tiles_n;
+        const int m0 = mt * 128, n0 = nt * BN;
+        const int kb0 = sp * kb_per_split;
+        const int kb1 = min(p.kblocks, kb0 + kb_per_split);
+        int b0 = 0, h0 = 0, w0 = 0;
+        if (p.conv) {
+          const int hw = p.H * p.W;
+          b0 = m0 / hw;
+          const int rem = m0 - b0 * hw;
+          h0 = rem / p.W;
+          w0 = rem - h0 * p.W;
+        }
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          uint8_t* st = smem + stage * Cfg::STAGE_BYTES;
+          mbar_arrive_expect_tx(&full[stage], Cfg::STAGE_BYTES);
+          if (p.conv) {
+            const int tap = kb / cpk, cc = kb - tap * cpk;
+            const int kh = tap / 3, kw = tap - kh * 3;
+            tma_load_4d(st, &tmAh, &full[stage], cc * 64, w0 + kw - 1, h0 + kh - 1, b0);
+            if (NMMA == 3) tma_load_4d(st + Cfg::A_BYTES, &tmAl, &full[stage], cc * 64, w0 + kw - 1, h0 + kh - 1, b0);
+          } else {
+            const int za = p.a_batched ? z : 0;
+            tma_load_3d(st, &tmAh, &full[stage], kb * 64, m0, za);
+            if (NMMA == 3) tma_load_3d(st + Cfg::A_BYTES, &tmAl, &full[stage], kb * 64, m0, za);
+          }
+          const int zb = p.b_batched ? z : 0;
+          uint8_t* sb = st + Cfg::PLANES * Cfg::A_BYTES;
+          tma_load_3d(sb, &tmBh, &full[stage], kb * 64, n0, zb);
+          if (NMMA == 3) tma_load_3d(sb + Cfg::B_BYTES, &tmBl, &full[stage], kb * 64, n0, zb);
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ------------------------------------------------------------ MMA issuer (one thread)
+      constexpr uint32_t idesc = umma_idesc_bf16(128, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t accphase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int r = tile % tiles_per_z;
+        const int sp = r / (p.tiles_m * p.tiles_n);
+        const int kb0 = sp * kb_per_split;
+        const int kb1 = min(p.kblocks, kb0 + kb_per_split);
+        mbar_wait(&tempty[acc], accphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * Cfg::ACC_STRIDE;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint32_t sb = sa + Cfg::PLANES * Cfg::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t a_hi = umma_desc_sw128(sa + k * 32);
+            const uint64_t b_hi = umma_desc_sw128(sb + k * 32);
+            umma_bf16(d_tmem, a_hi, b_hi, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if (NMMA == 3) {
+              const uint64_t a_lo = umma_desc_sw128(sa + Cfg::A_BYTES + k * 32);
+              const uint64_t b_lo = umma_desc_sw128(sb + Cfg::B_BYTES + k * 32);
+              umma_bf16(d_tmem, a_hi, b_lo, idesc, 1u);
+              umma_bf16(d_tmem, a_lo, b_hi, idesc, 1u);
+            }
+          }
+          umma_commit(&empty[stage]);  // smem slot reusable once these MMAs retire
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull[acc]);  // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; accphase ^= 1; }
+      }
+    }
+  } else {
+    // -------------------------------------------------------------- epilogue warps (4 x 32 rows)
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may touch
+    int acc = 0;
+    uint32_t accphase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int z = tile / tiles_per_z;
+      int r = tile - z * tiles_per_z;
+      const int sp = r / (p.tiles_m * p.tiles_n);
+      r -= sp * (p.tiles_m * p.tiles_n);
+      const int mt = r / p.tiles_n, nt = r - mt * p.tiles_n;
+      const int m = mt * 128 + quad * 32 + lane;
+      const int n0 = nt * BN;
+      mbar_wait(&tfull[acc], accphase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + acc * Cfg::ACC_STRIDE + ((uint32_t)(quad * 32) << 16);
+      const int kb0 = sp * kb_per_split;
+      const bool has_k = kb0 < p.kblocks;  // a split with no k-blocks contributes zeros
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(t_row + c0, v);
+        tmem_ld_wait();
+        const int n = n0 + c0;
+        if (m < p.M && n < p.N) {
+          float accv[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) accv[j] = has_k ? __uint_as_float(v[j]) : 0.f;
+          const int cnt = min(32, p.N - n);
+          if (p.splits > 1) {
+            float* dst = p.partial + ((long long)(sp * p.batch + z) * p.M + m) * p.N + n;
+            _Pragma("unroll") for (int j = 0; j < 32; ++j) if (j < cnt) dst[j] = accv[j];
+          } else {
+            epilogue_row(p, z, m, n, cnt, accv);
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty[acc]);
+      if (++acc == 2) { acc = 0; accphase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// split-K second pass: sum the partials and run the normal epilogue (32 columns per thread-row segment)
+__global__ void gemm_splitk_reduce_kernel(const GemmParams p) {
+  const int segs = (p.N + 31) / 32;
+  const long long total = (long long)p.batch * p.M * segs;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int seg = (int)(i % segs);
+    const long long zm = i / segs;
+    const int m = (int)(zm % p.M);
+    const int z = (int)(zm / p.M);
+    const int n = seg * 32;
+    const int cnt = min(32, p.N - n);
+    float acc[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+    for (int sp = 0; sp < p.splits; ++sp) {
+      const float* src = p.partial + ((long long)(sp * p.batch + z) * p.M + m) * p.N + n;
+      _Pragma("unroll") for (int j = 0; j < 32; ++j) if (j < cnt) acc[j] += src[j];
+    }
+    epilogue_row(p, z, m, n, cnt, acc);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(f);
+  });
+  return fn;
+}
+
+static int encode_map(CUtensorMap* tm, const void* base, int rank, const cuuint64_t* dims,
+                      const cuuint64_t* strides_bytes, const cuuint32_t* box) {
+  auto enc = get_encode();
+  if (!enc) return ODISE_ERR_DRIVER;
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), dims, strides_bytes, box,
+                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? ODISE_OK : ODISE_ERR_TENSORMAP;
+}
+
+int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <int BN, int NMMA>
+static int launch_cfg(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl,
+                      const GemmParams& p, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN, NMMA>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, NMMA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  const int total = p.tiles_m * p.tiles_n * p.splits * p.batch;
+  const int grid = total < num_sms() ? total : num_sms();
+  gemm_tc_kernel<BN, NMMA><<<grid, 192, Cfg::SMEM_BYTES, stream>>>(ah, al, bh, bl, p);
+  return (int)cudaGetLastError();
+}
+
+static int pick_bn(int M, int N, int batch, int forced) {
+  if (forced == 64 || forced == 128 || forced == 160 || forced == 256) return forced;
+  const int cands[4] = {256, 160, 128, 64};
+  const double eff[4] = {1.0, 1.0, 1.0, 1.45};  // BN=64 is smem-bandwidth bound on the A re-read
+  const long long tm = (M + 127) / 128;
+  double best = 1e30;
+  int best_bn = 128;
+  for (int i = 0; i < 4; ++i) {
+    const int bn = cands[i];
+    const long long tiles = tm * ((N + bn - 1) / bn) * batch;
+    const long long waves = (tiles + num_sms() - 1) / num_sms();
+    const double cost = (double)waves * bn * eff[i] + 0.02 * bn;  // mild bias toward smaller tiles on ties
+    if (cost < best) { best = cost; best_bn = bn; }
+  }
+  return best_bn;
+}
+
+}  // namespace ob
+
+using namespace ob;
+
+extern "C" int odise_gemm_bf16(const odise_gemm_desc* d, void* stream_v) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
+  if (!d || !d->a_hi || !d->b_hi) return ODISE_ERR_ARG;
+  if (d->nmma != 1 && d->nmma != 3) return ODISE_ERR_ARG;
+  if (d->nmma == 3 && (!d->a_lo || !d->b_lo)) return ODISE_ERR_ARG;
+  if (d->M <= 0 || d->N <= 0 || d->K <= 0 || d->batch <= 0) return ODISE_ERR_ARG;
+  if (!d->out_f32 && !d->out_hi) return ODISE_ERR_ARG;
+
+  GemmParams p{};
+  p.M = d->M; p.N = d->N; p.K = d->K; p.batch = d->batch;
+  p.a_batched = d->a_batch_stride != 0; p.b_batched = d->b_batch_stride != 0;
+  p.conv = d->conv3x3; p.C = d->conv_C; p.H = d->conv_H; p.W = d->conv_W;
+  p.alpha = d->alpha;
+  p.bias = d->bias; p.rowbias = d->rowbias; p.rows_per_group = d->rows_per_group > 0 ? d->rows_per_group : 1;
+  p.rowbias_ld = d->rowbias_ld;
+  p.res = d->residual; p.ldres = d->ld_residual; p.res_bs = d->residual_batch_stride;
+  p.D = d->out_f32; p.ldd = d->ld_out; p.d_bs = d->out_batch_stride;
+  p.Dh = reinterpret_cast<__nv_bfloat16*>(d->out_hi); p.Dl = reinterpret_cast<__nv_bfloat16*>(d->out_lo);
+  p.ldh = d->ld_out_bf16; p.h_bs = d->out_bf16_batch_stride;
+  p.act = d->act;
+
+  // vector epilogue paths need 16-byte alignment
+  if (d->out_f32 && (d->ld_out % 4 || d->out_batch_stride % 4)) return ODISE_ERR_ALIGN;
+  if (d->residual && (d->ld_residual % 4 || d->residual_batch_stride % 4)) return ODISE_ERR_ALIGN;
+  if (d->out_hi && (d->ld_out_bf16 % 8 || d->out_bf16_batch_stride % 8)) return ODISE_ERR_ALIGN;
+  if (d->rowbias && d->rowbias_ld % 4) return ODISE_ERR_ALIGN;
+
+  CUtensorMap ah, al, bh, bl;
+  int rc;
+  if (p.conv) {
+    if (p.C % 64 || d->K != 9 * p.C || d->batch != 1) return ODISE_ERR_ARG;
+    const int hw = p.H * p.W;
+    if (d->M % hw) return ODISE_ERR_ARG;
+    const int B = d->M / hw;
+    if (p.W >= 128) {
+      if (p.W % 128) return ODISE_ERR_ARG;
+      p.bw = 128; p.bh = 1; p.bb = 1;
+    } else {
+      if (128 % p.W) return ODISE_ERR_ARG;
+      p.bw = p.W;
+      p.bh = 128 / p.W < p.H ? 128 / p.W : p.H;
+      if (p.H % p.bh) return ODISE_ERR_ARG;
+      if (128 % (p.bw * p.bh)) return ODISE_ERR_ARG;
+      p.bb = 128 / (p.bw * p.bh);
+    }
+    const long long pix = d->lda;  // elements between consecutive pixels (>= C: channel slices of wider buffers)
+    if (pix < p.C || pix % 8) return ODISE_ERR_ALIGN;
+    cuuint64_t dims[4] = {(cuuint64_t)p.C, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)B};
+    cuuint64_t str[3] = {(cuuint64_t)pix * 2, (cuuint64_t)pix * p.W * 2, (cuuint64_t)pix * hw * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)p.bw, (cuuint32_t)p.bh, (cuuint32_t)p.bb};
+    rc = encode_map(&ah, d->a_hi, 4, dims, str, box);
+    if (rc) return rc;
+    rc = encode_map(&al, d->nmma == 3 ? d->a_lo : d->a_hi, 4, dims, str, box);
+    if (rc) return rc;
+  } else {
+    if (d->lda % 8 || d->a_batch_stride % 8) return ODISE_ERR_ALIGN;
+    const long long bs = d->a_batch_stride ? d->a_batch_stride : (long long)d->M * d->lda;
+    cuuint64_t dims[3] = {(cuuint64_t)d->K, (cuuint64_t)d->M, (cuuint64_t)(d->a_batch_stride ? d->batch : 1)};
+    cuuint64_t str[2] = {(cuuint64_t)d->lda * 2, (cuuint64_t)bs * 2};
+    cuuint32_t box[3] = {64, 128, 1};
+    rc = encode_map(&ah, d->a_hi, 3, dims, str, box);
+    if (rc) return rc;
+    rc = encode_map(&al, d->nmma == 3 ? d->a_lo : d->a_hi, 3, dims, str, box);
+    if (rc) return rc;
+  }
+  const int BN = pick_bn(d->M, d->N, d->batch, d->force_bn);
+  {
+    if (d->ldb % 8 || d->b_batch_stride % 8) return ODISE_ERR_ALIGN;
+    const long long bs = d->b_batch_stride ? d->b_batch_stride : (long long)d->N * d->ldb;
+    cuuint64_t dims[3] = {(cuuint64_t)d->K, (cuuint64_t)d->N, (cuuint64_t)(d->b_batch_stride ? d->batch : 1)};
+    cuuint64_t str[2] = {(cuuint64_t)d->ldb * 2, (cuuint64_t)bs * 2};
+    cuuint32_t box[3] = {64, (cuuint32_t)BN, 1};
+    rc = encode_map(&bh, d->b_hi, 3, dims, str, box);
+    if (rc) return rc;
+    rc = encode_map(&bl, d->nmma == 3 ? d->b_lo : d->b_hi, 3, dims, str, box);
+    if (rc) return rc;
+  }
+  p.tiles_m = (d->M + 127) / 128;
+  p.tiles_n = (d->N + BN - 1) / BN;
+  p.kblocks = (d->K + 63) / 64;
+  p.splits = d->split_k > 1 ? d->split_k : 1;
+  if (p.splits > p.kblocks) p.splits = p.kblocks;
+  if (p.splits > 1) {
+    if (!d->workspace ||
+        d->workspace_bytes < (long long)p.splits * d->batch * d->M * d->N * (long long)sizeof(float))
+      return ODISE_ERR_WORKSPACE;
+    p.partial = reinterpret_cast<float*>(d->workspace);
+  }
+
+#define ODISE_LAUNCH(BN_, NM_) rc = launch_cfg<BN_, NM_>(ah, al, bh, bl, p, stream)
+  if (d->nmma == 3) {
+    switch (BN) {
+      case 64: ODISE_LAUNCH(64, 3); break;
+      case 128: ODISE_LAUNCH(128, 3); break;
+      case 160: ODISE_LAUNCH(160, 3); break;
+      default: ODISE_LAUNCH(256, 3); break;
+    }
+  } else {
+    switch (BN) {
+      case 64: ODISE_LAUNCH(64, 1); break;
+      case 128: ODISE_LAUNCH(128, 1); break;
+      case 160: ODISE_LAUNCH(160, 1); break;
+      default: ODISE_LAUNCH(256, 1); break;
+    }
+  }
+#undef ODISE_LAUNCH
+  if (rc) return rc;
+  count_launch(p.splits > 1 ? 2 : 1);
+  if (p.splits > 1) {
+    const long long total = (long long)p.batch * p.M * ((p.N + 31) / 32);
+    int blocks = (int)((total + 127) / 128);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    gemm_splitk_reduce_kernel<<<blocks, 128, 0, stream>>>(p);
+    rc = (int)cudaGetLastError();
+  }
+  return rc;
+}

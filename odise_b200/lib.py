@@ -1,0 +1,235 @@
+"""ctypes binding of libodise_b200.so (include/odise_b200.h).
+
+PyTorch is used for device memory and streams only; every op here launches hand-written sm_100a kernels through
+the C ABI.  There is NO fallback: if the library is missing or a call fails, an exception is raised.
+"""
+import ctypes
+import os
+from ctypes import c_int, c_float, c_longlong, c_void_p, POINTER
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libodise_b200.so")
+
+ACT_NONE, ACT_RELU, ACT_SILU, ACT_GELU = 0, 1, 2, 3
+
+
+class OdiseError(RuntimeError):
+    pass
+
+
+class GemmDesc(ctypes.Structure):
+    _fields_ = [
+        ("M", c_int), ("N", c_int), ("K", c_int), ("batch", c_int),
+        ("nmma", c_int), ("conv3x3", c_int),
+        ("conv_C", c_int), ("conv_H", c_int), ("conv_W", c_int),
+        ("a_hi", c_void_p), ("a_lo", c_void_p), ("lda", c_longlong), ("a_batch_stride", c_longlong),
+        ("b_hi", c_void_p), ("b_lo", c_void_p), ("ldb", c_longlong), ("b_batch_stride", c_longlong),
+        ("alpha", c_float),
+        ("bias", c_void_p),
+        ("rowbias", c_void_p), ("rows_per_group", c_int), ("rowbias_ld", c_longlong),
+        ("act", c_int),
+        ("residual", c_void_p), ("ld_residual", c_longlong), ("residual_batch_stride", c_longlong),
+        ("out_f32", c_void_p), ("ld_out", c_longlong), ("out_batch_stride", c_longlong),
+        ("out_hi", c_void_p), ("out_lo", c_void_p), ("ld_out_bf16", c_longlong), ("out_bf16_batch_stride", c_longlong),
+        ("split_k", c_int), ("workspace", c_void_p), ("workspace_bytes", c_longlong),
+        ("force_bn", c_int),
+    ]
+
+
+_lib = None
+
+# name -> argtypes (all return int); kept in one place so tests can check every header symbol is bound
+_SIGS = {
+    "odise_msda_forward_f32": [c_void_p] * 6 + [c_int] * 7 + [c_void_p],
+    "odise_msda_fused_f32": [c_void_p] * 9 + [c_int] * 7 + [c_void_p],
+    "odise_gemm_bf16": [POINTER(GemmDesc), c_void_p],
+    "odise_split_f32": [c_void_p, c_longlong, c_void_p, c_void_p, c_longlong, c_longlong, c_int, c_void_p],
+    "odise_groupnorm_stats_f32": [c_void_p, c_longlong, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float,
+                                  c_void_p],
+    "odise_groupnorm_apply_f32": [c_void_p, c_longlong, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
+                                  c_longlong, c_void_p, c_void_p, c_longlong, c_int, c_int, c_int, c_int, c_void_p],
+    "odise_layernorm_f32": [c_void_p, c_longlong, c_void_p, c_longlong, c_void_p, c_void_p, c_float, c_void_p,
+                            c_longlong, c_void_p, c_longlong, c_void_p, c_void_p, c_longlong, c_longlong, c_int,
+                            c_void_p],
+    "odise_geglu_f32": [c_void_p, c_longlong, c_void_p, c_void_p, c_longlong, c_longlong, c_int, c_void_p],
+    "odise_add_split_f32": [c_void_p, c_longlong, c_void_p, c_longlong, c_longlong, c_void_p, c_longlong, c_void_p,
+                            c_void_p, c_longlong, c_longlong, c_int, c_void_p],
+    "odise_upsample2x_split_f32": [c_void_p, c_longlong, c_void_p, c_void_p, c_longlong, c_int, c_int, c_int, c_int,
+                                   c_void_p],
+    "odise_im2col3x3_split_f32": [c_void_p, c_longlong, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
+                                  c_int, c_int, c_void_p],
+    "odise_copy2d_f32": [c_void_p, c_longlong, c_void_p, c_longlong, c_longlong, c_int, c_float, c_int, c_void_p],
+    "odise_resize_nhwc_f32": [c_void_p, c_longlong, c_void_p, c_longlong, c_int, c_int, c_int, c_int, c_int, c_int,
+                              c_int, c_int, c_void_p],
+    "odise_nchw_to_nhwc_f32": [c_void_p, c_void_p, c_longlong, c_int, c_int, c_int, c_void_p],
+    "odise_nhwc_to_nchw_f32": [c_void_p, c_longlong, c_void_p, c_int, c_int, c_int, c_void_p],
+    "odise_attn_mask_bits_f32": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p],
+    "odise_mha_d32_f32": [c_void_p] * 8 + [c_int, c_int, c_int, c_int, c_float, c_void_p],
+    "odise_mask_binarize_f32": [c_void_p, c_void_p, c_longlong, c_void_p, c_int, c_int, c_int, c_void_p],
+    "odise_pool_normalize_f32": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
+    "odise_l2_normalize_split_f32": [c_void_p, c_longlong, c_void_p, c_void_p, c_longlong, c_longlong, c_int,
+                                     c_void_p],
+    "odise_class_max_f32": [c_void_p, c_longlong, c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_void_p],
+    "odise_attention_tc": [c_void_p, c_void_p, c_longlong, c_void_p, c_void_p, c_longlong, c_void_p, c_void_p,
+                           c_longlong, c_longlong, c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_int, c_int,
+                           c_int, c_int, c_float, c_int, c_void_p],
+}
+
+
+def load():
+    """Load the shared library (building is __graft_entry__.build()'s job). Raises if absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB_PATH):
+        raise OdiseError(
+            f"{_LIB_PATH} not found: run `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(odise_b200 has no CPU / eager fallback)")
+    lib = ctypes.CDLL(_LIB_PATH)
+    lib.odise_version.restype = c_int
+    lib.odise_launch_count.restype = c_longlong
+    for name, args in _SIGS.items():
+        fn = getattr(lib, name)
+        fn.argtypes = args
+        fn.restype = c_int
+    _lib = lib
+    return lib
+
+
+def launch_count():
+    return int(load().odise_launch_count())
+
+
+def _check(rc, what):
+    if rc != 0:
+        raise OdiseError(f"{what} failed with code {rc}")
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _req(t, dtype, name):
+    if not t.is_cuda:
+        raise OdiseError(f"{name}: expected a CUDA tensor (odise_b200 kernels only run on the GPU)")
+    if t.dtype != dtype:
+        raise OdiseError(f"{name}: expected {dtype}, got {t.dtype}")
+    return t
+
+
+class Planes:
+    """(hi, lo) bf16 operand planes of a 2-D fp32 matrix [rows, cols] (row stride ld elements)."""
+
+    __slots__ = ("hi", "lo", "rows", "cols", "ld")
+
+    def __init__(self, hi, lo, rows, cols, ld):
+        self.hi, self.lo, self.rows, self.cols, self.ld = hi, lo, rows, cols, ld
+
+    @staticmethod
+    def empty(rows, cols, device, lo=True, ld=None):
+        ld = ld or ((cols + 7) // 8 * 8)
+        hi = torch.empty(rows * ld, dtype=torch.bfloat16, device=device)
+        lo_t = torch.empty(rows * ld, dtype=torch.bfloat16, device=device) if lo else None
+        if ld != cols:
+            hi.zero_()
+            if lo_t is not None:
+                lo_t.zero_()
+        return Planes(hi, lo_t, rows, cols, ld)
+
+    def float(self):
+        h = self.hi.view(self.rows, self.ld)[:, : self.cols].float()
+        if self.lo is not None:
+            h = h + self.lo.view(self.rows, self.ld)[:, : self.cols].float()
+        return h
+
+    def col_slice(self, c0, cols):
+        """Planes viewing columns [c0, c0+cols) of every row (same ld); c0 % 8 == 0."""
+        assert c0 % 8 == 0
+        return Planes(self.hi[c0:], None if self.lo is None else self.lo[c0:], self.rows, cols, self.ld)
+
+    def row_slice(self, r0, rows):
+        return Planes(self.hi[r0 * self.ld:], None if self.lo is None else self.lo[r0 * self.ld:], rows, self.cols,
+                      self.ld)
+
+
+def split(x, out=None, lo=True):
+    """fp32 [rows, cols] (last dim contiguous) -> Planes."""
+    _req(x, torch.float32, "x")
+    x2 = x.reshape(-1, x.shape[-1])
+    rows, cols = x2.shape
+    assert x2.stride(1) == 1
+    if out is None:
+        out = Planes.empty(rows, cols, x.device, lo=lo)
+    _check(load().odise_split_f32(_ptr(x2), x2.stride(0), _ptr(out.hi), _ptr(out.lo), out.ld, rows, cols, _stream()),
+           "odise_split_f32")
+    return out
+
+
+def gemm(a, b, *, M=None, N=None, K=None, nmma=3, batch=1, a_bs=0, b_bs=0, conv=None, alpha=1.0, bias=None,
+         rowbias=None, rows_per_group=1, act=ACT_NONE, residual=None, ld_res=None, res_bs=0, out=None, ld_out=None,
+         out_bs=0, out_planes=None, outp_bs=0, split_k=1, workspace=None, force_bn=0):
+    """out[z] = epi(alpha * A[z] @ B[z]^T).  a, b: Planes (K-major).  conv = (C, H, W) for implicit 3x3."""
+    d = GemmDesc()
+    d.M = M if M is not None else a.rows
+    d.N = N if N is not None else b.rows
+    d.K = K if K is not None else (9 * conv[0] if conv else a.cols)
+    d.batch = batch
+    d.nmma = nmma
+    if conv:
+        d.conv3x3, d.conv_C, d.conv_H, d.conv_W = 1, conv[0], conv[1], conv[2]
+    d.a_hi, d.a_lo, d.lda, d.a_batch_stride = _ptr(a.hi), _ptr(a.lo), a.ld, a_bs
+    d.b_hi, d.b_lo, d.ldb, d.b_batch_stride = _ptr(b.hi), _ptr(b.lo), b.ld, b_bs
+    d.alpha = alpha
+    d.bias = _ptr(bias)
+    if rowbias is not None:
+        d.rowbias, d.rows_per_group, d.rowbias_ld = _ptr(rowbias), rows_per_group, rowbias.stride(0)
+    d.act = act
+    if residual is not None:
+        d.residual = _ptr(residual)
+        d.ld_residual = ld_res if ld_res is not None else residual.stride(-2)
+        d.residual_batch_stride = res_bs
+    if out is not None:
+        d.out_f32 = _ptr(out)
+        d.ld_out = ld_out if ld_out is not None else out.stride(-2)
+        d.out_batch_stride = out_bs
+    if out_planes is not None:
+        d.out_hi, d.out_lo, d.ld_out_bf16 = _ptr(out_planes.hi), _ptr(out_planes.lo), out_planes.ld
+        d.out_bf16_batch_stride = outp_bs
+    d.split_k = split_k
+    if split_k > 1:
+        need = split_k * batch * d.M * d.N * 4
+        if workspace is None or workspace.numel() * workspace.element_size() < need:
+            raise OdiseError("gemm: split_k needs a workspace of %d bytes" % need)
+        d.workspace, d.workspace_bytes = _ptr(workspace), workspace.numel() * workspace.element_size()
+    d.force_bn = force_bn
+    _check(load().odise_gemm_bf16(ctypes.byref(d), _stream()), "odise_gemm_bf16")
+    return out if out is not None else out_planes
+
+
+def msda_forward(value, spatial_shapes, level_start_index, sampling_locations, attention_weights, im2col_step=128):
+    """Drop-in for MSDA.ms_deform_attn_forward (reference ops/src/vision.cpp:19): same arguments, same result
+    shape [N, Lq, M*D], same error behaviour class (RuntimeError on non-contiguous / non-CUDA input)."""
+    for t, nm in ((value, "value"), (sampling_locations, "sampling_loc"), (attention_weights, "attn_weight")):
+        if not t.is_cuda:
+            raise OdiseError(f"{nm} must be a CUDA tensor")  # reference: AT_ERROR("Not implemented on the CPU")
+        if not t.is_contiguous():
+            raise OdiseError(f"{nm} tensor has to be contiguous")  # reference .cu:33-37
+        _req(t, torch.float32, nm)
+    N, S, M, D = value.shape
+    _, Lq, _, L, P, _ = sampling_locations.shape
+    step = min(N, im2col_step)
+    if N % step != 0:
+        raise OdiseError(f"batch({N}) must divide im2col_step({step})")  # reference .cu:57
+    ss = spatial_shapes.to(device=value.device, dtype=torch.int64).contiguous()
+    ls = level_start_index.to(device=value.device, dtype=torch.int64).contiguous()
+    out = torch.empty(N, Lq, M * D, dtype=torch.float32, device=value.device)
+    _check(load().odise_msda_forward_f32(_ptr(value), _ptr(ss), _ptr(ls), _ptr(sampling_locations),
+                                         _ptr(attention_weights), _ptr(out), N, S, M, D, L, Lq, P, _stream()),
+           "odise_msda_forward_f32")
+    return out
