@@ -40,6 +40,7 @@ struct GemmParams {
   __nv_bfloat16* Dl;
   long long ldh, h_bs;
   int act;
+  int vec_ok;  // all epilogue pointers / leading dims allow 16-byte vector access
   float* partial;  // [splits][batch][M][N] when splits > 1
 };
 
@@ -52,7 +53,7 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 
 // epilogue for one row segment of `cnt` (<=32) consecutive columns starting at n, values in acc[]
 __device__ __forceinline__ void epilogue_row(const GemmParams& p, int z, int m, int n, int cnt, float* acc) {
-  const bool vec = (cnt == 32);
+  const bool vec = (cnt == 32) && p.vec_ok;
   if (p.alpha != 1.f) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) acc[j] *= p.alpha;
@@ -447,11 +448,18 @@ extern "C" int odise_gemm_bf16(const odise_gemm_desc* d, void* stream_v) {
   p.ldh = d->ld_out_bf16; p.h_bs = d->out_bf16_batch_stride;
   p.act = d->act;
 
-  // vector epilogue paths need 16-byte alignment
-  if (d->out_f32 && (d->ld_out % 4 || d->out_batch_stride % 4)) return ODISE_ERR_ALIGN;
-  if (d->residual && (d->ld_residual % 4 || d->residual_batch_stride % 4)) return ODISE_ERR_ALIGN;
-  if (d->out_hi && (d->ld_out_bf16 % 8 || d->out_bf16_batch_stride % 8)) return ODISE_ERR_ALIGN;
-  if (d->rowbias && d->rowbias_ld % 4) return ODISE_ERR_ALIGN;
+  // vector epilogue paths need 16-byte alignment; otherwise the kernel takes the scalar path
+  {
+    auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+    bool ok = true;
+    if (d->out_f32) ok = ok && d->ld_out % 4 == 0 && d->out_batch_stride % 4 == 0 && al16(d->out_f32);
+    if (d->residual) ok = ok && d->ld_residual % 4 == 0 && d->residual_batch_stride % 4 == 0 && al16(d->residual);
+    if (d->out_hi) ok = ok && d->ld_out_bf16 % 8 == 0 && d->out_bf16_batch_stride % 8 == 0 && al16(d->out_hi) &&
+                        (!d->out_lo || al16(d->out_lo));
+    if (d->rowbias) ok = ok && d->rowbias_ld % 4 == 0 && al16(d->rowbias);
+    if (d->bias) ok = ok && al16(d->bias);
+    p.vec_ok = ok ? 1 : 0;
+  }
 
   CUtensorMap ah, al, bh, bl;
   int rc;
