@@ -451,7 +451,7 @@ def encoder_features(vae, x, tap_blocks=ENC_TAP_BLOCKS):
 def decoder_features(vae, latent, tap_blocks=DEC_TAP_BLOCKS):
     """LdmExtractor.decode_to_image / decoder_forward (ldm.py:493-541) truncated after the last tap."""
     dec = vae.decoder
-    z = vae.post_quant_conv(latent / SCALE_FACTOR)
+    z = vae.post_quant_conv(1.0 / SCALE_FACTOR * latent)   # ldm.py:536
     h = dec.conv_in(z)
     h = dec.mid.block_2(dec.mid.attn_1(dec.mid.block_1(h, None)), None)
     feats = []

@@ -1,0 +1,155 @@
+"""CPU tests that PIN the oracle (oracle/) against the reference's own code imported from /root/reference
+(skipped where that tree is absent, i.e. on the GPU box) and check the parameter inventory of odise_b200/spec.py."""
+import types
+
+import pytest
+import torch
+
+from odise_b200 import spec
+from oracle import ldm as oldm
+from oracle import m2f, refshim
+
+needs_ref = pytest.mark.skipif(not refshim.available(), reason="/root/reference not present")
+
+
+def _shapes(params, prefix):
+    return {n[len(prefix):]: tuple(s) for n, s, _ in params}
+
+
+def test_unet_and_vae_inventory_matches_oracle_modules():
+    with torch.device("meta"):
+        unet, vae = oldm.UNetModel(), oldm.AutoencoderKL()
+    assert _shapes(spec.unet_params(), spec.UNET_PREFIX) == {k: tuple(v.shape) for k, v in unet.state_dict().items()}
+    assert _shapes(spec.vae_params(), spec.VAE_PREFIX) == {k: tuple(v.shape) for k, v in vae.state_dict().items()}
+    n = sum(torch.Size(s).numel() for _, s, _ in spec.unet_params())
+    assert n == 859_520_964          # the published SD-v1 UNet parameter count
+    assert sum(torch.Size(s).numel() for _, s, _ in spec.vae_params()) == 83_653_863
+
+
+def test_tap_table():
+    """reset_dim_stride expectations of the reference (ldm.py:284-346): tap channels / strides."""
+    inp, mid, out = spec.unet_blocks()
+    assert [out[i][0][1] for i in (2, 5, 8, 11)] == [2560, 1920, 960, 640]
+    assert spec.FEATURE_DIMS == (512, 512, 2560, 1920, 960, 640, 512, 512)
+
+
+def _head_sd(seed=0):
+    return spec.synth_state_dict(spec.head_params(), seed)
+
+
+@needs_ref
+def test_head_inventory_matches_reference_modules():
+    m = refshim.modules()
+    pd, dec = _ref_head(m)
+    want = {**{"sem_seg_head.pixel_decoder." + k: tuple(v.shape) for k, v in pd.state_dict().items()},
+            **{"sem_seg_head.predictor." + k: tuple(v.shape) for k, v in dec.state_dict().items()}}
+    got = {n: tuple(s) for n, s, _ in spec.pixel_decoder_params() + spec.decoder_params()}
+    assert got == want
+
+
+def _ref_head(m):
+    S = m.ShapeSpec
+    shape = {f"s{i}": S(channels=512, stride=2 ** i) for i in (2, 3, 4, 5)}
+    pd = m.MSDeformAttnPixelDecoder(shape, transformer_dropout=0.0, transformer_nheads=8,
+                                    transformer_dim_feedforward=1024, transformer_enc_layers=6, conv_dim=256,
+                                    mask_dim=256, norm="GN", transformer_in_features=["s3", "s4", "s5"],
+                                    common_stride=4).eval()
+    dec = m.ODISEMultiScaleMaskedTransformerDecoder(
+        class_embed=m.PseudoClassEmbed(133), post_mask_embed=m.PooledMaskEmbed(256, 256, 256), in_channels=256,
+        mask_classification=True, num_classes=133, hidden_dim=256, num_queries=100, nheads=8, dim_feedforward=2048,
+        dec_layers=9, pre_norm=False, enforce_input_project=False, mask_dim=256).eval()
+    return pd, dec
+
+
+def _strip(sd, prefix):
+    return {k[len(prefix):]: v for k, v in sd.items() if k.startswith(prefix)}
+
+
+@needs_ref
+@torch.no_grad()
+def test_head_oracle_equals_reference():
+    m = refshim.modules()
+    pd, dec = _ref_head(m)
+    sd = _head_sd(1)
+    pd.load_state_dict(_strip(sd, "sem_seg_head.pixel_decoder."))
+    dec.load_state_dict(_strip(sd, "sem_seg_head.predictor."))
+    g = torch.Generator().manual_seed(5)
+    feats = {f"s{i}": torch.randn(2, 512, 128 // 2 ** i, 128 // 2 ** i, generator=g) for i in (2, 3, 4, 5)}
+    mf_r, t_r, ms_r = pd.forward_features(feats)
+    mf_o, t_o, ms_o = m2f.pixel_decoder(sd, feats, "sem_seg_head.pixel_decoder.")
+    assert torch.allclose(mf_o, mf_r, rtol=1e-4, atol=1e-5)
+    for a, b in zip(ms_o, ms_r):
+        assert torch.allclose(a, b, rtol=1e-4, atol=1e-5)
+    out_r = dec(ms_r, mf_r)
+    out_o, _ = m2f.transformer_decoder(sd, ms_r, mf_r, "sem_seg_head.predictor.")
+    for k in ("pred_masks", "mask_embed", "mask_pooled_features"):
+        assert torch.allclose(out_o[k], out_r[k], rtol=1e-3, atol=1e-4), k
+    assert torch.equal(out_o["logit_scale"], out_r["logit_scale"])
+    for a, b in zip(out_o["aux_outputs"], out_r["aux_outputs"]):
+        assert torch.allclose(a["pred_masks"], b["pred_masks"], rtol=1e-3, atol=1e-4)
+    # scoring: CategoryODISE.cal_pred_logits on the reference class itself
+    sizes = [1, 3, 2, 1, 4] * 4
+    te = torch.randn(sum(sizes), 256, generator=g)
+    ne = torch.randn(1, 256, generator=g)
+    labels = [["x"] * n for n in sizes]
+    ref = m.CategoryODISE.cal_pred_logits(None, dict(mask_embed=out_r["mask_embed"], text_embed=te, null_embed=ne,
+                                                     labels=labels, logit_scale=out_r["logit_scale"]))
+    mine = m2f.cal_pred_logits(out_r["mask_embed"], te, ne, out_r["logit_scale"], sizes)
+    assert torch.allclose(mine, ref, rtol=1e-5, atol=1e-5)
+
+
+@needs_ref
+@torch.no_grad()
+def test_position_embedding_and_msdeformattn_equal_reference():
+    m = refshim.modules()
+    x = torch.zeros(2, 256, 7, 9)
+    assert torch.allclose(m2f.position_embedding_sine(2, 7, 9), m.PositionEmbeddingSine(128, normalize=True)(x), atol=1e-6)
+
+
+@needs_ref
+@torch.no_grad()
+def test_reference_ldm_driver_runs_on_oracle_unet():
+    """The reference's LdmExtractor.unet_forward / encoder_forward / decoder_forward (ldm.py:424-533) executed
+    VERBATIM on the oracle modules == oracle.ldm.unet_features / encoder_features / decoder_features."""
+    import importlib
+    refshim.install()
+    rl = importlib.import_module("odise.modeling.meta_arch.ldm")
+    rl.timestep_embedding = oldm.timestep_embedding
+    rl.DiagonalGaussianDistribution = oldm.DiagonalGaussianDistribution
+    torch.manual_seed(0)
+    unet = oldm.UNetModel(model_channels=64, num_heads=8, context_dim=48).eval()
+    for p in unet.parameters():
+        torch.nn.init.normal_(p, std=0.05)
+    x, ctx = torch.randn(2, 4, 16, 16), torch.randn(2, 5, 48)
+    cond = torch.randn(2, 256)
+    fake = types.SimpleNamespace(ldm=types.SimpleNamespace(unet=unet),
+                                 unet_blocks=[unet.output_blocks[i] for i in oldm.UNET_TAP_BLOCKS])
+    _, ref_feats = rl.LdmExtractor.unet_forward(fake, x, torch.zeros(2, dtype=torch.long), ctx, cond_emb=cond.clone())
+    mine = oldm.unet_features(unet, x, ctx, cond)
+    assert len(ref_feats) == 4
+    for a, b in zip(mine, ref_feats):
+        assert torch.equal(a, b)
+    vae = oldm.AutoencoderKL().eval()
+    enc_blocks = [vae.encoder.down[i].block[j] for i in range(4) for j in range(2)]
+    dec_blocks = [vae.decoder.up[i].block[j] for i in reversed(range(4)) for j in range(3)]
+    fake = types.SimpleNamespace(
+        ldm=types.SimpleNamespace(encoder=vae.encoder, decoder=vae.decoder,
+                                  ldm=types.SimpleNamespace(first_stage_model=vae, scale_factor=oldm.SCALE_FACTOR)),
+        encoder_blocks=[enc_blocks[i] for i in oldm.ENC_TAP_BLOCKS],
+        decoder_blocks=[dec_blocks[i] for i in oldm.DEC_TAP_BLOCKS])
+    fake.encoder_forward = lambda im: rl.LdmExtractor.encoder_forward(fake, im)
+    fake.decoder_forward = lambda z: rl.LdmExtractor.decoder_forward(fake, z)
+    img = torch.randn(1, 3, 64, 64)
+    lat_r, ef_r = rl.LdmExtractor.encode_to_latent(fake, img)
+    lat_o, ef_o = oldm.encoder_features(vae, img)
+    assert torch.equal(lat_r, lat_o) and all(torch.equal(a, b) for a, b in zip(ef_r, ef_o))
+    _, df_r = rl.LdmExtractor.decode_to_image(fake, lat_r)
+    df_o = oldm.decoder_features(vae, lat_o)
+    assert len(df_r) == 2 and all(torch.equal(a, b) for a, b in zip(df_r, df_o))
+
+
+def test_q_sample_constants():
+    a, b = oldm.SQRT_ALPHA_BAR_0, oldm.SQRT_ONE_MINUS_ALPHA_BAR_0
+    assert abs(a - 0.999575) < 1e-6 and abs(b - 0.029155) < 1e-6
+    n = oldm.shared_noise()
+    assert n.shape == (1, 4, 64, 64)
