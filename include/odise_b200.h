@@ -135,12 +135,21 @@ int odise_nchw_to_nhwc_f32(const float* src, float* dst, long long ldd, int B, i
 int odise_nhwc_to_nchw_f32(const float* src, long long lds, float* dst, int B, int C, int HW, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
- * Attention.  q [B, Tq, heads*d] / k,v [B, Tk, heads*d] as (hi, lo) planes; softmax(q k^T * scale) v.
- * UNet self / cross attention (ldm CrossAttention) — tcgen05 flash kernel. */
+ * Fused flash attention on tcgen05 (UNet SpatialTransformer self- and cross-attention; ldm CrossAttention,
+ * SURVEY.md App. A): out[b, t, h*d + j] = softmax_k(scale * q.k) v.
+ * Operands are HEAD-PADDED (hi, lo) planes: head h occupies columns [h*HS, h*HS + d) with HS = 64 (d <= 48) or
+ * 128 (d <= 80), pad columns zero:  q [B*Tq, heads*HS] (ldq), k [B*Tk, heads*HS] (ldk), and V TRANSPOSED
+ * vt [vt_rows >= heads*HS, ldvt >= B*Tk] with vt[h*HS + j][b*Tk + t] = v[b, t, h, j] (the projection GEMM writes
+ * it directly by swapping its operands).  d % 8 == 0, d <= 80 (larger heads: odise_gemm_bf16 + odise_softmax_split_f32).
+ * out fp32 and/or (hi, lo) planes, UNPADDED [B*Tq, heads*d] with row stride ldo. */
 int odise_attention_tc(const void* q_hi, const void* q_lo, long long ldq, const void* k_hi, const void* k_lo,
-                       long long ldk, const void* vt_hi, const void* vt_lo, long long ldvt, long long vt_bs,
+                       long long ldk, const void* vt_hi, const void* vt_lo, long long ldvt, long long vt_rows,
                        float* out, void* out_hi, void* out_lo, long long ldo, int B, int heads, int d, int Tq,
                        int Tk, float scale, int nmma, void* stream);
+/* row softmax of scale * x over the first `cols` columns -> (hi, lo) planes [rows, ldo], columns [cols, cols_pad)
+ * written as zeros (the unfused attention path for head dims > 80 and the VAE mid-block attention). */
+int odise_softmax_split_f32(const float* x, long long ldx, void* hi, void* lo, long long ldo, long long rows,
+                            int cols, int cols_pad, float scale, void* stream);
 
 /* Masked cross-attention of the Mask2Former decoder (odise.py:683-692 + 760-774,
  * mask2former_transformer_decoder.py:98-110).  The boolean attn_mask [B*8, Q, HW] of the reference is replaced by

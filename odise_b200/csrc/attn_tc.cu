@@ -1,7 +1,389 @@
-// placeholder translation unit: replaced by the tcgen05 flash-attention kernel
+// Fused flash attention on tcgen05 for the SD-v1 UNet SpatialTransformer: self-attention
+// (4096 / 1024 tokens, head dim 40 / 80) and cross-attention over the 77-token context.  Reference: ldm
+// CrossAttention = softmax(q k^T * d^-0.5) v via einsum or xformers (un-vendored; call sites ldm.py:481-489).
+//
+// One CTA = 128 queries of one (image, head).  warp0: TMA producer; warp1: single-thread tcgen05.mma issuer;
+// warps 2-5: softmax, one thread per query row (= TMEM lane).  Per 64-key block j:
+//     S_j = Q K_j^T            (tcgen05, fp32 in TMEM, double buffered so S_{j+1} overlaps softmax of S_j)
+//     online softmax in registers (running max m, sum l), P_j -> (hi, lo) bf16 -> shared memory (SW128 K-major)
+//     O_j = P_j V_j            (tcgen05 into a double-buffered TMEM tile, NOT accumulated in TMEM)
+//     acc = acc * exp2(m_{j-1} - m_j) + O_j   in registers (consumed one block late so it overlaps the next softmax)
+// Operands are head-padded planes: head h occupies columns [h*HS, h*HS + DP) of q / k and rows of v^T with
+// HS = 64 (d=40, DP=48) or 128 (d=80, DP=80); pad columns are zeros (produced by zero weight rows in the
+// projection GEMM).  bf16x3: S and O each use hi*hi + hi*lo + lo*hi.
+#include "ptx.cuh"
 #include "odise_b200.h"
-extern "C" int odise_attention_tc(const void*, const void*, long long, const void*, const void*, long long,
-                                  const void*, const void*, long long, long long, float*, void*, void*, long long,
-                                  int, int, int, int, int, float, int, void*) {
-  return ODISE_ERR_UNSUPPORTED;
+#include "launch_count.h"
+#include <cudaTypedefs.h>
+#include <mutex>
+
+namespace ob {
+
+struct AttnParams {
+  int B, heads, d, Tq, Tk;
+  float scale_log2;  // softmax scale * log2(e)
+  float* out;
+  __nv_bfloat16* out_hi;
+  __nv_bfloat16* out_lo;
+  long long ldo;
+};
+
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+template <int DP, int NMMA>
+struct AttnCfg {
+  static constexpr int NC = (DP + 63) / 64;          // 64-column chunks per head
+  static constexpr int HS = NC * 64;                 // head stride in q / k planes
+  static constexpr int NP = (NMMA == 3) ? 2 : 1;
+  static constexpr int BK = 64;                      // keys per block
+  static constexpr int STAGES = 2;
+  static constexpr int Q_BYTES = NC * NP * 128 * 128;       // [chunk][plane][128 rows x 128 B]
+  static constexpr int K_BYTES = NC * NP * BK * 128;        // per stage
+  static constexpr int V_TILE = DP * 128;                   // one plane: DP rows x 64 tokens
+  static constexpr int V_BYTES = NP * V_TILE;               // per stage
+  static constexpr int P_BYTES = NP * 128 * 128;
+  static constexpr int SMEM_BYTES = Q_BYTES + STAGES * (K_BYTES + V_BYTES) + P_BYTES + 1024 + 256;
+  static constexpr int TMEM_COLS = 512;               // S: 2 x 64 @ 0, O: 2 x 128 @ 128
+};
+
+template <int DP, int NMMA>
+__global__ void __launch_bounds__(192, 1)
+attn_tc_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ CUtensorMap tmQl,
+               const __grid_constant__ CUtensorMap tmKh, const __grid_constant__ CUtensorMap tmKl,
+               const __grid_constant__ CUtensorMap tmVh, const __grid_constant__ CUtensorMap tmVl,
+               const AttnParams p) {
+  using Cfg = AttnCfg<DP, NMMA>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + Cfg::Q_BYTES;
+  uint8_t* sV = sK + Cfg::STAGES * Cfg::K_BYTES;
+  uint8_t* sP = sV + Cfg::STAGES * Cfg::V_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + Cfg::P_BYTES);
+  uint64_t* q_full = bars;            // 1
+  uint64_t* k_full = bars + 1;        // [2]
+  uint64_t* k_empty = bars + 3;       // [2]
+  uint64_t* v_full = bars + 5;        // [2]
+  uint64_t* v_empty = bars + 7;       // [2]
+  uint64_t* s_full = bars + 9;        // [2]
+  uint64_t* s_empty = bars + 11;      // [2]
+  uint64_t* o_full = bars + 13;       // [2]
+  uint64_t* o_empty = bars + 15;      // [2]
+  uint64_t* p_full = bars + 17;       // 1
+  uint64_t* p_empty = bars + 18;      // 1
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
+  const int nblk = (p.Tk + Cfg::BK - 1) / Cfg::BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQh); tma_prefetch_desc(&tmKh); tma_prefetch_desc(&tmVh);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1);
+      mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1);
+      mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], 128);
+      mbar_init(&o_full[s], 1); mbar_init(&o_empty[s], 128);
+    }
+    mbar_init(p_full, 128);
+    mbar_init(p_empty, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------------------------------------------------------- TMA producer
+      mbar_arrive_expect_tx(q_full, Cfg::Q_BYTES);
+      for (int c = 0; c < Cfg::NC; ++c) {
+        tma_load_3d(sQ + (c * Cfg::NP) * 16384, &tmQh, q_full, h * Cfg::HS + c * 64, b * p.Tq + q0, 0);
+        if (NMMA == 3) tma_load_3d(sQ + (c * Cfg::NP + 1) * 16384, &tmQl, q_full, h * Cfg::HS + c * 64, b * p.Tq + q0, 0);
+      }
+      for (int j = 0; j < nblk; ++j) {
+        const int st = j & 1;
+        const uint32_t ph = (j >> 1) & 1;
+        mbar_wait(&k_empty[st], ph ^ 1);
+        mbar_arrive_expect_tx(&k_full[st], Cfg::K_BYTES);
+        uint8_t* kd = sK + st * Cfg::K_BYTES;
+        for (int c = 0; c < Cfg::NC; ++c) {
+          tma_load_3d(kd + (c * Cfg::NP) * 8192, &tmKh, &k_full[st], h * Cfg::HS + c * 64, b * p.Tk + j * 64, 0);
+          if (NMMA == 3)
+            tma_load_3d(kd + (c * Cfg::NP + 1) * 8192, &tmKl, &k_full[st], h * Cfg::HS + c * 64, b * p.Tk + j * 64, 0);
+        }
+        mbar_wait(&v_empty[st], ph ^ 1);
+        mbar_arrive_expect_tx(&v_full[st], Cfg::V_BYTES);
+        uint8_t* vd = sV + st * Cfg::V_BYTES;
+        tma_load_3d(vd, &tmVh, &v_full[st], b * p.Tk + j * 64, h * Cfg::HS, 0);
+        if (NMMA == 3) tma_load_3d(vd + Cfg::V_TILE, &tmVl, &v_full[st], b * p.Tk + j * 64, h * Cfg::HS, 0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ---------------------------------------------------------------- MMA issuer
+      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64);
+      constexpr uint32_t idesc_o = umma_idesc_bf16(128, DP);
+      constexpr int KS = DP / 16;
+      auto issue_s = [&](int j) {
+        const int st = j & 1;
+        mbar_wait(&k_full[st], (j >> 1) & 1);
+        mbar_wait(&s_empty[st], ((j >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + st * 64;
+        const uint32_t kq = smem_u32(sQ), kk = smem_u32(sK + st * Cfg::K_BYTES);
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+          const int c = ks >> 2, off = (ks & 3) * 32;
+          const uint64_t qh = umma_desc_sw128(kq + (c * Cfg::NP) * 16384 + off);
+          const uint64_t kh = umma_desc_sw128(kk + (c * Cfg::NP) * 8192 + off);
+          umma_bf16(d_tmem, qh, kh, idesc_s, ks > 0 ? 1u : 0u);
+          if (NMMA == 3) {
+            const uint64_t ql = umma_desc_sw128(kq + (c * Cfg::NP + 1) * 16384 + off);
+            const uint64_t kl = umma_desc_sw128(kk + (c * Cfg::NP + 1) * 8192 + off);
+            umma_bf16(d_tmem, qh, kl, idesc_s, 1u);
+            umma_bf16(d_tmem, ql, kh, idesc_s, 1u);
+          }
+        }
+        umma_commit(&k_empty[st]);
+        umma_commit(&s_full[st]);
+      };
+      mbar_wait(q_full, 0);
+      issue_s(0);
+      for (int j = 0; j < nblk; ++j) {
+        if (j + 1 < nblk) issue_s(j + 1);
+        const int st = j & 1;
+        const uint32_t ph = (j >> 1) & 1;
+        mbar_wait(p_full, j & 1);
+        mbar_wait(&v_full[st], ph);
+        mbar_wait(&o_empty[st], ph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + 128 + st * 128;
+        const uint32_t pp = smem_u32(sP), vv = smem_u32(sV + st * Cfg::V_BYTES);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          const uint64_t ph_ = umma_desc_sw128(pp + ks * 32);
+          const uint64_t vh = umma_desc_sw128(vv + ks * 32);
+          umma_bf16(d_tmem, ph_, vh, idesc_o, ks > 0 ? 1u : 0u);
+          if (NMMA == 3) {
+            const uint64_t pl = umma_desc_sw128(pp + 16384 + ks * 32);
+            const uint64_t vl = umma_desc_sw128(vv + Cfg::V_TILE + ks * 32);
+            umma_bf16(d_tmem, ph_, vl, idesc_o, 1u);
+            umma_bf16(d_tmem, pl, vh, idesc_o, 1u);
+          }
+        }
+        umma_commit(&v_empty[st]);
+        umma_commit(p_empty);
+        umma_commit(&o_full[st]);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ softmax / epilogue (thread = query row)
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
+    float m = -INFINITY, l = 0.f, alpha_pending = 1.f;
+    float acc[DP];
+#pragma unroll
+    for (int i = 0; i < DP; ++i) acc[i] = 0.f;
+
+    auto consume_o = [&](int j, float alpha) {
+      const int st = j & 1;
+      mbar_wait(&o_full[st], (j >> 1) & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int c0 = 0; c0 < DP; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(t_lane + 128 + st * 128 + c0, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) acc[c0 + i] = fmaf(acc[c0 + i], alpha, __uint_as_float(v[i]));
+      }
+      tc_fence_before();
+      mbar_arrive(&o_empty[st]);
+    };
+
+    for (int j = 0; j < nblk; ++j) {
+      const int st = j & 1;
+      mbar_wait(&s_full[st], (j >> 1) & 1);
+      tc_fence_after();
+      float s[64];
+      {
+        uint32_t v[32];
+        tmem_ld32(t_lane + st * 64, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) s[i] = __uint_as_float(v[i]);
+        tmem_ld32(t_lane + st * 64 + 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) s[32 + i] = __uint_as_float(v[i]);
+      }
+      tc_fence_before();
+      mbar_arrive(&s_empty[st]);
+      const int valid = p.Tk - j * 64;  // keys of this block that exist
+      float mx = m;
+#pragma unroll
+      for (int i = 0; i < 64; ++i) {
+        s[i] = (i < valid) ? s[i] * p.scale_log2 : -INFINITY;
+        mx = fmaxf(mx, s[i]);
+      }
+      const float alpha = fast_exp2(m - mx);  // first block: exp2(-inf) = 0
+      float sum = 0.f;
+#pragma unroll
+      for (int i = 0; i < 64; ++i) {
+        s[i] = fast_exp2(s[i] - mx);
+        sum += s[i];
+      }
+      l = l * alpha + sum;
+      m = mx;
+      // P_j -> shared memory (SW128 K-major [128 x 64]); wait until PV_{j-1} has finished reading the buffer
+      mbar_wait(p_empty, (j & 1) ^ 1);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        __align__(16) __nv_bfloat16 hi[8];
+        __align__(16) __nv_bfloat16 lo[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) split_bf16(s[c * 8 + t], hi[t], lo[t]);
+        const uint32_t off = sw128_offset(row, c);
+        *reinterpret_cast<uint4*>(sP + off) = *reinterpret_cast<const uint4*>(hi);
+        if (NMMA == 3) *reinterpret_cast<uint4*>(sP + 16384 + off) = *reinterpret_cast<const uint4*>(lo);
+      }
+      fence_proxy_async();
+      mbar_arrive(p_full);
+      if (j > 0) consume_o(j - 1, alpha_pending);
+      alpha_pending = alpha;
+    }
+    consume_o(nblk - 1, alpha_pending);
+
+    const int q = q0 + row;
+    if (q < p.Tq) {
+      const float inv = 1.f / l;
+      const long long o = ((long long)b * p.Tq + q) * p.ldo + (long long)h * p.d;
+      if (p.out) {
+#pragma unroll
+        for (int i = 0; i < DP; i += 4)
+          if (i < p.d)
+            *reinterpret_cast<float4*>(p.out + o + i) =
+                make_float4(acc[i] * inv, acc[i + 1] * inv, acc[i + 2] * inv, acc[i + 3] * inv);
+      }
+      if (p.out_hi) {
+#pragma unroll
+        for (int i = 0; i < DP; i += 8) {
+          if (i < p.d) {
+            __align__(16) __nv_bfloat16 hi[8];
+            __align__(16) __nv_bfloat16 lo[8];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) split_bf16(acc[i + t] * inv, hi[t], lo[t]);
+            *reinterpret_cast<uint4*>(p.out_hi + o + i) = *reinterpret_cast<const uint4*>(hi);
+            if (p.out_lo) *reinterpret_cast<uint4*>(p.out_lo + o + i) = *reinterpret_cast<const uint4*>(lo);
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+static PFN_cuTensorMapEncodeTiled_v12000 attn_get_encode() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(f);
+  });
+  return fn;
+}
+
+static int attn_map(CUtensorMap* tm, const void* base, long long cols, long long rows, long long ld, int box_c,
+                    int box_r) {
+  auto enc = attn_get_encode();
+  if (!enc) return ODISE_ERR_DRIVER;
+  cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, 1};
+  cuuint64_t str[2] = {(cuuint64_t)ld * 2, (cuuint64_t)ld * rows * 2};
+  cuuint32_t box[3] = {(cuuint32_t)box_c, (cuuint32_t)box_r, 1};
+  cuuint32_t es[3] = {1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, str, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? ODISE_OK : ODISE_ERR_TENSORMAP;
+}
+
+template <int DP, int NMMA>
+static int attn_launch(const CUtensorMap* m, const AttnParams& p, cudaStream_t stream) {
+  using Cfg = AttnCfg<DP, NMMA>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel<DP, NMMA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  dim3 grid((p.Tq + 127) / 128, p.heads, p.B);
+  attn_tc_kernel<DP, NMMA><<<grid, 192, Cfg::SMEM_BYTES, stream>>>(m[0], m[1], m[2], m[3], m[4], m[5], p);
+  return (int)cudaGetLastError();
+}
+
+}  // namespace ob
+
+using namespace ob;
+
+// q [B*Tq, heads*HS], k [B*Tk, heads*HS] head-padded planes (HS = 64 for d <= 48, 128 for d <= 80);
+// vt [heads*HS, ldvt >= B*Tk] (V transposed: row = head-padded channel, col = b*Tk + t).
+extern "C" int odise_attention_tc(const void* q_hi, const void* q_lo, long long ldq, const void* k_hi,
+                                  const void* k_lo, long long ldk, const void* vt_hi, const void* vt_lo,
+                                  long long ldvt, long long vt_rows, float* out, void* out_hi, void* out_lo,
+                                  long long ldo, int B, int heads, int d, int Tq, int Tk, float scale, int nmma,
+                                  void* stream_v) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
+  if (!q_hi || !k_hi || !vt_hi || (!out && !out_hi)) return ODISE_ERR_ARG;
+  if (nmma != 1 && nmma != 3) return ODISE_ERR_ARG;
+  if (nmma == 3 && (!q_lo || !k_lo || !vt_lo)) return ODISE_ERR_ARG;
+  if (B <= 0 || heads <= 0 || Tq <= 0 || Tk <= 0) return ODISE_ERR_ARG;
+  int DP;
+  if (d <= 48) DP = 48; else if (d <= 80) DP = 80; else return ODISE_ERR_UNSUPPORTED;
+  if (d % 8) return ODISE_ERR_UNSUPPORTED;
+  const int HS = DP == 48 ? 64 : 128;
+  if (ldq % 8 || ldk % 8 || ldvt % 8 || ldq < (long long)heads * HS || ldk < (long long)heads * HS ||
+      vt_rows < (long long)heads * HS || ldvt < (long long)B * Tk)
+    return ODISE_ERR_ALIGN;
+  if ((out && ldo % 4) || (out_hi && ldo % 8) || (d % 8)) return ODISE_ERR_ALIGN;
+  CUtensorMap m[6];
+  int rc;
+  if ((rc = attn_map(&m[0], q_hi, (long long)heads * HS, (long long)B * Tq, ldq, 64, 128))) return rc;
+  if ((rc = attn_map(&m[1], nmma == 3 ? q_lo : q_hi, (long long)heads * HS, (long long)B * Tq, ldq, 64, 128))) return rc;
+  if ((rc = attn_map(&m[2], k_hi, (long long)heads * HS, (long long)B * Tk, ldk, 64, 64))) return rc;
+  if ((rc = attn_map(&m[3], nmma == 3 ? k_lo : k_hi, (long long)heads * HS, (long long)B * Tk, ldk, 64, 64))) return rc;
+  if ((rc = attn_map(&m[4], vt_hi, (long long)B * Tk, vt_rows, ldvt, 64, DP))) return rc;
+  if ((rc = attn_map(&m[5], nmma == 3 ? vt_lo : vt_hi, (long long)B * Tk, vt_rows, ldvt, 64, DP))) return rc;
+  AttnParams p{};
+  p.B = B; p.heads = heads; p.d = d; p.Tq = Tq; p.Tk = Tk;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  p.out = out; p.out_hi = reinterpret_cast<__nv_bfloat16*>(out_hi); p.out_lo = reinterpret_cast<__nv_bfloat16*>(out_lo);
+  p.ldo = ldo;
+  if (DP == 48) rc = nmma == 3 ? attn_launch<48, 3>(m, p, stream) : attn_launch<48, 1>(m, p, stream);
+  else rc = nmma == 3 ? attn_launch<80, 3>(m, p, stream) : attn_launch<80, 1>(m, p, stream);
+  if (rc) return rc;
+  count_launch(1);
+  return ODISE_OK;
 }

@@ -440,6 +440,30 @@ __global__ void pool_normalize_kernel(const float* __restrict__ sums, const floa
   }
 }
 
+// ---------------------------------------------------------------------------------------------- softmax
+// one warp per row
+__global__ void softmax_split_kernel(const float* __restrict__ x, long long ldx, __nv_bfloat16* __restrict__ hi,
+                                     __nv_bfloat16* __restrict__ lo, long long ldo, long long rows, int cols,
+                                     int cols_pad, float scale) {
+  const long long row = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const float* xr = x + row * ldx;
+  float mx = -INFINITY;
+  for (int c = lane; c < cols; c += 32) mx = fmaxf(mx, xr[c] * scale);
+  mx = warp_max(mx);
+  float sum = 0.f;
+  for (int c = lane; c < cols; c += 32) sum += expf(xr[c] * scale - mx);
+  sum = warp_sum(sum);
+  for (int c = lane; c < cols_pad; c += 32) {
+    const float v = c < cols ? expf(xr[c] * scale - mx) / sum : 0.f;
+    __nv_bfloat16 h, l;
+    split_bf16(v, h, l);
+    hi[row * ldo + c] = h;
+    if (lo) lo[row * ldo + c] = l;
+  }
+}
+
 }  // namespace ob
 
 using namespace ob;
@@ -611,6 +635,15 @@ extern "C" int odise_pool_normalize_f32(const float* sums, const float* counts, 
   if (!sums || !counts || !pooled || B <= 0 || Q <= 0 || C <= 0) return ODISE_ERR_ARG;
   const long long rows = (long long)B * Q;
   pool_normalize_kernel<<<grid_for(rows * C, 256), 256, 0, STREAM(stream)>>>(sums, counts, pooled, rows, C);
+  count_launch(1);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int odise_softmax_split_f32(const float* x, long long ldx, void* hi, void* lo, long long ldo,
+                                       long long rows, int cols, int cols_pad, float scale, void* stream) {
+  if (!x || !hi || rows <= 0 || cols <= 0 || cols_pad < cols) return ODISE_ERR_ARG;
+  softmax_split_kernel<<<(int)((rows + 7) / 8), 256, 0, STREAM(stream)>>>(x, ldx, BF(hi), BF(lo), ldo, rows, cols,
+                                                                         cols_pad, scale);
   count_launch(1);
   return (int)cudaGetLastError();
 }

@@ -1,0 +1,151 @@
+"""Thin typed wrappers over the C ABI used by the engines (unet.py, head.py).  Activations are token-major /
+NHWC fp32 matrices [rows, C]; GEMM operands are lib.Planes.  No torch math on the hot path: torch only allocates."""
+import math
+
+import torch
+
+from . import lib
+from .lib import Planes, _check, _ptr, _stream, load
+
+ACT_NONE, ACT_RELU, ACT_SILU, ACT_GELU = 0, 1, 2, 3
+
+
+def empty(rows, cols, device):
+    return torch.empty(rows, cols, dtype=torch.float32, device=device)
+
+
+def split(x, lo=True):
+    return lib.split(x, lo=lo)
+
+
+def group_norm(x, B, HW, gamma, beta, eps, act=ACT_NONE, G=32, want_f32=False, want_planes=True, lo=True, ldx=None):
+    """x [B*HW, C] (row stride ldx) -> (y fp32 | None, planes | None)"""
+    C = gamma.numel()
+    ldx = ldx or x.stride(0)
+    dev = x.device
+    mean = torch.empty(B * G, dtype=torch.float32, device=dev)
+    rstd = torch.empty(B * G, dtype=torch.float32, device=dev)
+    L = load()
+    _check(L.odise_groupnorm_stats_f32(_ptr(x), ldx, _ptr(mean), _ptr(rstd), B, HW, C, G, eps, _stream()),
+           "groupnorm_stats")
+    y = empty(B * HW, C, dev) if want_f32 else None
+    p = Planes.empty(B * HW, C, dev, lo=lo) if want_planes else None
+    _check(L.odise_groupnorm_apply_f32(_ptr(x), ldx, _ptr(mean), _ptr(rstd), _ptr(gamma), _ptr(beta), act, _ptr(y),
+                                       C, _ptr(p.hi) if p else None, _ptr(p.lo) if p else None, p.ld if p else 0,
+                                       B, HW, C, G, _stream()), "groupnorm_apply")
+    return y, p
+
+
+def layer_norm(x, gamma, beta, eps=1e-5, res=None, want_f32=False, want_planes=True, post_add=None, lo=True):
+    rows, cols = x.shape
+    dev = x.device
+    y = empty(rows, cols, dev) if want_f32 else None
+    p = Planes.empty(rows, cols, dev, lo=lo) if want_planes else None
+    _check(load().odise_layernorm_f32(_ptr(x), x.stride(0), _ptr(res), res.stride(0) if res is not None else 0,
+                                      _ptr(gamma), _ptr(beta), eps, _ptr(y), cols, _ptr(post_add),
+                                      post_add.stride(0) if post_add is not None else 0,
+                                      _ptr(p.hi) if p else None, _ptr(p.lo) if p else None, p.ld if p else 0, rows,
+                                      cols, _stream()), "layernorm")
+    return y, p
+
+
+def geglu(x, lo=True):
+    rows, c2 = x.shape
+    p = Planes.empty(rows, c2 // 2, x.device, lo=lo)
+    _check(load().odise_geglu_f32(_ptr(x), x.stride(0), _ptr(p.hi), _ptr(p.lo), p.ld, rows, c2 // 2, _stream()), "geglu")
+    return p
+
+
+def add_split(a, b=None, b_rows=0, want_f32=False, want_planes=True, lo=True):
+    rows, cols = a.shape
+    y = empty(rows, cols, a.device) if want_f32 else None
+    p = Planes.empty(rows, cols, a.device, lo=lo) if want_planes else None
+    _check(load().odise_add_split_f32(_ptr(a), a.stride(0), _ptr(b), b.stride(0) if b is not None else 0, b_rows,
+                                      _ptr(y), cols, _ptr(p.hi) if p else None, _ptr(p.lo) if p else None,
+                                      p.ld if p else 0, rows, cols, _stream()), "add_split")
+    return y, p
+
+
+def upsample2x_split(x, B, H, W, lo=True):
+    C = x.shape[1]
+    p = Planes.empty(B * 4 * H * W, C, x.device, lo=lo)
+    _check(load().odise_upsample2x_split_f32(_ptr(x), x.stride(0), _ptr(p.hi), _ptr(p.lo), p.ld, B, H, W, C, _stream()),
+           "upsample2x")
+    return p
+
+
+def im2col3x3_split(x, B, H, W, stride=1, pad_lo=1, pad_hi=1, lo=True):
+    C = x.shape[1]
+    Ho = (H + pad_lo + pad_hi - 3) // stride + 1
+    Wo = (W + pad_lo + pad_hi - 3) // stride + 1
+    Kpad = (9 * C + 7) // 8 * 8
+    p = Planes.empty(B * Ho * Wo, Kpad, x.device, lo=lo, ld=Kpad)
+    _check(load().odise_im2col3x3_split_f32(_ptr(x), x.stride(0), _ptr(p.hi), _ptr(p.lo), Kpad, B, H, W, C, stride,
+                                            pad_lo, pad_hi, _stream()), "im2col3x3")
+    return p, Ho, Wo
+
+
+def copy2d(src, dst, scale=1.0, accumulate=False):
+    rows, cols = src.shape
+    _check(load().odise_copy2d_f32(_ptr(src), src.stride(0), _ptr(dst), dst.stride(0), rows, cols, scale,
+                                   1 if accumulate else 0, _stream()), "copy2d")
+
+
+def resize_nhwc(src, B, Hs, Ws, Hd, Wd, bilinear, dst=None, accumulate=False):
+    C = src.shape[1]
+    if dst is None:
+        dst = empty(B * Hd * Wd, C, src.device)
+    _check(load().odise_resize_nhwc_f32(_ptr(src), src.stride(0), _ptr(dst), dst.stride(0), B, Hs, Ws, Hd, Wd, C,
+                                        1 if bilinear else 0, 1 if accumulate else 0, _stream()), "resize")
+    return dst
+
+
+def nchw_to_nhwc(x):
+    B, C, H, W = x.shape
+    x = x.contiguous()
+    y = empty(B * H * W, C, x.device)
+    _check(load().odise_nchw_to_nhwc_f32(_ptr(x), _ptr(y), C, B, C, H * W, _stream()), "nchw_to_nhwc")
+    return y
+
+
+def nhwc_to_nchw(x, B, H, W):
+    C = x.shape[1]
+    y = torch.empty(B, C, H, W, dtype=torch.float32, device=x.device)
+    _check(load().odise_nhwc_to_nchw_f32(_ptr(x), x.stride(0), _ptr(y), B, C, H * W, _stream()), "nhwc_to_nchw")
+    return y
+
+
+def attention_tc(q, k, vt, B, heads, d, Tq, Tk, scale, nmma, want_f32=False, want_planes=True):
+    """q, k head-padded Planes; vt Planes [heads*HS, >= B*Tk]. Returns (fp32 | None, Planes | None) [B*Tq, heads*d]."""
+    dev = q.hi.device
+    C = heads * d
+    out = empty(B * Tq, C, dev) if want_f32 else None
+    p = Planes.empty(B * Tq, C, dev, lo=(nmma == 3)) if want_planes else None
+    _check(load().odise_attention_tc(_ptr(q.hi), _ptr(q.lo), q.ld, _ptr(k.hi), _ptr(k.lo), k.ld, _ptr(vt.hi),
+                                     _ptr(vt.lo), vt.ld, vt.rows, _ptr(out), _ptr(p.hi) if p else None,
+                                     _ptr(p.lo) if p else None, p.ld if p else C, B, heads, d, Tq, Tk, scale, nmma,
+                                     _stream()), "attention_tc")
+    return out, p
+
+
+def softmax_split(x, rows, cols, cols_pad, scale, lo=True):
+    p = Planes.empty(rows, cols_pad, x.device, lo=lo, ld=cols_pad)
+    _check(load().odise_softmax_split_f32(_ptr(x), x.stride(0), _ptr(p.hi), _ptr(p.lo), p.ld, rows, cols, cols_pad,
+                                          scale, _stream()), "softmax_split")
+    return p
+
+
+def head_pad_rows(w, heads, d, HS):
+    """[heads*d, K] projection weight -> [heads*HS, K] with zero rows in the pad (host-side, one time)."""
+    K = w.shape[1]
+    out = torch.zeros(heads, HS, K, dtype=w.dtype, device=w.device)
+    out[:, :d] = w.view(heads, d, K)
+    return out.view(heads * HS, K)
+
+
+def head_stride(d):
+    if d <= 48:
+        return 64
+    if d <= 80:
+        return 128
+    return None   # unfused path

@@ -1,0 +1,49 @@
+"""GPU parity of the fused tcgen05 flash attention (odise_attention_tc) vs fp64 softmax attention.
+Shapes are the SD-v1 UNet ones: self-attention d=40 / d=80, cross-attention over 77 context tokens."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    return ((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30)).item()
+
+
+@pytest.mark.parametrize("nmma", [3, 1])
+@pytest.mark.parametrize("cfg", [(2, 8, 40, 256, 256), (1, 8, 40, 1024, 1024), (2, 8, 80, 256, 256), (3, 8, 40, 128, 77),
+                                 (2, 8, 80, 64, 77), (1, 4, 80, 64, 64), (2, 2, 40, 200, 130), (1, 8, 40, 4096, 4096)])
+def test_attention_tc(cuda, nmma, cfg):
+    from odise_b200 import lib, ops
+    B, heads, d, Tq, Tk = cfg
+    g = torch.Generator().manual_seed(Tq * 3 + Tk + d)
+    q = torch.randn(B, Tq, heads, d, generator=g).to(cuda)
+    k = torch.randn(B, Tk, heads, d, generator=g).to(cuda)
+    v = torch.randn(B, Tk, heads, d, generator=g).to(cuda)
+    HS = ops.head_stride(d)
+    qp = torch.zeros(B * Tq, heads, HS, device=cuda)
+    qp[:, :, :d] = q.view(B * Tq, heads, d)
+    kp = torch.zeros(B * Tk, heads, HS, device=cuda)
+    kp[:, :, :d] = k.view(B * Tk, heads, d)
+    ldv = (B * Tk + 7) // 8 * 8
+    vt = torch.zeros(heads, HS, ldv, device=cuda)
+    vt[:, :d, :B * Tk] = v.view(B * Tk, heads, d).permute(1, 2, 0)
+    qP, kP = lib.split(qp.view(B * Tq, heads * HS)), lib.split(kp.view(B * Tk, heads * HS))
+    vP = lib.split(vt.view(heads * HS, ldv))
+    scale = d ** -0.5
+    out, outp = ops.attention_tc(qP, kP, vP, B, heads, d, Tq, Tk, scale, nmma, want_f32=True, want_planes=True)
+    torch.cuda.synchronize()
+    s = torch.einsum("bqhd,bkhd->bhqk", q.double(), k.double()) * scale
+    ref = torch.einsum("bhqk,bkhd->bqhd", s.softmax(-1), v.double()).reshape(B * Tq, heads * d)
+    tol = 3e-5 if nmma == 3 else 3e-2
+    assert _rel(out, ref) < tol
+    assert _rel(outp.float(), ref) < tol + 1e-2 * (nmma == 1)
+
+
+def test_softmax_split(cuda):
+    from odise_b200 import ops
+    x = torch.randn(300, 77, device=cuda) * 3
+    p = ops.softmax_split(x, 300, 77, 80, 0.5)
+    ref = (x.double() * 0.5).softmax(-1)
+    got = p.float()
+    assert _rel(got[:, :77], ref) < 2e-5 and got[:, 77:].abs().max() == 0
