@@ -115,6 +115,9 @@ int odise_geglu_f32(const float* x, long long ldx, void* hi, void* lo, long long
 /* y = a + b (optional b, optional fp32 y) -> (hi, lo); b_rows > 0 broadcasts b over rows modulo b_rows */
 int odise_add_split_f32(const float* a, long long lda, const float* b, long long ldb, long long b_rows, float* y,
                         long long ldy, void* hi, void* lo, long long ldo, long long rows, int cols, void* stream);
+/* y = act(x) -> (hi, lo)  (SiLU(emb) in front of ResBlock.emb_layers) */
+int odise_act_split_f32(const float* x, long long ldx, int act, void* hi, void* lo, long long ldo, long long rows,
+                        int cols, void* stream);
 /* nearest 2x upsample of NHWC x[B,H,W,C] -> (hi, lo) [B,2H,2W,C] (ldm Upsample before its conv3x3) */
 int odise_upsample2x_split_f32(const float* x, long long ldx, void* hi, void* lo, long long ldo, int B, int H,
                                int W, int C, void* stream);
@@ -138,14 +141,15 @@ int odise_nhwc_to_nchw_f32(const float* src, long long lds, float* dst, int B, i
  * Fused flash attention on tcgen05 (UNet SpatialTransformer self- and cross-attention; ldm CrossAttention,
  * SURVEY.md App. A): out[b, t, h*d + j] = softmax_k(scale * q.k) v.
  * Operands are HEAD-PADDED (hi, lo) planes: head h occupies columns [h*HS, h*HS + d) with HS = 64 (d <= 48) or
- * 128 (d <= 80), pad columns zero:  q [B*Tq, heads*HS] (ldq), k [B*Tk, heads*HS] (ldk), and V TRANSPOSED
- * vt [vt_rows >= heads*HS, ldvt >= B*Tk] with vt[h*HS + j][b*Tk + t] = v[b, t, h, j] (the projection GEMM writes
- * it directly by swapping its operands).  d % 8 == 0, d <= 80 (larger heads: odise_gemm_bf16 + odise_softmax_split_f32).
+ * 128 (d <= 80), pad columns zero:  q [B*Tq, heads*HS] (ldq), k [B*tk_stride, heads*HS] (ldk), and V TRANSPOSED
+ * vt [vt_rows >= heads*HS, ldvt >= B*tk_stride] with vt[h*HS + j][b*tk_stride + t] = v[b, t, h, j] (the projection
+ * GEMM writes it directly by swapping its operands).  tk_stride >= Tk is the per-image row count of the key /
+ * value planes (multiple of 8: TMA box starts must be 16-byte aligned); keys t >= Tk are masked out.  d % 8 == 0, d <= 80 (larger heads: odise_gemm_bf16 + odise_softmax_split_f32).
  * out fp32 and/or (hi, lo) planes, UNPADDED [B*Tq, heads*d] with row stride ldo. */
 int odise_attention_tc(const void* q_hi, const void* q_lo, long long ldq, const void* k_hi, const void* k_lo,
                        long long ldk, const void* vt_hi, const void* vt_lo, long long ldvt, long long vt_rows,
                        float* out, void* out_hi, void* out_lo, long long ldo, int B, int heads, int d, int Tq,
-                       int Tk, float scale, int nmma, void* stream);
+                       int Tk, int tk_stride, float scale, int nmma, void* stream);
 /* row softmax of scale * x over the first `cols` columns -> (hi, lo) planes [rows, ldo], columns [cols, cols_pad)
  * written as zeros (the unfused attention path for head dims > 80 and the VAE mid-block attention). */
 int odise_softmax_split_f32(const float* x, long long ldx, void* hi, void* lo, long long ldo, long long rows,

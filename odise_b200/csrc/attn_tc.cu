@@ -20,7 +20,7 @@
 namespace ob {
 
 struct AttnParams {
-  int B, heads, d, Tq, Tk;
+  int B, heads, d, Tq, Tk, TkS;  // TkS: rows per image in the k / v^T planes (>= Tk, multiple of 8)
   float scale_log2;  // softmax scale * log2(e)
   float* out;
   __nv_bfloat16* out_hi;
@@ -118,15 +118,15 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__
         mbar_arrive_expect_tx(&k_full[st], Cfg::K_BYTES);
         uint8_t* kd = sK + st * Cfg::K_BYTES;
         for (int c = 0; c < Cfg::NC; ++c) {
-          tma_load_3d(kd + (c * Cfg::NP) * 8192, &tmKh, &k_full[st], h * Cfg::HS + c * 64, b * p.Tk + j * 64, 0);
+          tma_load_3d(kd + (c * Cfg::NP) * 8192, &tmKh, &k_full[st], h * Cfg::HS + c * 64, b * p.TkS + j * 64, 0);
           if (NMMA == 3)
-            tma_load_3d(kd + (c * Cfg::NP + 1) * 8192, &tmKl, &k_full[st], h * Cfg::HS + c * 64, b * p.Tk + j * 64, 0);
+            tma_load_3d(kd + (c * Cfg::NP + 1) * 8192, &tmKl, &k_full[st], h * Cfg::HS + c * 64, b * p.TkS + j * 64, 0);
         }
         mbar_wait(&v_empty[st], ph ^ 1);
         mbar_arrive_expect_tx(&v_full[st], Cfg::V_BYTES);
         uint8_t* vd = sV + st * Cfg::V_BYTES;
-        tma_load_3d(vd, &tmVh, &v_full[st], b * p.Tk + j * 64, h * Cfg::HS, 0);
-        if (NMMA == 3) tma_load_3d(vd + Cfg::V_TILE, &tmVl, &v_full[st], b * p.Tk + j * 64, h * Cfg::HS, 0);
+        tma_load_3d(vd, &tmVh, &v_full[st], b * p.TkS + j * 64, h * Cfg::HS, 0);
+        if (NMMA == 3) tma_load_3d(vd + Cfg::V_TILE, &tmVl, &v_full[st], b * p.TkS + j * 64, h * Cfg::HS, 0);
       }
     }
   } else if (warp == 1) {
@@ -348,36 +348,39 @@ static int attn_launch(const CUtensorMap* m, const AttnParams& p, cudaStream_t s
 
 using namespace ob;
 
-// q [B*Tq, heads*HS], k [B*Tk, heads*HS] head-padded planes (HS = 64 for d <= 48, 128 for d <= 80);
-// vt [heads*HS, ldvt >= B*Tk] (V transposed: row = head-padded channel, col = b*Tk + t).
+// q [B*Tq, heads*HS], k [B*TkS, heads*HS] head-padded planes (HS = 64 for d <= 48, 128 for d <= 80);
+// vt [heads*HS, ldvt >= B*TkS] (V transposed: row = head-padded channel, col = b*TkS + t); keys t >= Tk are masked.
 extern "C" int odise_attention_tc(const void* q_hi, const void* q_lo, long long ldq, const void* k_hi,
                                   const void* k_lo, long long ldk, const void* vt_hi, const void* vt_lo,
                                   long long ldvt, long long vt_rows, float* out, void* out_hi, void* out_lo,
-                                  long long ldo, int B, int heads, int d, int Tq, int Tk, float scale, int nmma,
-                                  void* stream_v) {
+                                  long long ldo, int B, int heads, int d, int Tq, int Tk, int tk_stride, float scale,
+                                  int nmma, void* stream_v) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
   if (!q_hi || !k_hi || !vt_hi || (!out && !out_hi)) return ODISE_ERR_ARG;
   if (nmma != 1 && nmma != 3) return ODISE_ERR_ARG;
   if (nmma == 3 && (!q_lo || !k_lo || !vt_lo)) return ODISE_ERR_ARG;
-  if (B <= 0 || heads <= 0 || Tq <= 0 || Tk <= 0) return ODISE_ERR_ARG;
+  if (B <= 0 || heads <= 0 || Tq <= 0 || Tk <= 0 || tk_stride < Tk) return ODISE_ERR_ARG;
+  // TMA needs 16-byte aligned box starts: tokens are the inner dimension of v^T
+  if (tk_stride % 8) return ODISE_ERR_ALIGN;
+  const int TkS = tk_stride;
   int DP;
   if (d <= 48) DP = 48; else if (d <= 80) DP = 80; else return ODISE_ERR_UNSUPPORTED;
   if (d % 8) return ODISE_ERR_UNSUPPORTED;
   const int HS = DP == 48 ? 64 : 128;
   if (ldq % 8 || ldk % 8 || ldvt % 8 || ldq < (long long)heads * HS || ldk < (long long)heads * HS ||
-      vt_rows < (long long)heads * HS || ldvt < (long long)B * Tk)
+      vt_rows < (long long)heads * HS || ldvt < (long long)B * TkS)
     return ODISE_ERR_ALIGN;
   if ((out && ldo % 4) || (out_hi && ldo % 8) || (d % 8)) return ODISE_ERR_ALIGN;
   CUtensorMap m[6];
   int rc;
   if ((rc = attn_map(&m[0], q_hi, (long long)heads * HS, (long long)B * Tq, ldq, 64, 128))) return rc;
   if ((rc = attn_map(&m[1], nmma == 3 ? q_lo : q_hi, (long long)heads * HS, (long long)B * Tq, ldq, 64, 128))) return rc;
-  if ((rc = attn_map(&m[2], k_hi, (long long)heads * HS, (long long)B * Tk, ldk, 64, 64))) return rc;
-  if ((rc = attn_map(&m[3], nmma == 3 ? k_lo : k_hi, (long long)heads * HS, (long long)B * Tk, ldk, 64, 64))) return rc;
-  if ((rc = attn_map(&m[4], vt_hi, (long long)B * Tk, vt_rows, ldvt, 64, DP))) return rc;
-  if ((rc = attn_map(&m[5], nmma == 3 ? vt_lo : vt_hi, (long long)B * Tk, vt_rows, ldvt, 64, DP))) return rc;
+  if ((rc = attn_map(&m[2], k_hi, (long long)heads * HS, (long long)B * TkS, ldk, 64, 64))) return rc;
+  if ((rc = attn_map(&m[3], nmma == 3 ? k_lo : k_hi, (long long)heads * HS, (long long)B * TkS, ldk, 64, 64))) return rc;
+  if ((rc = attn_map(&m[4], vt_hi, (long long)B * TkS, vt_rows, ldvt, 64, DP))) return rc;
+  if ((rc = attn_map(&m[5], nmma == 3 ? vt_lo : vt_hi, (long long)B * TkS, vt_rows, ldvt, 64, DP))) return rc;
   AttnParams p{};
-  p.B = B; p.heads = heads; p.d = d; p.Tq = Tq; p.Tk = Tk;
+  p.B = B; p.heads = heads; p.d = d; p.Tq = Tq; p.Tk = Tk; p.TkS = TkS;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.out = out; p.out_hi = reinterpret_cast<__nv_bfloat16*>(out_hi); p.out_lo = reinterpret_cast<__nv_bfloat16*>(out_lo);
   p.ldo = ldo;

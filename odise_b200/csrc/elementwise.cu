@@ -440,6 +440,20 @@ __global__ void pool_normalize_kernel(const float* __restrict__ sums, const floa
   }
 }
 
+// y = act(x) -> (hi, lo)   (SiLU(emb) in front of the ResBlock emb_layers linear)
+__global__ void act_split_kernel(const float* __restrict__ x, long long ldx, int act, __nv_bfloat16* __restrict__ hi,
+                                 __nv_bfloat16* __restrict__ lo, long long ldo, long long rows, int cols4) {
+  const long long total = rows * cols4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / cols4;
+    const int c = (int)(i - r * cols4) * 4;
+    float4 v = *reinterpret_cast<const float4*>(x + r * ldx + c);
+    v.x = act_apply(v.x, act); v.y = act_apply(v.y, act); v.z = act_apply(v.z, act); v.w = act_apply(v.w, act);
+    store_split4(hi + r * ldo + c, lo ? lo + r * ldo + c : nullptr, v);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- softmax
 // one warp per row
 __global__ void softmax_split_kernel(const float* __restrict__ x, long long ldx, __nv_bfloat16* __restrict__ hi,
@@ -644,6 +658,16 @@ extern "C" int odise_softmax_split_f32(const float* x, long long ldx, void* hi, 
   if (!x || !hi || rows <= 0 || cols <= 0 || cols_pad < cols) return ODISE_ERR_ARG;
   softmax_split_kernel<<<(int)((rows + 7) / 8), 256, 0, STREAM(stream)>>>(x, ldx, BF(hi), BF(lo), ldo, rows, cols,
                                                                          cols_pad, scale);
+  count_launch(1);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int odise_act_split_f32(const float* x, long long ldx, int act, void* hi, void* lo, long long ldo,
+                                   long long rows, int cols, void* stream) {
+  if (!x || !hi || rows <= 0 || cols <= 0) return ODISE_ERR_ARG;
+  if (cols % 4 || ldx % 4 || ldo % 4) return ODISE_ERR_ALIGN;
+  act_split_kernel<<<grid_for(rows * (cols / 4), 256), 256, 0, STREAM(stream)>>>(x, ldx, act, BF(hi), BF(lo), ldo,
+                                                                               rows, cols / 4);
   count_launch(1);
   return (int)cudaGetLastError();
 }

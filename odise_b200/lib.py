@@ -72,11 +72,12 @@ _SIGS = {
     "odise_l2_normalize_split_f32": [c_void_p, c_longlong, c_void_p, c_void_p, c_longlong, c_longlong, c_int,
                                      c_void_p],
     "odise_class_max_f32": [c_void_p, c_longlong, c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_void_p],
+    "odise_act_split_f32": [c_void_p, c_longlong, c_int, c_void_p, c_void_p, c_longlong, c_longlong, c_int, c_void_p],
     "odise_softmax_split_f32": [c_void_p, c_longlong, c_void_p, c_void_p, c_longlong, c_longlong, c_int, c_int,
                                 c_float, c_void_p],
     "odise_attention_tc": [c_void_p, c_void_p, c_longlong, c_void_p, c_void_p, c_longlong, c_void_p, c_void_p,
                            c_longlong, c_longlong, c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_int, c_int,
-                           c_int, c_int, c_float, c_int, c_void_p],
+                           c_int, c_int, c_int, c_float, c_int, c_void_p],
 }
 
 

@@ -66,6 +66,14 @@ def add_split(a, b=None, b_rows=0, want_f32=False, want_planes=True, lo=True):
     return y, p
 
 
+def act_split(x, act, lo=True):
+    rows, cols = x.shape
+    p = Planes.empty(rows, cols, x.device, lo=lo)
+    _check(load().odise_act_split_f32(_ptr(x), x.stride(0), act, _ptr(p.hi), _ptr(p.lo), p.ld, rows, cols, _stream()),
+           "act_split")
+    return p
+
+
 def upsample2x_split(x, B, H, W, lo=True):
     C = x.shape[1]
     p = Planes.empty(B * 4 * H * W, C, x.device, lo=lo)
@@ -115,7 +123,7 @@ def nhwc_to_nchw(x, B, H, W):
     return y
 
 
-def attention_tc(q, k, vt, B, heads, d, Tq, Tk, scale, nmma, want_f32=False, want_planes=True):
+def attention_tc(q, k, vt, B, heads, d, Tq, Tk, scale, nmma, want_f32=False, want_planes=True, tk_stride=None):
     """q, k head-padded Planes; vt Planes [heads*HS, >= B*Tk]. Returns (fp32 | None, Planes | None) [B*Tq, heads*d]."""
     dev = q.hi.device
     C = heads * d
@@ -123,7 +131,7 @@ def attention_tc(q, k, vt, B, heads, d, Tq, Tk, scale, nmma, want_f32=False, wan
     p = Planes.empty(B * Tq, C, dev, lo=(nmma == 3)) if want_planes else None
     _check(load().odise_attention_tc(_ptr(q.hi), _ptr(q.lo), q.ld, _ptr(k.hi), _ptr(k.lo), k.ld, _ptr(vt.hi),
                                      _ptr(vt.lo), vt.ld, vt.rows, _ptr(out), _ptr(p.hi) if p else None,
-                                     _ptr(p.lo) if p else None, p.ld if p else C, B, heads, d, Tq, Tk, scale, nmma,
+                                     _ptr(p.lo) if p else None, p.ld if p else C, B, heads, d, Tq, Tk, tk_stride or Tk, scale, nmma,
                                      _stream()), "attention_tc")
     return out, p
 

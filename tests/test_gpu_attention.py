@@ -21,17 +21,20 @@ def test_attention_tc(cuda, nmma, cfg):
     k = torch.randn(B, Tk, heads, d, generator=g).to(cuda)
     v = torch.randn(B, Tk, heads, d, generator=g).to(cuda)
     HS = ops.head_stride(d)
+    TkS = (Tk + 7) // 8 * 8            # rows per image in the key / value planes (TMA alignment)
     qp = torch.zeros(B * Tq, heads, HS, device=cuda)
     qp[:, :, :d] = q.view(B * Tq, heads, d)
-    kp = torch.zeros(B * Tk, heads, HS, device=cuda)
-    kp[:, :, :d] = k.view(B * Tk, heads, d)
-    ldv = (B * Tk + 7) // 8 * 8
-    vt = torch.zeros(heads, HS, ldv, device=cuda)
-    vt[:, :d, :B * Tk] = v.view(B * Tk, heads, d).permute(1, 2, 0)
-    qP, kP = lib.split(qp.view(B * Tq, heads * HS)), lib.split(kp.view(B * Tk, heads * HS))
-    vP = lib.split(vt.view(heads * HS, ldv))
+    kp = torch.zeros(B, TkS, heads, HS, device=cuda)
+    kp[:, :Tk, :, :d] = k
+    kp[:, Tk:] = 7.0                   # pad keys must be masked, not merely zero
+    vt = torch.zeros(heads, HS, B, TkS, device=cuda)
+    vt[:, :d, :, :Tk] = v.permute(2, 3, 0, 1)
+    vt[:, :, :, Tk:] = 5.0
+    qP, kP = lib.split(qp.view(B * Tq, heads * HS)), lib.split(kp.view(B * TkS, heads * HS))
+    vP = lib.split(vt.view(heads * HS, B * TkS))
     scale = d ** -0.5
-    out, outp = ops.attention_tc(qP, kP, vP, B, heads, d, Tq, Tk, scale, nmma, want_f32=True, want_planes=True)
+    out, outp = ops.attention_tc(qP, kP, vP, B, heads, d, Tq, Tk, scale, nmma, want_f32=True, want_planes=True,
+                                 tk_stride=TkS)
     torch.cuda.synchronize()
     s = torch.einsum("bqhd,bkhd->bhqk", q.double(), k.double()) * scale
     ref = torch.einsum("bhqk,bkhd->bqhd", s.softmax(-1), v.double()).reshape(B * Tq, heads * d)
