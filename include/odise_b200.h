@@ -64,7 +64,7 @@ int odise_msda_fused_f32(const float* value, const int64_t* spatial_shapes, cons
  * Replaces F.conv2d / F.linear / torch.einsum call sites of the path (ldm ResBlock & attention linears via
  * odise/modeling/meta_arch/ldm.py:469-491; M2F linears; odise.py:746 mask einsum; odise.py:955-959 pooling;
  * odise.py:192-205 CLIP match).
- *   epi(v) = act(v + bias[n] + rowbias[(z*M+m)/rows_per_group][n]) + residual[z][m][n]
+ *   epi(v) = act(v + bias[n] + bias_m[m] + rowbias[(z*M+m)/rows_per_group][n]) + residual[z][m][n]
  * conv3x3 = 1: A is an NHWC activation [B, H, W, C] (pixel stride lda elements), M = B*H*W, K = 9*C with
  *   k = (kh*3 + kw)*C + c, padding 1, stride 1; C % 64 == 0 and tiles must cover whole rows (W | 128 or 128 | W).
  * All bf16 leading dimensions are multiples of 8 elements, fp32 ones multiples of 4; base pointers 16-byte aligned. */
@@ -84,6 +84,7 @@ typedef struct odise_gemm_desc {
   void* out_hi; void* out_lo; long long ld_out_bf16; long long out_bf16_batch_stride;
   int split_k; void* workspace; long long workspace_bytes;
   int force_bn;                      /* 0 = heuristic; 64/128/160/256 */
+  const float* bias_m;               /* [M] per-row bias or NULL (transposed-output projections) */
 } odise_gemm_desc;
 int odise_gemm_bf16(const odise_gemm_desc* desc, void* stream);
 
@@ -98,10 +99,18 @@ int odise_split_f32(const float* x, long long ldx, void* hi, void* lo, long long
  * (torch.nn.GroupNorm in ldm ResBlock / SpatialTransformer / d2 BottleneckBlock / M2F input_proj) */
 int odise_groupnorm_stats_f32(const float* x, long long ldx, float* mean, float* rstd, int B, int HW, int C, int G,
                               float eps, void* stream);
-/* y = act(gn(x) * gamma + beta): writes fp32 (optional) and (hi, lo) planes (optional). act: NONE/SILU/RELU */
+int odise_groupnorm_stats_bs_f32(const float* x, long long ldx, long long x_bs, float* mean, float* rstd, int B,
+                                 int HW, int C, int G, float eps, void* stream);
+/* y = act(gn(x) * gamma + beta): writes fp32 (optional) and (hi, lo) planes (optional). act: NONE/SILU/RELU.
+ * The *_bs variants take explicit per-image strides (elements; 0 = dense) so a level can be read from / written
+ * into the level-concatenated [B, S, C] token matrix of the pixel decoder (msdeformattn.py:61-78). */
 int odise_groupnorm_apply_f32(const float* x, long long ldx, const float* mean, const float* rstd,
                               const float* gamma, const float* beta, int act, float* y, long long ldy, void* hi,
                               void* lo, long long ldo, int B, int HW, int C, int G, void* stream);
+int odise_groupnorm_apply_bs_f32(const float* x, long long ldx, long long x_bs, const float* mean, const float* rstd,
+                                 const float* gamma, const float* beta, int act, float* y, long long ldy,
+                                 long long y_bs, void* hi, void* lo, long long ldo, long long o_bs, int B, int HW,
+                                 int C, int G, void* stream);
 /* LayerNorm over the last dim (cols <= 4096): optional fp32 output, optional residual add BEFORE the norm
  * (post-norm transformer: y = LN(x + res)), optional `post_add` AFTER the norm written only to the bf16 planes
  * (query_pos / pos added to the GEMM operand, M2F with_pos_embed). */
@@ -133,6 +142,9 @@ int odise_copy2d_f32(const float* src, long long lds, float* dst, long long ldd,
  * msdeformattn.py:349; F.interpolate nearest in feature_extractor.py:165) */
 int odise_resize_nhwc_f32(const float* src, long long lds, float* dst, long long ldd, int B, int Hs, int Ws, int Hd,
                           int Wd, int C, int bilinear, int accumulate, void* stream);
+int odise_resize_nhwc_bs_f32(const float* src, long long lds, long long src_bs, float* dst, long long ldd,
+                             long long dst_bs, int B, int Hs, int Ws, int Hd, int Wd, int C, int bilinear,
+                             int accumulate, void* stream);
 /* NHWC <-> NCHW transposes at the plugin boundary */
 int odise_nchw_to_nhwc_f32(const float* src, float* dst, long long ldd, int B, int C, int HW, void* stream);
 int odise_nhwc_to_nchw_f32(const float* src, long long lds, float* dst, int B, int C, int HW, void* stream);
@@ -163,12 +175,13 @@ int odise_softmax_split_f32(const float* x, long long ldx, void* hi, void* lo, l
 int odise_attn_mask_bits_f32(const float* mask_logits, uint32_t* bits, int32_t* row_any, int B, int Q, int Hm,
                              int Wm, int Hl, int Wl, void* stream);
 /* Multi-head attention for head_dim 32 (nn.MultiheadAttention(256, 8) core of the decoder's cross- and
- * self-attention layers): q [B, Tq, heads*32], k, v [B, Tk, heads*32] already projected, fp32;
+ * self-attention layers): q [B, Tq, heads*32] (row stride ldq), k, v [B, Tk, heads*32] (row stride ldkv; lets
+ * several layers' projections live side by side in one GEMM output) already projected, fp32;
  * out = softmax(scale * q k^T  (+ -inf where bit == 0 and row_any != 0)) v, written as fp32 and/or (hi, lo).
  * bits / row_any may be NULL (unmasked self-attention). */
-int odise_mha_d32_f32(const float* q, const float* k, const float* v, const uint32_t* bits, const int32_t* row_any,
-                      float* out, void* out_hi, void* out_lo, int B, int Tq, int Tk, int heads, float scale,
-                      void* stream);
+int odise_mha_d32_f32(const float* q, long long ldq, const float* k, const float* v, long long ldkv,
+                      const uint32_t* bits, const int32_t* row_any, float* out, void* out_hi, void* out_lo,
+                      long long ldo, int B, int Tq, int Tk, int heads, float scale, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Mask head helpers (odise.py:937-963 MaskPooling, odise.py:746 einsum) */

@@ -63,16 +63,15 @@ attn_mask_bits_kernel(const float* __restrict__ logits, uint32_t* __restrict__ b
 // grid (q_tiles, heads, B); 8 warps, QPW queries per warp; head_dim 32
 template <int QPW>
 __global__ void __launch_bounds__(256)
-mha_d32_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
-               const uint32_t* __restrict__ bits, const int32_t* __restrict__ row_any, float* __restrict__ out,
-               __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo, int Tq, int Tk, int heads,
-               float scale) {
+mha_d32_kernel(const float* __restrict__ q, long long ldq, const float* __restrict__ k,
+               const float* __restrict__ v, long long ldkv, const uint32_t* __restrict__ bits,
+               const int32_t* __restrict__ row_any, float* __restrict__ out, __nv_bfloat16* __restrict__ out_hi,
+               __nv_bfloat16* __restrict__ out_lo, long long ldo, int Tq, int Tk, int heads, float scale) {
   constexpr int KT = 128;                // keys per shared-memory tile
   __shared__ float Ks[KT][33];
   __shared__ float Vs[KT][32];
   const int b = blockIdx.z, h = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int C = heads * 32;
   const int words = (Tk + 31) / 32;
 
   float qreg[QPW][32];
@@ -85,7 +84,7 @@ mha_d32_kernel(const float* __restrict__ q, const float* __restrict__ k, const f
     m[t] = -INFINITY; l[t] = 0.f; o[t] = 0.f;
     use_mask[t] = false;
     if (qi[t] < Tq) {
-      const float* qp = q + ((long long)b * Tq + qi[t]) * C + h * 32;
+      const float* qp = q + ((long long)b * Tq + qi[t]) * ldq + h * 32;
 #pragma unroll
       for (int d = 0; d < 32; ++d) qreg[t][d] = __ldg(qp + d) * scale;
       if (bits) use_mask[t] = row_any[(long long)b * Tq + qi[t]] != 0;
@@ -101,8 +100,8 @@ mha_d32_kernel(const float* __restrict__ q, const float* __restrict__ k, const f
       const int r = i >> 3, c4 = (i & 7) * 4;
       float4 kv = make_float4(0, 0, 0, 0), vv = kv;
       if (k0 + r < Tk) {
-        kv = *reinterpret_cast<const float4*>(k + ((long long)b * Tk + k0 + r) * C + h * 32 + c4);
-        vv = *reinterpret_cast<const float4*>(v + ((long long)b * Tk + k0 + r) * C + h * 32 + c4);
+        kv = *reinterpret_cast<const float4*>(k + ((long long)b * Tk + k0 + r) * ldkv + h * 32 + c4);
+        vv = *reinterpret_cast<const float4*>(v + ((long long)b * Tk + k0 + r) * ldkv + h * 32 + c4);
       }
       Ks[r][c4] = kv.x; Ks[r][c4 + 1] = kv.y; Ks[r][c4 + 2] = kv.z; Ks[r][c4 + 3] = kv.w;
       *reinterpret_cast<float4*>(&Vs[r][c4]) = vv;
@@ -141,7 +140,7 @@ mha_d32_kernel(const float* __restrict__ q, const float* __restrict__ k, const f
   for (int t = 0; t < QPW; ++t) {
     if (qi[t] >= Tq) continue;
     const float r = o[t] / l[t];
-    const long long idx = ((long long)b * Tq + qi[t]) * C + h * 32 + lane;
+    const long long idx = ((long long)b * Tq + qi[t]) * ldo + h * 32 + lane;
     if (out) out[idx] = r;
     if (out_hi) {
       __nv_bfloat16 hh, ll;
@@ -166,16 +165,18 @@ extern "C" int odise_attn_mask_bits_f32(const float* mask_logits, uint32_t* bits
   return (int)cudaGetLastError();
 }
 
-extern "C" int odise_mha_d32_f32(const float* q, const float* k, const float* v, const uint32_t* bits,
-                                 const int32_t* row_any, float* out, void* out_hi, void* out_lo, int B, int Tq,
-                                 int Tk, int heads, float scale, void* stream) {
+extern "C" int odise_mha_d32_f32(const float* q, long long ldq, const float* k, const float* v, long long ldkv,
+                                 const uint32_t* bits, const int32_t* row_any, float* out, void* out_hi,
+                                 void* out_lo, long long ldo, int B, int Tq, int Tk, int heads, float scale,
+                                 void* stream) {
   if (!q || !k || !v || (!out && !out_hi) || B <= 0 || Tq <= 0 || Tk <= 0 || heads <= 0) return ODISE_ERR_ARG;
+  if (ldq < heads * 32 || ldkv < heads * 32 || ldo < heads * 32 || ldkv % 4) return ODISE_ERR_ALIGN;
   if (bits && !row_any) return ODISE_ERR_ARG;
   constexpr int QPW = 2;
   dim3 grid((Tq + 8 * QPW - 1) / (8 * QPW), heads, B);
   mha_d32_kernel<QPW><<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      q, k, v, bits, row_any, out, reinterpret_cast<__nv_bfloat16*>(out_hi), reinterpret_cast<__nv_bfloat16*>(out_lo),
-      Tq, Tk, heads, scale);
+      q, ldq, k, v, ldkv, bits, row_any, out, reinterpret_cast<__nv_bfloat16*>(out_hi),
+      reinterpret_cast<__nv_bfloat16*>(out_lo), ldo, Tq, Tk, heads, scale);
   count_launch(1);
   return (int)cudaGetLastError();
 }

@@ -96,10 +96,10 @@ __global__ void copy2d_kernel(const float* __restrict__ src, long long lds, floa
 // torch.nn.GroupNorm's fp32 statistics to ~1e-7 relative).
 __global__ void __launch_bounds__(256)
 gn_stats_kernel(const float* __restrict__ x, long long ldx, float* __restrict__ mean, float* __restrict__ rstd,
-                int HW, int C, int G, float eps) {
+                int HW, int C, int G, float eps, long long x_bs) {
   const int b = blockIdx.x / G, g = blockIdx.x % G;
   const int cpg = C / G;
-  const float* xb = x + (long long)b * HW * ldx + g * cpg;
+  const float* xb = x + (long long)b * x_bs + g * cpg;
   const long long n = (long long)HW * cpg;
   __shared__ double red[8];
   __shared__ double s_mean;
@@ -155,7 +155,7 @@ __global__ void gn_apply_kernel(const float* __restrict__ x, long long ldx, cons
                                 const float* __restrict__ rstd, const float* __restrict__ gamma,
                                 const float* __restrict__ beta, int act, float* __restrict__ y, long long ldy,
                                 __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, long long ldo,
-                                long long rows, int HW, int C, int G) {
+                                long long rows, int HW, int C, int G, long long x_bs, long long y_bs, long long o_bs) {
   const int c4n = C / 4;
   const int cpg = C / G;
   const long long total = rows * c4n;
@@ -164,7 +164,8 @@ __global__ void gn_apply_kernel(const float* __restrict__ x, long long ldx, cons
     const long long r = i / c4n;
     const int c = (int)(i - r * c4n) * 4;
     const int b = (int)(r / HW);
-    const float4 v = *reinterpret_cast<const float4*>(x + r * ldx + c);
+    const long long hw = r - (long long)b * HW;
+    const float4 v = *reinterpret_cast<const float4*>(x + b * x_bs + hw * ldx + c);
     const float in[4] = {v.x, v.y, v.z, v.w};
     float o[4];
 #pragma unroll
@@ -177,8 +178,8 @@ __global__ void gn_apply_kernel(const float* __restrict__ x, long long ldx, cons
       o[t] = act_apply(u, act);
     }
     const float4 ov = make_float4(o[0], o[1], o[2], o[3]);
-    if (y) *reinterpret_cast<float4*>(y + r * ldy + c) = ov;
-    if (hi) store_split4(hi + r * ldo + c, lo ? lo + r * ldo + c : nullptr, ov);
+    if (y) *reinterpret_cast<float4*>(y + b * y_bs + hw * ldy + c) = ov;
+    if (hi) store_split4(hi + b * o_bs + hw * ldo + c, lo ? lo + b * o_bs + hw * ldo + c : nullptr, ov);
   }
 }
 
@@ -309,7 +310,7 @@ __global__ void im2col3x3_split_kernel(const float* __restrict__ x, long long ld
 // F.interpolate(mode="bilinear", align_corners=False) / mode="nearest" on NHWC
 __global__ void resize_nhwc_kernel(const float* __restrict__ src, long long lds, float* __restrict__ dst,
                                    long long ldd, int B, int Hs, int Ws, int Hd, int Wd, int C, int bilinear,
-                                   int accumulate) {
+                                   int accumulate, long long src_bs, long long dst_bs) {
   const int c4n = C / 4;
   const long long total = (long long)B * Hd * Wd * c4n;
   const float sy = (float)Hs / (float)Hd, sx = (float)Ws / (float)Wd;
@@ -320,7 +321,7 @@ __global__ void resize_nhwc_kernel(const float* __restrict__ src, long long lds,
     const int ox = (int)(p % Wd); p /= Wd;
     const int oy = (int)(p % Hd);
     const int b = (int)(p / Hd);
-    const float* sb = src + (long long)b * Hs * Ws * lds + c;
+    const float* sb = src + (long long)b * src_bs + c;
     float4 v;
     if (bilinear) {
       // ATen area_pixel_compute_source_index(align_corners=False): max(0, (dst + 0.5) * scale - 0.5)
@@ -340,7 +341,7 @@ __global__ void resize_nhwc_kernel(const float* __restrict__ src, long long lds,
       const int y0 = min((int)floorf(oy * sy), Hs - 1), x0 = min((int)floorf(ox * sx), Ws - 1);
       v = *reinterpret_cast<const float4*>(sb + ((long long)y0 * Ws + x0) * lds);
     }
-    float4* dp = reinterpret_cast<float4*>(dst + (((long long)b * Hd + oy) * Wd + ox) * ldd + c);
+    float4* dp = reinterpret_cast<float4*>(dst + (long long)b * dst_bs + ((long long)oy * Wd + ox) * ldd + c);
     if (accumulate) { const float4 o = *dp; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
     *dp = v;
   }
@@ -515,8 +516,14 @@ extern "C" int odise_copy2d_f32(const float* src, long long lds, float* dst, lon
 
 extern "C" int odise_groupnorm_stats_f32(const float* x, long long ldx, float* mean, float* rstd, int B, int HW,
                                          int C, int G, float eps, void* stream) {
+  return odise_groupnorm_stats_bs_f32(x, ldx, 0, mean, rstd, B, HW, C, G, eps, stream);
+}
+
+extern "C" int odise_groupnorm_stats_bs_f32(const float* x, long long ldx, long long x_bs, float* mean, float* rstd,
+                                            int B, int HW, int C, int G, float eps, void* stream) {
   if (!x || !mean || !rstd || B <= 0 || HW <= 0 || C <= 0 || G <= 0 || C % G) return ODISE_ERR_ARG;
-  gn_stats_kernel<<<B * G, 256, 0, STREAM(stream)>>>(x, ldx, mean, rstd, HW, C, G, eps);
+  gn_stats_kernel<<<B * G, 256, 0, STREAM(stream)>>>(x, ldx, mean, rstd, HW, C, G, eps,
+                                                     x_bs ? x_bs : (long long)HW * ldx);
   count_launch(1);
   return (int)cudaGetLastError();
 }
@@ -525,11 +532,21 @@ extern "C" int odise_groupnorm_apply_f32(const float* x, long long ldx, const fl
                                          const float* gamma, const float* beta, int act, float* y, long long ldy,
                                          void* hi, void* lo, long long ldo, int B, int HW, int C, int G,
                                          void* stream) {
+  return odise_groupnorm_apply_bs_f32(x, ldx, 0, mean, rstd, gamma, beta, act, y, ldy, 0, hi, lo, ldo, 0, B, HW, C, G,
+                                      stream);
+}
+
+extern "C" int odise_groupnorm_apply_bs_f32(const float* x, long long ldx, long long x_bs, const float* mean,
+                                            const float* rstd, const float* gamma, const float* beta, int act,
+                                            float* y, long long ldy, long long y_bs, void* hi, void* lo,
+                                            long long ldo, long long o_bs, int B, int HW, int C, int G, void* stream) {
   if (!x || !mean || !rstd || !gamma || !beta || (!y && !hi) || C % G) return ODISE_ERR_ARG;
-  if (C % 4 || ldx % 4 || (y && ldy % 4) || (hi && ldo % 4)) return ODISE_ERR_ALIGN;
+  if (C % 4 || ldx % 4 || x_bs % 4 || (y && (ldy % 4 || y_bs % 4)) || (hi && (ldo % 4 || o_bs % 4)))
+    return ODISE_ERR_ALIGN;
   const long long rows = (long long)B * HW;
-  gn_apply_kernel<<<grid_for(rows * (C / 4), 256), 256, 0, STREAM(stream)>>>(x, ldx, mean, rstd, gamma, beta, act, y,
-                                                                           ldy, BF(hi), BF(lo), ldo, rows, HW, C, G);
+  gn_apply_kernel<<<grid_for(rows * (C / 4), 256), 256, 0, STREAM(stream)>>>(
+      x, ldx, mean, rstd, gamma, beta, act, y, ldy, BF(hi), BF(lo), ldo, rows, HW, C, G,
+      x_bs ? x_bs : (long long)HW * ldx, y_bs ? y_bs : (long long)HW * ldy, o_bs ? o_bs : (long long)HW * ldo);
   count_launch(1);
   return (int)cudaGetLastError();
 }
@@ -588,10 +605,17 @@ extern "C" int odise_im2col3x3_split_f32(const float* x, long long ldx, void* hi
 
 extern "C" int odise_resize_nhwc_f32(const float* src, long long lds, float* dst, long long ldd, int B, int Hs,
                                      int Ws, int Hd, int Wd, int C, int bilinear, int accumulate, void* stream) {
+  return odise_resize_nhwc_bs_f32(src, lds, 0, dst, ldd, 0, B, Hs, Ws, Hd, Wd, C, bilinear, accumulate, stream);
+}
+
+extern "C" int odise_resize_nhwc_bs_f32(const float* src, long long lds, long long src_bs, float* dst, long long ldd,
+                                        long long dst_bs, int B, int Hs, int Ws, int Hd, int Wd, int C, int bilinear,
+                                        int accumulate, void* stream) {
   if (!src || !dst || B <= 0 || Hs <= 0 || Ws <= 0 || Hd <= 0 || Wd <= 0 || C <= 0) return ODISE_ERR_ARG;
-  if (C % 4 || lds % 4 || ldd % 4) return ODISE_ERR_ALIGN;
+  if (C % 4 || lds % 4 || ldd % 4 || src_bs % 4 || dst_bs % 4) return ODISE_ERR_ALIGN;
   resize_nhwc_kernel<<<grid_for((long long)B * Hd * Wd * (C / 4), 256), 256, 0, STREAM(stream)>>>(
-      src, lds, dst, ldd, B, Hs, Ws, Hd, Wd, C, bilinear, accumulate);
+      src, lds, dst, ldd, B, Hs, Ws, Hd, Wd, C, bilinear, accumulate,
+      src_bs ? src_bs : (long long)Hs * Ws * lds, dst_bs ? dst_bs : (long long)Hd * Wd * ldd);
   count_launch(1);
   return (int)cudaGetLastError();
 }

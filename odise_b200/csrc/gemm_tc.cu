@@ -29,6 +29,7 @@ struct GemmParams {
   int tiles_m, tiles_n, splits, kblocks;
   float alpha;
   const float* bias;
+  const float* bias_m;  // per-row (m) bias, for swapped-operand (transposed-output) projections
   const float* rowbias;
   int rows_per_group;
   long long rowbias_ld;
@@ -68,6 +69,11 @@ __device__ __forceinline__ void epilogue_row(const GemmParams& p, int z, int m, 
     } else {
       _Pragma("unroll") for (int j = 0; j < 32; ++j) if (j < cnt) acc[j] += __ldg(p.bias + n + j);
     }
+  }
+  if (p.bias_m) {
+    const float bm = __ldg(p.bias_m + m);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc[j] += bm;
   }
   if (p.rowbias) {
     const float* rb = p.rowbias + (long long)(((long long)z * p.M + m) / p.rows_per_group) * p.rowbias_ld + n;
@@ -440,7 +446,7 @@ extern "C" int odise_gemm_bf16(const odise_gemm_desc* d, void* stream_v) {
   p.a_batched = d->a_batch_stride != 0; p.b_batched = d->b_batch_stride != 0;
   p.conv = d->conv3x3; p.C = d->conv_C; p.H = d->conv_H; p.W = d->conv_W;
   p.alpha = d->alpha;
-  p.bias = d->bias; p.rowbias = d->rowbias; p.rows_per_group = d->rows_per_group > 0 ? d->rows_per_group : 1;
+  p.bias = d->bias; p.bias_m = d->bias_m; p.rowbias = d->rowbias; p.rows_per_group = d->rows_per_group > 0 ? d->rows_per_group : 1;
   p.rowbias_ld = d->rowbias_ld;
   p.res = d->residual; p.ldres = d->ld_residual; p.res_bs = d->residual_batch_stride;
   p.D = d->out_f32; p.ldd = d->ld_out; p.d_bs = d->out_batch_stride;

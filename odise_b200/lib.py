@@ -35,6 +35,7 @@ class GemmDesc(ctypes.Structure):
         ("out_hi", c_void_p), ("out_lo", c_void_p), ("ld_out_bf16", c_longlong), ("out_bf16_batch_stride", c_longlong),
         ("split_k", c_int), ("workspace", c_void_p), ("workspace_bytes", c_longlong),
         ("force_bn", c_int),
+        ("bias_m", c_void_p),
     ]
 
 
@@ -50,6 +51,13 @@ _SIGS = {
                                   c_void_p],
     "odise_groupnorm_apply_f32": [c_void_p, c_longlong, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
                                   c_longlong, c_void_p, c_void_p, c_longlong, c_int, c_int, c_int, c_int, c_void_p],
+    "odise_groupnorm_stats_bs_f32": [c_void_p, c_longlong, c_longlong, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                     c_float, c_void_p],
+    "odise_groupnorm_apply_bs_f32": [c_void_p, c_longlong, c_longlong, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                                     c_void_p, c_longlong, c_longlong, c_void_p, c_void_p, c_longlong, c_longlong,
+                                     c_int, c_int, c_int, c_int, c_void_p],
+    "odise_resize_nhwc_bs_f32": [c_void_p, c_longlong, c_longlong, c_void_p, c_longlong, c_longlong, c_int, c_int,
+                                 c_int, c_int, c_int, c_int, c_int, c_int, c_void_p],
     "odise_layernorm_f32": [c_void_p, c_longlong, c_void_p, c_longlong, c_void_p, c_void_p, c_float, c_void_p,
                             c_longlong, c_void_p, c_longlong, c_void_p, c_void_p, c_longlong, c_longlong, c_int,
                             c_void_p],
@@ -66,7 +74,8 @@ _SIGS = {
     "odise_nchw_to_nhwc_f32": [c_void_p, c_void_p, c_longlong, c_int, c_int, c_int, c_void_p],
     "odise_nhwc_to_nchw_f32": [c_void_p, c_longlong, c_void_p, c_int, c_int, c_int, c_void_p],
     "odise_attn_mask_bits_f32": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p],
-    "odise_mha_d32_f32": [c_void_p] * 8 + [c_int, c_int, c_int, c_int, c_float, c_void_p],
+    "odise_mha_d32_f32": [c_void_p, c_longlong, c_void_p, c_void_p, c_longlong, c_void_p, c_void_p, c_void_p, c_void_p,
+                          c_void_p, c_longlong, c_int, c_int, c_int, c_int, c_float, c_void_p],
     "odise_mask_binarize_f32": [c_void_p, c_void_p, c_longlong, c_void_p, c_int, c_int, c_int, c_void_p],
     "odise_pool_normalize_f32": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
     "odise_l2_normalize_split_f32": [c_void_p, c_longlong, c_void_p, c_void_p, c_longlong, c_longlong, c_int,
@@ -174,7 +183,7 @@ def split(x, out=None, lo=True):
     return out
 
 
-def gemm(a, b, *, M=None, N=None, K=None, nmma=3, batch=1, a_bs=0, b_bs=0, conv=None, alpha=1.0, bias=None,
+def gemm(a, b, *, M=None, N=None, K=None, nmma=3, batch=1, a_bs=0, b_bs=0, conv=None, alpha=1.0, bias=None, bias_m=None,
          rowbias=None, rows_per_group=1, act=ACT_NONE, residual=None, ld_res=None, res_bs=0, out=None, ld_out=None,
          out_bs=0, out_planes=None, outp_bs=0, split_k=1, workspace=None, force_bn=0):
     """out[z] = epi(alpha * A[z] @ B[z]^T).  a, b: Planes (K-major).  conv = (C, H, W) for implicit 3x3."""
@@ -190,6 +199,7 @@ def gemm(a, b, *, M=None, N=None, K=None, nmma=3, batch=1, a_bs=0, b_bs=0, conv=
     d.b_hi, d.b_lo, d.ldb, d.b_batch_stride = _ptr(b.hi), _ptr(b.lo), b.ld, b_bs
     d.alpha = alpha
     d.bias = _ptr(bias)
+    d.bias_m = _ptr(bias_m)
     if rowbias is not None:
         d.rowbias, d.rows_per_group, d.rowbias_ld = _ptr(rowbias), rows_per_group, rowbias.stride(0)
     d.act = act

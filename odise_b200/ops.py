@@ -18,21 +18,27 @@ def split(x, lo=True):
     return lib.split(x, lo=lo)
 
 
-def group_norm(x, B, HW, gamma, beta, eps, act=ACT_NONE, G=32, want_f32=False, want_planes=True, lo=True, ldx=None):
-    """x [B*HW, C] (row stride ldx) -> (y fp32 | None, planes | None)"""
+def group_norm(x, B, HW, gamma, beta, eps, act=ACT_NONE, G=32, want_f32=False, want_planes=True, lo=True, ldx=None,
+               x_bs=0, y=None, ldy=None, y_bs=0, planes=None, o_bs=0):
+    """x [B*HW, C] (row stride ldx, per-image stride x_bs) -> (y fp32 | None, planes | None).
+    y / planes may be given (with explicit strides) to write into a slice of a larger buffer."""
     C = gamma.numel()
     ldx = ldx or x.stride(0)
     dev = x.device
     mean = torch.empty(B * G, dtype=torch.float32, device=dev)
     rstd = torch.empty(B * G, dtype=torch.float32, device=dev)
     L = load()
-    _check(L.odise_groupnorm_stats_f32(_ptr(x), ldx, _ptr(mean), _ptr(rstd), B, HW, C, G, eps, _stream()),
+    _check(L.odise_groupnorm_stats_bs_f32(_ptr(x), ldx, x_bs, _ptr(mean), _ptr(rstd), B, HW, C, G, eps, _stream()),
            "groupnorm_stats")
-    y = empty(B * HW, C, dev) if want_f32 else None
-    p = Planes.empty(B * HW, C, dev, lo=lo) if want_planes else None
-    _check(L.odise_groupnorm_apply_f32(_ptr(x), ldx, _ptr(mean), _ptr(rstd), _ptr(gamma), _ptr(beta), act, _ptr(y),
-                                       C, _ptr(p.hi) if p else None, _ptr(p.lo) if p else None, p.ld if p else 0,
-                                       B, HW, C, G, _stream()), "groupnorm_apply")
+    if y is None and want_f32:
+        y = empty(B * HW, C, dev)
+    if y is not None and ldy is None:
+        ldy = y.stride(0)
+    p = planes if planes is not None else (Planes.empty(B * HW, C, dev, lo=lo) if want_planes else None)
+    _check(L.odise_groupnorm_apply_bs_f32(_ptr(x), ldx, x_bs, _ptr(mean), _ptr(rstd), _ptr(gamma), _ptr(beta), act,
+                                          _ptr(y), ldy or C, y_bs, _ptr(p.hi) if p else None,
+                                          _ptr(p.lo) if p else None, p.ld if p else 0, o_bs, B, HW, C, G, _stream()),
+           "groupnorm_apply")
     return y, p
 
 
@@ -99,12 +105,13 @@ def copy2d(src, dst, scale=1.0, accumulate=False):
                                    1 if accumulate else 0, _stream()), "copy2d")
 
 
-def resize_nhwc(src, B, Hs, Ws, Hd, Wd, bilinear, dst=None, accumulate=False):
+def resize_nhwc(src, B, Hs, Ws, Hd, Wd, bilinear, dst=None, accumulate=False, src_bs=0, dst_bs=0):
     C = src.shape[1]
     if dst is None:
         dst = empty(B * Hd * Wd, C, src.device)
-    _check(load().odise_resize_nhwc_f32(_ptr(src), src.stride(0), _ptr(dst), dst.stride(0), B, Hs, Ws, Hd, Wd, C,
-                                        1 if bilinear else 0, 1 if accumulate else 0, _stream()), "resize")
+    _check(load().odise_resize_nhwc_bs_f32(_ptr(src), src.stride(0), src_bs, _ptr(dst), dst.stride(0), dst_bs, B, Hs,
+                                           Ws, Hd, Wd, C, 1 if bilinear else 0, 1 if accumulate else 0, _stream()),
+           "resize")
     return dst
 
 
@@ -157,3 +164,60 @@ def head_stride(d):
     if d <= 80:
         return 128
     return None   # unfused path
+
+
+def msda_fused(value, spatial_shapes, level_start, ref, offs, logits, N, S, M, D, L, Lq, P, want_f32=False, lo=True):
+    dev = value.device
+    out = empty(N * Lq, M * D, dev) if want_f32 else None
+    p = Planes.empty(N * Lq, M * D, dev, lo=lo)
+    _check(load().odise_msda_fused_f32(_ptr(value), _ptr(spatial_shapes), _ptr(level_start), _ptr(ref), _ptr(offs),
+                                       _ptr(logits), _ptr(out), _ptr(p.hi), _ptr(p.lo), N, S, M, D, L, Lq, P,
+                                       _stream()), "msda_fused")
+    return out, p
+
+
+def attn_mask_bits(mask_logits, B, Q, Hm, Wm, Hl, Wl):
+    dev = mask_logits.device
+    bits = torch.empty(B * Q * ((Hl * Wl + 31) // 32), dtype=torch.int32, device=dev)
+    row_any = torch.empty(B * Q, dtype=torch.int32, device=dev)
+    _check(load().odise_attn_mask_bits_f32(_ptr(mask_logits), _ptr(bits), _ptr(row_any), B, Q, Hm, Wm, Hl, Wl,
+                                           _stream()), "attn_mask_bits")
+    return bits, row_any
+
+
+def mha_d32(q, ldq, k, v, ldkv, B, Tq, Tk, heads, scale, bits=None, row_any=None, lo=True):
+    """q/k/v fp32 device tensors (any views whose data_ptr is the first element); returns Planes [B*Tq, heads*32]."""
+    p = Planes.empty(B * Tq, heads * 32, q.device, lo=lo)
+    _check(load().odise_mha_d32_f32(_ptr(q), ldq, _ptr(k), _ptr(v), ldkv, _ptr(bits), _ptr(row_any), None, _ptr(p.hi),
+                                    _ptr(p.lo), p.ld, B, Tq, Tk, heads, scale, _stream()), "mha_d32")
+    return p
+
+
+def mask_binarize(logits, B, Q, HW):
+    dev = logits.device
+    binp = torch.empty(B * Q * HW, dtype=torch.bfloat16, device=dev)
+    counts = torch.empty(B * Q, dtype=torch.float32, device=dev)
+    _check(load().odise_mask_binarize_f32(_ptr(logits), _ptr(binp), HW, _ptr(counts), B, Q, HW, _stream()),
+           "mask_binarize")
+    return binp, counts
+
+
+def pool_normalize(sums, counts, B, Q, C):
+    out = empty(B * Q, C, sums.device)
+    _check(load().odise_pool_normalize_f32(_ptr(sums), _ptr(counts), _ptr(out), B, Q, C, _stream()), "pool_normalize")
+    return out
+
+
+def l2_normalize_split(x, lo=True):
+    rows, cols = x.shape
+    p = Planes.empty(rows, cols, x.device, lo=lo)
+    _check(load().odise_l2_normalize_split_f32(_ptr(x), x.stride(0), _ptr(p.hi), _ptr(p.lo), p.ld, rows, cols,
+                                               _stream()), "l2_normalize")
+    return p
+
+
+def class_max(sims, group_start, null_sim, rows, n_classes):
+    out = empty(rows, n_classes + 1, sims.device)
+    _check(load().odise_class_max_f32(_ptr(sims), sims.stride(0), _ptr(group_start), _ptr(null_sim), _ptr(out), rows,
+                                      n_classes, _stream()), "class_max")
+    return out

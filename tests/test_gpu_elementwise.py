@@ -182,8 +182,9 @@ def test_mha_d32(cuda, cfg):
         am[torch.where(am.sum(-1) == am.shape[-1])] = False
         assert rowany[0, 3].item() == 0
         bias = torch.zeros(B, 1, Tq, Tk, device=cuda, dtype=torch.float64).masked_fill(am[:, None], float("-inf"))
-    _call("odise_mha_d32_f32", q.data_ptr(), k.data_ptr(), v.data_ptr(), None if bits is None else bits.data_ptr(),
-          None if rowany is None else rowany.data_ptr(), out.data_ptr(), None, None, B, Tq, Tk, heads, scale)
+    _call("odise_mha_d32_f32", q.data_ptr(), heads * d, k.data_ptr(), v.data_ptr(), heads * d,
+          None if bits is None else bits.data_ptr(), None if rowany is None else rowany.data_ptr(), out.data_ptr(),
+          None, None, heads * d, B, Tq, Tk, heads, scale)
     qh = q.double().view(B, Tq, heads, d).transpose(1, 2)
     kh = k.double().view(B, Tk, heads, d).transpose(1, 2)
     vh = v.double().view(B, Tk, heads, d).transpose(1, 2)

@@ -49,8 +49,8 @@ def _run(unet_sd, oracle_unet, cuda, B, hw, nmma, with_cond=True):
 
 
 def test_unet_taps_small_latent(cuda, unet_sd, oracle_unet):
-    errs = _run(unet_sd, oracle_unet, cuda, B=2, hw=16, nmma=3)
-    print("unet 16x16 bf16x3 tap errors", errs)
+    errs = _run(unet_sd, oracle_unet, cuda, B=2, hw=32, nmma=3)
+    print("unet 32x32 bf16x3 tap errors", errs)
     assert max(errs) < 1e-3, errs
 
 
@@ -63,6 +63,6 @@ def test_unet_taps_full_latent(cuda, unet_sd, oracle_unet):
 
 def test_unet_taps_fast_mode_reported(cuda, unet_sd, oracle_unet):
     """plain bf16 (nmma=1) is NOT the parity mode; its error is recorded, only sanity-bounded."""
-    errs = _run(unet_sd, oracle_unet, cuda, B=1, hw=16, nmma=1, with_cond=False)
-    print("unet 16x16 bf16 tap errors", errs)
+    errs = _run(unet_sd, oracle_unet, cuda, B=1, hw=32, nmma=1, with_cond=False)
+    print("unet 32x32 bf16 tap errors", errs)
     assert max(errs) < 0.2, errs
