@@ -111,6 +111,19 @@ int odise_groupnorm_apply_bs_f32(const float* x, long long ldx, long long x_bs, 
                                  const float* gamma, const float* beta, int act, float* y, long long ldy,
                                  long long y_bs, void* hi, void* lo, long long ldo, long long o_bs, int B, int HW,
                                  int C, int G, void* stream);
+/* y (+)= act(gn(x) * gamma + beta + res): the tail of detectron2's BottleneckBlock (relu(gn(conv3) + shortcut)),
+ * optionally accumulated into y — the per-stride sum of FeatureExtractorBackbone.forward_features
+ * (feature_extractor.py:157-179). */
+int odise_groupnorm_apply_res_f32(const float* x, long long ldx, const float* mean, const float* rstd,
+                                  const float* gamma, const float* beta, const float* res, long long ldres, int act,
+                                  float* y, long long ldy, int accumulate, void* hi, void* lo, long long ldo, int B,
+                                  int HW, int C, int G, void* stream);
+/* out[b, t, c] = a0[t, c] + ta[t, c] * p[b, c]: LdmImplicitCaptionerExtractor.forward (ldm.py:705-714) with the
+ * weight-only terms folded: cond = (uncond + tanh(alpha) * pos) + tanh(alpha) * clip_project(prefix). */
+int odise_bcast_fma_f32(const float* a0, const float* ta, const float* p, float* out, int B, int T, int C,
+                        void* stream);
+/* y[r, :] *= s[r]  (slide_forward's division by the crop-overlap count, feature_extractor.py:246-248) */
+int odise_rowscale_f32(float* y, long long ldy, const float* s, long long rows, int cols, void* stream);
 /* LayerNorm over the last dim (cols <= 4096): optional fp32 output, optional residual add BEFORE the norm
  * (post-norm transformer: y = LN(x + res)), optional `post_add` AFTER the norm written only to the bf16 planes
  * (query_pos / pos added to the GEMM operand, M2F with_pos_embed). */

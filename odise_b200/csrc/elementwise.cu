@@ -155,7 +155,8 @@ __global__ void gn_apply_kernel(const float* __restrict__ x, long long ldx, cons
                                 const float* __restrict__ rstd, const float* __restrict__ gamma,
                                 const float* __restrict__ beta, int act, float* __restrict__ y, long long ldy,
                                 __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, long long ldo,
-                                long long rows, int HW, int C, int G, long long x_bs, long long y_bs, long long o_bs) {
+                                long long rows, int HW, int C, int G, long long x_bs, long long y_bs, long long o_bs,
+                                const float* __restrict__ res, long long ldres, int accumulate) {
   const int c4n = C / 4;
   const int cpg = C / G;
   const long long total = rows * c4n;
@@ -175,9 +176,14 @@ __global__ void gn_apply_kernel(const float* __restrict__ x, long long ldx, cons
       // torch: (x - mean) * rstd * gamma + beta
       float u = (in[t] - mu) * rs;
       u = fmaf(u, __ldg(gamma + c + t), __ldg(beta + c + t));
+      if (res) u += res[r * ldres + c + t];   // BottleneckBlock: relu(gn(conv3) + shortcut)
       o[t] = act_apply(u, act);
     }
-    const float4 ov = make_float4(o[0], o[1], o[2], o[3]);
+    float4 ov = make_float4(o[0], o[1], o[2], o[3]);
+    if (y && accumulate) {
+      const float4 prev = *reinterpret_cast<const float4*>(y + b * y_bs + hw * ldy + c);
+      ov.x += prev.x; ov.y += prev.y; ov.z += prev.z; ov.w += prev.w;
+    }
     if (y) *reinterpret_cast<float4*>(y + b * y_bs + hw * ldy + c) = ov;
     if (hi) store_split4(hi + b * o_bs + hw * ldo + c, lo ? lo + b * o_bs + hw * ldo + c : nullptr, ov);
   }
@@ -455,6 +461,35 @@ __global__ void act_split_kernel(const float* __restrict__ x, long long ldx, int
   }
 }
 
+// out[b, t, c] = a0[t, c] + ta[t, c] * p[b, c]   (implicit captioner: cond = uncond + tanh(alpha) * (proj + pos))
+__global__ void bcast_fma_kernel(const float* __restrict__ a0, const float* __restrict__ ta,
+                                 const float* __restrict__ p, float* __restrict__ out, int B, int T, int C) {
+  const long long total = (long long)B * T * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const long long bt = i / C;
+    const int t = (int)(bt % T), b = (int)(bt / T);
+    out[i] = fmaf(ta[(long long)t * C + c], p[(long long)b * C + c], a0[(long long)t * C + c]);
+  }
+}
+
+// y[r, :] *= s[r]
+__global__ void rowscale_kernel(float* __restrict__ y, long long ldy, const float* __restrict__ s, long long rows,
+                                int cols4) {
+  const long long total = rows * cols4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / cols4;
+    const int c = (int)(i - r * cols4) * 4;
+    float4* q = reinterpret_cast<float4*>(y + r * ldy + c);
+    float4 v = *q;
+    const float f = s[r];
+    v.x *= f; v.y *= f; v.z *= f; v.w *= f;
+    *q = v;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- softmax
 // one warp per row
 __global__ void softmax_split_kernel(const float* __restrict__ x, long long ldx, __nv_bfloat16* __restrict__ hi,
@@ -546,7 +581,8 @@ extern "C" int odise_groupnorm_apply_bs_f32(const float* x, long long ldx, long 
   const long long rows = (long long)B * HW;
   gn_apply_kernel<<<grid_for(rows * (C / 4), 256), 256, 0, STREAM(stream)>>>(
       x, ldx, mean, rstd, gamma, beta, act, y, ldy, BF(hi), BF(lo), ldo, rows, HW, C, G,
-      x_bs ? x_bs : (long long)HW * ldx, y_bs ? y_bs : (long long)HW * ldy, o_bs ? o_bs : (long long)HW * ldo);
+      x_bs ? x_bs : (long long)HW * ldx, y_bs ? y_bs : (long long)HW * ldy, o_bs ? o_bs : (long long)HW * ldo,
+      nullptr, 0, 0);
   count_launch(1);
   return (int)cudaGetLastError();
 }
@@ -692,6 +728,37 @@ extern "C" int odise_act_split_f32(const float* x, long long ldx, int act, void*
   if (cols % 4 || ldx % 4 || ldo % 4) return ODISE_ERR_ALIGN;
   act_split_kernel<<<grid_for(rows * (cols / 4), 256), 256, 0, STREAM(stream)>>>(x, ldx, act, BF(hi), BF(lo), ldo,
                                                                                rows, cols / 4);
+  count_launch(1);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int odise_groupnorm_apply_res_f32(const float* x, long long ldx, const float* mean, const float* rstd,
+                                             const float* gamma, const float* beta, const float* res,
+                                             long long ldres, int act, float* y, long long ldy, int accumulate,
+                                             void* hi, void* lo, long long ldo, int B, int HW, int C, int G,
+                                             void* stream) {
+  if (!x || !mean || !rstd || !gamma || !beta || (!y && !hi) || C % G) return ODISE_ERR_ARG;
+  if (C % 4 || ldx % 4 || (y && ldy % 4) || (hi && ldo % 4) || (res && ldres % 4)) return ODISE_ERR_ALIGN;
+  const long long rows = (long long)B * HW;
+  gn_apply_kernel<<<grid_for(rows * (C / 4), 256), 256, 0, STREAM(stream)>>>(
+      x, ldx, mean, rstd, gamma, beta, act, y, ldy, BF(hi), BF(lo), ldo, rows, HW, C, G, (long long)HW * ldx,
+      (long long)HW * ldy, (long long)HW * ldo, res, ldres, accumulate);
+  count_launch(1);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int odise_bcast_fma_f32(const float* a0, const float* ta, const float* p, float* out, int B, int T, int C,
+                                   void* stream) {
+  if (!a0 || !ta || !p || !out || B <= 0 || T <= 0 || C <= 0) return ODISE_ERR_ARG;
+  bcast_fma_kernel<<<grid_for((long long)B * T * C, 256), 256, 0, STREAM(stream)>>>(a0, ta, p, out, B, T, C);
+  count_launch(1);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int odise_rowscale_f32(float* y, long long ldy, const float* s, long long rows, int cols, void* stream) {
+  if (!y || !s || rows <= 0 || cols <= 0) return ODISE_ERR_ARG;
+  if (cols % 4 || ldy % 4) return ODISE_ERR_ALIGN;
+  rowscale_kernel<<<grid_for(rows * (cols / 4), 256), 256, 0, STREAM(stream)>>>(y, ldy, s, rows, cols / 4);
   count_launch(1);
   return (int)cudaGetLastError();
 }

@@ -58,6 +58,11 @@ _SIGS = {
                                      c_int, c_int, c_int, c_int, c_void_p],
     "odise_resize_nhwc_bs_f32": [c_void_p, c_longlong, c_longlong, c_void_p, c_longlong, c_longlong, c_int, c_int,
                                  c_int, c_int, c_int, c_int, c_int, c_int, c_void_p],
+    "odise_groupnorm_apply_res_f32": [c_void_p, c_longlong, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                      c_longlong, c_int, c_void_p, c_longlong, c_int, c_void_p, c_void_p, c_longlong,
+                                      c_int, c_int, c_int, c_int, c_void_p],
+    "odise_bcast_fma_f32": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
+    "odise_rowscale_f32": [c_void_p, c_longlong, c_void_p, c_longlong, c_int, c_void_p],
     "odise_layernorm_f32": [c_void_p, c_longlong, c_void_p, c_longlong, c_void_p, c_void_p, c_float, c_void_p,
                             c_longlong, c_void_p, c_longlong, c_void_p, c_void_p, c_longlong, c_longlong, c_int,
                             c_void_p],

@@ -221,3 +221,31 @@ def class_max(sims, group_start, null_sim, rows, n_classes):
     _check(load().odise_class_max_f32(_ptr(sims), sims.stride(0), _ptr(group_start), _ptr(null_sim), _ptr(out), rows,
                                       n_classes, _stream()), "class_max")
     return out
+
+
+def group_norm_res(x, B, HW, gamma, beta, eps, res, act, y, accumulate, G=32):
+    """y (+)= act(gn(x) + res); x, res, y dense [B*HW, C] fp32."""
+    C = gamma.numel()
+    dev = x.device
+    mean = torch.empty(B * G, dtype=torch.float32, device=dev)
+    rstd = torch.empty(B * G, dtype=torch.float32, device=dev)
+    L = load()
+    _check(L.odise_groupnorm_stats_bs_f32(_ptr(x), x.stride(0), 0, _ptr(mean), _ptr(rstd), B, HW, C, G, eps, _stream()),
+           "groupnorm_stats")
+    _check(L.odise_groupnorm_apply_res_f32(_ptr(x), x.stride(0), _ptr(mean), _ptr(rstd), _ptr(gamma), _ptr(beta),
+                                           _ptr(res), res.stride(0) if res is not None else 0, act, _ptr(y),
+                                           y.stride(0), 1 if accumulate else 0, None, None, 0, B, HW, C, G, _stream()),
+           "groupnorm_apply_res")
+    return y
+
+
+def bcast_fma(a0, ta, p, B, T, C):
+    out = torch.empty(B * T, C, dtype=torch.float32, device=p.device)
+    _check(load().odise_bcast_fma_f32(_ptr(a0), _ptr(ta), _ptr(p), _ptr(out), B, T, C, _stream()), "bcast_fma")
+    return out
+
+
+def rowscale(y, s):
+    rows, cols = y.shape
+    _check(load().odise_rowscale_f32(_ptr(y), y.stride(0), _ptr(s), rows, cols, _stream()), "rowscale")
+    return y
