@@ -87,6 +87,10 @@ typedef struct odise_gemm_desc {
   const float* bias_m;               /* [M] per-row bias or NULL (transposed-output projections) */
 } odise_gemm_desc;
 int odise_gemm_bf16(const odise_gemm_desc* desc, void* stream);
+/* optional per-launch timing of odise_gemm_bf16 (CUDA events on the launch stream; not for use under graph capture):
+ * begin() starts recording, end() synchronises and returns launch count, summed device ms and algorithmic FLOPs. */
+int odise_profile_begin(void);
+int odise_profile_end(long long* launches, double* total_ms, double* total_flops);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Elementwise / normalisation passes (HBM-bound).  Every one of them also produces the (hi, lo) bf16 operand

@@ -19,6 +19,7 @@
 #include "launch_count.h"
 #include <cudaTypedefs.h>
 #include <mutex>
+#include <vector>
 
 namespace ob {
 
@@ -384,6 +385,11 @@ static int encode_map(CUtensorMap* tm, const void* base, int rank, const cuuint6
   return r == CUDA_SUCCESS ? ODISE_OK : ODISE_ERR_TENSORMAP;
 }
 
+// ---- optional per-launch timing (bench.py roofline): CUDA events on the launch stream around every GEMM launch
+struct ProfRec { cudaEvent_t a, b; double flops; };
+static std::vector<ProfRec> g_prof;
+static bool g_prof_on = false;
+
 int num_sms() {
   static int n = 0;
   if (!n) {
@@ -529,6 +535,13 @@ extern "C" int odise_gemm_bf16(const odise_gemm_desc* d, void* stream_v) {
     p.partial = reinterpret_cast<float*>(d->workspace);
   }
 
+  ProfRec rec{};
+  if (g_prof_on) {
+    cudaEventCreate(&rec.a);
+    cudaEventCreate(&rec.b);
+    rec.flops = 2.0 * d->M * d->N * (double)d->K * d->batch;
+    cudaEventRecord(rec.a, stream);
+  }
 #define ODISE_LAUNCH(BN_, NM_) rc = launch_cfg<BN_, NM_>(ah, al, bh, bl, p, stream)
   if (d->nmma == 3) {
     switch (BN) {
@@ -555,5 +568,36 @@ extern "C" int odise_gemm_bf16(const odise_gemm_desc* d, void* stream_v) {
     gemm_splitk_reduce_kernel<<<blocks, 128, 0, stream>>>(p);
     rc = (int)cudaGetLastError();
   }
+  if (g_prof_on) {
+    cudaEventRecord(rec.b, stream);
+    g_prof.push_back(rec);
+  }
   return rc;
+}
+
+extern "C" int odise_profile_begin(void) {
+  for (auto& r : g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  g_prof.clear();
+  g_prof_on = true;
+  return ODISE_OK;
+}
+
+// stops recording; returns launches, summed device ms and summed algorithmic FLOPs (2*M*N*K*batch) of the GEMMs
+extern "C" int odise_profile_end(long long* launches, double* total_ms, double* total_flops) {
+  g_prof_on = false;
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) return (int)e;
+  double ms = 0, fl = 0;
+  for (auto& r : g_prof) {
+    float t = 0;
+    cudaEventElapsedTime(&t, r.a, r.b);
+    ms += t;
+    fl += r.flops;
+  }
+  if (launches) *launches = (long long)g_prof.size();
+  if (total_ms) *total_ms = ms;
+  if (total_flops) *total_flops = fl;
+  for (auto& r : g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  g_prof.clear();
+  return ODISE_OK;
 }

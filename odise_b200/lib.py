@@ -46,6 +46,8 @@ _SIGS = {
     "odise_msda_forward_f32": [c_void_p] * 6 + [c_int] * 7 + [c_void_p],
     "odise_msda_fused_f32": [c_void_p] * 9 + [c_int] * 7 + [c_void_p],
     "odise_gemm_bf16": [POINTER(GemmDesc), c_void_p],
+    "odise_profile_begin": [],
+    "odise_profile_end": [c_void_p, c_void_p, c_void_p],
     "odise_split_f32": [c_void_p, c_longlong, c_void_p, c_void_p, c_longlong, c_longlong, c_int, c_void_p],
     "odise_groupnorm_stats_f32": [c_void_p, c_longlong, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float,
                                   c_void_p],
@@ -251,3 +253,14 @@ def msda_forward(value, spatial_shapes, level_start_index, sampling_locations, a
                                          _ptr(attention_weights), _ptr(out), N, S, M, D, L, Lq, P, _stream()),
            "odise_msda_forward_f32")
     return out
+
+
+def profile_begin():
+    _check(load().odise_profile_begin(), "odise_profile_begin")
+
+
+def profile_end():
+    """-> (launches, total_ms, total_flops) of the GEMM launches since profile_begin()"""
+    n, ms, fl = ctypes.c_longlong(0), ctypes.c_double(0), ctypes.c_double(0)
+    _check(load().odise_profile_end(ctypes.byref(n), ctypes.byref(ms), ctypes.byref(fl)), "odise_profile_end")
+    return n.value, ms.value, fl.value

@@ -1,0 +1,117 @@
+"""Inference meta-arch of the B200 engine: the eval branch of CategoryODISE.forward
+(odise/modeling/meta_arch/odise.py:209-246, :282-331) restricted to the north-star hot path:
+
+    images -> [sliding 512^2 crops] -> UNet feature pass -> projections -> pixel decoder -> masked-attention decoder
+           -> mask_embed x CLIP-text scoring -> (pred_logits [B, Q, K+1], pred_masks [B, Q, H/4, W/4])
+
+One process per GPU; images shard over ranks with a single NCCL all-gather of the final logits (reference analogue:
+d2 evaluator gather).  A step at fixed (batch, H, W) is captured once into a CUDA graph and replayed.
+"""
+import torch
+
+from . import lib, ops, spec
+from .backbone import BackboneEngine
+from .head import HeadEngine
+
+
+def full_param_list():
+    return spec.unet_params() + spec.backbone_params() + spec.head_params()
+
+
+class ODISEEngine:
+    def __init__(self, sd, device, nmma=3, num_queries=100):
+        self.dev = torch.device(device)
+        self.nmma = nmma
+        self.backbone = BackboneEngine(sd, device, nmma=nmma)
+        self.head = HeadEngine(sd, device, nmma=nmma, num_queries=num_queries)
+        self.Q = num_queries
+        self._graphs = {}
+        self.vocab_key = None
+        self.launches_per_step = None
+
+    def set_vocabulary(self, key, text_bank, null_bank, group_sizes):
+        """OpenPanopticInference / CategoryEmbed.test_labels analogue (pano_wrapper.py:58-68, odise.py:1281-1307):
+        the vocabulary is a [K', 768] CLIP text bank + per-class prompt counts."""
+        self.head.set_vocabulary(key, text_bank, null_bank, group_sizes)
+        self.vocab_key = key
+
+    # ------------------------------------------------------------------------------------------- device step
+    @torch.no_grad()
+    def step(self, n_images, H, W, vae_taps=None):
+        """One pass of the hot path for n_images resident images (eager). Returns device tensors."""
+        feats = self.backbone.forward(n_images, H, W, vae_taps)
+        out = self.head.forward(feats, n_images, vocab_key=self.vocab_key)
+        h2, w2 = out["pd"]["mask_hw"]
+        last = out["heads"][-1]
+        res = dict(pred_masks=last["pred_masks"].view(n_images, self.Q, h2, w2),
+                   mask_embed=last["mask_embed"].view(n_images, self.Q, -1),
+                   mask_pooled_features=last["mask_pooled_features"].view(n_images, self.Q, -1))
+        if "pred_logits" in out:
+            res["pred_logits"] = out["pred_logits"]
+        res["aux"] = out["heads"][:-1]
+        return res
+
+    def capture(self, n_images, H, W):
+        """Warm up eagerly, then capture the step into a CUDA graph (static shapes, static buffers)."""
+        key = (n_images, H, W, self.vocab_key)
+        if key in self._graphs:
+            return self._graphs[key]
+        s = torch.cuda.Stream(device=self.dev)
+        s.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(s):
+            for _ in range(2):
+                self.step(n_images, H, W)
+        torch.cuda.current_stream(self.dev).wait_stream(s)
+        torch.cuda.synchronize(self.dev)
+        before = lib.launch_count()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            out = self.step(n_images, H, W)
+        self.launches_per_step = lib.launch_count() - before
+        self._graphs[key] = (g, out)
+        return self._graphs[key]
+
+    # ------------------------------------------------------------------------------------------- user API
+    @torch.no_grad()
+    def infer(self, images_u8_pinned, use_graph=True):
+        """End-to-end call on a host batch: uint8 [B, 3, H, W] in pinned memory -> host dict
+        (pred_logits [B, Q, K+1], pred_masks [B, Q, H/4, W/4]).  H2D and D2H inside."""
+        B, _, H, W = images_u8_pinned.shape
+        if not hasattr(self, "_img_dev") or self._img_dev.shape != images_u8_pinned.shape:
+            self._img_dev = torch.empty_like(images_u8_pinned, device=self.dev)
+            self._host_logits = None
+        self._img_dev.copy_(images_u8_pinned, non_blocking=True)
+        if use_graph:
+            g, out = self.capture(B, H, W)
+            g.replay()
+        else:
+            out = self.step(B, H, W)
+        if self._host_logits is None:
+            self._host_logits = torch.empty(out["pred_logits"].shape, dtype=torch.float32).pin_memory()
+            self._host_masks = torch.empty(out["pred_masks"].shape, dtype=torch.float32).pin_memory()
+        self._host_logits.copy_(out["pred_logits"], non_blocking=True)
+        self._host_masks.copy_(out["pred_masks"], non_blocking=True)
+        torch.cuda.current_stream(self.dev).synchronize()
+        return dict(pred_logits=self._host_logits, pred_masks=self._host_masks)
+
+
+def gather_logits(local_logits):
+    """Image-sharded inference: one all-gather of the final class logits over the ranks (NCCL on NVLink)."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return local_logits
+    out = torch.empty((dist.get_world_size() * local_logits.shape[0],) + tuple(local_logits.shape[1:]),
+                      dtype=local_logits.dtype, device=local_logits.device)
+    dist.all_gather_into_tensor(out, local_logits.contiguous())
+    return out
+
+
+def synthetic_vocabulary(n_classes, n_prompts, seed=11):
+    """Seeded stand-in for the CLIP text bank of a vocabulary with n_classes classes and n_prompts prompt strings
+    (ADE-150: 150 / 403, COCO-133: 133 / 254, ADE-847: 847 / 1342) -> (bank, null, group sizes)."""
+    g = torch.Generator().manual_seed(seed)
+    bank = torch.randn(n_prompts, 768, generator=g)
+    null = torch.randn(1, 768, generator=torch.Generator().manual_seed(13))
+    base, extra = divmod(n_prompts, n_classes)
+    sizes = [base + (1 if i < extra else 0) for i in range(n_classes)]
+    return bank, null, sizes
