@@ -101,7 +101,8 @@ def cpu_hot_path_sample(size, vocab, threads=None):
     size^2 (pixel decoder + decoder + scoring); images/s = 1 / (crops * t_unet + t_head)."""
     from odise_b200 import spec
     from oracle import ldm, m2f
-    n = threads or os.cpu_count()
+    # torch CPU ops stop scaling (and regress) far below the 100+ threads of the GPU hosts: cap at 32
+    n = threads or min(os.cpu_count(), 32)
     torch.set_num_threads(n)
     sd_u = spec.synth_state_dict(spec.unet_params(), 0)
     with torch.device("meta"):

@@ -490,6 +490,27 @@ __global__ void rowscale_kernel(float* __restrict__ y, long long ldy, const floa
   }
 }
 
+// uint8 NCHW image -> normalised NHWC fp32 crop: ((x / 255) - 0.5) / 0.5, i.e. CategoryODISE's (x - 0) / 255
+// (odise.py:237) followed by LdmExtractor's (img - 0.5) / 0.5 (ldm.py:556); crop b reads image img_of[b] at (y0[b], x0[b])
+__global__ void image_crops_kernel(const uint8_t* __restrict__ img, float* __restrict__ out,
+                                   const int32_t* __restrict__ boxes, int n_crops, int H, int W, int ch, int cw) {
+  const long long total = (long long)n_crops * ch * cw;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(i % cw);
+    long long t = i / cw;
+    const int y = (int)(t % ch);
+    const int b = (int)(t / ch);
+    const int im = boxes[3 * b], y0 = boxes[3 * b + 1], x0 = boxes[3 * b + 2];
+    const uint8_t* src = img + ((long long)im * 3 * H + (y0 + y)) * W + x0 + x;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float v = (float)src[(long long)c * H * W] / 255.f;
+      out[i * 3 + c] = (v - 0.5f) / 0.5f;
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- softmax
 // one warp per row
 __global__ void softmax_split_kernel(const float* __restrict__ x, long long ldx, __nv_bfloat16* __restrict__ hi,
@@ -759,6 +780,15 @@ extern "C" int odise_rowscale_f32(float* y, long long ldy, const float* s, long 
   if (!y || !s || rows <= 0 || cols <= 0) return ODISE_ERR_ARG;
   if (cols % 4 || ldy % 4) return ODISE_ERR_ALIGN;
   rowscale_kernel<<<grid_for(rows * (cols / 4), 256), 256, 0, STREAM(stream)>>>(y, ldy, s, rows, cols / 4);
+  count_launch(1);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int odise_image_crops_u8_f32(const uint8_t* img, float* out, const int32_t* boxes, int n_crops, int H,
+                                        int W, int ch, int cw, void* stream) {
+  if (!img || !out || !boxes || n_crops <= 0 || H <= 0 || W <= 0 || ch <= 0 || cw <= 0) return ODISE_ERR_ARG;
+  image_crops_kernel<<<grid_for((long long)n_crops * ch * cw, 256), 256, 0, STREAM(stream)>>>(img, out, boxes, n_crops,
+                                                                                            H, W, ch, cw);
   count_launch(1);
   return (int)cudaGetLastError();
 }

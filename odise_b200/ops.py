@@ -249,3 +249,10 @@ def rowscale(y, s):
     rows, cols = y.shape
     _check(load().odise_rowscale_f32(_ptr(y), y.stride(0), _ptr(s), rows, cols, _stream()), "rowscale")
     return y
+
+
+def image_crops(img_u8, boxes_dev, n_crops, H, W, ch, cw):
+    out = torch.empty(n_crops * ch * cw, 3, dtype=torch.float32, device=img_u8.device)
+    _check(load().odise_image_crops_u8_f32(_ptr(img_u8), _ptr(out), _ptr(boxes_dev), n_crops, H, W, ch, cw, _stream()),
+           "image_crops")
+    return out

@@ -1,0 +1,28 @@
+"""Runs the eager (non-graph) hot-path step a few times — the command ncu wraps for the launch list / captures."""
+import argparse
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
+from odise_b200 import lib, spec  # noqa: E402
+from odise_b200.pipeline import ODISEEngine, full_param_list, synthetic_vocabulary  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--batch", type=int, default=4)
+ap.add_argument("--size", type=int, default=1024)
+ap.add_argument("--iters", type=int, default=2)
+ap.add_argument("--precision", default="bf16x3")
+ap.add_argument("--full", action="store_true", help="include the VAE stages (f-1)")
+a = ap.parse_args()
+dev = torch.device("cuda:0")
+params = full_param_list() + (spec.vae_params() if a.full else [])
+sd = spec.synth_state_dict(params, 0)
+eng = ODISEEngine(sd, dev, nmma=3 if a.precision == "bf16x3" else 1, **({"with_vae": True} if a.full else {}))
+eng.set_vocabulary("ade150", *synthetic_vocabulary(150, 403))
+n0 = lib.launch_count()
+for i in range(a.iters):
+    eng.step(a.batch, a.size, a.size)
+    torch.cuda.synchronize()
+    print("iter", i, "launches so far", lib.launch_count() - n0, flush=True)
