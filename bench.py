@@ -38,6 +38,8 @@ def parse():
     ap.add_argument("--precision", default="bf16x3", choices=["bf16x3", "bf16"])
     ap.add_argument("--vocab", default="ade150", choices=["ade150", "coco133", "ade847"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--full", action="store_true",
+                    help="also run the KL-VAE encoder / truncated decoder (SURVEY.md 8f-1) instead of synthetic taps")
     return ap.parse_args()
 
 
@@ -94,63 +96,73 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------- CPU baseline
-def cpu_hot_path_sample(size, vocab, threads=None):
-    """The reference's CPU path through the oracle (oracle/ldm.py restatement driven like LdmExtractor.unet_forward,
-    oracle/m2f.py == the reference's own Mask2Former/ODISE code, pinned in tests/test_oracle_cpu.py), fp32, all host
-    threads.  Bounded sample: ONE 512^2 crop through the UNet feature pass + ONE image's projections-free head at
-    size^2 (pixel decoder + decoder + scoring); images/s = 1 / (crops * t_unet + t_head)."""
-    from odise_b200 import spec
-    from oracle import ldm, m2f
-    # torch CPU ops stop scaling (and regress) far below the 100+ threads of the GPU hosts: cap at 32
-    n = threads or min(os.cpu_count(), 32)
-    torch.set_num_threads(n)
-    sd_u = spec.synth_state_dict(spec.unet_params(), 0)
-    with torch.device("meta"):
-        unet = ldm.UNetModel()
-    unet.load_state_dict({k[len(spec.UNET_PREFIX):]: v for k, v in sd_u.items()}, assign=True)
-    unet.eval()
-    sd_h = spec.synth_state_dict(spec.head_params(), 1)
-    g = torch.Generator().manual_seed(3)
-    x, ctx, cond = torch.randn(1, 4, 64, 64, generator=g), torch.randn(1, 77, 768, generator=g), torch.randn(1, 1280, generator=g)
-    feats = {f"s{i}": torch.randn(1, 512, size // 2 ** i, size // 2 ** i, generator=g) for i in (2, 3, 4, 5)}
-    ncls, npr = VOCABS[vocab]
-    from odise_b200.pipeline import synthetic_vocabulary
-    bank, null, sizes = synthetic_vocabulary(ncls, npr)
-    with torch.no_grad():
+class CpuHotPath:
+    """The reference's CPU path through the oracle (oracle/ldm.py restatement driven like LdmExtractor.unet_forward;
+    oracle/m2f.py == the reference's own Mask2Former/ODISE code, pinned in tests/test_oracle_cpu.py), fp32.
+    Bounded sample: ONE 512^2 crop through the UNet feature pass + ONE image through the head at size^2 (pixel
+    decoder + decoder + scoring); images/s = 1 / (crops * t_unet + t_head)."""
+
+    def __init__(self, size, vocab, threads=None):
+        from odise_b200 import spec
+        from odise_b200.pipeline import synthetic_vocabulary
+        from oracle import ldm, m2f
+        self.ldm, self.m2f = ldm, m2f
+        # torch CPU ops stop scaling (and regress) far below the 100+ threads of the GPU hosts: cap at 32
+        self.n = threads or min(os.cpu_count(), 32)
+        torch.set_num_threads(self.n)
+        sd_u = spec.synth_state_dict(spec.unet_params(), 0)
+        with torch.device("meta"):
+            unet = ldm.UNetModel()
+        unet.load_state_dict({k[len(spec.UNET_PREFIX):]: v for k, v in sd_u.items()}, assign=True)
+        self.unet = unet.eval()
+        self.sd_h = spec.synth_state_dict(spec.head_params(), 1)
+        g = torch.Generator().manual_seed(3)
+        self.x, self.ctx = torch.randn(1, 4, 64, 64, generator=g), torch.randn(1, 77, 768, generator=g)
+        self.cond = torch.randn(1, 1280, generator=g)
+        self.feats = {f"s{i}": torch.randn(1, 512, size // 2 ** i, size // 2 ** i, generator=g) for i in (2, 3, 4, 5)}
+        self.bank, self.null, self.sizes = synthetic_vocabulary(*VOCABS[vocab])
+        self.size = size
+        self.crops = max(1, (size // 512)) ** 2
+
+    @torch.no_grad()
+    def sample(self):
+        ldm, m2f = self.ldm, self.m2f
         t0 = time.perf_counter()
-        ldm.unet_features(unet, x, ctx, cond)
+        ldm.unet_features(self.unet, self.x, self.ctx, self.cond)
         t_unet = time.perf_counter() - t0
         t0 = time.perf_counter()
-        mf, _, ms = m2f.pixel_decoder(sd_h, feats, "sem_seg_head.pixel_decoder.")
-        out, _ = m2f.transformer_decoder(sd_h, ms, mf, "sem_seg_head.predictor.")
-        te, ne = m2f.category_embed(sd_h, bank, null)
-        m2f.cal_pred_logits(out["mask_embed"], te, ne, out["logit_scale"], sizes)
+        mf, _, ms = m2f.pixel_decoder(self.sd_h, self.feats, "sem_seg_head.pixel_decoder.")
+        out, _ = m2f.transformer_decoder(self.sd_h, ms, mf, "sem_seg_head.predictor.")
+        te, ne = m2f.category_embed(self.sd_h, self.bank, self.null)
+        m2f.cal_pred_logits(out["mask_embed"], te, ne, out["logit_scale"], self.sizes)
         t_head = time.perf_counter() - t0
-    crops = max(1, (size // 512)) ** 2
-    ips = 1.0 / (crops * t_unet + t_head)
-    return dict(value=ips, unit="images/s", cores=n, kind="port",
-                sample=f"1 UNet feature pass on one 512^2 crop ({t_unet:.2f} s) + 1 image head at {size}^2 "
-                       f"({t_head:.2f} s); images/s = 1/({crops}*t_unet + t_head); fp32 torch CPU, {n} threads"), t_unet, t_head
+        ips = 1.0 / (self.crops * t_unet + t_head)
+        return dict(value=ips, unit="images/s", cores=self.n, kind="port",
+                    sample=f"1 UNet feature pass on one 512^2 crop ({t_unet:.2f} s) + 1 image head at {self.size}^2 "
+                           f"({t_head:.2f} s); images/s = 1/({self.crops}*t_unet + t_head); fp32 torch CPU, "
+                           f"{self.n} threads of {os.cpu_count()}")
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    vals = []
-    info = None
-    for i in range(args.warmup + args.steps):
-        info, _, _ = cpu_hot_path_sample(args.size, args.vocab)
-        if i >= args.warmup:
-            vals.append(info["value"])
-        if len(vals) and sum(1.0 / v for v in vals) > 240:      # keep the arm within a few minutes
+    cpu = CpuHotPath(args.size, args.vocab)
+    t_start = time.perf_counter()
+    for _ in range(min(args.warmup, 1)):
+        cpu.sample()
+    vals, info = [], None
+    for _ in range(args.steps):
+        info = cpu.sample()
+        vals.append(info["value"])
+        if time.perf_counter() - t_start > 200:                 # keep the arm within a few minutes
             break
     v = statistics.mean(vals)
     info["value"] = v
     ncls, npr = VOCABS[args.vocab]
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "images/s", "n_gpus": args.gpus,
-        "steps": len(vals), "warmup": args.warmup, "ms_per_step": 1000.0 / v, "higher_is_better": True,
+        "steps": len(vals), "warmup": min(args.warmup, 1), "ms_per_step": 1000.0 / v, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"ODISE hot path, {args.size}x{args.size}, {args.vocab} ({npr} prompts), CPU oracle",
                    "note": "reference arm = CPU restatement (reference not installable: detectron2/ldm/open_clip absent)"},
@@ -178,8 +190,8 @@ def main():
     from odise_b200.pipeline import ODISEEngine, full_param_list, gather_logits, synthetic_vocabulary
     lib.load()
     nmma = 3 if args.precision == "bf16x3" else 1
-    sd = spec.synth_state_dict(full_param_list(), seed=0)
-    eng = ODISEEngine(sd, dev, nmma=nmma)
+    sd = spec.synth_state_dict(full_param_list(with_vae=args.full), seed=0)
+    eng = ODISEEngine(sd, dev, nmma=nmma, with_vae=args.full)
     del sd
     ncls, npr = VOCABS[args.vocab]
     eng.set_vocabulary(args.vocab, *synthetic_vocabulary(ncls, npr))
@@ -261,8 +273,10 @@ def main():
                    "stages": "implicit-captioner front, q_sample, SD-v1 UNet feature pass (4 taps), 8 projections, "
                              "MSDeformAttn pixel decoder, 9-layer masked-attention decoder, CLIP-text scoring, "
                              "NCCL all-gather of logits",
-                   "not_in_path": "KL-VAE encoder/decoder taps and CLIP image embedding enter as seeded synthetic "
-                                  "tensors (SURVEY.md §8f rows f-1/f-2)",
+                   "not_in_path": ("CLIP image embedding enters as a seeded synthetic tensor (SURVEY.md §8f-2); KL-VAE "
+                                   "encoder + truncated decoder ARE executed (--full)") if args.full else
+                                  ("KL-VAE encoder/decoder taps and CLIP image embedding enter as seeded synthetic "
+                                   "tensors (SURVEY.md §8f rows f-1/f-2)"),
                    "weights": "random-init (seed 0), SD-v1 / ODISE shapes", "global_batch": world * B,
                    "parallelism": f"dp{world} (image sharded)", "precision_mode": args.precision,
                    "l2": "working set >> 126 MB L2: ~3.6 GB of weight planes + multi-GB activations stream every step",
@@ -284,8 +298,7 @@ def main():
     }
     if not args.no_cpu_baseline:
         try:
-            info, _, _ = cpu_hot_path_sample(S, args.vocab)
-            line["cpu_baseline"] = info
+            line["cpu_baseline"] = CpuHotPath(S, args.vocab).sample()
         except Exception as ex:  # noqa
             line["cpu_baseline"] = {"error": str(ex)}
     print(json.dumps(line))

@@ -105,6 +105,11 @@ int odise_groupnorm_stats_f32(const float* x, long long ldx, float* mean, float*
                               float eps, void* stream);
 int odise_groupnorm_stats_bs_f32(const float* x, long long ldx, long long x_bs, float* mean, float* rstd, int B,
                                  int HW, int C, int G, float eps, void* stream);
+/* Coalesced single-pass statistics with a caller-provided workspace of odise_groupnorm_ws_floats() floats
+ * (deterministic fixed-order combine; shifted sums) — the variant the engines use. */
+long long odise_groupnorm_ws_floats(int B, int HW, int C, int G);
+int odise_groupnorm_stats_ws_f32(const float* x, long long ldx, long long x_bs, float* ws, float* mean, float* rstd,
+                                 int B, int HW, int C, int G, float eps, void* stream);
 /* y = act(gn(x) * gamma + beta): writes fp32 (optional) and (hi, lo) planes (optional). act: NONE/SILU/RELU.
  * The *_bs variants take explicit per-image strides (elements; 0 = dense) so a level can be read from / written
  * into the level-concatenated [B, S, C] token matrix of the pixel decoder (msdeformattn.py:61-78). */

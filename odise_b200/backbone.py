@@ -58,11 +58,14 @@ class SyntheticTaps:
 
 
 class BackboneEngine:
-    def __init__(self, sd, device, nmma=3, prefix="backbone.", unet_prefix=spec.UNET_PREFIX, uncond=None):
+    def __init__(self, sd, device, nmma=3, prefix="backbone.", unet_prefix=spec.UNET_PREFIX, uncond=None, vae=None):
         """sd: state dict with `backbone.feature_projections.*`, `backbone.feature_extractor.*` and the UNet.
-        uncond: the frozen text-encoder output for "" ([1, 77, 768]; ldm.py:116) — an input of the path."""
+        uncond: the frozen text-encoder output for "" ([1, 77, 768]; ldm.py:116) — an input of the path.
+        vae: optional VAEEngine; without it the VAE taps / latent are synthetic."""
         self.dev = torch.device(device)
         self.nmma, self.lo = nmma, nmma == 3
+        self.vae = vae
+        self._boxes = {}
         self.unet = UNetEngine(sd, device, nmma=nmma, prefix=unet_prefix)
         self.W, self.F = {}, {}
         f = lambda t: t.to(self.dev, torch.float32).contiguous()
@@ -156,9 +159,16 @@ class BackboneEngine:
         return out
 
     @torch.no_grad()
-    def extract(self, B, crop_hw=(512, 512), vae_taps=None):
-        """single_forward for a batch of B crops whose VAE taps / CLIP embedding are given (or synthetic)."""
+    def extract(self, B, crop_hw=(512, 512), vae_taps=None, crops=None):
+        """single_forward for a batch of B crops.  crops: normalised NHWC fp32 [B*h*w, 3] -> the VAE engine produces
+        latent + taps; otherwise they are given / synthetic.  The CLIP image embedding is synthetic (§8f-2)."""
         t = vae_taps if vae_taps is not None else self.taps_provider(B, crop_hw)
+        if crops is not None and self.vae is not None:
+            enc = self.vae.encode(crops, B, crop_hw[0], crop_hw[1])
+            lat, lh, lw = enc["latent"]
+            dec = self.vae.decode_taps(lat, B, lh, lw)
+            t = dict(latent=enc["latent"], enc5=enc["enc5"], enc7=enc["enc7"], dec2=dec["dec2"], dec5=dec["dec5"],
+                     clip_embed=t["clip_embed"])
         ctx, cemb = self.conditioning(t["clip_embed"], B)
         lat, lh, lw = t["latent"]
         x = self.q_sample(lat, B, lh, lw)
@@ -183,13 +193,21 @@ class BackboneEngine:
         return boxes, short
 
     @torch.no_grad()
-    def forward(self, n_images, h_img, w_img, vae_taps=None):
+    def forward(self, n_images, h_img, w_img, vae_taps=None, images_u8=None):
         """slide_forward over n_images images of h_img x w_img: all crops in one batch, paste + average.
+        images_u8: device uint8 [n_images, 3, H, W] (used when a VAE engine is attached).
         Returns {"s2".."s5": (NHWC fp32 [n_images * H/s * W/s, 512], H/s, W/s)}."""
         boxes, short = self.crop_grid(h_img, w_img)
         nc = len(boxes)
         B = n_images * nc                                # crop batch, image-major: b = img * nc + crop
-        feats = self.extract(B, (short, short), vae_taps)
+        crops = None
+        if images_u8 is not None and self.vae is not None:
+            key = (n_images, h_img, w_img)
+            if key not in self._boxes:
+                self._boxes[key] = torch.tensor([[i, y, x] for i in range(n_images) for (y, x) in boxes],
+                                                dtype=torch.int32).to(self.dev)
+            crops = ops.image_crops(images_u8, self._boxes[key], B, h_img, w_img, short, short)
+        feats = self.extract(B, (short, short), vae_taps, crops)
         if nc == 1 and short == h_img == w_img:
             return feats
         out = {}

@@ -189,6 +189,65 @@ __global__ void gn_apply_kernel(const float* __restrict__ x, long long ldx, cons
   }
 }
 
+// ---------------------------------------------------------------------------------------------- GroupNorm stats v2
+// One coalesced pass: block = (image, pixel chunk); thread = (pixel lane, channel quad).  Shifted sums
+// (pivot = first element of the group) keep E[x^2] - E[x]^2 free of cancellation; per-block partials go to a
+// workspace and are combined in fixed order (deterministic), in double.
+__global__ void gn_partial_kernel(const float* __restrict__ x, long long ldx, long long x_bs, float* __restrict__ ws,
+                                  int HW, int C, int G, int nchunk, int pix_per_chunk) {
+  extern __shared__ float sm[];   // [PL][C] sums, [PL][C] sumsq
+  const int b = blockIdx.x / nchunk, chunk = blockIdx.x % nchunk;
+  const int C4 = C >> 2, cpg = C / G;
+  const int PL = blockDim.x / C4;
+  const int q = threadIdx.x % C4, pl = threadIdx.x / C4;
+  const float* xb = x + (long long)b * x_bs;
+  float s[4] = {0, 0, 0, 0}, ss[4] = {0, 0, 0, 0};
+  if (pl < PL) {
+    float pv[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) pv[t] = __ldg(xb + ((q * 4 + t) / cpg) * cpg);
+    const int p0 = chunk * pix_per_chunk, p1 = min(HW, p0 + pix_per_chunk);
+    for (int p = p0 + pl; p < p1; p += PL) {
+      const float4 v = *reinterpret_cast<const float4*>(xb + (long long)p * ldx + q * 4);
+      const float d0 = v.x - pv[0], d1 = v.y - pv[1], d2 = v.z - pv[2], d3 = v.w - pv[3];
+      s[0] += d0; s[1] += d1; s[2] += d2; s[3] += d3;
+      ss[0] = fmaf(d0, d0, ss[0]); ss[1] = fmaf(d1, d1, ss[1]); ss[2] = fmaf(d2, d2, ss[2]); ss[3] = fmaf(d3, d3, ss[3]);
+    }
+    float* a = sm + (long long)pl * C + q * 4;
+    float* bq = sm + (long long)PL * C + (long long)pl * C + q * 4;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) { a[t] = s[t]; bq[t] = ss[t]; }
+  }
+  __syncthreads();
+  for (int g = threadIdx.x; g < G; g += blockDim.x) {
+    double ds = 0, dss = 0;
+    for (int l = 0; l < PL; ++l)
+      for (int c = g * cpg; c < (g + 1) * cpg; ++c) { ds += sm[l * C + c]; dss += sm[(PL + l) * C + c]; }
+    float* o = ws + (((long long)b * nchunk + chunk) * G + g) * 2;
+    o[0] = (float)ds; o[1] = (float)dss;
+  }
+}
+
+__global__ void gn_finalize_kernel(const float* __restrict__ x, long long x_bs, const float* __restrict__ ws,
+                                   float* __restrict__ mean, float* __restrict__ rstd, int B, int HW, int C, int G,
+                                   int nchunk, float eps) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * G) return;
+  const int b = i / G, g = i % G, cpg = C / G;
+  double s = 0, ss = 0;
+  for (int k = 0; k < nchunk; ++k) {
+    const float* o = ws + (((long long)b * nchunk + k) * G + g) * 2;
+    s += o[0]; ss += o[1];
+  }
+  const double n = (double)HW * cpg;
+  const double pivot = x[(long long)b * x_bs + g * cpg];
+  const double m = s / n;
+  double var = ss / n - m * m;
+  if (var < 0) var = 0;
+  mean[i] = (float)(pivot + m);
+  rstd[i] = (float)(1.0 / sqrt(var + (double)eps));
+}
+
 // ---------------------------------------------------------------------------------------------- LayerNorm
 // one warp per row, row cached in registers (cols <= 4096)
 template <int MAXV>
@@ -410,30 +469,37 @@ __global__ void class_max_kernel(const float* __restrict__ sims, long long ld, c
 }
 
 // ---------------------------------------------------------------------------------------------- mask pooling
-// one warp per (b, q) row: binary mask (sigmoid(x) > 0.5  <=>  x > 0) as bf16 0/1 + count
+// binary mask (sigmoid(x) > 0.5) as bf16 0/1 + per-row count.  grid = (chunks, rows); counts must be zeroed first.
+// sigmoid(x) > 0.5 <=> x > 0 except in the fp32 rounding band |x| < ~1.2e-7 where torch's sigmoid rounds to exactly
+// 0.5: only there the sigmoid itself is evaluated (MaskPooling, odise.py:945-951).
 __global__ void mask_binarize_kernel(const float* __restrict__ logits, __nv_bfloat16* __restrict__ bin,
-                                     long long ld_bin, float* __restrict__ counts, long long rows, int HW) {
-  const long long row = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= rows) return;
-  const int lane = threadIdx.x & 31;
+                                     long long ld_bin, float* __restrict__ counts, int HW) {
+  const long long row = blockIdx.y;
   const float* src = logits + row * HW;
   __nv_bfloat16* dst = bin + row * ld_bin;
   float cnt = 0.f;
-  for (int c = lane * 4; c < HW; c += 128) {
+  for (int c = (blockIdx.x * blockDim.x + threadIdx.x) * 4; c < HW; c += gridDim.x * blockDim.x * 4) {
     const float4 v = *reinterpret_cast<const float4*>(src + c);
+    const float in[4] = {v.x, v.y, v.z, v.w};
     __align__(8) __nv_bfloat16 o[4];
-    // MaskPooling: (sigmoid(mask) > 0.5).  sigmoid is monotone with sigmoid(0) = 0.5, and torch's fp32 sigmoid of a
-    // tiny positive x rounds to exactly 0.5 for |x| < ~6e-8; use the same predicate on the sigmoid value.
-    const float s0 = 1.f / (1.f + expf(-v.x)), s1 = 1.f / (1.f + expf(-v.y));
-    const float s2 = 1.f / (1.f + expf(-v.z)), s3 = 1.f / (1.f + expf(-v.w));
-    const float b0 = s0 > 0.5f, b1 = s1 > 0.5f, b2 = s2 > 0.5f, b3 = s3 > 0.5f;
-    o[0] = __float2bfloat16_rn(b0); o[1] = __float2bfloat16_rn(b1);
-    o[2] = __float2bfloat16_rn(b2); o[3] = __float2bfloat16_rn(b3);
-    cnt += (b0 + b1) + (b2 + b3);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      bool on = in[t] > 0.f;
+      if (fabsf(in[t]) < 1e-6f) on = (1.f / (1.f + expf(-in[t]))) > 0.5f;
+      o[t] = __float2bfloat16_rn(on ? 1.f : 0.f);
+      cnt += on ? 1.f : 0.f;
+    }
     *reinterpret_cast<uint2*>(dst + c) = *reinterpret_cast<const uint2*>(o);
   }
   cnt = warp_sum(cnt);
-  if (lane == 0) counts[row] = cnt;
+  __shared__ float red[8];
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = cnt;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < (blockDim.x >> 5); ++i) t += red[i];
+    atomicAdd(counts + row, t);   // integer-valued partial counts < 2^24: exact and order independent
+  }
 }
 
 __global__ void pool_normalize_kernel(const float* __restrict__ sums, const float* __restrict__ counts,
@@ -719,8 +785,12 @@ extern "C" int odise_mask_binarize_f32(const float* logits, void* bin_bf16, long
   if (!logits || !bin_bf16 || !counts || B <= 0 || Q <= 0 || HW <= 0) return ODISE_ERR_ARG;
   if (HW % 4 || ld_bin % 4) return ODISE_ERR_ALIGN;
   const long long rows = (long long)B * Q;
-  mask_binarize_kernel<<<(int)((rows + 7) / 8), 256, 0, STREAM(stream)>>>(logits, BF(bin_bf16), ld_bin, counts, rows,
-                                                                         HW);
+  cudaError_t e = cudaMemsetAsync(counts, 0, sizeof(float) * rows, STREAM(stream));
+  if (e != cudaSuccess) return (int)e;
+  int chunks = (HW / 4 + 255) / 256;
+  if (chunks > 16) chunks = 16;
+  dim3 grid(chunks, (unsigned)rows);
+  mask_binarize_kernel<<<grid, 256, 0, STREAM(stream)>>>(logits, BF(bin_bf16), ld_bin, counts, HW);
   count_launch(1);
   return (int)cudaGetLastError();
 }
@@ -790,5 +860,38 @@ extern "C" int odise_image_crops_u8_f32(const uint8_t* img, float* out, const in
   image_crops_kernel<<<grid_for((long long)n_crops * ch * cw, 256), 256, 0, STREAM(stream)>>>(img, out, boxes, n_crops,
                                                                                             H, W, ch, cw);
   count_launch(1);
+  return (int)cudaGetLastError();
+}
+
+// workspace-based, coalesced statistics (see gn_partial_kernel).  ws: >= odise_groupnorm_ws_floats(B, HW, C, G) floats.
+extern "C" long long odise_groupnorm_ws_floats(int B, int HW, int C, int G) {
+  (void)C;
+  int nchunk = (4 * 148 + B - 1) / B;
+  if (nchunk > HW) nchunk = HW;
+  if (nchunk < 1) nchunk = 1;
+  return (long long)B * nchunk * G * 2;
+}
+
+extern "C" int odise_groupnorm_stats_ws_f32(const float* x, long long ldx, long long x_bs, float* ws, float* mean,
+                                            float* rstd, int B, int HW, int C, int G, float eps, void* stream) {
+  if (!x || !ws || !mean || !rstd || B <= 0 || HW <= 0 || C <= 0 || G <= 0 || C % G) return ODISE_ERR_ARG;
+  if (C % 4 || ldx % 4 || x_bs % 4 || C / 4 > 1024) return ODISE_ERR_ALIGN;
+  int nchunk = (4 * 148 + B - 1) / B;
+  if (nchunk > HW) nchunk = HW;
+  if (nchunk < 1) nchunk = 1;
+  const int ppc = (HW + nchunk - 1) / nchunk;
+  nchunk = (HW + ppc - 1) / ppc;
+  const int C4 = C / 4;
+  int PL = 256 / C4;
+  if (PL < 1) PL = 1;
+  if (PL > ppc) PL = ppc;
+  const int threads = C4 * PL;
+  const size_t smem = (size_t)2 * PL * C * sizeof(float);
+  if (smem > 48 * 1024) return ODISE_ERR_UNSUPPORTED;
+  const long long xbs = x_bs ? x_bs : (long long)HW * ldx;
+  // NOTE: nchunk here must match odise_groupnorm_ws_floats' upper bound (it is <= that value)
+  gn_partial_kernel<<<B * nchunk, threads, smem, STREAM(stream)>>>(x, ldx, xbs, ws, HW, C, G, nchunk, ppc);
+  gn_finalize_kernel<<<(B * G + 127) / 128, 128, 0, STREAM(stream)>>>(x, xbs, ws, mean, rstd, B, HW, C, G, nchunk, eps);
+  count_launch(2);
   return (int)cudaGetLastError();
 }

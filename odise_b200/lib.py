@@ -55,6 +55,8 @@ _SIGS = {
                                   c_longlong, c_void_p, c_void_p, c_longlong, c_int, c_int, c_int, c_int, c_void_p],
     "odise_groupnorm_stats_bs_f32": [c_void_p, c_longlong, c_longlong, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                      c_float, c_void_p],
+    "odise_groupnorm_stats_ws_f32": [c_void_p, c_longlong, c_longlong, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                                     c_int, c_int, c_float, c_void_p],
     "odise_groupnorm_apply_bs_f32": [c_void_p, c_longlong, c_longlong, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                                      c_void_p, c_longlong, c_longlong, c_void_p, c_void_p, c_longlong, c_longlong,
                                      c_int, c_int, c_int, c_int, c_void_p],
@@ -110,6 +112,8 @@ def load():
     lib = ctypes.CDLL(_LIB_PATH)
     lib.odise_version.restype = c_int
     lib.odise_launch_count.restype = c_longlong
+    lib.odise_groupnorm_ws_floats.restype = c_longlong
+    lib.odise_groupnorm_ws_floats.argtypes = [c_int, c_int, c_int, c_int]
     for name, args in _SIGS.items():
         fn = getattr(lib, name)
         fn.argtypes = args

@@ -18,6 +18,12 @@ def split(x, lo=True):
     return lib.split(x, lo=lo)
 
 
+def _gn_stats(L, x, ldx, x_bs, mean, rstd, B, HW, C, G, eps):
+    ws = torch.empty(int(L.odise_groupnorm_ws_floats(B, HW, C, G)), dtype=torch.float32, device=x.device)
+    _check(L.odise_groupnorm_stats_ws_f32(_ptr(x), ldx, x_bs, _ptr(ws), _ptr(mean), _ptr(rstd), B, HW, C, G, eps,
+                                          _stream()), "groupnorm_stats")
+
+
 def group_norm(x, B, HW, gamma, beta, eps, act=ACT_NONE, G=32, want_f32=False, want_planes=True, lo=True, ldx=None,
                x_bs=0, y=None, ldy=None, y_bs=0, planes=None, o_bs=0):
     """x [B*HW, C] (row stride ldx, per-image stride x_bs) -> (y fp32 | None, planes | None).
@@ -28,8 +34,7 @@ def group_norm(x, B, HW, gamma, beta, eps, act=ACT_NONE, G=32, want_f32=False, w
     mean = torch.empty(B * G, dtype=torch.float32, device=dev)
     rstd = torch.empty(B * G, dtype=torch.float32, device=dev)
     L = load()
-    _check(L.odise_groupnorm_stats_bs_f32(_ptr(x), ldx, x_bs, _ptr(mean), _ptr(rstd), B, HW, C, G, eps, _stream()),
-           "groupnorm_stats")
+    _gn_stats(L, x, ldx, x_bs, mean, rstd, B, HW, C, G, eps)
     if y is None and want_f32:
         y = empty(B * HW, C, dev)
     if y is not None and ldy is None:
@@ -230,8 +235,7 @@ def group_norm_res(x, B, HW, gamma, beta, eps, res, act, y, accumulate, G=32):
     mean = torch.empty(B * G, dtype=torch.float32, device=dev)
     rstd = torch.empty(B * G, dtype=torch.float32, device=dev)
     L = load()
-    _check(L.odise_groupnorm_stats_bs_f32(_ptr(x), x.stride(0), 0, _ptr(mean), _ptr(rstd), B, HW, C, G, eps, _stream()),
-           "groupnorm_stats")
+    _gn_stats(L, x, x.stride(0), 0, mean, rstd, B, HW, C, G, eps)
     _check(L.odise_groupnorm_apply_res_f32(_ptr(x), x.stride(0), _ptr(mean), _ptr(rstd), _ptr(gamma), _ptr(beta),
                                            _ptr(res), res.stride(0) if res is not None else 0, act, _ptr(y),
                                            y.stride(0), 1 if accumulate else 0, None, None, 0, B, HW, C, G, _stream()),

@@ -14,15 +14,20 @@ from .backbone import BackboneEngine
 from .head import HeadEngine
 
 
-def full_param_list():
-    return spec.unet_params() + spec.backbone_params() + spec.head_params()
+def full_param_list(with_vae=False):
+    return spec.unet_params() + spec.backbone_params() + spec.head_params() + (spec.vae_params() if with_vae else [])
 
 
 class ODISEEngine:
-    def __init__(self, sd, device, nmma=3, num_queries=100):
+    def __init__(self, sd, device, nmma=3, num_queries=100, with_vae=False):
         self.dev = torch.device(device)
         self.nmma = nmma
-        self.backbone = BackboneEngine(sd, device, nmma=nmma)
+        vae = None
+        if with_vae:                      # real KL-VAE taps instead of synthetic ones
+            from .vae import VAEEngine
+            vae = VAEEngine(sd, device, nmma=nmma)
+        self.with_vae = with_vae
+        self.backbone = BackboneEngine(sd, device, nmma=nmma, vae=vae)
         self.head = HeadEngine(sd, device, nmma=nmma, num_queries=num_queries)
         self.Q = num_queries
         self._graphs = {}
@@ -37,9 +42,11 @@ class ODISEEngine:
 
     # ------------------------------------------------------------------------------------------- device step
     @torch.no_grad()
-    def step(self, n_images, H, W, vae_taps=None):
+    def step(self, n_images, H, W, vae_taps=None, images_u8=None):
         """One pass of the hot path for n_images resident images (eager). Returns device tensors."""
-        feats = self.backbone.forward(n_images, H, W, vae_taps)
+        if images_u8 is None and self.with_vae:
+            images_u8 = self._image_buffer(n_images, H, W)
+        feats = self.backbone.forward(n_images, H, W, vae_taps, images_u8)
         out = self.head.forward(feats, n_images, vocab_key=self.vocab_key)
         h2, w2 = out["pd"]["mask_hw"]
         last = out["heads"][-1]
@@ -50,6 +57,14 @@ class ODISEEngine:
             res["pred_logits"] = out["pred_logits"]
         res["aux"] = out["heads"][:-1]
         return res
+
+    def _image_buffer(self, n_images, H, W):
+        shp = (n_images, 3, H, W)
+        if not hasattr(self, "_img_dev") or tuple(self._img_dev.shape) != shp:
+            g = torch.Generator().manual_seed(99)
+            self._img_dev = torch.randint(0, 256, shp, generator=g, dtype=torch.uint8).to(self.dev)
+            self._host_logits = None
+        return self._img_dev
 
     def capture(self, n_images, H, W):
         """Warm up eagerly, then capture the step into a CUDA graph (static shapes, static buffers)."""
@@ -77,15 +92,14 @@ class ODISEEngine:
         """End-to-end call on a host batch: uint8 [B, 3, H, W] in pinned memory -> host dict
         (pred_logits [B, Q, K+1], pred_masks [B, Q, H/4, W/4]).  H2D and D2H inside."""
         B, _, H, W = images_u8_pinned.shape
-        if not hasattr(self, "_img_dev") or self._img_dev.shape != images_u8_pinned.shape:
-            self._img_dev = torch.empty_like(images_u8_pinned, device=self.dev)
+        self._image_buffer(B, H, W).copy_(images_u8_pinned, non_blocking=True)
+        if not hasattr(self, "_host_logits"):
             self._host_logits = None
-        self._img_dev.copy_(images_u8_pinned, non_blocking=True)
         if use_graph:
             g, out = self.capture(B, H, W)
             g.replay()
         else:
-            out = self.step(B, H, W)
+            out = self.step(B, H, W, images_u8=self._img_dev)
         if self._host_logits is None:
             self._host_logits = torch.empty(out["pred_logits"].shape, dtype=torch.float32).pin_memory()
             self._host_masks = torch.empty(out["pred_masks"].shape, dtype=torch.float32).pin_memory()

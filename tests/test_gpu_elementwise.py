@@ -193,3 +193,19 @@ def test_mha_d32(cuda, cfg):
         s = s + bias
     ref = (s.softmax(-1) @ vh).transpose(1, 2).reshape(B, Tq, heads * d)
     assert _rel(out, ref) < 1e-5
+
+
+@pytest.mark.parametrize("shape", [(16, 64 * 64, 320), (4, 16 * 16, 1920), (2, 8 * 8, 2560), (3, 100, 256), (1, 512 * 64, 128), (2, 7, 512)])
+def test_groupnorm_workspace_stats(cuda, shape):
+    """ops.group_norm -> odise_groupnorm_stats_ws_f32 (coalesced single pass, shifted sums) incl. a large-mean input
+    and a strided (column-slice) input."""
+    from odise_b200 import ops
+    B, HW, C = shape
+    g = torch.Generator().manual_seed(C + HW)
+    wide = (torch.randn(B * HW, C + 64, generator=g) * 1.7 + 25.0).to(cuda)       # mean >> std: cancellation test
+    x = wide[:, 32:32 + C]
+    gamma, beta = torch.randn(C, generator=g).to(cuda), torch.randn(C, generator=g).to(cuda)
+    y, p = ops.group_norm(x, B, HW, gamma, beta, 1e-6, act=2, want_f32=True)
+    ref = F.silu(F.group_norm(x.double().view(B, HW, C).transpose(1, 2), 32, gamma.double(), beta.double(), 1e-6)).transpose(1, 2)
+    assert _rel(y.view(B, HW, C), ref) < 5e-6
+    assert _rel(p.float().view(B, HW, C), ref) < 2e-5
