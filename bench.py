@@ -4,8 +4,9 @@
     python bench.py --gpus N --steps K --warmup W            # our arm (one rank per GPU under torchrun for N > 1)
     python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's CPU path (oracle), rank 0 only
 
-A step = one pass of the hot path (UNet feature pass on all 512^2 crops -> projections -> pixel decoder -> masked
-attention decoder -> CLIP-text scoring) over a batch of synthetic 1024x1024 images, ADE-150 vocabulary (K' = 403
+A step = one pass of the pipeline (KL-VAE encoder/decoder taps [unless --hot-path-only] -> UNet feature pass on all
+512^2 crops -> projections -> pixel decoder -> masked attention decoder -> CLIP-text scoring) over a batch of
+synthetic 1024x1024 images, ADE-150 vocabulary (K' = 403
 prompts), random-init weights (BASELINE.json configs[1]).  `value` times the CUDA-graph replay with inputs resident in
 HBM; `e2e` times the public call ODISEEngine.infer() with pinned-host uint8 images in and fp32 logits + mask logits out.
 """
@@ -38,8 +39,8 @@ def parse():
     ap.add_argument("--precision", default="bf16x3", choices=["bf16x3", "bf16"])
     ap.add_argument("--vocab", default="ade150", choices=["ade150", "coco133", "ade847"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--full", action="store_true",
-                    help="also run the KL-VAE encoder / truncated decoder (SURVEY.md 8f-1) instead of synthetic taps")
+    ap.add_argument("--hot-path-only", action="store_true",
+                    help="skip the KL-VAE stages (SURVEY.md 8f-1): their taps / latent enter as synthetic tensors")
     return ap.parse_args()
 
 
@@ -102,7 +103,7 @@ class CpuHotPath:
     Bounded sample: ONE 512^2 crop through the UNet feature pass + ONE image through the head at size^2 (pixel
     decoder + decoder + scoring); images/s = 1 / (crops * t_unet + t_head)."""
 
-    def __init__(self, size, vocab, threads=None):
+    def __init__(self, size, vocab, threads=None, full=True):
         from odise_b200 import spec
         from odise_b200.pipeline import synthetic_vocabulary
         from oracle import ldm, m2f
@@ -123,12 +124,24 @@ class CpuHotPath:
         self.bank, self.null, self.sizes = synthetic_vocabulary(*VOCABS[vocab])
         self.size = size
         self.crops = max(1, (size // 512)) ** 2
+        self.full = full
+        if full:
+            sd_v = spec.synth_state_dict(spec.vae_params(), 3)
+            with torch.device("meta"):
+                vae = ldm.AutoencoderKL()
+            vae.load_state_dict({k[len(spec.VAE_PREFIX):]: v for k, v in sd_v.items()}, assign=True)
+            self.vae = vae.eval()
+            self.img = torch.rand(1, 3, 512, 512, generator=g) * 2 - 1
 
     @torch.no_grad()
     def sample(self):
         ldm, m2f = self.ldm, self.m2f
         t0 = time.perf_counter()
-        ldm.unet_features(self.unet, self.x, self.ctx, self.cond)
+        # as the reference executes it: output block 11 + unet.out run too, and the VAE decoder runs to the full image
+        ldm.unet_features(self.unet, self.x, self.ctx, self.cond, stop_early=False)
+        if self.full:
+            lat, _ = ldm.encoder_features(self.vae, self.img)
+            ldm.decoder_features(self.vae, lat, truncate=False)
         t_unet = time.perf_counter() - t0
         t0 = time.perf_counter()
         mf, _, ms = m2f.pixel_decoder(self.sd_h, self.feats, "sem_seg_head.pixel_decoder.")
@@ -138,8 +151,9 @@ class CpuHotPath:
         t_head = time.perf_counter() - t0
         ips = 1.0 / (self.crops * t_unet + t_head)
         return dict(value=ips, unit="images/s", cores=self.n, kind="port",
-                    sample=f"1 UNet feature pass on one 512^2 crop ({t_unet:.2f} s) + 1 image head at {self.size}^2 "
-                           f"({t_head:.2f} s); images/s = 1/({self.crops}*t_unet + t_head); fp32 torch CPU, "
+                    sample=f"1 crop (512^2) through {'VAE enc + UNet + full VAE dec' if self.full else 'the UNet'} as the "
+                           f"reference executes it ({t_unet:.2f} s) + 1 image head at {self.size}^2 "
+                           f"({t_head:.2f} s); images/s = 1/({self.crops}*t_crop + t_head); fp32 torch CPU, "
                            f"{self.n} threads of {os.cpu_count()}")
 
 
@@ -147,7 +161,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cpu = CpuHotPath(args.size, args.vocab)
+    cpu = CpuHotPath(args.size, args.vocab, full=args.full)
     t_start = time.perf_counter()
     for _ in range(min(args.warmup, 1)):
         cpu.sample()
@@ -173,6 +187,7 @@ def run_reference(args):
 # ----------------------------------------------------------------------------------------------- our arm
 def main():
     args = parse()
+    args.full = not args.hot_path_only
     if args.impl == "reference":
         return run_reference(args)
 
@@ -270,7 +285,8 @@ def main():
         "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
         "config": {"workload": f"ODISE(label) hot path, batch {B}/GPU x {S}x{S}, {crops} crops/image, {args.vocab} "
                                f"({ncls} classes / {npr} prompts), Q=100",
-                   "stages": "implicit-captioner front, q_sample, SD-v1 UNet feature pass (4 taps), 8 projections, "
+                   "stages": ("KL-VAE encoder + truncated decoder (taps), " if args.full else "") +
+                             "implicit-captioner front, q_sample, SD-v1 UNet feature pass (4 taps), 8 projections, "
                              "MSDeformAttn pixel decoder, 9-layer masked-attention decoder, CLIP-text scoring, "
                              "NCCL all-gather of logits",
                    "not_in_path": ("CLIP image embedding enters as a seeded synthetic tensor (SURVEY.md §8f-2); KL-VAE "
@@ -298,7 +314,7 @@ def main():
     }
     if not args.no_cpu_baseline:
         try:
-            line["cpu_baseline"] = CpuHotPath(S, args.vocab).sample()
+            line["cpu_baseline"] = CpuHotPath(S, args.vocab, full=args.full).sample()
         except Exception as ex:  # noqa
             line["cpu_baseline"] = {"error": str(ex)}
     print(json.dumps(line))

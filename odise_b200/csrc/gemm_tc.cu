@@ -20,6 +20,8 @@
 #include <cudaTypedefs.h>
 #include <mutex>
 #include <vector>
+#include <cstdlib>
+#include <cstdio>
 
 namespace ob {
 
@@ -53,87 +55,74 @@ __device__ __forceinline__ float apply_act(float v, int act) {
   return v;
 }
 
-// epilogue for one row segment of `cnt` (<=32) consecutive columns starting at n, values in acc[]
-__device__ __forceinline__ void epilogue_row(const GemmParams& p, int z, int m, int n, int cnt, float* acc) {
-  const bool vec = (cnt == 32) && p.vec_ok;
+// epilogue for 4 consecutive columns [n, n+4) of row m (n % 4 == 0); `valid` = how many of them exist (N tail)
+__device__ __forceinline__ void epilogue_quad(const GemmParams& p, int z, int m, int n, int valid, float4 a4) {
+  float acc[4] = {a4.x, a4.y, a4.z, a4.w};
+  const bool vec = (valid == 4) && p.vec_ok;
   if (p.alpha != 1.f) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) acc[j] *= p.alpha;
+    for (int j = 0; j < 4; ++j) acc[j] *= p.alpha;
   }
   if (p.bias) {
     if (vec) {
-#pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n + j));
-        acc[j] += b.x; acc[j + 1] += b.y; acc[j + 2] += b.z; acc[j + 3] += b.w;
-      }
+      const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+      acc[0] += b.x; acc[1] += b.y; acc[2] += b.z; acc[3] += b.w;
     } else {
-      _Pragma("unroll") for (int j = 0; j < 32; ++j) if (j < cnt) acc[j] += __ldg(p.bias + n + j);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) if (j < valid) acc[j] += __ldg(p.bias + n + j);
     }
   }
   if (p.bias_m) {
     const float bm = __ldg(p.bias_m + m);
 #pragma unroll
-    for (int j = 0; j < 32; ++j) acc[j] += bm;
+    for (int j = 0; j < 4; ++j) acc[j] += bm;
   }
   if (p.rowbias) {
     const float* rb = p.rowbias + (long long)(((long long)z * p.M + m) / p.rows_per_group) * p.rowbias_ld + n;
     if (vec) {
-#pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        float4 b = __ldg(reinterpret_cast<const float4*>(rb + j));
-        acc[j] += b.x; acc[j + 1] += b.y; acc[j + 2] += b.z; acc[j + 3] += b.w;
-      }
+      const float4 b = __ldg(reinterpret_cast<const float4*>(rb));
+      acc[0] += b.x; acc[1] += b.y; acc[2] += b.z; acc[3] += b.w;
     } else {
-      _Pragma("unroll") for (int j = 0; j < 32; ++j) if (j < cnt) acc[j] += __ldg(rb + j);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) if (j < valid) acc[j] += __ldg(rb + j);
     }
   }
   if (p.act != ODISE_ACT_NONE) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) acc[j] = apply_act(acc[j], p.act);
+    for (int j = 0; j < 4; ++j) acc[j] = apply_act(acc[j], p.act);
   }
   if (p.res) {
     const float* r = p.res + (long long)z * p.res_bs + (long long)m * p.ldres + n;
     if (vec) {
-#pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        float4 b = *reinterpret_cast<const float4*>(r + j);
-        acc[j] += b.x; acc[j + 1] += b.y; acc[j + 2] += b.z; acc[j + 3] += b.w;
-      }
+      const float4 b = *reinterpret_cast<const float4*>(r);
+      acc[0] += b.x; acc[1] += b.y; acc[2] += b.z; acc[3] += b.w;
     } else {
-      _Pragma("unroll") for (int j = 0; j < 32; ++j) if (j < cnt) acc[j] += r[j];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) if (j < valid) acc[j] += r[j];
     }
   }
   if (p.D) {
     float* d = p.D + (long long)z * p.d_bs + (long long)m * p.ldd + n;
     if (vec) {
-#pragma unroll
-      for (int j = 0; j < 32; j += 4)
-        *reinterpret_cast<float4*>(d + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+      *reinterpret_cast<float4*>(d) = make_float4(acc[0], acc[1], acc[2], acc[3]);
     } else {
-      _Pragma("unroll") for (int j = 0; j < 32; ++j) if (j < cnt) d[j] = acc[j];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) if (j < valid) d[j] = acc[j];
     }
   }
   if (p.Dh) {
     __nv_bfloat16* dh = p.Dh + (long long)z * p.h_bs + (long long)m * p.ldh + n;
     __nv_bfloat16* dl = p.Dl ? p.Dl + (long long)z * p.h_bs + (long long)m * p.ldh + n : nullptr;
+    __align__(8) __nv_bfloat16 h[4];
+    __align__(8) __nv_bfloat16 l[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) split_bf16(acc[t], h[t], l[t]);
     if (vec) {
-#pragma unroll
-      for (int j = 0; j < 32; j += 8) {
-        __align__(16) __nv_bfloat16 h[8];
-        __align__(16) __nv_bfloat16 l[8];
-#pragma unroll
-        for (int t = 0; t < 8; ++t) split_bf16(acc[j + t], h[t], l[t]);
-        *reinterpret_cast<uint4*>(dh + j) = *reinterpret_cast<const uint4*>(h);
-        if (dl) *reinterpret_cast<uint4*>(dl + j) = *reinterpret_cast<const uint4*>(l);
-      }
+      *reinterpret_cast<uint2*>(dh) = *reinterpret_cast<const uint2*>(h);
+      if (dl) *reinterpret_cast<uint2*>(dl) = *reinterpret_cast<const uint2*>(l);
     } else {
-      _Pragma("unroll") for (int j = 0; j < 32; ++j) if (j < cnt) {
-        __nv_bfloat16 h, l;
-        split_bf16(acc[j], h, l);
-        dh[j] = h;
-        if (dl) dl[j] = l;
-      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) if (j < valid) { dh[j] = h[j]; if (dl) dl[j] = l[j]; }
     }
   }
 }
@@ -145,11 +134,12 @@ struct GemmCfg {
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int PLANES = (NMMA == 3) ? 2 : 1;
   static constexpr int STAGE_BYTES = PLANES * (A_BYTES + B_BYTES);
-  static constexpr int STAGES_RAW = (220 * 1024) / STAGE_BYTES;
+  static constexpr int EPI_BYTES = 4 * 32 * 16 * 4;  // 4 epilogue warps x [32 rows x 16 fp32] staging (XOR swizzled)
+  static constexpr int STAGES_RAW = (232448 - EPI_BYTES - 256) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr int ACC_STRIDE = (BN <= 64) ? 64 : (BN <= 128 ? 128 : 256);  // TMEM columns per accumulator
   static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 256 /*barriers*/;
 };
 
 template <int BN, int NMMA>
@@ -158,9 +148,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
                const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
                const GemmParams p) {
   using Cfg = GemmCfg<BN, NMMA>;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  extern __shared__ __align__(1024) uint8_t smem[];   // SWIZZLE_128B tiles need 1024-byte alignment
+  float* epi_smem = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::EPI_BYTES);
   uint64_t* full = bars;                       // [STAGES]
   uint64_t* empty = bars + Cfg::STAGES;        // [STAGES]
   uint64_t* tfull = bars + 2 * Cfg::STAGES;    // [2]
@@ -171,6 +161,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
   const int lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
+    if (smem_u32(smem) & 1023u) {
+      printf("odise_b200: dynamic shared memory base not 1024-byte aligned\n");
+      __trap();
+    }
     tma_prefetch_desc(&tmAh);
     tma_prefetch_desc(&tmBh);
     if (NMMA == 3) {
@@ -296,30 +290,48 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
       const int sp = r / (p.tiles_m * p.tiles_n);
       r -= sp * (p.tiles_m * p.tiles_n);
       const int mt = r / p.tiles_n, nt = r - mt * p.tiles_n;
-      const int m = mt * 128 + quad * 32 + lane;
       const int n0 = nt * BN;
       mbar_wait(&tfull[acc], accphase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + acc * Cfg::ACC_STRIDE + ((uint32_t)(quad * 32) << 16);
       const int kb0 = sp * kb_per_split;
       const bool has_k = kb0 < p.kblocks;  // a split with no k-blocks contributes zeros
+      // TMEM -> registers (thread = row) -> XOR-swizzled shared staging -> coalesced epilogue: each warp-level
+      // global access covers 8 rows x 64 contiguous bytes (full 32-byte sectors) instead of 32 rows x 16 bytes.
+      float* stg = epi_smem + (warp - 2) * (32 * 16);
+      const int m_base = mt * 128 + quad * 32;
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld32(t_row + c0, v);
+      for (int c0 = 0; c0 < BN; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(t_row + c0, v);
         tmem_ld_wait();
-        const int n = n0 + c0;
-        if (m < p.M && n < p.N) {
-          float accv[32];
+        if (n0 + c0 < p.N) {   // warp-uniform
 #pragma unroll
-          for (int j = 0; j < 32; ++j) accv[j] = has_k ? __uint_as_float(v[j]) : 0.f;
-          const int cnt = min(32, p.N - n);
-          if (p.splits > 1) {
-            float* dst = p.partial + ((long long)(sp * p.batch + z) * p.M + m) * p.N + n;
-            _Pragma("unroll") for (int j = 0; j < 32; ++j) if (j < cnt) dst[j] = accv[j];
-          } else {
-            epilogue_row(p, z, m, n, cnt, accv);
+          for (int j = 0; j < 4; ++j) {
+            const float4 q4 = has_k ? make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                                  __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]))
+                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+            *reinterpret_cast<float4*>(stg + lane * 16 + ((j ^ ((lane >> 1) & 3)) << 2)) = q4;
           }
+          __syncwarp();
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            const int rr = it * 8 + (lane >> 2), cq = lane & 3;
+            const float4 q4 = *reinterpret_cast<const float4*>(stg + rr * 16 + ((cq ^ ((rr >> 1) & 3)) << 2));
+            const int m = m_base + rr, n = n0 + c0 + cq * 4;
+            if (m < p.M && n < p.N) {
+              const int valid = min(4, p.N - n);
+              if (p.splits > 1) {
+                float* dst = p.partial + ((long long)(sp * p.batch + z) * p.M + m) * p.N + n;
+                const float e[4] = {q4.x, q4.y, q4.z, q4.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) if (j < valid) dst[j] = e[j];
+              } else {
+                epilogue_quad(p, z, m, n, valid, q4);
+              }
+            }
+          }
+          __syncwarp();
         }
       }
       tc_fence_before();
@@ -337,26 +349,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
   }
 }
 
-// split-K second pass: sum the partials and run the normal epilogue (32 columns per thread-row segment)
+// split-K second pass: sum the partials and run the normal epilogue (4 columns per thread)
 __global__ void gemm_splitk_reduce_kernel(const GemmParams p) {
-  const int segs = (p.N + 31) / 32;
-  const long long total = (long long)p.batch * p.M * segs;
+  const int quads = (p.N + 3) / 4;
+  const long long total = (long long)p.batch * p.M * quads;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
-    const int seg = (int)(i % segs);
-    const long long zm = i / segs;
+    const int qd = (int)(i % quads);
+    const long long zm = i / quads;
     const int m = (int)(zm % p.M);
     const int z = (int)(zm / p.M);
-    const int n = seg * 32;
-    const int cnt = min(32, p.N - n);
-    float acc[32];
-#pragma unroll
-    for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+    const int n = qd * 4;
+    const int valid = min(4, p.N - n);
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
     for (int sp = 0; sp < p.splits; ++sp) {
       const float* src = p.partial + ((long long)(sp * p.batch + z) * p.M + m) * p.N + n;
-      _Pragma("unroll") for (int j = 0; j < 32; ++j) if (j < cnt) acc[j] += src[j];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) if (j < valid) acc[j] += src[j];
     }
-    epilogue_row(p, z, m, n, cnt, acc);
+    epilogue_quad(p, z, m, n, valid, make_float4(acc[0], acc[1], acc[2], acc[3]));
   }
 }
 
@@ -386,7 +397,7 @@ static int encode_map(CUtensorMap* tm, const void* base, int rank, const cuuint6
 }
 
 // ---- optional per-launch timing (bench.py roofline): CUDA events on the launch stream around every GEMM launch
-struct ProfRec { cudaEvent_t a, b; double flops; };
+struct ProfRec { cudaEvent_t a, b; double flops; int M, N, K, batch, conv, bn, nmma, splits; };
 static std::vector<ProfRec> g_prof;
 static bool g_prof_on = false;
 
@@ -540,6 +551,8 @@ extern "C" int odise_gemm_bf16(const odise_gemm_desc* d, void* stream_v) {
     cudaEventCreate(&rec.a);
     cudaEventCreate(&rec.b);
     rec.flops = 2.0 * d->M * d->N * (double)d->K * d->batch;
+    rec.M = d->M; rec.N = d->N; rec.K = d->K; rec.batch = d->batch; rec.conv = d->conv3x3; rec.bn = BN;
+    rec.nmma = d->nmma; rec.splits = p.splits;
     cudaEventRecord(rec.a, stream);
   }
 #define ODISE_LAUNCH(BN_, NM_) rc = launch_cfg<BN_, NM_>(ah, al, bh, bl, p, stream)
@@ -562,7 +575,7 @@ extern "C" int odise_gemm_bf16(const odise_gemm_desc* d, void* stream_v) {
   if (rc) return rc;
   count_launch(p.splits > 1 ? 2 : 1);
   if (p.splits > 1) {
-    const long long total = (long long)p.batch * p.M * ((p.N + 31) / 32);
+    const long long total = (long long)p.batch * p.M * ((p.N + 3) / 4);
     int blocks = (int)((total + 127) / 128);
     if (blocks > 148 * 8) blocks = 148 * 8;
     gemm_splitk_reduce_kernel<<<blocks, 128, 0, stream>>>(p);
@@ -582,18 +595,26 @@ extern "C" int odise_profile_begin(void) {
   return ODISE_OK;
 }
 
-// stops recording; returns launches, summed device ms and summed algorithmic FLOPs (2*M*N*K*batch) of the GEMMs
+// stops recording; returns launches, summed device ms and summed algorithmic FLOPs (2*M*N*K*batch) of the GEMMs;
+// if the environment variable ODISE_PROFILE_CSV names a file, one line per launch is appended to it
 extern "C" int odise_profile_end(long long* launches, double* total_ms, double* total_flops) {
   g_prof_on = false;
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) return (int)e;
   double ms = 0, fl = 0;
+  FILE* fcsv = nullptr;
+  if (const char* path = getenv("ODISE_PROFILE_CSV")) fcsv = fopen(path, "a");
+  if (fcsv) fprintf(fcsv, "M,N,K,batch,conv,bn,nmma,splits,ms,tflops\n");
   for (auto& r : g_prof) {
     float t = 0;
     cudaEventElapsedTime(&t, r.a, r.b);
     ms += t;
     fl += r.flops;
+    if (fcsv)
+      fprintf(fcsv, "%d,%d,%d,%d,%d,%d,%d,%d,%.4f,%.1f\n", r.M, r.N, r.K, r.batch, r.conv, r.bn, r.nmma, r.splits, t,
+              r.flops / (t * 1e9));
   }
+  if (fcsv) fclose(fcsv);
   if (launches) *launches = (long long)g_prof.size();
   if (total_ms) *total_ms = ms;
   if (total_flops) *total_flops = fl;

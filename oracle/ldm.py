@@ -405,9 +405,10 @@ def shared_noise(latent_hw=(64, 64)):
     return n
 
 
-def unet_features(unet, x, context, cond_emb=None, tap_blocks=UNET_TAP_BLOCKS):
+def unet_features(unet, x, context, cond_emb=None, tap_blocks=UNET_TAP_BLOCKS, stop_early=True):
     """LdmExtractor.unet_forward (ldm.py:469-491) at t = 0: returns the inputs of the tapped output blocks.
-    (The reference also runs unet.out on the last block; its result is discarded, ldm.py:600.)"""
+    stop_early=False also executes output block 11 and unet.out like the reference does (results discarded,
+    ldm.py:600) — used when timing the reference's CPU path."""
     t = torch.zeros(x.shape[0], dtype=torch.long, device=x.device)
     emb = unet.time_embed(timestep_embedding(t, unet.model_channels))
     if cond_emb is not None:
@@ -422,9 +423,11 @@ def unet_features(unet, x, context, cond_emb=None, tap_blocks=UNET_TAP_BLOCKS):
         h = torch.cat([h, hs.pop()], dim=1)
         if i in tap_blocks:
             feats.append(h.contiguous())
-        if i == max(tap_blocks):
+        if stop_early and i == max(tap_blocks):
             break   # remaining work is dead code for ODISE
         h = m(h, emb, context)
+    if not stop_early:
+        unet.out(h)
     return feats
 
 
@@ -448,8 +451,9 @@ def encoder_features(vae, x, tap_blocks=ENC_TAP_BLOCKS):
     return SCALE_FACTOR * DiagonalGaussianDistribution(moments).mean, feats
 
 
-def decoder_features(vae, latent, tap_blocks=DEC_TAP_BLOCKS):
-    """LdmExtractor.decode_to_image / decoder_forward (ldm.py:493-541) truncated after the last tap."""
+def decoder_features(vae, latent, tap_blocks=DEC_TAP_BLOCKS, truncate=True):
+    """LdmExtractor.decode_to_image / decoder_forward (ldm.py:493-541) truncated after the last tap
+    (truncate=False runs on to the full RGB image like the reference, for CPU timing)."""
     dec = vae.decoder
     z = vae.post_quant_conv(1.0 / SCALE_FACTOR * latent)   # ldm.py:536
     h = dec.conv_in(z)
@@ -460,12 +464,14 @@ def decoder_features(vae, latent, tap_blocks=DEC_TAP_BLOCKS):
         for j in range(dec.num_res_blocks + 1):
             if idx in tap_blocks:
                 feats.append(h.contiguous())
-                if idx == max(tap_blocks):
+                if truncate and idx == max(tap_blocks):
                     return feats
             h = dec.up[i].block[j](h, None)
             idx += 1
         if i != 0:
             h = dec.up[i].upsample(h)
+    if not truncate:
+        dec.conv_out(nonlinearity(dec.norm_out(h)))
     return feats
 
 
