@@ -134,7 +134,11 @@ struct GemmCfg {
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int PLANES = (NMMA == 3) ? 2 : 1;
   static constexpr int STAGE_BYTES = PLANES * (A_BYTES + B_BYTES);
-  static constexpr int EPI_BYTES = 4 * 32 * 16 * 4;  // 4 epilogue warps x [32 rows x 16 fp32] staging (XOR swizzled)
+  // epilogue warps: one warp per scheduler is latency bound (ncu: IPC 0.17/warp), so two warps share each TMEM lane
+  // quadrant and alternate 16-column chunks; BN=160/bf16x3 has no shared memory left for the second set
+  static constexpr int NEPI = (BN == 160 && NMMA == 3) ? 4 : 8;
+  static constexpr int THREADS = 64 + 32 * NEPI;
+  static constexpr int EPI_BYTES = NEPI * 32 * 16 * 4;  // per warp [32 rows x 16 fp32] staging (XOR swizzled)
   static constexpr int STAGES_RAW = (232448 - EPI_BYTES - 256) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr int ACC_STRIDE = (BN <= 64) ? 64 : (BN <= 128 ? 128 : 256);  // TMEM columns per accumulator
@@ -143,7 +147,7 @@ struct GemmCfg {
 };
 
 template <int BN, int NMMA>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(GemmCfg<BN, NMMA>::THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
                const GemmParams p) {
@@ -177,7 +181,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull[s], 1);
-      mbar_init(&tempty[s], 128);
+      mbar_init(&tempty[s], 32 * Cfg::NEPI);
     }
     fence_barrier_init();
   }
@@ -300,38 +304,110 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
       // global access covers 8 rows x 64 contiguous bytes (full 32-byte sectors) instead of 32 rows x 16 bytes.
       float* stg = epi_smem + (warp - 2) * (32 * 16);
       const int m_base = mt * 128 + quad * 32;
-#pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 16) {
-        uint32_t v[16];
-        tmem_ld16(t_row + c0, v);
-        tmem_ld_wait();
-        if (n0 + c0 < p.N) {   // warp-uniform
+      const int c_first = (Cfg::NEPI == 8 && warp >= 6) ? 16 : 0;
+      const int c_step = (Cfg::NEPI == 8) ? 32 : 16;
+      const int cq = lane & 3, rsub = lane >> 2;
+      const bool interior = p.vec_ok && p.splits == 1 && (mt * 128 + 128 <= p.M) && (n0 + BN <= p.N);
+      if (interior) {
+        // fast path: whole tile in range, vector accesses; per-row offsets hoisted out of the column loop
+        long long oD[4], oR[4], oH[4];
+        const float* rbp[4];
+        float bm[4];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float4 q4 = has_k ? make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                                                  __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]))
-                                    : make_float4(0.f, 0.f, 0.f, 0.f);
-            *reinterpret_cast<float4*>(stg + lane * 16 + ((j ^ ((lane >> 1) & 3)) << 2)) = q4;
-          }
+        for (int it = 0; it < 4; ++it) {
+          const long long m = m_base + it * 8 + rsub;
+          const int nn = n0 + cq * 4;
+          oD[it] = (long long)z * p.d_bs + m * p.ldd + nn;
+          oR[it] = (long long)z * p.res_bs + m * p.ldres + nn;
+          oH[it] = (long long)z * p.h_bs + m * p.ldh + nn;
+          rbp[it] = p.rowbias ? p.rowbias + (((long long)z * p.M + m) / p.rows_per_group) * p.rowbias_ld + nn : nullptr;
+          bm[it] = p.bias_m ? __ldg(p.bias_m + m) : 0.f;
+        }
+#pragma unroll 1
+        for (int c0 = c_first; c0 < BN; c0 += c_step) {
+          uint32_t v[16];
+          tmem_ld16(t_row + c0, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<float4*>(stg + lane * 16 + ((j ^ ((lane >> 1) & 3)) << 2)) =
+                make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                            __uint_as_float(v[4 * j + 3]));
           __syncwarp();
+          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p.bias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c0 + cq * 4));
+          float4 q[4];
 #pragma unroll
           for (int it = 0; it < 4; ++it) {
-            const int rr = it * 8 + (lane >> 2), cq = lane & 3;
-            const float4 q4 = *reinterpret_cast<const float4*>(stg + rr * 16 + ((cq ^ ((rr >> 1) & 3)) << 2));
-            const int m = m_base + rr, n = n0 + c0 + cq * 4;
-            if (m < p.M && n < p.N) {
-              const int valid = min(4, p.N - n);
-              if (p.splits > 1) {
-                float* dst = p.partial + ((long long)(sp * p.batch + z) * p.M + m) * p.N + n;
-                const float e[4] = {q4.x, q4.y, q4.z, q4.w};
+            const int rr = it * 8 + rsub;
+            q[it] = *reinterpret_cast<const float4*>(stg + rr * 16 + ((cq ^ ((rr >> 1) & 3)) << 2));
+          }
+          float4 r4[4];
+          if (p.res) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) if (j < valid) dst[j] = e[j];
-              } else {
-                epilogue_quad(p, z, m, n, valid, q4);
-              }
+            for (int it = 0; it < 4; ++it) r4[it] = *reinterpret_cast<const float4*>(p.res + oR[it] + c0);
+          }
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            float e[4] = {q[it].x, q[it].y, q[it].z, q[it].w};
+            const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) e[j] = fmaf(e[j], p.alpha, bb[j] + bm[it]);
+            if (rbp[it]) {
+              const float4 rb = __ldg(reinterpret_cast<const float4*>(rbp[it] + c0));
+              e[0] += rb.x; e[1] += rb.y; e[2] += rb.z; e[3] += rb.w;
+            }
+            if (p.act != ODISE_ACT_NONE) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) e[j] = apply_act(e[j], p.act);
+            }
+            if (p.res) { e[0] += r4[it].x; e[1] += r4[it].y; e[2] += r4[it].z; e[3] += r4[it].w; }
+            if (p.D) *reinterpret_cast<float4*>(p.D + oD[it] + c0) = make_float4(e[0], e[1], e[2], e[3]);
+            if (p.Dh) {
+              __align__(8) __nv_bfloat16 h[4];
+              __align__(8) __nv_bfloat16 l[4];
+#pragma unroll
+              for (int t = 0; t < 4; ++t) split_bf16(e[t], h[t], l[t]);
+              *reinterpret_cast<uint2*>(p.Dh + oH[it] + c0) = *reinterpret_cast<const uint2*>(h);
+              if (p.Dl) *reinterpret_cast<uint2*>(p.Dl + oH[it] + c0) = *reinterpret_cast<const uint2*>(l);
             }
           }
           __syncwarp();
+        }
+      } else {
+#pragma unroll 1
+        for (int c0 = c_first; c0 < BN; c0 += c_step) {
+          uint32_t v[16];
+          tmem_ld16(t_row + c0, v);
+          tmem_ld_wait();
+          if (n0 + c0 < p.N) {   // warp-uniform
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float4 q4 = has_k ? make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                                    __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]))
+                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+              *reinterpret_cast<float4*>(stg + lane * 16 + ((j ^ ((lane >> 1) & 3)) << 2)) = q4;
+            }
+            __syncwarp();
+#pragma unroll 1
+            for (int it = 0; it < 4; ++it) {
+              const int rr = it * 8 + rsub;
+              const float4 q4 = *reinterpret_cast<const float4*>(stg + rr * 16 + ((cq ^ ((rr >> 1) & 3)) << 2));
+              const int m = m_base + rr, n = n0 + c0 + cq * 4;
+              if (m < p.M && n < p.N) {
+                const int valid = min(4, p.N - n);
+                if (p.splits > 1) {
+                  float* dst = p.partial + ((long long)(sp * p.batch + z) * p.M + m) * p.N + n;
+                  const float e[4] = {q4.x, q4.y, q4.z, q4.w};
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) if (j < valid) dst[j] = e[j];
+                } else {
+                  epilogue_quad(p, z, m, n, valid, q4);
+                }
+              }
+            }
+            __syncwarp();
+          }
         }
       }
       tc_fence_before();
@@ -425,7 +501,7 @@ static int launch_cfg(const CUtensorMap& ah, const CUtensorMap& al, const CUtens
   }
   const int total = p.tiles_m * p.tiles_n * p.splits * p.batch;
   const int grid = total < num_sms() ? total : num_sms();
-  gemm_tc_kernel<BN, NMMA><<<grid, 192, Cfg::SMEM_BYTES, stream>>>(ah, al, bh, bl, p);
+  gemm_tc_kernel<BN, NMMA><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(ah, al, bh, bl, p);
   return (int)cudaGetLastError();
 }
 

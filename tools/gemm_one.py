@@ -1,0 +1,30 @@
+"""Single-shape GEMM runner for ncu captures: python tools/gemm_one.py M N K [planes|f32|both] [nmma] [bn]"""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
+from odise_b200 import lib  # noqa: E402
+
+M, N, K = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])
+mode = sys.argv[4] if len(sys.argv) > 4 else "f32"
+nmma = int(sys.argv[5]) if len(sys.argv) > 5 else 3
+bn = int(sys.argv[6]) if len(sys.argv) > 6 else 0
+dev = torch.device("cuda")
+a = lib.split(torch.randn(M, K, device=dev))
+b = lib.split(torch.randn(N, K, device=dev) * 0.05)
+bias = torch.randn(N, device=dev)
+out = torch.empty(M, N, device=dev) if mode in ("f32", "both") else None
+outp = lib.Planes.empty(M, N, dev) if mode in ("planes", "both") else None
+for i in range(5):
+    lib.gemm(a, b, nmma=nmma, bias=bias, out=out, out_planes=outp, force_bn=bn)
+torch.cuda.synchronize()
+s, e = torch.cuda.Event(True), torch.cuda.Event(True)
+s.record()
+for i in range(10):
+    lib.gemm(a, b, nmma=nmma, bias=bias, out=out, out_planes=outp, force_bn=bn)
+e.record()
+torch.cuda.synchronize()
+ms = s.elapsed_time(e) / 10
+print(f"M={M} N={N} K={K} {mode} nmma={nmma} bn={bn}: {ms*1000:.1f} us, {2*M*N*K/ms/1e9:.1f} TFLOP/s")
