@@ -85,6 +85,8 @@ typedef struct odise_gemm_desc {
   int split_k; void* workspace; long long workspace_bytes;
   int force_bn;                      /* 0 = heuristic; 64/128/160/256 */
   const float* bias_m;               /* [M] per-row bias or NULL (transposed-output projections) */
+  int geglu;                         /* 1: N = 2*Nh, weight rows quad-interleaved (a0-3, g0-3, a4-7, g4-7, ...):
+                                        out planes [M, Nh] = a * gelu(gate)  (ldm GEGLU fused into FF1) */
 } odise_gemm_desc;
 int odise_gemm_bf16(const odise_gemm_desc* desc, void* stream);
 /* optional per-launch timing of odise_gemm_bf16 (CUDA events on the launch stream; not for use under graph capture):

@@ -228,24 +228,30 @@ __global__ void gn_partial_kernel(const float* __restrict__ x, long long ldx, lo
   }
 }
 
+// one warp per (image, group): lanes stride over the chunk partials, fixed-order shuffle reduction (deterministic)
 __global__ void gn_finalize_kernel(const float* __restrict__ x, long long x_bs, const float* __restrict__ ws,
                                    float* __restrict__ mean, float* __restrict__ rstd, int B, int HW, int C, int G,
                                    int nchunk, float eps) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (i >= B * G) return;
+  const int lane = threadIdx.x & 31;
   const int b = i / G, g = i % G, cpg = C / G;
   double s = 0, ss = 0;
-  for (int k = 0; k < nchunk; ++k) {
+  for (int k = lane; k < nchunk; k += 32) {
     const float* o = ws + (((long long)b * nchunk + k) * G + g) * 2;
     s += o[0]; ss += o[1];
   }
-  const double n = (double)HW * cpg;
-  const double pivot = x[(long long)b * x_bs + g * cpg];
-  const double m = s / n;
-  double var = ss / n - m * m;
-  if (var < 0) var = 0;
-  mean[i] = (float)(pivot + m);
-  rstd[i] = (float)(1.0 / sqrt(var + (double)eps));
+  s = warp_sum_d(s);
+  ss = warp_sum_d(ss);
+  if (lane == 0) {
+    const double n = (double)HW * cpg;
+    const double pivot = x[(long long)b * x_bs + g * cpg];
+    const double m = s / n;
+    double var = ss / n - m * m;
+    if (var < 0) var = 0;
+    mean[i] = (float)(pivot + m);
+    rstd[i] = (float)(1.0 / sqrt(var + (double)eps));
+  }
 }
 
 // ---------------------------------------------------------------------------------------------- LayerNorm
@@ -891,7 +897,7 @@ extern "C" int odise_groupnorm_stats_ws_f32(const float* x, long long ldx, long 
   const long long xbs = x_bs ? x_bs : (long long)HW * ldx;
   // NOTE: nchunk here must match odise_groupnorm_ws_floats' upper bound (it is <= that value)
   gn_partial_kernel<<<B * nchunk, threads, smem, STREAM(stream)>>>(x, ldx, xbs, ws, HW, C, G, nchunk, ppc);
-  gn_finalize_kernel<<<(B * G + 127) / 128, 128, 0, STREAM(stream)>>>(x, xbs, ws, mean, rstd, B, HW, C, G, nchunk, eps);
+  gn_finalize_kernel<<<(B * G + 7) / 8, 256, 0, STREAM(stream)>>>(x, xbs, ws, mean, rstd, B, HW, C, G, nchunk, eps);
   count_launch(2);
   return (int)cudaGetLastError();
 }

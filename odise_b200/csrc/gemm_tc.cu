@@ -44,6 +44,7 @@ struct GemmParams {
   __nv_bfloat16* Dl;
   long long ldh, h_bs;
   int act;
+  int geglu;   // N = 2*Nh with quad-interleaved (a, gate) columns: out[:, j] = a_j * gelu(g_j) -> planes [M, Nh]
   int vec_ok;  // all epilogue pointers / leading dims allow 16-byte vector access
   float* partial;  // [splits][batch][M][N] when splits > 1
 };
@@ -357,6 +358,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
               const float4 rb = __ldg(reinterpret_cast<const float4*>(rbp[it] + c0));
               e[0] += rb.x; e[1] += rb.y; e[2] += rb.z; e[3] += rb.w;
             }
+            if (p.geglu) {
+              // ldm GEGLU fused: lanes with even cq hold 4 `a` values, their xor-1 partner the 4 gates of the same
+              // channels (weight rows were quad-interleaved at load time); output planes have N/2 columns
+              float gt[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) gt[j] = __shfl_xor_sync(0xffffffffu, e[j], 1);
+              if ((cq & 1) == 0) {
+                __align__(8) __nv_bfloat16 h[4];
+                __align__(8) __nv_bfloat16 l[4];
+#pragma unroll
+                for (int t = 0; t < 4; ++t) split_bf16(e[t] * apply_act(gt[t], ODISE_ACT_GELU), h[t], l[t]);
+                const long long og = (long long)z * p.h_bs + (long long)(m_base + it * 8 + rsub) * p.ldh +
+                                     ((n0 + c0) >> 1) + (cq >> 1) * 4;
+                *reinterpret_cast<uint2*>(p.Dh + og) = *reinterpret_cast<const uint2*>(h);
+                if (p.Dl) *reinterpret_cast<uint2*>(p.Dl + og) = *reinterpret_cast<const uint2*>(l);
+              }
+              continue;
+            }
             if (p.act != ODISE_ACT_NONE) {
 #pragma unroll
               for (int j = 0; j < 4; ++j) e[j] = apply_act(e[j], p.act);
@@ -546,6 +565,7 @@ extern "C" int odise_gemm_bf16(const odise_gemm_desc* d, void* stream_v) {
   p.Dh = reinterpret_cast<__nv_bfloat16*>(d->out_hi); p.Dl = reinterpret_cast<__nv_bfloat16*>(d->out_lo);
   p.ldh = d->ld_out_bf16; p.h_bs = d->out_bf16_batch_stride;
   p.act = d->act;
+  p.geglu = d->geglu;
 
   // vector epilogue paths need 16-byte alignment; otherwise the kernel takes the scalar path
   {
@@ -609,6 +629,12 @@ extern "C" int odise_gemm_bf16(const odise_gemm_desc* d, void* stream_v) {
     if (rc) return rc;
     rc = encode_map(&bl, d->nmma == 3 ? d->b_lo : d->b_hi, 3, dims, str, box);
     if (rc) return rc;
+  }
+  if (d->geglu) {
+    // fused GEGLU needs whole tiles and the vector path (UNet FF shapes satisfy this)
+    if (!d->out_hi || d->out_f32 || d->residual || d->split_k > 1 || d->M % 128 || d->N % BN || !p.vec_ok ||
+        d->act != ODISE_ACT_NONE)
+      return ODISE_ERR_UNSUPPORTED;
   }
   p.tiles_m = (d->M + 127) / 128;
   p.tiles_n = (d->N + BN - 1) / BN;

@@ -91,8 +91,13 @@ class UNetEngine:
                 self.W[t + a + ".v"] = self._planes(wv)
                 self.W[t + a + ".out"] = self._planes(g(t + a + ".to_out.0.weight"))
                 self.F[t + a + ".out.b"] = self._f(g(t + a + ".to_out.0.bias"))
-            self.W[t + "ff1"] = self._planes(g(t + "ff.net.0.proj.weight"))
-            self.F[t + "ff1.b"] = self._f(g(t + "ff.net.0.proj.bias"))
+            # GEGLU fused into the FF1 epilogue: interleave (a, gate) rows in quads so both land in one lane pair
+            w1, b1 = g(t + "ff.net.0.proj.weight"), g(t + "ff.net.0.proj.bias")
+            h4 = 4 * ch
+            w1 = torch.stack([w1[:h4].reshape(h4 // 4, 4, ch), w1[h4:].reshape(h4 // 4, 4, ch)], 1).reshape(2 * h4, ch)
+            b1 = torch.stack([b1[:h4].reshape(h4 // 4, 4), b1[h4:].reshape(h4 // 4, 4)], 1).reshape(2 * h4)
+            self.W[t + "ff1"] = self._planes(w1)
+            self.F[t + "ff1.b"] = self._f(b1)
             self.W[t + "ff2"] = self._planes(g(t + "ff.net.2.weight"))
             self.F[t + "ff2.b"] = self._f(g(t + "ff.net.2.bias"))
             for n in ("norm1", "norm2", "norm3"):
@@ -220,9 +225,8 @@ class UNetEngine:
         h3 = ops.empty(M, ch, self.dev)
         self._gemm(o2, t + "attn2.out", t + "attn2.out.b", residual=h2, out=h3)
         _, n3 = ops.layer_norm(h3, self.F[t + "norm3.g"], self.F[t + "norm3.b"], lo=self.lo)
-        f1 = ops.empty(M, 8 * ch, self.dev)
-        self._gemm(n3, t + "ff1", t + "ff1.b", out=f1)
-        gg = ops.geglu(f1, lo=self.lo)
+        gg = Planes.empty(M, 4 * ch, self.dev, lo=self.lo)
+        self._gemm(n3, t + "ff1", t + "ff1.b", out_planes=gg, geglu=True)
         h4p = Planes.empty(M, ch, self.dev, lo=self.lo)
         self._gemm(gg, t + "ff2", t + "ff2.b", residual=h3, out_planes=h4p)
         self._gemm(h4p, q + "proj_out", q + "proj_out.b", residual=x, out=dst)

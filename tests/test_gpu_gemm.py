@@ -104,3 +104,21 @@ def test_gemm_channel_slice_output(cuda):
     ref = a.double() @ b.double().t()
     assert _rel(buf[:, 64:64 + N], ref) < 2e-5
     assert buf[:, :64].abs().max() == 0 and buf[:, 64 + N:].abs().max() == 0
+
+
+def test_gemm_geglu_fused(cuda):
+    """FF1 + GEGLU in one launch: quad-interleaved (a, gate) weight rows, out planes = a * gelu(gate)."""
+    from odise_b200 import lib
+    M, C = 512, 320
+    g = torch.Generator().manual_seed(12)
+    x = torch.randn(M, C, generator=g).to(cuda)
+    w = (torch.randn(8 * C, C, generator=g) / C ** 0.5).to(cuda)
+    b = torch.randn(8 * C, generator=g).to(cuda)
+    h4 = 4 * C
+    wi = torch.stack([w[:h4].reshape(h4 // 4, 4, C), w[h4:].reshape(h4 // 4, 4, C)], 1).reshape(2 * h4, C).contiguous()
+    bi = torch.stack([b[:h4].reshape(h4 // 4, 4), b[h4:].reshape(h4 // 4, 4)], 1).reshape(2 * h4).contiguous()
+    out = lib.Planes.empty(M, h4, cuda)
+    lib.gemm(lib.split(x), lib.split(wi), bias=bi, out_planes=out, geglu=True)
+    y = x.double() @ w.double().t() + b.double()
+    ref = y[:, :h4] * F.gelu(y[:, h4:])
+    assert _rel(out.float(), ref) < 3e-5
