@@ -40,18 +40,22 @@ struct AttnCfg {
   static constexpr int HS = NC * 64;                 // head stride in q / k planes
   static constexpr int NP = (NMMA == 3) ? 2 : 1;
   static constexpr int BK = 64;                      // keys per block
-  static constexpr int STAGES = 2;
+  static constexpr int STAGES = 2;                           // K stages
+  // d = 40: one V stage + 256 TMEM columns so that TWO CTAs fit per SM (softmax of one overlaps the MMAs of the other)
+  static constexpr int VSTAGES = (DP <= 64) ? 1 : 2;
+  static constexpr int CTAS_PER_SM = (DP <= 64) ? 2 : 1;
   static constexpr int Q_BYTES = NC * NP * 128 * 128;       // [chunk][plane][128 rows x 128 B]
   static constexpr int K_BYTES = NC * NP * BK * 128;        // per stage
   static constexpr int V_TILE = DP * 128;                   // one plane: DP rows x 64 tokens
   static constexpr int V_BYTES = NP * V_TILE;               // per stage
   static constexpr int P_BYTES = NP * 128 * 128;
-  static constexpr int SMEM_BYTES = Q_BYTES + STAGES * (K_BYTES + V_BYTES) + P_BYTES + 1024 + 256;
-  static constexpr int TMEM_COLS = 512;               // S: 2 x 64 @ 0, O: 2 x 128 @ 128
+  static constexpr int SMEM_BYTES = Q_BYTES + STAGES * K_BYTES + VSTAGES * V_BYTES + P_BYTES + 1024 + 256;
+  static constexpr int OSTRIDE = (DP <= 64) ? 64 : 128;     // TMEM columns per O buffer
+  static constexpr int TMEM_COLS = (DP <= 64) ? 256 : 512;  // S: 2 x 64 @ 0, O: 2 x OSTRIDE @ 128
 };
 
 template <int DP, int NMMA>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(192, AttnCfg<DP, NMMA>::CTAS_PER_SM)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ CUtensorMap tmQl,
                const __grid_constant__ CUtensorMap tmKh, const __grid_constant__ CUtensorMap tmKl,
                const __grid_constant__ CUtensorMap tmVh, const __grid_constant__ CUtensorMap tmVl,
@@ -62,7 +66,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + Cfg::Q_BYTES;
   uint8_t* sV = sK + Cfg::STAGES * Cfg::K_BYTES;
-  uint8_t* sP = sV + Cfg::STAGES * Cfg::V_BYTES;
+  uint8_t* sP = sV + Cfg::VSTAGES * Cfg::V_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sP + Cfg::P_BYTES);
   uint64_t* q_full = bars;            // 1
   uint64_t* k_full = bars + 1;        // [2]
@@ -111,10 +115,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__
         tma_load_3d(sQ + (c * Cfg::NP) * 16384, &tmQh, q_full, h * Cfg::HS + c * 64, b * p.Tq + q0, 0);
         if (NMMA == 3) tma_load_3d(sQ + (c * Cfg::NP + 1) * 16384, &tmQl, q_full, h * Cfg::HS + c * 64, b * p.Tq + q0, 0);
       }
-      for (int j = 0; j < nblk; ++j) {
+      auto load_k = [&](int j) {
         const int st = j & 1;
-        const uint32_t ph = (j >> 1) & 1;
-        mbar_wait(&k_empty[st], ph ^ 1);
+        mbar_wait(&k_empty[st], ((j >> 1) & 1) ^ 1);
         mbar_arrive_expect_tx(&k_full[st], Cfg::K_BYTES);
         uint8_t* kd = sK + st * Cfg::K_BYTES;
         for (int c = 0; c < Cfg::NC; ++c) {
@@ -122,11 +125,16 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__
           if (NMMA == 3)
             tma_load_3d(kd + (c * Cfg::NP + 1) * 8192, &tmKl, &k_full[st], h * Cfg::HS + c * 64, b * p.TkS + j * 64, 0);
         }
-        mbar_wait(&v_empty[st], ph ^ 1);
-        mbar_arrive_expect_tx(&v_full[st], Cfg::V_BYTES);
-        uint8_t* vd = sV + st * Cfg::V_BYTES;
-        tma_load_3d(vd, &tmVh, &v_full[st], b * p.TkS + j * 64, h * Cfg::HS, 0);
-        if (NMMA == 3) tma_load_3d(vd + Cfg::V_TILE, &tmVl, &v_full[st], b * p.TkS + j * 64, h * Cfg::HS, 0);
+      };
+      load_k(0);
+      for (int j = 0; j < nblk; ++j) {
+        if (j + 1 < nblk) load_k(j + 1);        // K runs one block ahead; V is loaded just in time
+        const int sv = j % Cfg::VSTAGES;
+        mbar_wait(&v_empty[sv], ((j / Cfg::VSTAGES) & 1) ^ 1);
+        mbar_arrive_expect_tx(&v_full[sv], Cfg::V_BYTES);
+        uint8_t* vd = sV + sv * Cfg::V_BYTES;
+        tma_load_3d(vd, &tmVh, &v_full[sv], b * p.TkS + j * 64, h * Cfg::HS, 0);
+        if (NMMA == 3) tma_load_3d(vd + Cfg::V_TILE, &tmVl, &v_full[sv], b * p.TkS + j * 64, h * Cfg::HS, 0);
       }
     }
   } else if (warp == 1) {
@@ -164,12 +172,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__
         if (j + 1 < nblk) issue_s(j + 1);
         const int st = j & 1;
         const uint32_t ph = (j >> 1) & 1;
+        const int sv = j % Cfg::VSTAGES;
         mbar_wait(p_full, j & 1);
-        mbar_wait(&v_full[st], ph);
+        mbar_wait(&v_full[sv], (j / Cfg::VSTAGES) & 1);
         mbar_wait(&o_empty[st], ph ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + 128 + st * 128;
-        const uint32_t pp = smem_u32(sP), vv = smem_u32(sV + st * Cfg::V_BYTES);
+        const uint32_t d_tmem = tmem_base + 128 + st * Cfg::OSTRIDE;
+        const uint32_t pp = smem_u32(sP), vv = smem_u32(sV + sv * Cfg::V_BYTES);
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
           const uint64_t ph_ = umma_desc_sw128(pp + ks * 32);
@@ -182,7 +191,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__
             umma_bf16(d_tmem, pl, vh, idesc_o, 1u);
           }
         }
-        umma_commit(&v_empty[st]);
+        umma_commit(&v_empty[sv]);
         umma_commit(p_empty);
         umma_commit(&o_full[st]);
       }
@@ -204,7 +213,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__
 #pragma unroll
       for (int c0 = 0; c0 < DP; c0 += 16) {
         uint32_t v[16];
-        tmem_ld16(t_lane + 128 + st * 128 + c0, v);
+        tmem_ld16(t_lane + 128 + st * Cfg::OSTRIDE + c0, v);
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 16; ++i) acc[c0 + i] = fmaf(acc[c0 + i], alpha, __uint_as_float(v[i]));
