@@ -85,6 +85,9 @@ typedef struct odise_gemm_desc {
   int split_k; void* workspace; long long workspace_bytes;
   int force_bn;                      /* 0 = heuristic; 64/128/160/256 */
   const float* bias_m;               /* [M] per-row bias or NULL (transposed-output projections) */
+  int conv_mode;                     /* conv3x3: 0 = stride 1 pad 1; 1 = stride 2 pad (1,1) (ldm Downsample);
+                                        2 = stride 2 pad (0,1) (ldm VAE Downsample). conv_H/W are INPUT dims,
+                                        M = B * (H/stride) * (W/stride) */
   int geglu;                         /* 1: N = 2*Nh, weight rows quad-interleaved (a0-3, g0-3, a4-7, g4-7, ...):
                                         out planes [M, Nh] = a * gelu(gate)  (ldm GEGLU fused into FF1) */
 } odise_gemm_desc;

@@ -151,42 +151,77 @@ gn_stats_kernel(const float* __restrict__ x, long long ldx, float* __restrict__ 
   }
 }
 
+// grid (pixel chunks, B); thread = fixed channel quad (+ pixel lane): the per-channel constants
+// (mean, rstd, gamma, beta of the quad) are loaded once, the inner loop is load / 2 FMA-class ops / act / store.
 __global__ void gn_apply_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ mean,
                                 const float* __restrict__ rstd, const float* __restrict__ gamma,
                                 const float* __restrict__ beta, int act, float* __restrict__ y, long long ldy,
                                 __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, long long ldo,
-                                long long rows, int HW, int C, int G, long long x_bs, long long y_bs, long long o_bs,
-                                const float* __restrict__ res, long long ldres, int accumulate) {
-  const int c4n = C / 4;
-  const int cpg = C / G;
-  const long long total = rows * c4n;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const long long r = i / c4n;
-    const int c = (int)(i - r * c4n) * 4;
-    const int b = (int)(r / HW);
-    const long long hw = r - (long long)b * HW;
-    const float4 v = *reinterpret_cast<const float4*>(x + b * x_bs + hw * ldx + c);
+                                int HW, int C, int G, long long x_bs, long long y_bs, long long o_bs,
+                                const float* __restrict__ res, long long ldres, int accumulate, int pix_per_block) {
+  const int b = blockIdx.y;
+  const int C4 = C >> 2, cpg = C / G;
+  const int PL = blockDim.x / C4;
+  const int q = threadIdx.x % C4, pl = threadIdx.x / C4;
+  if (pl >= PL) return;
+  const int c = q * 4;
+  float mu[4], rs[4], ga[4], be[4];
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const int g = (c + t) / cpg;
+    mu[t] = __ldg(mean + b * G + g);
+    rs[t] = __ldg(rstd + b * G + g);
+    ga[t] = __ldg(gamma + c + t);
+    be[t] = __ldg(beta + c + t);
+  }
+  const float* xb = x + (long long)b * x_bs + c;
+  const int p0 = blockIdx.x * pix_per_block, p1 = min(HW, p0 + pix_per_block);
+  for (int pix = p0 + pl; pix < p1; pix += PL) {
+    const float4 v = *reinterpret_cast<const float4*>(xb + (long long)pix * ldx);
     const float in[4] = {v.x, v.y, v.z, v.w};
     float o[4];
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      const int g = (c + t) / cpg;
-      const float mu = __ldg(mean + b * G + g), rs = __ldg(rstd + b * G + g);
-      // torch: (x - mean) * rstd * gamma + beta
-      float u = (in[t] - mu) * rs;
-      u = fmaf(u, __ldg(gamma + c + t), __ldg(beta + c + t));
-      if (res) u += res[r * ldres + c + t];   // BottleneckBlock: relu(gn(conv3) + shortcut)
-      o[t] = act_apply(u, act);
+    for (int t = 0; t < 4; ++t) o[t] = fmaf((in[t] - mu[t]) * rs[t], ga[t], be[t]);   // torch order
+    if (res) {   // BottleneckBlock: relu(gn(conv3) + shortcut); res is dense [B*HW, C]
+      const float4 r4 = *reinterpret_cast<const float4*>(res + ((long long)b * HW + pix) * ldres + c);
+      o[0] += r4.x; o[1] += r4.y; o[2] += r4.z; o[3] += r4.w;
+    }
+    if (act != ODISE_ACT_NONE) {
+#pragma unroll
+      for (int t = 0; t < 4; ++t) o[t] = act_apply(o[t], act);
     }
     float4 ov = make_float4(o[0], o[1], o[2], o[3]);
-    if (y && accumulate) {
-      const float4 prev = *reinterpret_cast<const float4*>(y + b * y_bs + hw * ldy + c);
-      ov.x += prev.x; ov.y += prev.y; ov.z += prev.z; ov.w += prev.w;
+    if (y) {
+      float4* yp = reinterpret_cast<float4*>(y + (long long)b * y_bs + (long long)pix * ldy + c);
+      if (accumulate) { const float4 prev = *yp; ov.x += prev.x; ov.y += prev.y; ov.z += prev.z; ov.w += prev.w; }
+      *yp = ov;
     }
-    if (y) *reinterpret_cast<float4*>(y + b * y_bs + hw * ldy + c) = ov;
-    if (hi) store_split4(hi + b * o_bs + hw * ldo + c, lo ? lo + b * o_bs + hw * ldo + c : nullptr, ov);
+    if (hi) {
+      const long long o_ = (long long)b * o_bs + (long long)pix * ldo + c;
+      store_split4(hi + o_, lo ? lo + o_ : nullptr, ov);
+    }
   }
+}
+
+static int launch_gn_apply(const float* x, long long ldx, const float* mean, const float* rstd, const float* gamma,
+                           const float* beta, int act, float* y, long long ldy, __nv_bfloat16* hi,
+                           __nv_bfloat16* lo, long long ldo, int B, int HW, int C, int G, long long x_bs,
+                           long long y_bs, long long o_bs, const float* res, long long ldres, int accumulate,
+                           cudaStream_t stream) {
+  const int C4 = C / 4;
+  if (C4 > 1024) return ODISE_ERR_UNSUPPORTED;
+  int PL = 256 / C4;
+  if (PL < 1) PL = 1;
+  const int threads = C4 * PL;
+  int chunks = (6 * 148 + B - 1) / B;            // ~6 blocks per SM
+  if (chunks > (HW + PL - 1) / PL) chunks = (HW + PL - 1) / PL;
+  if (chunks < 1) chunks = 1;
+  const int ppb = (HW + chunks - 1) / chunks;
+  chunks = (HW + ppb - 1) / ppb;
+  dim3 grid(chunks, B);
+  gn_apply_kernel<<<grid, threads, 0, stream>>>(x, ldx, mean, rstd, gamma, beta, act, y, ldy, hi, lo, ldo, HW, C, G,
+                                                x_bs, y_bs, o_bs, res, ldres, accumulate, ppb);
+  return (int)cudaGetLastError();
 }
 
 // ---------------------------------------------------------------------------------------------- GroupNorm stats v2
@@ -671,11 +706,10 @@ extern "C" int odise_groupnorm_apply_bs_f32(const float* x, long long ldx, long 
   if (!x || !mean || !rstd || !gamma || !beta || (!y && !hi) || C % G) return ODISE_ERR_ARG;
   if (C % 4 || ldx % 4 || x_bs % 4 || (y && (ldy % 4 || y_bs % 4)) || (hi && (ldo % 4 || o_bs % 4)))
     return ODISE_ERR_ALIGN;
-  const long long rows = (long long)B * HW;
-  gn_apply_kernel<<<grid_for(rows * (C / 4), 256), 256, 0, STREAM(stream)>>>(
-      x, ldx, mean, rstd, gamma, beta, act, y, ldy, BF(hi), BF(lo), ldo, rows, HW, C, G,
-      x_bs ? x_bs : (long long)HW * ldx, y_bs ? y_bs : (long long)HW * ldy, o_bs ? o_bs : (long long)HW * ldo,
-      nullptr, 0, 0);
+  int rc = launch_gn_apply(x, ldx, mean, rstd, gamma, beta, act, y, ldy, BF(hi), BF(lo), ldo, B, HW, C, G,
+                           x_bs ? x_bs : (long long)HW * ldx, y_bs ? y_bs : (long long)HW * ldy,
+                           o_bs ? o_bs : (long long)HW * ldo, nullptr, 0, 0, STREAM(stream));
+  if (rc) return rc;
   count_launch(1);
   return (int)cudaGetLastError();
 }
@@ -836,10 +870,10 @@ extern "C" int odise_groupnorm_apply_res_f32(const float* x, long long ldx, cons
                                              void* stream) {
   if (!x || !mean || !rstd || !gamma || !beta || (!y && !hi) || C % G) return ODISE_ERR_ARG;
   if (C % 4 || ldx % 4 || (y && ldy % 4) || (hi && ldo % 4) || (res && ldres % 4)) return ODISE_ERR_ALIGN;
-  const long long rows = (long long)B * HW;
-  gn_apply_kernel<<<grid_for(rows * (C / 4), 256), 256, 0, STREAM(stream)>>>(
-      x, ldx, mean, rstd, gamma, beta, act, y, ldy, BF(hi), BF(lo), ldo, rows, HW, C, G, (long long)HW * ldx,
-      (long long)HW * ldy, (long long)HW * ldo, res, ldres, accumulate);
+  int rc = launch_gn_apply(x, ldx, mean, rstd, gamma, beta, act, y, ldy, BF(hi), BF(lo), ldo, B, HW, C, G,
+                           (long long)HW * ldx, (long long)HW * ldy, (long long)HW * ldo, res, ldres, accumulate,
+                           STREAM(stream));
+  if (rc) return rc;
   count_launch(1);
   return (int)cudaGetLastError();
 }

@@ -28,7 +28,8 @@ namespace ob {
 struct GemmParams {
   int M, N, K, batch;
   int a_batched, b_batched;
-  int conv, C, H, W, bw, bh, bb;
+  int conv, C, H, W, bw, bh, bb;   // H, W: OUTPUT spatial dims of the conv
+  int cstride, cpad;               // conv stride (1 | 2) and low-side zero padding (0 | 1)
   int tiles_m, tiles_n, splits, kblocks;
   float alpha;
   const float* bias;
@@ -229,8 +230,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
           if (p.conv) {
             const int tap = kb / cpk, cc = kb - tap * cpk;
             const int kh = tap / 3, kw = tap - kh * 3;
-            tma_load_4d(st, &tmAh, &full[stage], cc * 64, w0 + kw - 1, h0 + kh - 1, b0);
-            if (NMMA == 3) tma_load_4d(st + Cfg::A_BYTES, &tmAl, &full[stage], cc * 64, w0 + kw - 1, h0 + kh - 1, b0);
+            const int cx = w0 * p.cstride + kw - p.cpad, cy = h0 * p.cstride + kh - p.cpad;
+            tma_load_4d(st, &tmAh, &full[stage], cc * 64, cx, cy, b0);
+            if (NMMA == 3) tma_load_4d(st + Cfg::A_BYTES, &tmAl, &full[stage], cc * 64, cx, cy, b0);
           } else {
             const int za = p.a_batched ? z : 0;
             tma_load_3d(st, &tmAh, &full[stage], kb * 64, m0, za);
@@ -413,6 +415,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
               const int rr = it * 8 + rsub;
               const float4 q4 = *reinterpret_cast<const float4*>(stg + rr * 16 + ((cq ^ ((rr >> 1) & 3)) << 2));
               const int m = m_base + rr, n = n0 + c0 + cq * 4;
+              if (p.geglu) {   // warp-uniform; N % 16 == 0 so a chunk is either fully valid or skipped above
+                float e[4] = {q4.x, q4.y, q4.z, q4.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) e[j] = fmaf(e[j], p.alpha, p.bias ? __ldg(p.bias + n + j) : 0.f);
+                float gt[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) gt[j] = __shfl_xor_sync(0xffffffffu, e[j], 1);
+                if ((cq & 1) == 0 && m < p.M) {
+                  __align__(8) __nv_bfloat16 h[4];
+                  __align__(8) __nv_bfloat16 l[4];
+#pragma unroll
+                  for (int t = 0; t < 4; ++t) split_bf16(e[t] * apply_act(gt[t], ODISE_ACT_GELU), h[t], l[t]);
+                  const long long og = (long long)z * p.h_bs + (long long)m * p.ldh + ((n0 + c0) >> 1) + (cq >> 1) * 4;
+                  *reinterpret_cast<uint2*>(p.Dh + og) = *reinterpret_cast<const uint2*>(h);
+                  if (p.Dl) *reinterpret_cast<uint2*>(p.Dl + og) = *reinterpret_cast<const uint2*>(l);
+                }
+                continue;
+              }
               if (m < p.M && n < p.N) {
                 const int valid = min(4, p.N - n);
                 if (p.splits > 1) {
@@ -481,10 +501,11 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
 }
 
 static int encode_map(CUtensorMap* tm, const void* base, int rank, const cuuint64_t* dims,
-                      const cuuint64_t* strides_bytes, const cuuint32_t* box) {
+                      const cuuint64_t* strides_bytes, const cuuint32_t* box, int spatial_stride = 1) {
   auto enc = get_encode();
   if (!enc) return ODISE_ERR_DRIVER;
-  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  // strided implicit conv: W and H (dims 1, 2) are traversed with element stride 2
+  cuuint32_t estr[5] = {1, (cuuint32_t)spatial_stride, (cuuint32_t)spatial_stride, 1, 1};
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), dims, strides_bytes, box,
                    estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -584,6 +605,13 @@ extern "C" int odise_gemm_bf16(const odise_gemm_desc* d, void* stream_v) {
   int rc;
   if (p.conv) {
     if (p.C % 64 || d->K != 9 * p.C || d->batch != 1) return ODISE_ERR_ARG;
+    // conv_mode 0: stride 1, pad 1 | 1: stride 2, pad (1,1) (ldm Downsample) | 2: stride 2, pad (0,1) (VAE Downsample)
+    if (d->conv_mode < 0 || d->conv_mode > 2) return ODISE_ERR_ARG;
+    p.cstride = d->conv_mode == 0 ? 1 : 2;
+    p.cpad = d->conv_mode == 2 ? 0 : 1;
+    const int Hin = d->conv_H, Win = d->conv_W;
+    if (Hin % p.cstride || Win % p.cstride) return ODISE_ERR_ARG;
+    p.H = Hin / p.cstride; p.W = Win / p.cstride;      // output dims: tiles walk output pixels
     const int hw = p.H * p.W;
     if (d->M % hw) return ODISE_ERR_ARG;
     const int B = d->M / hw;
@@ -600,12 +628,13 @@ extern "C" int odise_gemm_bf16(const odise_gemm_desc* d, void* stream_v) {
     }
     const long long pix = d->lda;  // elements between consecutive pixels (>= C: channel slices of wider buffers)
     if (pix < p.C || pix % 8) return ODISE_ERR_ALIGN;
-    cuuint64_t dims[4] = {(cuuint64_t)p.C, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)B};
-    cuuint64_t str[3] = {(cuuint64_t)pix * 2, (cuuint64_t)pix * p.W * 2, (cuuint64_t)pix * hw * 2};
-    cuuint32_t box[4] = {64, (cuuint32_t)p.bw, (cuuint32_t)p.bh, (cuuint32_t)p.bb};
-    rc = encode_map(&ah, d->a_hi, 4, dims, str, box);
+    cuuint64_t dims[4] = {(cuuint64_t)p.C, (cuuint64_t)Win, (cuuint64_t)Hin, (cuuint64_t)B};
+    cuuint64_t str[3] = {(cuuint64_t)pix * 2, (cuuint64_t)pix * Win * 2, (cuuint64_t)pix * Hin * Win * 2};
+    // with element stride s the box spans bw*s input columns and yields bw of them
+    cuuint32_t box[4] = {64, (cuuint32_t)(p.bw * p.cstride), (cuuint32_t)(p.bh * p.cstride), (cuuint32_t)p.bb};
+    rc = encode_map(&ah, d->a_hi, 4, dims, str, box, p.cstride);
     if (rc) return rc;
-    rc = encode_map(&al, d->nmma == 3 ? d->a_lo : d->a_hi, 4, dims, str, box);
+    rc = encode_map(&al, d->nmma == 3 ? d->a_lo : d->a_hi, 4, dims, str, box, p.cstride);
     if (rc) return rc;
   } else {
     if (d->lda % 8 || d->a_batch_stride % 8) return ODISE_ERR_ALIGN;
@@ -631,9 +660,9 @@ extern "C" int odise_gemm_bf16(const odise_gemm_desc* d, void* stream_v) {
     if (rc) return rc;
   }
   if (d->geglu) {
-    // fused GEGLU needs whole tiles and the vector path (UNet FF shapes satisfy this)
-    if (!d->out_hi || d->out_f32 || d->residual || d->split_k > 1 || d->M % 128 || d->N % BN || !p.vec_ok ||
-        d->act != ODISE_ACT_NONE)
+    // fused GEGLU: (a, gate) quads must share a 16-column chunk; 8-byte plane stores need the aligned path
+    if (!d->out_hi || d->out_f32 || d->residual || d->rowbias || d->bias_m || d->split_k > 1 || d->N % 16 ||
+        !p.vec_ok || d->act != ODISE_ACT_NONE)
       return ODISE_ERR_UNSUPPORTED;
   }
   p.tiles_m = (d->M + 127) / 128;

@@ -36,6 +36,7 @@ class GemmDesc(ctypes.Structure):
         ("split_k", c_int), ("workspace", c_void_p), ("workspace_bytes", c_longlong),
         ("force_bn", c_int),
         ("bias_m", c_void_p),
+        ("conv_mode", c_int),
         ("geglu", c_int),
     ]
 
@@ -198,7 +199,7 @@ def split(x, out=None, lo=True):
 
 def gemm(a, b, *, M=None, N=None, K=None, nmma=3, batch=1, a_bs=0, b_bs=0, conv=None, alpha=1.0, bias=None, bias_m=None,
          rowbias=None, rows_per_group=1, act=ACT_NONE, residual=None, ld_res=None, res_bs=0, out=None, ld_out=None,
-         out_bs=0, out_planes=None, outp_bs=0, split_k=1, workspace=None, force_bn=0, geglu=False):
+         out_bs=0, out_planes=None, outp_bs=0, split_k=1, workspace=None, force_bn=0, geglu=False, conv_mode=0):
     """out[z] = epi(alpha * A[z] @ B[z]^T).  a, b: Planes (K-major).  conv = (C, H, W) for implicit 3x3."""
     d = GemmDesc()
     d.M = M if M is not None else a.rows
@@ -235,6 +236,7 @@ def gemm(a, b, *, M=None, N=None, K=None, nmma=3, batch=1, a_bs=0, b_bs=0, conv=
         d.workspace, d.workspace_bytes = _ptr(workspace), workspace.numel() * workspace.element_size()
     d.force_bn = force_bn
     d.geglu = 1 if geglu else 0
+    d.conv_mode = conv_mode
     _check(load().odise_gemm_bf16(ctypes.byref(d), _stream()), "odise_gemm_bf16")
     return out if out is not None else out_planes
 

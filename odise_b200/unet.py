@@ -279,8 +279,11 @@ class UNetEngine:
                 cols, _, _ = ops.im2col3x3_split(x, B, H, W, lo=self.lo)
                 self._gemm(cols, q + "0.conv", q + "0.conv.b", out=dst)
             elif kind == "down":
-                cols, ch_, cw_ = ops.im2col3x3_split(cur, B, ch_, cw_, stride=2, lo=self.lo)
-                self._gemm(cols, q + "0.conv", q + "0.conv.b", out=dst)
+                # ldm Downsample = conv3x3 stride 2 pad 1: strided implicit GEMM (TMA element strides), no im2col
+                cdim = layers[0][1]
+                self._gemm(ops.split(cur, lo=self.lo), q + "0.conv", q + "0.conv.b", M=B * (ch_ // 2) * (cw_ // 2),
+                           N=cdim, conv=(cdim, ch_, cw_), conv_mode=1, out=dst)
+                ch_, cw_ = ch_ // 2, cw_ // 2
             else:
                 _, cin, cout = layers[0]
                 if len(layers) == 1:

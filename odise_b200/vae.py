@@ -140,9 +140,11 @@ class VAEEngine:
             h = self._res(n, h, B, ch, cw, cin, cout)
             if idx % 2 == 1 and lvl != 3:
                 # ldm Downsample (with_conv): F.pad(x, (0,1,0,1)) then conv3x3 stride 2, no padding
-                cols, ch, cw = ops.im2col3x3_split(h, B, ch, cw, stride=2, pad_lo=0, pad_hi=1, lo=self.lo)
-                d = ops.empty(B * ch * cw, cout, self.dev)
-                self._gemm(cols, f"e.d{lvl}.down", out=d)
+                # strided implicit GEMM: conv_mode 2 = stride 2 with zero padding on the high side only
+                d = ops.empty(B * (ch // 2) * (cw // 2), cout, self.dev)
+                self._gemm(ops.split(h, lo=self.lo), f"e.d{lvl}.down", M=B * (ch // 2) * (cw // 2), N=cout,
+                           conv=(cout, ch, cw), conv_mode=2, out=d)
+                ch, cw = ch // 2, cw // 2
                 h = d
         h = self._res("e.m1.", h, B, ch, cw, 512, 512)
         h = self._attn("e.ma.", h, B, ch, cw)

@@ -106,10 +106,11 @@ def test_gemm_channel_slice_output(cuda):
     assert buf[:, :64].abs().max() == 0 and buf[:, 64 + N:].abs().max() == 0
 
 
-def test_gemm_geglu_fused(cuda):
+@pytest.mark.parametrize("M", [512, 64, 200])
+def test_gemm_geglu_fused(cuda, M):
     """FF1 + GEGLU in one launch: quad-interleaved (a, gate) weight rows, out planes = a * gelu(gate)."""
     from odise_b200 import lib
-    M, C = 512, 320
+    C = 320
     g = torch.Generator().manual_seed(12)
     x = torch.randn(M, C, generator=g).to(cuda)
     w = (torch.randn(8 * C, C, generator=g) / C ** 0.5).to(cuda)
@@ -122,3 +123,26 @@ def test_gemm_geglu_fused(cuda):
     y = x.double() @ w.double().t() + b.double()
     ref = y[:, :h4] * F.gelu(y[:, h4:])
     assert _rel(out.float(), ref) < 3e-5
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("shape", [(2, 64, 64, 64, 96), (1, 16, 16, 320, 320), (3, 8, 8, 128, 64), (1, 256, 256, 64, 64), (1, 512, 512, 128, 32)])
+def test_conv3x3_stride2_implicit(cuda, mode, shape):
+    """stride-2 3x3 conv as a strided implicit GEMM: mode 1 = pad (1,1) (ldm Downsample), mode 2 = F.pad(0,1,0,1) + no pad (VAE)."""
+    from odise_b200 import lib
+    B, H, W, C, Co = shape
+    g = torch.Generator().manual_seed(B + H + C + mode)
+    x = torch.randn(B, C, H, W, generator=g).to(cuda)
+    w = (torch.randn(Co, C, 3, 3, generator=g) / (3 * C ** 0.5)).to(cuda)
+    bias = torch.randn(Co, generator=g).to(cuda)
+    if mode == 1:
+        ref = F.conv2d(x.double(), w.double(), bias.double(), stride=2, padding=1)
+    else:
+        ref = F.conv2d(F.pad(x.double(), (0, 1, 0, 1)), w.double(), bias.double(), stride=2)
+    Ho, Wo = ref.shape[-2:]
+    assert (Ho, Wo) == (H // 2, W // 2)
+    xp = lib.split(x.permute(0, 2, 3, 1).contiguous().view(B * H * W, C))
+    wp = lib.split(w.permute(0, 2, 3, 1).contiguous().view(Co, 9 * C))
+    out = torch.empty(B * Ho * Wo, Co, device=cuda)
+    lib.gemm(xp, wp, M=B * Ho * Wo, N=Co, conv=(C, H, W), conv_mode=mode, bias=bias, out=out)
+    assert _rel(out, ref.permute(0, 2, 3, 1).reshape(B * Ho * Wo, Co)) < 2e-5
