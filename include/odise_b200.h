@@ -176,6 +176,9 @@ int odise_resize_nhwc_bs_f32(const float* src, long long lds, long long src_bs, 
  * (odise.py:237 + ldm.py:556); boxes [n_crops, 3] int32 = (image index, y0, x0) (device). */
 int odise_image_crops_u8_f32(const uint8_t* img, float* out, const int32_t* boxes, int n_crops, int H, int W, int ch,
                              int cw, void* stream);
+/* same for a float NCHW image already in [0, 1] (the Backbone plugin input, feature_extractor.py:252) */
+int odise_image_crops_f32(const float* img, float* out, const int32_t* boxes, int n_crops, int H, int W, int ch, int cw,
+                          void* stream);
 /* NHWC <-> NCHW transposes at the plugin boundary */
 int odise_nchw_to_nhwc_f32(const float* src, float* dst, long long ldd, int B, int C, int HW, void* stream);
 int odise_nhwc_to_nchw_f32(const float* src, long long lds, float* dst, int B, int C, int HW, void* stream);

@@ -195,7 +195,8 @@ class BackboneEngine:
     @torch.no_grad()
     def forward(self, n_images, h_img, w_img, vae_taps=None, images_u8=None):
         """slide_forward over n_images images of h_img x w_img: all crops in one batch, paste + average.
-        images_u8: device uint8 [n_images, 3, H, W] (used when a VAE engine is attached).
+        images_u8: device image batch [n_images, 3, H, W], uint8 (0..255) or float32 in [0, 1] (used when a VAE
+        engine is attached).
         Returns {"s2".."s5": (NHWC fp32 [n_images * H/s * W/s, 512], H/s, W/s)}."""
         boxes, short = self.crop_grid(h_img, w_img)
         nc = len(boxes)

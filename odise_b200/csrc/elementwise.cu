@@ -618,6 +618,24 @@ __global__ void image_crops_kernel(const uint8_t* __restrict__ img, float* __res
   }
 }
 
+// float NCHW image in [0, 1] -> normalised NHWC fp32 crops ((x - 0.5) / 0.5): the Backbone plugin entry
+// (FeatureExtractorBackbone.forward receives the already /255-normalised tensor, feature_extractor.py:252)
+__global__ void image_crops_f32_kernel(const float* __restrict__ img, float* __restrict__ out,
+                                       const int32_t* __restrict__ boxes, int n_crops, int H, int W, int ch, int cw) {
+  const long long total = (long long)n_crops * ch * cw;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(i % cw);
+    long long t = i / cw;
+    const int y = (int)(t % ch);
+    const int b = (int)(t / ch);
+    const int im = boxes[3 * b], y0 = boxes[3 * b + 1], x0 = boxes[3 * b + 2];
+    const float* src = img + ((long long)im * 3 * H + (y0 + y)) * W + x0 + x;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) out[i * 3 + c] = (src[(long long)c * H * W] - 0.5f) / 0.5f;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- softmax
 // one warp per row
 __global__ void softmax_split_kernel(const float* __restrict__ x, long long ldx, __nv_bfloat16* __restrict__ hi,
@@ -933,5 +951,14 @@ extern "C" int odise_groupnorm_stats_ws_f32(const float* x, long long ldx, long 
   gn_partial_kernel<<<B * nchunk, threads, smem, STREAM(stream)>>>(x, ldx, xbs, ws, HW, C, G, nchunk, ppc);
   gn_finalize_kernel<<<(B * G + 7) / 8, 256, 0, STREAM(stream)>>>(x, xbs, ws, mean, rstd, B, HW, C, G, nchunk, eps);
   count_launch(2);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int odise_image_crops_f32(const float* img, float* out, const int32_t* boxes, int n_crops, int H, int W,
+                                     int ch, int cw, void* stream) {
+  if (!img || !out || !boxes || n_crops <= 0 || H <= 0 || W <= 0 || ch <= 0 || cw <= 0) return ODISE_ERR_ARG;
+  image_crops_f32_kernel<<<grid_for((long long)n_crops * ch * cw, 256), 256, 0, STREAM(stream)>>>(img, out, boxes,
+                                                                                                n_crops, H, W, ch, cw);
+  count_launch(1);
   return (int)cudaGetLastError();
 }

@@ -255,8 +255,11 @@ def rowscale(y, s):
     return y
 
 
-def image_crops(img_u8, boxes_dev, n_crops, H, W, ch, cw):
-    out = torch.empty(n_crops * ch * cw, 3, dtype=torch.float32, device=img_u8.device)
-    _check(load().odise_image_crops_u8_f32(_ptr(img_u8), _ptr(out), _ptr(boxes_dev), n_crops, H, W, ch, cw, _stream()),
-           "image_crops")
+def image_crops(img, boxes_dev, n_crops, H, W, ch, cw):
+    """uint8 [N,3,H,W] (0..255) or float32 [N,3,H,W] in [0,1] -> normalised NHWC crops [n_crops*ch*cw, 3]."""
+    out = torch.empty(n_crops * ch * cw, 3, dtype=torch.float32, device=img.device)
+    fn = load().odise_image_crops_u8_f32 if img.dtype == torch.uint8 else load().odise_image_crops_f32
+    if img.dtype not in (torch.uint8, torch.float32):
+        raise lib.OdiseError("image_crops: uint8 or float32 image expected")
+    _check(fn(_ptr(img), _ptr(out), _ptr(boxes_dev), n_crops, H, W, ch, cw, _stream()), "image_crops")
     return out

@@ -1,0 +1,97 @@
+"""The reference's plugin surface, backed by the B200 engines.
+
+`B200FeatureExtractorBackbone` and `B200MaskFormerHead` keep the forward contracts of
+odise.modeling.backbone.FeatureExtractorBackbone (feature_extractor.py:29-256) and
+mask2former MaskFormerHead + ODISEMultiScaleMaskedTransformerDecoder (mask_former_head.py:115-132,
+odise.py:713-727): NCHW tensors in, the same dict keys out — so a LazyConfig can point `model.backbone` /
+`model.sem_seg_head` at them.  NCHW <-> NHWC conversion happens once at this boundary (odise_nchw_to_nhwc_f32).
+detectron2 is not required: `output_shape()` returns lightweight ShapeSpec objects with .channels / .stride.
+"""
+from collections import OrderedDict, namedtuple
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .backbone import BackboneEngine
+from .head import HeadEngine
+
+ShapeSpec = namedtuple("ShapeSpec", ["channels", "height", "width", "stride"])
+
+
+class B200FeatureExtractorBackbone(nn.Module):
+    """Drop-in for FeatureExtractorBackbone(feature_extractor=LdmImplicitCaptionerExtractor(...), slide_training=True).
+    forward(img: [B, 3, H, W] in [0, 1], H, W % 64 == 0) -> {"s2".."s5": [B, 512, H/2^k, W/2^k]}."""
+
+    def __init__(self, state_dict, device, out_features=("s2", "s3", "s4", "s5"), nmma=3, with_vae=True,
+                 clip_embed_fn=None):
+        super().__init__()
+        vae = None
+        if with_vae:
+            from .vae import VAEEngine
+            vae = VAEEngine(state_dict, device, nmma=nmma)
+        self.engine = BackboneEngine(state_dict, device, nmma=nmma, vae=vae)
+        self._out_features = list(out_features)
+        self._out_feature_strides = {f"s{k}": 2 ** k for k in (2, 3, 4, 5)}
+        self._out_feature_channels = {f"s{k}": 512 for k in (2, 3, 4, 5)}
+        self.clip_embed_fn = clip_embed_fn      # f-2: CLIP image tower; None -> seeded synthetic embedding
+
+    @property
+    def size_divisibility(self):
+        return 64                                # feature_extractor.py:126-128
+
+    def output_shape(self):
+        return {n: ShapeSpec(self._out_feature_channels[n], None, None, self._out_feature_strides[n])
+                for n in self._out_features}
+
+    def ignored_state_dict(self, destination=None, prefix=""):
+        return OrderedDict() if destination is None else destination     # frozen SD / CLIP weights: nothing to save
+
+    @torch.no_grad()
+    def forward(self, img):
+        if not img.is_cuda:
+            raise RuntimeError("B200FeatureExtractorBackbone: CUDA tensor required (no CPU path)")
+        B, _, H, W = img.shape
+        if H % 64 or W % 64:
+            raise RuntimeError("input must be padded to a multiple of size_divisibility=64")
+        feats = self.engine.forward(B, H, W, images_u8=img.contiguous().float())
+        return {k: ops.nhwc_to_nchw(t, B, h, w) for k, (t, h, w) in feats.items() if k in self._out_features}
+
+
+class B200MaskFormerHead(nn.Module):
+    """Drop-in for MaskFormerHead(pixel_decoder=MSDeformAttnPixelDecoder, transformer_predictor=
+    ODISEMultiScaleMaskedTransformerDecoder(class_embed=PseudoClassEmbed, post_mask_embed=PooledMaskEmbed))."""
+
+    def __init__(self, state_dict, device, num_classes=133, num_queries=100, nmma=3):
+        super().__init__()
+        self.engine = HeadEngine(state_dict, device, nmma=nmma, num_queries=num_queries)
+        self.num_classes = num_classes          # set by OpenPanopticInference through open_state_dict (odise.py:135)
+        self._pseudo_classes = num_classes      # PseudoClassEmbed.num_classes is NOT updated by the wrapper
+
+    def _pseudo_logits(self, B, Q, dev):
+        # PseudoClassEmbed (odise.py:910-920): ones for every class, zero for background
+        lg = torch.ones(B, Q, self._pseudo_classes + 1, device=dev)
+        lg[..., -1] = 0
+        return lg
+
+    @torch.no_grad()
+    def forward(self, features, mask=None):
+        B = features["s2"].shape[0]
+        feats = {k: (ops.nchw_to_nhwc(v.float()), v.shape[2], v.shape[3]) for k, v in features.items()}
+        out = self.engine.forward(feats, B)
+        h2, w2 = out["pd"]["mask_hw"]
+        Q = self.engine.Q
+        dev = features["s2"].device
+
+        def pack(hd):
+            return dict(pred_logits=self._pseudo_logits(B, Q, dev), pred_masks=hd["pred_masks"].view(B, Q, h2, w2),
+                        mask_embed=hd["mask_embed"].view(B, Q, -1),
+                        mask_pooled_features=hd["mask_pooled_features"].view(B, Q, -1),
+                        logit_scale=torch.tensor(self.engine.logit_scale, device=dev))
+
+        res = pack(out["heads"][-1])
+        res["aux_outputs"] = [pack(h) for h in out["heads"][:-1]]
+        return res
+
+    def layers(self, features, mask=None):
+        return self.forward(features, mask)
