@@ -72,7 +72,7 @@ def test_slide_paste_average(cuda, bb):
     per = {k: torch.randn(B, crop // s, crop // s, 512, generator=g) for k, s in (("s2", 4), ("s3", 8), ("s4", 16), ("s5", 32))}
     eng_extract = eng.extract
     try:
-        eng.extract = lambda B_, hw, taps=None: {k: (v.reshape(-1, 512).contiguous().to(cuda), v.shape[1], v.shape[2]) for k, v in per.items()}
+        eng.extract = lambda B_, hw, *a, **kw: {k: (v.reshape(-1, 512).contiguous().to(cuda), v.shape[1], v.shape[2]) for k, v in per.items()}
         eng_crop_grid = eng.crop_grid
         eng.crop_grid = lambda h, w, c=512: eng_crop_grid(h, w, crop)
         out = eng.forward(n_img, Himg, Himg)
