@@ -216,6 +216,12 @@ int odise_attn_mask_bits_f32(const float* mask_logits, uint32_t* bits, int32_t* 
 int odise_mha_d32_f32(const float* q, long long ldq, const float* k, const float* v, long long ldkv,
                       const uint32_t* bits, const int32_t* row_any, float* out, void* out_hi, void* out_lo,
                       long long ldo, int B, int Tq, int Tk, int heads, float scale, void* stream);
+/* same with a workspace of odise_mha_d32_ws_floats() floats: long key ranges (>= 2048 keys) are split over 2-4
+ * blocks per query tile (flash-decoding style) and merged by a second kernel */
+long long odise_mha_d32_ws_floats(int B, int Tq, int Tk, int heads);
+int odise_mha_d32_ws_f32(const float* q, long long ldq, const float* k, const float* v, long long ldkv,
+                         const uint32_t* bits, const int32_t* row_any, float* out, void* out_hi, void* out_lo,
+                         long long ldo, int B, int Tq, int Tk, int heads, float scale, float* ws, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Mask head helpers (odise.py:937-963 MaskPooling, odise.py:746 einsum) */

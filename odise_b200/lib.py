@@ -89,6 +89,8 @@ _SIGS = {
     "odise_attn_mask_bits_f32": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p],
     "odise_mha_d32_f32": [c_void_p, c_longlong, c_void_p, c_void_p, c_longlong, c_void_p, c_void_p, c_void_p, c_void_p,
                           c_void_p, c_longlong, c_int, c_int, c_int, c_int, c_float, c_void_p],
+    "odise_mha_d32_ws_f32": [c_void_p, c_longlong, c_void_p, c_void_p, c_longlong, c_void_p, c_void_p, c_void_p, c_void_p,
+                             c_void_p, c_longlong, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p],
     "odise_mask_binarize_f32": [c_void_p, c_void_p, c_longlong, c_void_p, c_int, c_int, c_int, c_void_p],
     "odise_pool_normalize_f32": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
     "odise_l2_normalize_split_f32": [c_void_p, c_longlong, c_void_p, c_void_p, c_longlong, c_longlong, c_int,
@@ -117,6 +119,8 @@ def load():
     lib.odise_launch_count.restype = c_longlong
     lib.odise_groupnorm_ws_floats.restype = c_longlong
     lib.odise_groupnorm_ws_floats.argtypes = [c_int, c_int, c_int, c_int]
+    lib.odise_mha_d32_ws_floats.restype = c_longlong
+    lib.odise_mha_d32_ws_floats.argtypes = [c_int, c_int, c_int, c_int]
     for name, args in _SIGS.items():
         fn = getattr(lib, name)
         fn.argtypes = args

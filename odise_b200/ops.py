@@ -193,8 +193,11 @@ def attn_mask_bits(mask_logits, B, Q, Hm, Wm, Hl, Wl):
 def mha_d32(q, ldq, k, v, ldkv, B, Tq, Tk, heads, scale, bits=None, row_any=None, lo=True):
     """q/k/v fp32 device tensors (any views whose data_ptr is the first element); returns Planes [B*Tq, heads*32]."""
     p = Planes.empty(B * Tq, heads * 32, q.device, lo=lo)
-    _check(load().odise_mha_d32_f32(_ptr(q), ldq, _ptr(k), _ptr(v), ldkv, _ptr(bits), _ptr(row_any), None, _ptr(p.hi),
-                                    _ptr(p.lo), p.ld, B, Tq, Tk, heads, scale, _stream()), "mha_d32")
+    L = load()
+    nws = int(L.odise_mha_d32_ws_floats(B, Tq, Tk, heads))
+    ws = torch.empty(nws, dtype=torch.float32, device=q.device) if nws else None
+    _check(L.odise_mha_d32_ws_f32(_ptr(q), ldq, _ptr(k), _ptr(v), ldkv, _ptr(bits), _ptr(row_any), None, _ptr(p.hi),
+                                  _ptr(p.lo), p.ld, B, Tq, Tk, heads, scale, _ptr(ws), _stream()), "mha_d32")
     return p
 
 

@@ -193,6 +193,10 @@ def test_mha_d32(cuda, cfg):
         s = s + bias
     ref = (s.softmax(-1) @ vh).transpose(1, 2).reshape(B, Tq, heads * d)
     assert _rel(out, ref) < 1e-5
+    # the engine path: key-split (flash-decoding) variant with workspace, planes out
+    from odise_b200 import ops
+    p = ops.mha_d32(q, heads * d, k, v, heads * d, B, Tq, Tk, heads, scale, bits, rowany)
+    assert _rel(p.float().view(B, Tq, heads * d), ref) < 2e-5
 
 
 @pytest.mark.parametrize("shape", [(16, 64 * 64, 320), (4, 16 * 16, 1920), (2, 8 * 8, 2560), (3, 100, 256), (1, 512 * 64, 128), (2, 7, 512)])
