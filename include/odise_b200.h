@@ -241,6 +241,25 @@ int odise_l2_normalize_split_f32(const float* x, long long ldx, void* hi, void* 
 int odise_class_max_f32(const float* sims, long long ld_sims, const int32_t* group_start, const float* null_sim,
                         float* out, long long rows, int n_classes, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Post-processing on the device (odise.py:326-370; maskformer_model.py:280-342) — no host syncs.
+ * upsample: bilinear (align_corners=False) of mask logits [B, Q, hs, ws] to (H, W), sigmoid, written pixel-major as
+ *   (hi, lo) planes [B*H*W, Qpad] (operand of the semantic GEMM) and optionally the upsampled logits up_f32 [B,Q,H,W]. */
+int odise_upsample_sigmoid_split_f32(const float* logits, void* hi, void* lo, float* up_f32, int B, int Q, int Qpad,
+                                     int hs, int ws, int H, int W, void* stream);
+/* softmax over the K+1 class logits of every query: probs [B*Q, K1] (optional), probs_t [B, K, Qpad] (optional,
+ * transposed without the void class, pad columns untouched: pre-zero it), max prob, argmax (first among ties),
+ * keep = (label != K) && (score > threshold)   (maskformer_model.py:287-290) */
+int odise_query_scores_f32(const float* cls, float* probs, float* probs_t, float* scores, int32_t* labels,
+                           int32_t* keep, int B, int Q, int Qpad, int K1, float threshold, void* stream);
+/* MaskFormer.panoptic_inference on the device: pan int32 [B, H, W] (0 = void), seg_info int32 [B, Q, 3] =
+ * (id, isthing, category) for the first n_segments[b] rows.  ws: odise_panoptic_ws_bytes() bytes. */
+long long odise_panoptic_ws_bytes(int B, int Q, int H, int W);
+int odise_panoptic_inference_f32(const float* logits, const float* scores, const int32_t* labels, const int32_t* keep,
+                                 const uint8_t* is_thing, int32_t* pan, int32_t* seg_info, int32_t* n_segments,
+                                 void* ws, int B, int Q, int K, int hs, int ws_, int H, int W, double overlap_thr,
+                                 void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -241,17 +241,21 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__
       tc_fence_before();
       mbar_arrive(&s_empty[st]);
       const int valid = p.Tk - j * 64;  // keys of this block that exist
+      if (valid < 64) {                 // only the last block can be ragged (warp-uniform)
+#pragma unroll
+        for (int i = 0; i < 64; ++i) if (i >= valid) s[i] = -INFINITY;
+      }
+      // running max on the raw scores (scale > 0), exponent as one FFMA + ex2: p = 2^(s*c - m*c)
       float mx = m;
 #pragma unroll
-      for (int i = 0; i < 64; ++i) {
-        s[i] = (i < valid) ? s[i] * p.scale_log2 : -INFINITY;
-        mx = fmaxf(mx, s[i]);
-      }
-      const float alpha = fast_exp2(m - mx);  // first block: exp2(-inf) = 0
+      for (int i = 0; i < 64; ++i) mx = fmaxf(mx, s[i]);
+      const float c = p.scale_log2;
+      const float alpha = fast_exp2((m - mx) * c);  // first block: exp2(-inf) = 0
+      const float mc = -mx * c;
       float sum = 0.f;
 #pragma unroll
       for (int i = 0; i < 64; ++i) {
-        s[i] = fast_exp2(s[i] - mx);
+        s[i] = fast_exp2(fmaf(s[i], c, mc));
         sum += s[i];
       }
       l = l * alpha + sum;
@@ -259,14 +263,21 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__
       // P_j -> shared memory (SW128 K-major [128 x 64]); wait until PV_{j-1} has finished reading the buffer
       mbar_wait(p_empty, (j & 1) ^ 1);
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        __align__(16) __nv_bfloat16 hi[8];
-        __align__(16) __nv_bfloat16 lo[8];
+      for (int cch = 0; cch < 8; ++cch) {
+        // packed conversions: hi = bf16x2(p), lo = bf16x2(p - float(hi))
+        uint32_t hw[4], lw[4];
 #pragma unroll
-        for (int t = 0; t < 8; ++t) split_bf16(s[c * 8 + t], hi[t], lo[t]);
-        const uint32_t off = sw128_offset(row, c);
-        *reinterpret_cast<uint4*>(sP + off) = *reinterpret_cast<const uint4*>(hi);
-        if (NMMA == 3) *reinterpret_cast<uint4*>(sP + 16384 + off) = *reinterpret_cast<const uint4*>(lo);
+        for (int t = 0; t < 4; ++t) {
+          const float a0 = s[cch * 8 + 2 * t], a1 = s[cch * 8 + 2 * t + 1];
+          const __nv_bfloat162 h2 = __floats2bfloat162_rn(a0, a1);
+          const float2 hf = __bfloat1622float2(h2);
+          const __nv_bfloat162 l2 = __floats2bfloat162_rn(a0 - hf.x, a1 - hf.y);
+          hw[t] = *reinterpret_cast<const uint32_t*>(&h2);
+          lw[t] = *reinterpret_cast<const uint32_t*>(&l2);
+        }
+        const uint32_t off = sw128_offset(row, cch);
+        *reinterpret_cast<uint4*>(sP + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+        if (NMMA == 3) *reinterpret_cast<uint4*>(sP + 16384 + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
       }
       fence_proxy_async();
       mbar_arrive(p_full);

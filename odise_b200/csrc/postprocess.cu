@@ -1,0 +1,250 @@
+// GPU post-processing of ODISE / Mask2Former inference, sm_100a.
+//
+// Reference: CategoryODISE.forward tail (odise/modeling/meta_arch/odise.py:326-370: F.interpolate of the mask logits to
+// the padded image size, then per image semantic / panoptic / instance inference) and
+// MaskFormer.semantic_inference / panoptic_inference (third_party/Mask2Former/mask2former/maskformer_model.py:280-342),
+// which loops over queries in Python with ~4 `.item()` host syncs per query.  Here nothing leaves the device:
+//   * upsample_sigmoid: bilinear x4 (align_corners=False) + sigmoid of the [Q, h, w] logits, written PIXEL-MAJOR as
+//     (hi, lo) bf16 planes [H*W, Qpad] — the K-major operand of the semantic GEMM sem[c, p] = sum_q P[q, c] * sig[p, q]
+//     (odise_gemm_bf16 with swapped operands writes the reference's [K, H, W] layout directly);
+//   * panoptic: per-pixel argmax over kept queries of score_q * sigmoid(mask_q) with the upsample recomputed on the
+//     fly, area counters by integer atomics, a single-warp sequential pass that reproduces the reference's segment
+//     bookkeeping (overlap test, stuff merging), and a final relabel pass.
+#include "ptx.cuh"
+#include "odise_b200.h"
+#include "launch_count.h"
+
+namespace ob {
+
+__device__ __forceinline__ float bilerp(const float* __restrict__ src, int Hs, int Ws, int oy, int ox, float sy,
+                                        float sx) {
+  // ATen area_pixel_compute_source_index(align_corners=False) + upsample_bilinear2d
+  const float fy = fmaxf((oy + 0.5f) * sy - 0.5f, 0.f), fx = fmaxf((ox + 0.5f) * sx - 0.5f, 0.f);
+  const int y0 = (int)fy, x0 = (int)fx;
+  const int y1 = y0 + (y0 < Hs - 1 ? 1 : 0), x1 = x0 + (x0 < Ws - 1 ? 1 : 0);
+  const float ly = fy - y0, lx = fx - x0, hy = 1.f - ly, hx = 1.f - lx;
+  return hy * (hx * src[y0 * Ws + x0] + lx * src[y0 * Ws + x1]) + ly * (hx * src[y1 * Ws + x0] + lx * src[y1 * Ws + x1]);
+}
+
+// grid (W/32, H, B); block (32 x-pixels, 8): each y-thread strides over queries; smem transpose -> q-fastest writes
+__global__ void __launch_bounds__(256)
+upsample_sigmoid_split_kernel(const float* __restrict__ logits, __nv_bfloat16* __restrict__ hi,
+                              __nv_bfloat16* __restrict__ lo, float* __restrict__ up_f32, int Q, int Qpad, int hs,
+                              int ws, int H, int W) {
+  __shared__ float tile[32][33];   // [q within chunk][x]
+  const int b = blockIdx.z, oy = blockIdx.y, ox0 = blockIdx.x * 32;
+  const float sy = (float)hs / (float)H, sx = (float)ws / (float)W;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  for (int q0 = 0; q0 < Qpad; q0 += 32) {
+    for (int qq = ty; qq < 32; qq += 8) {
+      const int q = q0 + qq, ox = ox0 + tx;
+      float v = 0.f;
+      if (q < Q && ox < W) {
+        const float lg = bilerp(logits + ((long long)b * Q + q) * hs * ws, hs, ws, oy, ox, sy, sx);
+        if (up_f32) up_f32[(((long long)b * Q + q) * H + oy) * W + ox] = lg;
+        v = 1.f / (1.f + expf(-lg));
+      }
+      tile[qq][tx] = v;
+    }
+    __syncthreads();
+    for (int xx = ty; xx < 32; xx += 8) {
+      const int ox = ox0 + xx, q = q0 + tx;
+      if (ox < W && q < Qpad) {
+        __nv_bfloat16 h, l;
+        split_bf16(tile[tx][xx], h, l);
+        const long long o = (((long long)b * H + oy) * W + ox) * Qpad + q;
+        hi[o] = h;
+        if (lo) lo[o] = l;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// per-query class statistics: softmax over K+1, P[q, c] (c < K) as planes [Kpad rows?] handled on host via GEMM inputs;
+// here: scores[q] = max prob, labels[q] = argmax, keep[q]
+__global__ void query_scores_kernel(const float* __restrict__ cls, float* __restrict__ probs, float* __restrict__ scores,
+                                    int32_t* __restrict__ labels, int32_t* __restrict__ keep, int BQ, int K1,
+                                    float thr, float* __restrict__ probs_t, int Q, int Qpad) {
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (i >= BQ) return;
+  const int lane = threadIdx.x & 31;
+  const float* c = cls + (long long)i * K1;
+  float mx = -INFINITY;
+  for (int k = lane; k < K1; k += 32) mx = fmaxf(mx, c[k]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  float sum = 0.f;
+  for (int k = lane; k < K1; k += 32) sum += expf(c[k] - mx);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  float best = -1.f;
+  int bi = 0x7fffffff;
+  for (int k = lane; k < K1; k += 32) {
+    const float pr = expf(c[k] - mx) / sum;
+    if (probs) probs[(long long)i * K1 + k] = pr;
+    // transposed, per image [K, Qpad] (void class dropped): the A operand of the semantic GEMM
+    if (probs_t && k < K1 - 1) probs_t[((long long)(i / Q) * (K1 - 1) + k) * Qpad + (i % Q)] = pr;
+    if (pr > best) { best = pr; bi = k; }          // first maximal index within the lane's stride
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {               // torch.max returns the first index among ties
+    const float ob_ = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ob_ > best || (ob_ == best && oi < bi)) { best = ob_; bi = oi; }
+  }
+  if (lane == 0) {
+    scores[i] = best;
+    labels[i] = bi;
+    keep[i] = (bi != K1 - 1) && (best > thr);
+  }
+}
+
+// per pixel: argmax over kept queries of score * sigmoid(upsampled logit); counters per query
+//   area[q]  = #pixels whose argmax is q          (mask_area)
+//   orig[q]  = #pixels with sigmoid(q) >= 0.5     (original_area)
+//   inter[q] = #pixels with argmax == q and sigmoid(q) >= 0.5
+__global__ void __launch_bounds__(256)
+panoptic_argmax_kernel(const float* __restrict__ logits, const float* __restrict__ scores,
+                       const int32_t* __restrict__ keep, int16_t* __restrict__ ids, uint8_t* __restrict__ fg,
+                       int32_t* __restrict__ area, int32_t* __restrict__ orig, int32_t* __restrict__ inter, int Q,
+                       int hs, int ws, int H, int W) {
+  extern __shared__ int32_t cnt[];   // [3][Q]
+  const int b = blockIdx.y;
+  for (int i = threadIdx.x; i < 3 * Q; i += blockDim.x) cnt[i] = 0;
+  __syncthreads();
+  const float sy = (float)hs / (float)H, sx = (float)ws / (float)W;
+  const long long npix = (long long)H * W;
+  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < npix; p += (long long)gridDim.x * blockDim.x) {
+    const int oy = (int)(p / W), ox = (int)(p - (long long)oy * W);
+    float best = -INFINITY;
+    int bq = -1;
+    bool bfg = false;
+    for (int q = 0; q < Q; ++q) {
+      if (!keep[b * Q + q]) continue;      // warp-uniform
+      const float lg = bilerp(logits + ((long long)b * Q + q) * hs * ws, hs, ws, oy, ox, sy, sx);
+      const float s = 1.f / (1.f + expf(-lg));
+      const bool f = s >= 0.5f;
+      if (f) atomicAdd(&cnt[Q + q], 1);
+      const float pm = scores[b * Q + q] * s;
+      if (pm > best) { best = pm; bq = q; bfg = f; }   // argmax(0): first maximal kept query
+    }
+    ids[(long long)b * npix + p] = (int16_t)bq;
+    fg[(long long)b * npix + p] = bfg ? 1 : 0;
+    if (bq >= 0) {
+      atomicAdd(&cnt[bq], 1);
+      if (bfg) atomicAdd(&cnt[2 * Q + bq], 1);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < Q; i += blockDim.x) {
+    if (cnt[i]) atomicAdd(&area[b * Q + i], cnt[i]);
+    if (cnt[Q + i]) atomicAdd(&orig[b * Q + i], cnt[Q + i]);
+    if (cnt[2 * Q + i]) atomicAdd(&inter[b * Q + i], cnt[2 * Q + i]);
+  }
+}
+
+// one thread per image: the reference's sequential segment bookkeeping (maskformer_model.py:313-340)
+__global__ void panoptic_assign_kernel(const int32_t* __restrict__ keep, const int32_t* __restrict__ labels,
+                                       const int32_t* __restrict__ area, const int32_t* __restrict__ orig,
+                                       const int32_t* __restrict__ inter, const uint8_t* __restrict__ is_thing,
+                                       int32_t* __restrict__ seg_of_query, int32_t* __restrict__ seg_info,
+                                       int32_t* __restrict__ n_segments, int Q, int K, double overlap_thr) {
+  const int b = blockIdx.x;
+  if (threadIdx.x != 0) return;
+  extern __shared__ int32_t stuff_seg[];   // [K] segment id of an already created stuff class (0 = none)
+  for (int c = 0; c < K; ++c) stuff_seg[c] = 0;
+  int cur = 0;
+  for (int q = 0; q < Q; ++q) {
+    seg_of_query[b * Q + q] = 0;
+    if (!keep[b * Q + q]) continue;
+    const int a = area[b * Q + q], o = orig[b * Q + q], in = inter[b * Q + q];
+    if (!(a > 0 && o > 0 && in > 0)) continue;
+    if ((double)a / (double)o < overlap_thr) continue;     // python: int / int -> double, compared with the double threshold
+    const int c = labels[b * Q + q];
+    const bool thing = is_thing[c] != 0;
+    if (!thing) {
+      if (stuff_seg[c]) { seg_of_query[b * Q + q] = stuff_seg[c]; continue; }
+      stuff_seg[c] = cur + 1;
+    }
+    ++cur;
+    seg_of_query[b * Q + q] = cur;
+    seg_info[(b * Q + (cur - 1)) * 3 + 0] = cur;
+    seg_info[(b * Q + (cur - 1)) * 3 + 1] = thing ? 1 : 0;
+    seg_info[(b * Q + (cur - 1)) * 3 + 2] = c;
+  }
+  n_segments[b] = cur;
+}
+
+__global__ void panoptic_relabel_kernel(const int16_t* __restrict__ ids, const uint8_t* __restrict__ fg,
+                                        const int32_t* __restrict__ seg_of_query, int32_t* __restrict__ pan, int Q,
+                                        long long npix, int B) {
+  const long long total = npix * B;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / npix);
+    const int q = ids[i];
+    pan[i] = (q >= 0 && fg[i]) ? seg_of_query[b * Q + q] : 0;
+  }
+}
+
+}  // namespace ob
+
+using namespace ob;
+#define STREAM(s) reinterpret_cast<cudaStream_t>(s)
+
+extern "C" int odise_upsample_sigmoid_split_f32(const float* logits, void* hi, void* lo, float* up_f32, int B, int Q,
+                                                int Qpad, int hs, int ws, int H, int W, void* stream) {
+  if (!logits || !hi || B <= 0 || Q <= 0 || Qpad < Q || hs <= 0 || ws <= 0 || H <= 0 || W <= 0) return ODISE_ERR_ARG;
+  dim3 grid((W + 31) / 32, H, B), block(32, 8);
+  upsample_sigmoid_split_kernel<<<grid, block, 0, STREAM(stream)>>>(logits, reinterpret_cast<__nv_bfloat16*>(hi),
+                                                                    reinterpret_cast<__nv_bfloat16*>(lo), up_f32, Q, Qpad,
+                                                                    hs, ws, H, W);
+  count_launch(1);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int odise_query_scores_f32(const float* cls, float* probs, float* probs_t, float* scores, int32_t* labels,
+                                      int32_t* keep, int B, int Q, int Qpad, int K1, float threshold, void* stream) {
+  if (!cls || !scores || !labels || !keep || B <= 0 || Q <= 0 || Qpad < Q || K1 <= 1) return ODISE_ERR_ARG;
+  const int BQ = B * Q;
+  query_scores_kernel<<<(BQ + 7) / 8, 256, 0, STREAM(stream)>>>(cls, probs, scores, labels, keep, BQ, K1, threshold,
+                                                                probs_t, Q, Qpad);
+  count_launch(1);
+  return (int)cudaGetLastError();
+}
+
+// logits [B, Q, hs, ws]; scores/labels/keep [B*Q]; is_thing [K] uint8; outputs: pan int32 [B, H, W],
+// seg_info int32 [B, Q, 3] (id, isthing, category), n_segments int32 [B].
+// workspace: ids int16 [B*H*W] | fg uint8 [B*H*W] | area, orig, inter, seg_of_query int32 [B*Q] each  (see *_ws_bytes)
+extern "C" long long odise_panoptic_ws_bytes(int B, int Q, int H, int W) {
+  const long long npix = (long long)B * H * W;
+  return ((npix * 2 + 255) / 256 * 256) + ((npix + 255) / 256 * 256) + 4LL * B * Q * 4 + 256;
+}
+
+extern "C" int odise_panoptic_inference_f32(const float* logits, const float* scores, const int32_t* labels,
+                                            const int32_t* keep, const uint8_t* is_thing, int32_t* pan,
+                                            int32_t* seg_info, int32_t* n_segments, void* ws, int B, int Q, int K,
+                                            int hs, int ws_, int H, int W, double overlap_thr, void* stream) {
+  if (!logits || !scores || !labels || !keep || !is_thing || !pan || !seg_info || !n_segments || !ws) return ODISE_ERR_ARG;
+  if (B <= 0 || Q <= 0 || Q > 32767 || K <= 0 || K * 4 > 48 * 1024) return ODISE_ERR_ARG;
+  cudaStream_t st = STREAM(stream);
+  const long long npix = (long long)B * H * W;
+  uint8_t* base = reinterpret_cast<uint8_t*>(ws);
+  int16_t* ids = reinterpret_cast<int16_t*>(base);
+  uint8_t* fg = base + (npix * 2 + 255) / 256 * 256;
+  int32_t* counters = reinterpret_cast<int32_t*>(fg + (npix + 255) / 256 * 256);
+  int32_t *area = counters, *orig = counters + B * Q, *inter = counters + 2 * B * Q, *seg_of = counters + 3 * B * Q;
+  cudaError_t e = cudaMemsetAsync(counters, 0, sizeof(int32_t) * 3 * B * Q, st);
+  if (e != cudaSuccess) return (int)e;
+  int blocks = (int)(((long long)H * W + 255) / 256);
+  if (blocks > 148 * 4) blocks = 148 * 4;
+  panoptic_argmax_kernel<<<dim3(blocks, B), 256, 3 * Q * sizeof(int32_t), st>>>(logits, scores, keep, ids, fg, area, orig,
+                                                                            inter, Q, hs, ws_, H, W);
+  panoptic_assign_kernel<<<B, 32, K * sizeof(int32_t), st>>>(keep, labels, area, orig, inter, is_thing, seg_of, seg_info,
+                                                          n_segments, Q, K, overlap_thr);
+  int rb = (int)((npix + 255) / 256);
+  if (rb > 148 * 8) rb = 148 * 8;
+  panoptic_relabel_kernel<<<rb, 256, 0, st>>>(ids, fg, seg_of, pan, Q, (long long)H * W, B);
+  count_launch(3);
+  return (int)cudaGetLastError();
+}

@@ -1,0 +1,66 @@
+"""Device-side post-processing: the tail of CategoryODISE.forward without a clip_head
+(odise/modeling/meta_arch/odise.py:326-370) — bilinear mask upsample, MaskFormer.semantic_inference and
+MaskFormer.panoptic_inference (maskformer_model.py:280-342) with no host round trips: the reference syncs ~4x per
+query through `.item()`.  Output sizes must equal the padded input size (sem_seg_postprocess is then the identity)."""
+import torch
+
+from . import lib, ops
+from .lib import Planes, _check, _ptr, _stream, load
+
+
+class PostProcessor:
+    def __init__(self, device, num_classes, thing_ids, object_mask_threshold=0.0, overlap_threshold=0.8, nmma=3):
+        self.dev = torch.device(device)
+        self.K = num_classes
+        self.nmma, self.lo = nmma, nmma == 3
+        it = torch.zeros(num_classes, dtype=torch.uint8)
+        it[list(thing_ids)] = 1
+        self.is_thing = it.to(self.dev)
+        self.obj_thr, self.ov_thr = float(object_mask_threshold), float(overlap_threshold)
+
+    @torch.no_grad()
+    def __call__(self, pred_logits, pred_masks, H, W, semantic=True, panoptic=True):
+        """pred_logits [B, Q, K+1], pred_masks [B, Q, h, w] (device fp32) ->
+        dict(sem_seg [B, K, H, W], panoptic_seg int32 [B, H, W], seg_info int32 [B, Q, 3], n_segments int32 [B])."""
+        B, Q, K1 = pred_logits.shape
+        assert K1 == self.K + 1
+        hs, ws = pred_masks.shape[-2:]
+        dev, L = self.dev, load()
+        Qp = (Q + 7) // 8 * 8
+        probs_t = torch.zeros(B * self.K, Qp, dtype=torch.float32, device=dev) if semantic else None
+        scores = torch.empty(B * Q, dtype=torch.float32, device=dev)
+        labels = torch.empty(B * Q, dtype=torch.int32, device=dev)
+        keep = torch.empty(B * Q, dtype=torch.int32, device=dev)
+        cl = pred_logits.contiguous()
+        _check(L.odise_query_scores_f32(_ptr(cl), None, _ptr(probs_t), _ptr(scores), _ptr(labels), _ptr(keep), B, Q, Qp,
+                                        K1, self.obj_thr, _stream()), "query_scores")
+        out = {}
+        pm = pred_masks.contiguous()
+        if semantic:
+            sig = Planes.empty(B * H * W, Qp, dev, lo=self.lo, ld=Qp)
+            _check(L.odise_upsample_sigmoid_split_f32(_ptr(pm), _ptr(sig.hi), _ptr(sig.lo), None, B, Q, Qp, hs, ws, H, W,
+                                                      _stream()), "upsample_sigmoid")
+            # sem[b] = P_b^T [K, Q] @ sig_b^T [Q, HW]: swapped-operand GEMM writes the reference's [K, H, W] layout
+            ptp = ops.split(probs_t, lo=self.lo)
+            sem = torch.empty(B, self.K, H * W, dtype=torch.float32, device=dev)
+            lib.gemm(ptp, sig, M=self.K, N=H * W, K=Qp, nmma=self.nmma, batch=B, a_bs=self.K * ptp.ld, b_bs=H * W * sig.ld,
+                     out=sem, ld_out=H * W, out_bs=self.K * H * W)
+            out["sem_seg"] = sem.view(B, self.K, H, W)
+        if panoptic:
+            pan = torch.empty(B, H, W, dtype=torch.int32, device=dev)
+            seg_info = torch.zeros(B, Q, 3, dtype=torch.int32, device=dev)
+            nseg = torch.empty(B, dtype=torch.int32, device=dev)
+            wsb = torch.empty(int(L.odise_panoptic_ws_bytes(B, Q, H, W)), dtype=torch.uint8, device=dev)
+            _check(L.odise_panoptic_inference_f32(_ptr(pm), _ptr(scores), _ptr(labels), _ptr(keep), _ptr(self.is_thing),
+                                                  _ptr(pan), _ptr(seg_info), _ptr(nseg), _ptr(wsb), B, Q, self.K, hs, ws,
+                                                  H, W, self.ov_thr, _stream()), "panoptic_inference")
+            out.update(panoptic_seg=pan, seg_info=seg_info, n_segments=nseg)
+        out.update(scores=scores.view(B, Q), labels=labels.view(B, Q), keep=keep.view(B, Q))
+        return out
+
+    @staticmethod
+    def segments_info(seg_info, n_segments):
+        """host-side view (one D2H at the very end): list per image of dicts like the reference's."""
+        si, ns = seg_info.cpu(), n_segments.cpu()
+        return [[{"id": int(r[0]), "isthing": bool(r[1]), "category_id": int(r[2])} for r in si[b, :int(ns[b])]]
+                for b in range(si.shape[0])]

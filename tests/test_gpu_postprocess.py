@@ -1,0 +1,48 @@
+"""GPU parity of the device-side post-processing (odise_b200/postprocess.py) vs oracle/postprocess.py
+(== the reference's MaskFormer.semantic_inference / panoptic_inference, tests/test_oracle_cpu.py)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _case(seed, B, Q, K, h, w):
+    g = torch.Generator().manual_seed(seed)
+    cls = torch.randn(B, Q, K + 1, generator=g) * 3
+    cls[..., -1] -= 2.0                                    # most queries are "objects"
+    # blobby masks so that segments survive the overlap test
+    yy, xx = torch.meshgrid(torch.arange(h).float(), torch.arange(w).float(), indexing="ij")
+    masks = torch.empty(B, Q, h, w)
+    for b in range(B):
+        for q in range(Q):
+            cy, cx = torch.rand(2, generator=g) * torch.tensor([h, w])
+            r = 2 + torch.rand(1, generator=g) * min(h, w) / 3
+            masks[b, q] = (r - ((yy - cy) ** 2 + (xx - cx) ** 2).sqrt()) * 2 + torch.randn(h, w, generator=g) * 0.3
+    return cls, masks
+
+
+@pytest.mark.parametrize("cfg", [(1, 2, 20, 7, 24, 32, 4), (2, 1, 100, 150, 64, 64, 4), (3, 2, 50, 19, 32, 48, 2)])
+def test_postprocess(cuda, cfg):
+    from odise_b200.postprocess import PostProcessor
+    from oracle import postprocess as opp
+    seed, B, Q, K, h, w, up = cfg
+    H, W = h * up, w * up
+    cls, masks = _case(seed, B, Q, K, h, w)
+    things = list(range(0, K, 2))
+    pp = PostProcessor(cuda, K, things)
+    out = pp(cls.to(cuda), masks.to(cuda), H, W)
+    torch.cuda.synchronize()
+    infos = pp.segments_info(out["seg_info"], out["n_segments"])
+    n_nonempty = 0
+    for b in range(B):
+        up_masks = opp.upsample_masks(masks[b:b + 1], (H, W))[0]
+        sem = opp.semantic_inference(cls[b], up_masks)
+        got = out["sem_seg"][b].cpu()
+        rel = ((got.double() - sem.double()).abs().max() / sem.abs().max()).item()
+        assert rel < 1e-4, rel
+        pan, info = opp.panoptic_inference(cls[b], up_masks, K, things)
+        assert info == infos[b], (info, infos[b])
+        agree = (out["panoptic_seg"][b].cpu() == pan).float().mean().item()
+        assert agree > 0.9995, agree          # ties at sigmoid == 0.5 / argmax rounding may flip isolated pixels
+        n_nonempty += len(info) > 0
+    assert n_nonempty > 0
