@@ -34,11 +34,20 @@ class ODISEEngine:
         self.vocab_key = None
         self.launches_per_step = None
 
-    def set_vocabulary(self, key, text_bank, null_bank, group_sizes):
+    def set_vocabulary(self, key, text_bank, null_bank, group_sizes, thing_ids=None):
         """OpenPanopticInference / CategoryEmbed.test_labels analogue (pano_wrapper.py:58-68, odise.py:1281-1307):
-        the vocabulary is a [K', 768] CLIP text bank + per-class prompt counts."""
+        the vocabulary is a [K', 768] CLIP text bank + per-class prompt counts (+ which classes are "things" for
+        the panoptic merge, metadata.thing_dataset_id_to_contiguous_id in the reference)."""
         self.head.set_vocabulary(key, text_bank, null_bank, group_sizes)
         self.vocab_key = key
+        from .postprocess import PostProcessor
+        K = len(group_sizes)
+        self.post = PostProcessor(self.dev, K, thing_ids if thing_ids is not None else range(0, K, 2), nmma=self.nmma)
+
+    @torch.no_grad()
+    def postprocess(self, out, H, W, semantic=True, panoptic=True):
+        """semantic / panoptic inference on the device (odise.py:335-370 without a clip_head)."""
+        return self.post(out["pred_logits"], out["pred_masks"], H, W, semantic=semantic, panoptic=panoptic)
 
     # ------------------------------------------------------------------------------------------- device step
     @torch.no_grad()

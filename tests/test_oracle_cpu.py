@@ -153,3 +153,30 @@ def test_q_sample_constants():
     assert abs(a - 0.999575) < 1e-6 and abs(b - 0.029155) < 1e-6
     n = oldm.shared_noise()
     assert n.shape == (1, 4, 64, 64)
+
+
+@needs_ref
+@torch.no_grad()
+def test_postprocess_oracle_equals_reference_methods():
+    """oracle/postprocess.py vs the reference's MaskFormer.semantic_inference / panoptic_inference
+    (maskformer_model.py:280-342) called on a fake self through the shim."""
+    import importlib
+    from oracle import postprocess as opp
+    refshim.install()
+    MF = importlib.import_module("mask2former.maskformer_model").MaskFormer
+    g = torch.Generator().manual_seed(4)
+    Q, K, H, W = 30, 9, 40, 56
+    cls = torch.randn(Q, K + 1, generator=g) * 3
+    cls[:, -1] -= 2
+    yy, xx = torch.meshgrid(torch.arange(H).float(), torch.arange(W).float(), indexing="ij")
+    pred = torch.stack([(6 + 10 * torch.rand(1, generator=g) - ((yy - torch.rand(1, generator=g) * H) ** 2 +
+                                                               (xx - torch.rand(1, generator=g) * W) ** 2).sqrt()) * 2
+                        for _ in range(Q)])
+    things = [0, 2, 4]
+    fake = types.SimpleNamespace(sem_seg_head=types.SimpleNamespace(num_classes=K), object_mask_threshold=0.0,
+                                 overlap_threshold=0.8, num_queries=Q, test_topk_per_image=10, panoptic_on=True,
+                                 metadata=types.SimpleNamespace(thing_dataset_id_to_contiguous_id={i: t for i, t in enumerate(things)}))
+    assert torch.equal(MF.semantic_inference(fake, cls, pred), opp.semantic_inference(cls, pred))
+    pr, ir = MF.panoptic_inference(fake, cls, pred)
+    po, io = opp.panoptic_inference(cls, pred, K, things)
+    assert torch.equal(pr, po) and ir == io and len(ir) > 0
