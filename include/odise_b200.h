@@ -191,11 +191,14 @@ int odise_nhwc_to_nchw_f32(const float* src, long long lds, float* dst, int B, i
  * vt [vt_rows >= heads*HS, ldvt >= B*tk_stride] with vt[h*HS + j][b*tk_stride + t] = v[b, t, h, j] (the projection
  * GEMM writes it directly by swapping its operands).  tk_stride >= Tk is the per-image row count of the key /
  * value planes (multiple of 8: TMA box starts must be 16-byte aligned); keys t >= Tk are masked out.  d % 8 == 0, d <= 80 (larger heads: odise_gemm_bf16 + odise_softmax_split_f32).
- * out fp32 and/or (hi, lo) planes, UNPADDED [B*Tq, heads*d] with row stride ldo. */
+ * out fp32 and/or (hi, lo) planes, UNPADDED [B*Tq, heads*d] with row stride ldo.
+ * mask_bits / row_any (optional, from odise_attn_mask_bits_f32): the Mask2Former decoder's masked cross-attention
+ * (d = 32) on the same tensor-core kernel — key k of row (b, t) is dropped when its bit is 0 and row_any != 0. */
 int odise_attention_tc(const void* q_hi, const void* q_lo, long long ldq, const void* k_hi, const void* k_lo,
                        long long ldk, const void* vt_hi, const void* vt_lo, long long ldvt, long long vt_rows,
                        float* out, void* out_hi, void* out_lo, long long ldo, int B, int heads, int d, int Tq,
-                       int Tk, int tk_stride, float scale, int nmma, void* stream);
+                       int Tk, int tk_stride, float scale, int nmma, const uint32_t* mask_bits,
+                       const int32_t* row_any, void* stream);
 /* row softmax of scale * x over the first `cols` columns -> (hi, lo) planes [rows, ldo], columns [cols, cols_pad)
  * written as zeros (the unfused attention path for head dims > 80 and the VAE mid-block attention). */
 int odise_softmax_split_f32(const float* x, long long ldx, void* hi, void* lo, long long ldo, long long rows,

@@ -26,6 +26,8 @@ struct AttnParams {
   __nv_bfloat16* out_hi;
   __nv_bfloat16* out_lo;
   long long ldo;
+  const uint32_t* bits;     // optional [B, Tq, ceil(Tk/32)]: bit = key may be attended (Mask2Former masked attention)
+  const int32_t* row_any;   // [B, Tq]: 0 -> the row ignores the mask (odise.py:683 fix-up)
 };
 
 __device__ __forceinline__ float fast_exp2(float x) {
@@ -202,6 +204,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__
     const int row = quad * 32 + lane;
     const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
     float m = -INFINITY, l = 0.f, alpha_pending = 1.f;
+    const int n_words = (p.Tk + 31) / 32;
+    const uint32_t* mask_words = nullptr;
+    if (p.bits && q0 + row < p.Tq && p.row_any[(long long)b * p.Tq + q0 + row] != 0)
+      mask_words = p.bits + ((long long)b * p.Tq + q0 + row) * n_words;
     float acc[DP];
 #pragma unroll
     for (int i = 0; i < DP; ++i) acc[i] = 0.f;
@@ -245,13 +251,23 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__
 #pragma unroll
         for (int i = 0; i < 64; ++i) if (i >= valid) s[i] = -INFINITY;
       }
+      if (mask_words) {                 // per-row predicted-mask bits (masked cross-attention)
+        const uint32_t w0 = __ldg(mask_words + 2 * j);
+        const uint32_t w1 = (2 * j + 1 < n_words) ? __ldg(mask_words + 2 * j + 1) : 0u;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          if (!((w0 >> i) & 1u)) s[i] = -INFINITY;
+          if (!((w1 >> i) & 1u)) s[32 + i] = -INFINITY;
+        }
+      }
       // running max on the raw scores (scale > 0), exponent as one FFMA + ex2: p = 2^(s*c - m*c)
       float mx = m;
 #pragma unroll
       for (int i = 0; i < 64; ++i) mx = fmaxf(mx, s[i]);
       const float c = p.scale_log2;
-      const float alpha = fast_exp2((m - mx) * c);  // first block: exp2(-inf) = 0
-      const float mc = -mx * c;
+      // guards: a row may have seen no attendable key yet (mx = -inf) -> p = 0, nothing to rescale
+      const float alpha = (m == -INFINITY) ? 0.f : fast_exp2((m - mx) * c);
+      const float mc = (mx == -INFINITY) ? 0.f : -mx * c;
       float sum = 0.f;
 #pragma unroll
       for (int i = 0; i < 64; ++i) {
@@ -374,7 +390,7 @@ extern "C" int odise_attention_tc(const void* q_hi, const void* q_lo, long long 
                                   const void* k_lo, long long ldk, const void* vt_hi, const void* vt_lo,
                                   long long ldvt, long long vt_rows, float* out, void* out_hi, void* out_lo,
                                   long long ldo, int B, int heads, int d, int Tq, int Tk, int tk_stride, float scale,
-                                  int nmma, void* stream_v) {
+                                  int nmma, const uint32_t* mask_bits, const int32_t* row_any, void* stream_v) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
   if (!q_hi || !k_hi || !vt_hi || (!out && !out_hi)) return ODISE_ERR_ARG;
   if (nmma != 1 && nmma != 3) return ODISE_ERR_ARG;
@@ -383,10 +399,11 @@ extern "C" int odise_attention_tc(const void* q_hi, const void* q_lo, long long 
   // TMA needs 16-byte aligned box starts: tokens are the inner dimension of v^T
   if (tk_stride % 8) return ODISE_ERR_ALIGN;
   const int TkS = tk_stride;
+  if (mask_bits && !row_any) return ODISE_ERR_ARG;
   int DP;
-  if (d <= 48) DP = 48; else if (d <= 80) DP = 80; else return ODISE_ERR_UNSUPPORTED;
+  if (d <= 32) DP = 32; else if (d <= 48) DP = 48; else if (d <= 80) DP = 80; else return ODISE_ERR_UNSUPPORTED;
   if (d % 8) return ODISE_ERR_UNSUPPORTED;
-  const int HS = DP == 48 ? 64 : 128;
+  const int HS = DP <= 48 ? 64 : 128;
   if (ldq % 8 || ldk % 8 || ldvt % 8 || ldq < (long long)heads * HS || ldk < (long long)heads * HS ||
       vt_rows < (long long)heads * HS || ldvt < (long long)B * TkS)
     return ODISE_ERR_ALIGN;
@@ -404,7 +421,9 @@ extern "C" int odise_attention_tc(const void* q_hi, const void* q_lo, long long 
   p.scale_log2 = scale * 1.4426950408889634f;
   p.out = out; p.out_hi = reinterpret_cast<__nv_bfloat16*>(out_hi); p.out_lo = reinterpret_cast<__nv_bfloat16*>(out_lo);
   p.ldo = ldo;
-  if (DP == 48) rc = nmma == 3 ? attn_launch<48, 3>(m, p, stream) : attn_launch<48, 1>(m, p, stream);
+  p.bits = mask_bits; p.row_any = row_any;
+  if (DP == 32) rc = nmma == 3 ? attn_launch<32, 3>(m, p, stream) : attn_launch<32, 1>(m, p, stream);
+  else if (DP == 48) rc = nmma == 3 ? attn_launch<48, 3>(m, p, stream) : attn_launch<48, 1>(m, p, stream);
   else rc = nmma == 3 ? attn_launch<80, 3>(m, p, stream) : attn_launch<80, 1>(m, p, stream);
   if (rc) return rc;
   count_launch(1);

@@ -97,12 +97,15 @@ class HeadEngine:
         self.dec_level_embed = sd[dp + "level_embed.weight"].float()
         self.F["query_embed"] = self._f(sd[dp + "query_embed.weight"])
         self.query_feat = sd[dp + "query_feat.weight"].float()
-        for lvl in range(3):   # K / V projections of the layers that read level lvl, concatenated along N
+        for lvl in range(3):   # K / V projections of the layers that read level lvl, concatenated along N and
+            # head-padded 32 -> 64 columns per head (zero rows): the operands of the tcgen05 attention kernel
             ids = [i for i in range(self.n_dec) if i % 3 == lvl]
-            wk = torch.cat([sd[f"{dp}transformer_cross_attention_layers.{i}.multihead_attn.in_proj_weight"][C:2 * C] for i in ids])
-            bk = torch.cat([sd[f"{dp}transformer_cross_attention_layers.{i}.multihead_attn.in_proj_bias"][C:2 * C] for i in ids])
-            wv = torch.cat([sd[f"{dp}transformer_cross_attention_layers.{i}.multihead_attn.in_proj_weight"][2 * C:] for i in ids])
-            bv = torch.cat([sd[f"{dp}transformer_cross_attention_layers.{i}.multihead_attn.in_proj_bias"][2 * C:] for i in ids])
+            pad = lambda w: ops.head_pad_rows(w, M_HEADS, D_HEAD, 64)
+            padb = lambda b: ops.head_pad_rows(b.view(-1, 1), M_HEADS, D_HEAD, 64).view(-1)
+            wk = torch.cat([pad(sd[f"{dp}transformer_cross_attention_layers.{i}.multihead_attn.in_proj_weight"][C:2 * C]) for i in ids])
+            bk = torch.cat([padb(sd[f"{dp}transformer_cross_attention_layers.{i}.multihead_attn.in_proj_bias"][C:2 * C]) for i in ids])
+            wv = torch.cat([pad(sd[f"{dp}transformer_cross_attention_layers.{i}.multihead_attn.in_proj_weight"][2 * C:]) for i in ids])
+            bv = torch.cat([padb(sd[f"{dp}transformer_cross_attention_layers.{i}.multihead_attn.in_proj_bias"][2 * C:]) for i in ids])
             self._lin(f"dec.k{lvl}", wk, bk)
             self._lin(f"dec.v{lvl}", wv, bv)
         for i in range(self.n_dec):
@@ -110,7 +113,8 @@ class HeadEngine:
                        f"{dp}transformer_ffn_layers.{i}.")
             n = f"dec.l{i}."
             w, b = sd[c + "multihead_attn.in_proj_weight"], sd[c + "multihead_attn.in_proj_bias"]
-            self._lin(n + "cq", w[:C], b[:C])
+            self._lin(n + "cq", ops.head_pad_rows(w[:C], M_HEADS, D_HEAD, 64),
+                      ops.head_pad_rows(b[:C].view(-1, 1), M_HEADS, D_HEAD, 64).view(-1))
             self._lin(n + "co", sd[c + "multihead_attn.out_proj.weight"], sd[c + "multihead_attn.out_proj.bias"])
             self._norm(n + "cn", sd, c + "norm")
             w, b = sd[s + "self_attn.in_proj_weight"], sd[s + "self_attn.in_proj_bias"]
@@ -282,16 +286,18 @@ class HeadEngine:
         _, kin_p = ops.add_split(mem, g["dec_kpos"], b_rows=S, lo=self.lo)
         _, vin_p = ops.add_split(mem, g["dec_lvl"], b_rows=S, lo=self.lo)
         K, V = [], []
+        CP = M_HEADS * 64                      # head-padded width of one layer's K / V
         for lvl, (h, w) in enumerate(shapes):
             hw = h * w
-            k = torch.empty(B, hw, 768, dtype=torch.float32, device=dev)
-            v = torch.empty(B, hw, 768, dtype=torch.float32, device=dev)
-            lib.gemm(kin_p.row_slice(starts[lvl], hw), self.W[f"dec.k{lvl}"], M=hw, N=768, K=256, nmma=self.nmma, batch=B,
-                     a_bs=S * kin_p.ld, bias=self.F[f"dec.k{lvl}.b"], out=k, ld_out=768, out_bs=hw * 768)
-            lib.gemm(vin_p.row_slice(starts[lvl], hw), self.W[f"dec.v{lvl}"], M=hw, N=768, K=256, nmma=self.nmma, batch=B,
-                     a_bs=S * vin_p.ld, bias=self.F[f"dec.v{lvl}.b"], out=v, ld_out=768, out_bs=hw * 768)
+            k = Planes.empty(B * hw, 3 * CP, dev, lo=self.lo)            # [B*hw, 3 layers x 8 heads x 64]
+            lib.gemm(kin_p.row_slice(starts[lvl], hw), self.W[f"dec.k{lvl}"], M=hw, N=3 * CP, K=256, nmma=self.nmma,
+                     batch=B, a_bs=S * kin_p.ld, bias=self.F[f"dec.k{lvl}.b"], out_planes=k, outp_bs=hw * k.ld)
+            # V^T [3*CP, B*hw]: swapped operands, image z lands at column offset z*hw
+            vt = Planes.empty(3 * CP, B * hw, dev, lo=self.lo)
+            lib.gemm(self.W[f"dec.v{lvl}"], vin_p.row_slice(starts[lvl], hw), M=3 * CP, N=hw, K=256, nmma=self.nmma,
+                     batch=B, b_bs=S * vin_p.ld, bias_m=self.F[f"dec.v{lvl}.b"], out_planes=vt, outp_bs=hw)
             K.append(k)
-            V.append(v)
+            V.append(vt)
         fm = (lambda i: None) if forced_masks is None else (lambda i: forced_masks[i])
         output = g["query0"]
         heads = []
@@ -305,10 +311,10 @@ class HeadEngine:
             n = f"dec.l{i}."
             # masked cross-attention (mask2former_transformer_decoder.py:98-110, odise.py:683-692)
             _, qin_p = ops.add_split(output, qe, b_rows=Q, lo=self.lo)
-            qc = ops.empty(B * Q, 256, dev)
-            self._gemm(qin_p, n + "cq", out=qc)
-            o_p = ops.mha_d32(qc, 256, K[lvl][:, :, slot * 256:], V[lvl][:, :, slot * 256:], 768, B, Q, hw, M_HEADS,
-                              scale, bits, row_any, lo=self.lo)
+            qc = Planes.empty(B * Q, CP, dev, lo=self.lo)
+            self._gemm(qin_p, n + "cq", out_planes=qc)
+            _, o_p = ops.attention_tc(qc, K[lvl].col_slice(slot * CP, CP), V[lvl].row_slice(slot * CP, CP), B, M_HEADS,
+                                      D_HEAD, Q, hw, scale, self.nmma, tk_stride=hw, mask_bits=bits, row_any=row_any)
             t = ops.empty(B * Q, 256, dev)
             self._gemm(o_p, n + "co", residual=output, out=t)
             output, _ = self._ln(t, n + "cn", want_f32=True, want_planes=False)

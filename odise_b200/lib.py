@@ -106,7 +106,7 @@ _SIGS = {
     "odise_panoptic_inference_f32": [c_void_p] * 9 + [c_int] * 7 + [ctypes.c_double, c_void_p],
     "odise_attention_tc": [c_void_p, c_void_p, c_longlong, c_void_p, c_void_p, c_longlong, c_void_p, c_void_p,
                            c_longlong, c_longlong, c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_int, c_int,
-                           c_int, c_int, c_int, c_float, c_int, c_void_p],
+                           c_int, c_int, c_int, c_float, c_int, c_void_p, c_void_p, c_void_p],
 }
 
 

@@ -135,7 +135,8 @@ def nhwc_to_nchw(x, B, H, W):
     return y
 
 
-def attention_tc(q, k, vt, B, heads, d, Tq, Tk, scale, nmma, want_f32=False, want_planes=True, tk_stride=None):
+def attention_tc(q, k, vt, B, heads, d, Tq, Tk, scale, nmma, want_f32=False, want_planes=True, tk_stride=None,
+                 mask_bits=None, row_any=None):
     """q, k head-padded Planes; vt Planes [heads*HS, >= B*Tk]. Returns (fp32 | None, Planes | None) [B*Tq, heads*d]."""
     dev = q.hi.device
     C = heads * d
@@ -144,7 +145,7 @@ def attention_tc(q, k, vt, B, heads, d, Tq, Tk, scale, nmma, want_f32=False, wan
     _check(load().odise_attention_tc(_ptr(q.hi), _ptr(q.lo), q.ld, _ptr(k.hi), _ptr(k.lo), k.ld, _ptr(vt.hi),
                                      _ptr(vt.lo), vt.ld, vt.rows, _ptr(out), _ptr(p.hi) if p else None,
                                      _ptr(p.lo) if p else None, p.ld if p else C, B, heads, d, Tq, Tk, tk_stride or Tk, scale, nmma,
-                                     _stream()), "attention_tc")
+                                     _ptr(mask_bits), _ptr(row_any), _stream()), "attention_tc")
     return out, p
 
 
@@ -164,7 +165,7 @@ def head_pad_rows(w, heads, d, HS):
 
 
 def head_stride(d):
-    if d <= 48:
+    if d <= 48:    # incl. the decoder's d = 32
         return 64
     if d <= 80:
         return 128

@@ -40,7 +40,7 @@ def test_argument_validation_without_gpu(built):
     d = lib.GemmDesc()
     assert L.odise_gemm_bf16(ctypes.byref(d), None) == 10001
     assert L.odise_attention_tc(None, None, 0, None, None, 0, None, None, 0, 0, None, None, None, 0, 1, 1, 40, 1, 1, 8,
-                                1.0, 3, None) == 10001
+                                1.0, 3, None, None, None) == 10001
     assert L.odise_split_f32(None, 0, None, None, 0, 1, 4, None) == 10001
 
 

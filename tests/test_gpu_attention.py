@@ -50,3 +50,40 @@ def test_softmax_split(cuda):
     ref = (x.double() * 0.5).softmax(-1)
     got = p.float()
     assert _rel(got[:, :77], ref) < 2e-5 and got[:, 77:].abs().max() == 0
+
+
+@pytest.mark.parametrize("nmma", [3, 1])
+@pytest.mark.parametrize("cfg", [(2, 100, 32 * 32, 64, 64), (1, 100, 64 * 64, 256, 256), (2, 37, 8 * 8, 32, 32)])
+def test_masked_attention_tc_d32(cuda, nmma, cfg):
+    """Mask2Former masked cross-attention (odise.py:683-692, 760-774) on the tcgen05 kernel: head dim 32, mask bits from
+    odise_attn_mask_bits_f32, fully-masked rows attend everywhere."""
+    import torch.nn.functional as F
+    from odise_b200 import lib, ops
+    B, Tq, Tk, Hm, Wm = cfg
+    heads, d, HS = 8, 32, 64
+    Hl = Wl = int(Tk ** 0.5)
+    g = torch.Generator().manual_seed(Tk + Tq)
+    q = torch.randn(B, Tq, heads, d, generator=g).to(cuda)
+    k = torch.randn(B, Tk, heads, d, generator=g).to(cuda)
+    v = torch.randn(B, Tk, heads, d, generator=g).to(cuda)
+    ml = (torch.randn(B, Tq, Hm, Wm, generator=g) * 3 - 2.0).to(cuda)
+    ml[0, 3] = -5.0                      # fully masked row -> must attend everywhere
+    ml[0, 5, : Hm // 2] = -9.0           # first key blocks fully masked for this row (exercises the -inf guards)
+    bits, row_any = ops.attn_mask_bits(ml, B, Tq, Hm, Wm, Hl, Wl)
+    qp = torch.zeros(B * Tq, heads, HS, device=cuda)
+    qp[:, :, :d] = q.view(B * Tq, heads, d)
+    kp = torch.zeros(B * Tk, heads, HS, device=cuda)
+    kp[:, :, :d] = k.view(B * Tk, heads, d)
+    vt = torch.zeros(heads, HS, B * Tk, device=cuda)
+    vt[:, :d] = v.view(B * Tk, heads, d).permute(1, 2, 0)
+    scale = d ** -0.5
+    out, _ = ops.attention_tc(lib.split(qp.view(B * Tq, -1)), lib.split(kp.view(B * Tk, -1)), lib.split(vt.view(heads * HS, -1)),
+                              B, heads, d, Tq, Tk, scale, nmma, want_f32=True, want_planes=False, tk_stride=Tk,
+                              mask_bits=bits, row_any=row_any)
+    torch.cuda.synchronize()
+    am = F.interpolate(ml, size=(Hl, Wl), mode="bilinear", align_corners=False).sigmoid().flatten(2) < 0.5
+    am[torch.where(am.sum(-1) == am.shape[-1])] = False
+    s = torch.einsum("bqhd,bkhd->bhqk", q.double(), k.double()) * scale
+    s = s.masked_fill(am[:, None], float("-inf"))
+    ref = torch.einsum("bhqk,bkhd->bqhd", s.softmax(-1), v.double()).reshape(B * Tq, heads * d)
+    assert _rel(out, ref) < (3e-5 if nmma == 3 else 3e-2)
