@@ -244,7 +244,19 @@ __global__ void gn_partial_kernel(const float* __restrict__ x, long long ldx, lo
 #pragma unroll
     for (int t = 0; t < 4; ++t) pv[t] = __ldg(xb + ((q * 4 + t) / cpg) * cpg);
     const int p0 = chunk * pix_per_chunk, p1 = min(HW, p0 + pix_per_chunk);
-    for (int p = p0 + pl; p < p1; p += PL) {
+    int p = p0 + pl;
+    for (; p + 3 * PL < p1; p += 4 * PL) {   // 4 independent 16-byte loads in flight per thread
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = *reinterpret_cast<const float4*>(xb + (long long)(p + u * PL) * ldx + q * 4);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float d0 = v[u].x - pv[0], d1 = v[u].y - pv[1], d2 = v[u].z - pv[2], d3 = v[u].w - pv[3];
+        s[0] += d0; s[1] += d1; s[2] += d2; s[3] += d3;
+        ss[0] = fmaf(d0, d0, ss[0]); ss[1] = fmaf(d1, d1, ss[1]); ss[2] = fmaf(d2, d2, ss[2]); ss[3] = fmaf(d3, d3, ss[3]);
+      }
+    }
+    for (; p < p1; p += PL) {
       const float4 v = *reinterpret_cast<const float4*>(xb + (long long)p * ldx + q * 4);
       const float d0 = v.x - pv[0], d1 = v.y - pv[1], d2 = v.z - pv[2], d3 = v.w - pv[3];
       s[0] += d0; s[1] += d1; s[2] += d2; s[3] += d3;
