@@ -35,6 +35,7 @@ extern "C" {
 #define ODISE_ACT_RELU 1
 #define ODISE_ACT_SILU 2
 #define ODISE_ACT_GELU 3
+#define ODISE_ACT_QUICKGELU 4 /* x * sigmoid(1.702 x): open_clip QuickGELU (CLIP ViT MLP) */
 
 int odise_version(void);
 /* number of kernels launched through this library since load (bench.py "gpu_launches") */
@@ -179,6 +180,14 @@ int odise_image_crops_u8_f32(const uint8_t* img, float* out, const int32_t* boxe
 /* same for a float NCHW image already in [0, 1] (the Backbone plugin input, feature_extractor.py:252) */
 int odise_image_crops_f32(const float* img, float* out, const int32_t* boxes, int n_crops, int H, int W, int ch, int cw,
                           void* stream);
+/* CLIP image preprocessing of crops (clip.py:94: bicubic Resize(S) without antialias + CenterCrop(S) + Normalize with
+ * the CLIP mean / std): img uint8 (0..255) or float32 in [0, 1], NCHW [N, 3, H, W]; boxes as above; square crops;
+ * out NHWC fp32 [n_crops, S, S, 3]. */
+int odise_clip_preprocess(const void* img, int img_is_u8, float* out, const int32_t* boxes, int n_crops, int H, int W,
+                          int ch, int cw, int S, void* stream);
+/* P x P non-overlapping patches of NHWC [B, S, S, 3] -> (hi, lo) rows [B*(S/P)^2, Kpad] with k = c*P*P + ky*P + kx
+ * (visual.conv1 as a GEMM, clip.py:179) */
+int odise_patchify_split_f32(const float* x, void* hi, void* lo, int B, int S, int P, int Kpad, void* stream);
 /* NHWC <-> NCHW transposes at the plugin boundary */
 int odise_nchw_to_nhwc_f32(const float* src, float* dst, long long ldd, int B, int C, int HW, void* stream);
 int odise_nhwc_to_nchw_f32(const float* src, long long lds, float* dst, int B, int C, int HW, void* stream);

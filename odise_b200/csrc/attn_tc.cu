@@ -44,8 +44,8 @@ struct AttnCfg {
   static constexpr int BK = 64;                      // keys per block
   static constexpr int STAGES = 2;                           // K stages
   // d = 40: one V stage + 256 TMEM columns so that TWO CTAs fit per SM (softmax of one overlaps the MMAs of the other)
-  static constexpr int VSTAGES = (DP <= 64) ? 1 : 2;
-  static constexpr int CTAS_PER_SM = (DP <= 64) ? 2 : 1;
+  static constexpr int VSTAGES = (DP <= 48) ? 1 : 2;
+  static constexpr int CTAS_PER_SM = (DP <= 48) ? 2 : 1;   // DP = 64 misses two CTAs by 512 B of shared memory
   static constexpr int Q_BYTES = NC * NP * 128 * 128;       // [chunk][plane][128 rows x 128 B]
   static constexpr int K_BYTES = NC * NP * BK * 128;        // per stage
   static constexpr int V_TILE = DP * 128;                   // one plane: DP rows x 64 tokens
@@ -401,9 +401,10 @@ extern "C" int odise_attention_tc(const void* q_hi, const void* q_lo, long long 
   const int TkS = tk_stride;
   if (mask_bits && !row_any) return ODISE_ERR_ARG;
   int DP;
-  if (d <= 32) DP = 32; else if (d <= 48) DP = 48; else if (d <= 80) DP = 80; else return ODISE_ERR_UNSUPPORTED;
+  if (d <= 32) DP = 32; else if (d <= 48) DP = 48; else if (d <= 64) DP = 64; else if (d <= 80) DP = 80;
+  else return ODISE_ERR_UNSUPPORTED;
   if (d % 8) return ODISE_ERR_UNSUPPORTED;
-  const int HS = DP <= 48 ? 64 : 128;
+  const int HS = DP <= 64 ? 64 : 128;
   if (ldq % 8 || ldk % 8 || ldvt % 8 || ldq < (long long)heads * HS || ldk < (long long)heads * HS ||
       vt_rows < (long long)heads * HS || ldvt < (long long)B * TkS)
     return ODISE_ERR_ALIGN;
@@ -423,6 +424,7 @@ extern "C" int odise_attention_tc(const void* q_hi, const void* q_lo, long long 
   p.ldo = ldo;
   p.bits = mask_bits; p.row_any = row_any;
   if (DP == 32) rc = nmma == 3 ? attn_launch<32, 3>(m, p, stream) : attn_launch<32, 1>(m, p, stream);
+  else if (DP == 64) rc = nmma == 3 ? attn_launch<64, 3>(m, p, stream) : attn_launch<64, 1>(m, p, stream);
   else if (DP == 48) rc = nmma == 3 ? attn_launch<48, 3>(m, p, stream) : attn_launch<48, 1>(m, p, stream);
   else rc = nmma == 3 ? attn_launch<80, 3>(m, p, stream) : attn_launch<80, 1>(m, p, stream);
   if (rc) return rc;

@@ -650,6 +650,78 @@ __global__ void image_crops_f32_kernel(const float* __restrict__ img, float* __r
   }
 }
 
+// ---------------------------------------------------------------------------------------------- CLIP front
+// clip_preprocess (odise/modeling/meta_arch/clip.py:94 = open_clip Resize(bicubic) + CenterCrop + Normalize) of a crop
+// of the image batch: bicubic (A = -0.75, align_corners=False, no antialias: torchvision 0.14 on tensors), indices
+// clamped to the CROP (the reference resizes the already-cropped tensor).  Output NHWC fp32 [n_crops, S, S, 3].
+__device__ __forceinline__ float cubic1(float x, float A) { return ((A + 2.f) * x - (A + 3.f)) * x * x + 1.f; }
+__device__ __forceinline__ float cubic2(float x, float A) { return ((A * x - 5.f * A) * x + 8.f * A) * x - 4.f * A; }
+
+template <typename T>
+__global__ void clip_preprocess_kernel(const T* __restrict__ img, float* __restrict__ out,
+                                       const int32_t* __restrict__ boxes, int n_crops, int H, int W, int ch, int cw,
+                                       int S, float in_scale, float m0, float m1, float m2, float s0, float s1,
+                                       float s2) {
+  const long long total = (long long)n_crops * S * S;
+  const float A = -0.75f;
+  // square crops only (ODISE crops are short x short): resize ch x cw -> S x S, the centre crop is then the identity
+  const float sy = (float)ch / (float)S, sx = (float)cw / (float)S;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int ox = (int)(i % S);
+    long long t = i / S;
+    const int oy = (int)(t % S);
+    const int b = (int)(t / S);
+    const int im = boxes[3 * b], y0 = boxes[3 * b + 1], x0 = boxes[3 * b + 2];
+    const float fy = (oy + 0.5f) * sy - 0.5f, fx = (ox + 0.5f) * sx - 0.5f;
+    const int iy = (int)floorf(fy), ix = (int)floorf(fx);
+    const float ty = fy - iy, tx = fx - ix;
+    const float wy[4] = {cubic2(ty + 1.f, A), cubic1(ty, A), cubic1(1.f - ty, A), cubic2(2.f - ty, A)};
+    const float wx[4] = {cubic2(tx + 1.f, A), cubic1(tx, A), cubic1(1.f - tx, A), cubic2(2.f - tx, A)};
+    const float mean[3] = {m0, m1, m2}, stdv[3] = {s0, s1, s2};
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const T* src = img + ((long long)im * 3 + c) * H * W;
+      float acc = 0.f;
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        const int yy = y0 + min(max(iy - 1 + a, 0), ch - 1);
+        float row = 0.f;
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+          const int xx = x0 + min(max(ix - 1 + d, 0), cw - 1);
+          row += wx[d] * ((float)src[(long long)yy * W + xx] * in_scale);
+        }
+        acc += wy[a] * row;
+      }
+      out[i * 3 + c] = (acc - mean[c]) / stdv[c];
+    }
+  }
+}
+
+// non-overlapping P x P patches of an NHWC image [B, S, S, 3] -> (hi, lo) rows [B*G*G, Kpad], k = c*P*P + ky*P + kx
+// (the layout of visual.conv1.weight.reshape(width, 3*P*P); clip.py:179)
+__global__ void patchify_split_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi,
+                                      __nv_bfloat16* __restrict__ lo, int B, int S, int P, int Kpad) {
+  const int G = S / P;
+  const long long total = (long long)B * G * G * Kpad;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(i % Kpad);
+    long long r = i / Kpad;
+    const int gx = (int)(r % G); r /= G;
+    const int gy = (int)(r % G);
+    const int b = (int)(r / G);
+    float v = 0.f;
+    if (k < 3 * P * P) {
+      const int c = k / (P * P), rem = k - c * P * P, ky = rem / P, kx = rem - ky * P;
+      v = x[(((long long)b * S + gy * P + ky) * S + gx * P + kx) * 3 + c];
+    }
+    __nv_bfloat16 h, l;
+    split_bf16(v, h, l);
+    hi[i] = h;
+    if (lo) lo[i] = l;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- softmax
 // one warp per row
 __global__ void softmax_split_kernel(const float* __restrict__ x, long long ldx, __nv_bfloat16* __restrict__ hi,
@@ -973,6 +1045,32 @@ extern "C" int odise_image_crops_f32(const float* img, float* out, const int32_t
   if (!img || !out || !boxes || n_crops <= 0 || H <= 0 || W <= 0 || ch <= 0 || cw <= 0) return ODISE_ERR_ARG;
   image_crops_f32_kernel<<<grid_for((long long)n_crops * ch * cw, 256), 256, 0, STREAM(stream)>>>(img, out, boxes,
                                                                                                 n_crops, H, W, ch, cw);
+  count_launch(1);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int odise_clip_preprocess(const void* img, int img_is_u8, float* out, const int32_t* boxes, int n_crops,
+                                     int H, int W, int ch, int cw, int S, void* stream) {
+  if (!img || !out || !boxes || n_crops <= 0 || H <= 0 || W <= 0 || ch <= 0 || cw <= 0 || S <= 0) return ODISE_ERR_ARG;
+  if (ch != cw) return ODISE_ERR_UNSUPPORTED;
+  const int blocks = grid_for((long long)n_crops * S * S, 256);
+  const float m0 = 0.48145466f, m1 = 0.4578275f, m2 = 0.40821073f, s0 = 0.26862954f, s1 = 0.26130258f, s2 = 0.27577711f;
+  if (img_is_u8)
+    clip_preprocess_kernel<uint8_t><<<blocks, 256, 0, STREAM(stream)>>>(reinterpret_cast<const uint8_t*>(img), out, boxes,
+                                                                        n_crops, H, W, ch, cw, S, 1.f / 255.f, m0, m1, m2,
+                                                                        s0, s1, s2);
+  else
+    clip_preprocess_kernel<float><<<blocks, 256, 0, STREAM(stream)>>>(reinterpret_cast<const float*>(img), out, boxes,
+                                                                      n_crops, H, W, ch, cw, S, 1.f, m0, m1, m2, s0, s1, s2);
+  count_launch(1);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int odise_patchify_split_f32(const float* x, void* hi, void* lo, int B, int S, int P, int Kpad, void* stream) {
+  if (!x || !hi || B <= 0 || S <= 0 || P <= 0 || S % P || Kpad < 3 * P * P || Kpad % 8) return ODISE_ERR_ARG;
+  const int G = S / P;
+  patchify_split_kernel<<<grid_for((long long)B * G * G * Kpad, 256), 256, 0, STREAM(stream)>>>(x, BF(hi), BF(lo), B, S,
+                                                                                            P, Kpad);
   count_launch(1);
   return (int)cudaGetLastError();
 }

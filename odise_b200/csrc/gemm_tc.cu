@@ -54,6 +54,7 @@ __device__ __forceinline__ float apply_act(float v, int act) {
   if (act == ODISE_ACT_RELU) return fmaxf(v, 0.f);
   if (act == ODISE_ACT_SILU) return v / (1.f + __expf(-v));
   if (act == ODISE_ACT_GELU) return 0.5f * v * (1.f + erff(v * 0.70710678118654752f));
+  if (act == ODISE_ACT_QUICKGELU) return v / (1.f + __expf(-1.702f * v));   // open_clip QuickGELU
   return v;
 }
 

@@ -12,7 +12,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "libodise_b200.so")
 
-ACT_NONE, ACT_RELU, ACT_SILU, ACT_GELU = 0, 1, 2, 3
+ACT_NONE, ACT_RELU, ACT_SILU, ACT_GELU, ACT_QUICKGELU = 0, 1, 2, 3, 4
 
 
 class OdiseError(RuntimeError):
@@ -84,6 +84,8 @@ _SIGS = {
                               c_int, c_int, c_void_p],
     "odise_image_crops_u8_f32": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
     "odise_image_crops_f32": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
+    "odise_clip_preprocess": [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p],
+    "odise_patchify_split_f32": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     "odise_nchw_to_nhwc_f32": [c_void_p, c_void_p, c_longlong, c_int, c_int, c_int, c_void_p],
     "odise_nhwc_to_nchw_f32": [c_void_p, c_longlong, c_void_p, c_int, c_int, c_int, c_void_p],
     "odise_attn_mask_bits_f32": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p],

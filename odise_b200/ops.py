@@ -7,7 +7,7 @@ import torch
 from . import lib
 from .lib import Planes, _check, _ptr, _stream, load
 
-ACT_NONE, ACT_RELU, ACT_SILU, ACT_GELU = 0, 1, 2, 3
+ACT_NONE, ACT_RELU, ACT_SILU, ACT_GELU, ACT_QUICKGELU = 0, 1, 2, 3, 4
 
 
 def empty(rows, cols, device):
@@ -165,7 +165,7 @@ def head_pad_rows(w, heads, d, HS):
 
 
 def head_stride(d):
-    if d <= 48:    # incl. the decoder's d = 32
+    if d <= 64:    # incl. the decoder's d = 32 and CLIP's d = 64
         return 64
     if d <= 80:
         return 128
@@ -267,3 +267,20 @@ def image_crops(img, boxes_dev, n_crops, H, W, ch, cw):
         raise lib.OdiseError("image_crops: uint8 or float32 image expected")
     _check(fn(_ptr(img), _ptr(out), _ptr(boxes_dev), n_crops, H, W, ch, cw, _stream()), "image_crops")
     return out
+
+
+def clip_preprocess(img, boxes_dev, n_crops, H, W, ch, cw, S=336):
+    out = torch.empty(n_crops * S * S, 3, dtype=torch.float32, device=img.device)
+    if img.dtype not in (torch.uint8, torch.float32):
+        raise lib.OdiseError("clip_preprocess: uint8 or float32 image expected")
+    _check(load().odise_clip_preprocess(_ptr(img), 1 if img.dtype == torch.uint8 else 0, _ptr(out), _ptr(boxes_dev),
+                                        n_crops, H, W, ch, cw, S, _stream()), "clip_preprocess")
+    return out
+
+
+def patchify_split(x, B, S, P, lo=True):
+    Kpad = (3 * P * P + 7) // 8 * 8
+    G = S // P
+    p = Planes.empty(B * G * G, Kpad, x.device, lo=lo, ld=Kpad)
+    _check(load().odise_patchify_split_f32(_ptr(x), _ptr(p.hi), _ptr(p.lo), B, S, P, Kpad, _stream()), "patchify")
+    return p

@@ -246,6 +246,30 @@ def category_head_params(prefix="category_head."):
     return [(prefix + "text_proj.weight", (256, 768), "w"), (prefix + "text_proj.bias", (256,), "b")]
 
 
+CLIP_PREFIX = "clip.visual."
+
+
+def clip_visual_params(prefix=CLIP_PREFIX, width=1024, layers=24, patch=14, image=336, out_dim=768):
+    """open_clip VisionTransformer (ViT-L-14-336, pretrained "openai") parameter names — the image tower behind
+    ClipAdapter.embed_image (odise/modeling/meta_arch/clip.py:177-231): conv1 (no bias), class / positional embedding,
+    ln_pre, `layers` ResidualAttentionBlocks (ln_1, attn.in_proj, attn.out_proj, ln_2, mlp.c_fc, mlp.c_proj), ln_post, proj."""
+    n_tok = (image // patch) ** 2 + 1
+    ps = [(prefix + "conv1.weight", (width, 3, patch, patch), "w"), (prefix + "class_embedding", (width,), "cls"),
+          (prefix + "positional_embedding", (n_tok, width), "cls"),
+          (prefix + "ln_pre.weight", (width,), "gamma"), (prefix + "ln_pre.bias", (width,), "beta")]
+    for i in range(layers):
+        q = f"{prefix}transformer.resblocks.{i}."
+        ps += [(q + "ln_1.weight", (width,), "gamma"), (q + "ln_1.bias", (width,), "beta"),
+               (q + "attn.in_proj_weight", (3 * width, width), "w"), (q + "attn.in_proj_bias", (3 * width,), "b"),
+               (q + "attn.out_proj.weight", (width, width), "w"), (q + "attn.out_proj.bias", (width,), "b"),
+               (q + "ln_2.weight", (width,), "gamma"), (q + "ln_2.bias", (width,), "beta"),
+               (q + "mlp.c_fc.weight", (4 * width, width), "w"), (q + "mlp.c_fc.bias", (4 * width,), "b"),
+               (q + "mlp.c_proj.weight", (width, 4 * width), "w"), (q + "mlp.c_proj.bias", (width,), "b")]
+    ps += [(prefix + "ln_post.weight", (width,), "gamma"), (prefix + "ln_post.bias", (width,), "beta"),
+           (prefix + "proj", (width, out_dim), "proj")]
+    return ps
+
+
 def msda_offset_bias(M=8, L=3, P=4):
     """MSDeformAttn._reset_parameters directional grid (ops/modules/ms_deform_attn.py:66-74)."""
     thetas = torch.arange(M, dtype=torch.float32) * (2.0 * math.pi / M)
@@ -287,6 +311,10 @@ def synth_state_dict(params, seed=0, dtype=torch.float32):
             t = msda_offset_bias()
         elif kind == "logit_scale":
             t = torch.tensor(math.log(1 / 0.07))
+        elif kind == "cls":          # CLIP class / positional embeddings: scale = width ** -0.5 like open_clip
+            t = torch.randn(shape, generator=g) * (shape[-1] ** -0.5)
+        elif kind == "proj":         # [width, out]: used as x @ proj
+            t = torch.randn(shape, generator=g) * (shape[0] ** -0.5)
         else:
             raise ValueError(kind)
         sd[name] = t.to(dtype)

@@ -180,3 +180,32 @@ def test_postprocess_oracle_equals_reference_methods():
     pr, ir = MF.panoptic_inference(fake, cls, pred)
     po, io = opp.panoptic_inference(cls, pred, K, things)
     assert torch.equal(pr, po) and ir == io and len(ir) > 0
+
+
+def test_clip_inventory_matches_oracle_module():
+    from oracle import clip as oclip
+    with torch.device("meta"):
+        v = oclip.VisionTransformer()
+    got = {n[len(spec.CLIP_PREFIX):]: tuple(s) for n, s, _ in spec.clip_visual_params()}
+    assert got == {k: tuple(t.shape) for k, t in v.state_dict().items()}
+    assert 303e6 < sum(torch.Size(s).numel() for s in got.values()) < 305e6      # ViT-L/14-336 image tower
+
+
+@needs_ref
+@torch.no_grad()
+def test_reference_clip_glue_runs_on_oracle_visual():
+    """ClipAdapter._encode_image (clip.py:177-222) executed verbatim on the oracle VisionTransformer == oracle.encode_image."""
+    import importlib
+    from oracle import clip as oclip
+    refshim.install()
+    rc = importlib.import_module("odise.modeling.meta_arch.clip")
+    import einops
+    rc.rearrange = einops.rearrange
+    torch.manual_seed(0)
+    v = oclip.VisionTransformer(image_size=56, patch=14, width=64, layers=2, heads=4, out_dim=32).eval()
+    for p in v.parameters():
+        torch.nn.init.normal_(p, std=0.1)
+    img = torch.randn(2, 3, 56, 56)
+    fake = types.SimpleNamespace(clip=types.SimpleNamespace(visual=v))
+    emb_ref, _ = rc.ClipAdapter._encode_image(fake, img)
+    assert torch.allclose(emb_ref, oclip.encode_image(v, img), rtol=1e-5, atol=1e-6)
