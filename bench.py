@@ -40,7 +40,8 @@ def parse():
     ap.add_argument("--vocab", default="ade150", choices=["ade150", "coco133", "ade847"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--hot-path-only", action="store_true",
-                    help="skip the KL-VAE stages (SURVEY.md 8f-1): their taps / latent enter as synthetic tensors")
+                    help="skip the KL-VAE (SURVEY.md 8f-1) and CLIP image tower (8f-2) stages: their taps / latent / "
+                         "image embedding enter as synthetic tensors")
     return ap.parse_args()
 
 
@@ -132,6 +133,13 @@ class CpuHotPath:
             vae.load_state_dict({k[len(spec.VAE_PREFIX):]: v for k, v in sd_v.items()}, assign=True)
             self.vae = vae.eval()
             self.img = torch.rand(1, 3, 512, 512, generator=g) * 2 - 1
+            from oracle import clip as oclip
+            self.oclip = oclip
+            sd_c = spec.synth_state_dict(spec.clip_visual_params(), 5)
+            with torch.device("meta"):
+                vis = oclip.VisionTransformer()
+            vis.load_state_dict({k[len(spec.CLIP_PREFIX):]: v for k, v in sd_c.items()}, assign=True)
+            self.vis = vis.eval()
 
     @torch.no_grad()
     def sample(self):
@@ -142,6 +150,7 @@ class CpuHotPath:
         if self.full:
             lat, _ = ldm.encoder_features(self.vae, self.img)
             ldm.decoder_features(self.vae, lat, truncate=False)
+            self.oclip.embed_image(self.vis, self.img * 0.5 + 0.5)
         t_unet = time.perf_counter() - t0
         t0 = time.perf_counter()
         mf, _, ms = m2f.pixel_decoder(self.sd_h, self.feats, "sem_seg_head.pixel_decoder.")
@@ -151,7 +160,7 @@ class CpuHotPath:
         t_head = time.perf_counter() - t0
         ips = 1.0 / (self.crops * t_unet + t_head)
         return dict(value=ips, unit="images/s", cores=self.n, kind="port",
-                    sample=f"1 crop (512^2) through {'VAE enc + UNet + full VAE dec' if self.full else 'the UNet'} as the "
+                    sample=f"1 crop (512^2) through {'CLIP ViT-L/14 image tower + VAE enc + UNet + full VAE dec' if self.full else 'the UNet'} as the "
                            f"reference executes it ({t_unet:.2f} s) + 1 image head at {self.size}^2 "
                            f"({t_head:.2f} s); images/s = 1/({self.crops}*t_crop + t_head); fp32 torch CPU, "
                            f"{self.n} threads of {os.cpu_count()}")
@@ -205,8 +214,8 @@ def main():
     from odise_b200.pipeline import ODISEEngine, full_param_list, gather_logits, synthetic_vocabulary
     lib.load()
     nmma = 3 if args.precision == "bf16x3" else 1
-    sd = spec.synth_state_dict(full_param_list(with_vae=args.full), seed=0)
-    eng = ODISEEngine(sd, dev, nmma=nmma, with_vae=args.full)
+    sd = spec.synth_state_dict(full_param_list(with_vae=args.full, with_clip=args.full), seed=0)
+    eng = ODISEEngine(sd, dev, nmma=nmma, with_vae=args.full, with_clip=args.full)
     del sd
     ncls, npr = VOCABS[args.vocab]
     eng.set_vocabulary(args.vocab, *synthetic_vocabulary(ncls, npr))
@@ -285,12 +294,14 @@ def main():
         "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
         "config": {"workload": f"ODISE(label) hot path, batch {B}/GPU x {S}x{S}, {crops} crops/image, {args.vocab} "
                                f"({ncls} classes / {npr} prompts), Q=100",
-                   "stages": ("KL-VAE encoder + truncated decoder (taps), " if args.full else "") +
+                   "stages": ("CLIP ViT-L/14-336 image tower on every crop, KL-VAE encoder + truncated decoder (taps), "
+                              if args.full else "") +
                              "implicit-captioner front, q_sample, SD-v1 UNet feature pass (4 taps), 8 projections, "
                              "MSDeformAttn pixel decoder, 9-layer masked-attention decoder, CLIP-text scoring, "
                              "NCCL all-gather of logits",
-                   "not_in_path": ("CLIP image embedding enters as a seeded synthetic tensor (SURVEY.md §8f-2); KL-VAE "
-                                   "encoder + truncated decoder ARE executed (--full)") if args.full else
+                   "not_in_path": ("nothing of the per-image pass: CLIP image tower and KL-VAE taps ARE executed; the CLIP "
+                                   "TEXT bank of the vocabulary is precomputed per vocabulary (as in the reference)")
+                                  if args.full else
                                   ("KL-VAE encoder/decoder taps and CLIP image embedding enter as seeded synthetic "
                                    "tensors (SURVEY.md §8f rows f-1/f-2)"),
                    "weights": "random-init (seed 0), SD-v1 / ODISE shapes", "global_batch": world * B,

@@ -272,6 +272,16 @@ int odise_panoptic_inference_f32(const float* logits, const float* scores, const
                                  void* ws, int B, int Q, int K, int hs, int ws_, int H, int W, double overlap_thr,
                                  void* stream);
 
+/* MaskFormer.instance_inference (maskformer_model.py:344-380) on the device: top-k over the flattened [Q*K] class
+ * probabilities (probs [B*Q, K+1] from odise_query_scores_f32; void column dropped), sorted by probability
+ * (descending; ties -> lower flat index), times the mask score sum(sigmoid*m)/(sum(m)+1e-6), m = upsampled logit > 0.
+ * scores / classes / query_index / valid: [B, topk]; valid = is_thing[class] (the panoptic_on filter; all 1 when
+ * is_thing == NULL); masks u8 [B, Q, H, W] optional (instance i's mask = masks[b, query_index[b, i]]).  topk <= 1024. */
+long long odise_instance_ws_bytes(int B, int Q, int H, int W);
+int odise_instance_inference_f32(const float* probs, const float* logits, const uint8_t* is_thing, float* scores,
+                                 int32_t* classes, int32_t* query_index, int32_t* valid, uint8_t* masks, void* ws, int B,
+                                 int Q, int K, int topk, int hs, int ws_, int H, int W, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

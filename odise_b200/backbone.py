@@ -58,13 +58,15 @@ class SyntheticTaps:
 
 
 class BackboneEngine:
-    def __init__(self, sd, device, nmma=3, prefix="backbone.", unet_prefix=spec.UNET_PREFIX, uncond=None, vae=None):
+    def __init__(self, sd, device, nmma=3, prefix="backbone.", unet_prefix=spec.UNET_PREFIX, uncond=None, vae=None, clip=None):
         """sd: state dict with `backbone.feature_projections.*`, `backbone.feature_extractor.*` and the UNet.
         uncond: the frozen text-encoder output for "" ([1, 77, 768]; ldm.py:116) — an input of the path.
-        vae: optional VAEEngine; without it the VAE taps / latent are synthetic."""
+        vae: optional VAEEngine; without it the VAE taps / latent are synthetic.
+        clip: optional ClipVisualEngine (§8f-2); without it the CLIP image embedding is a seeded synthetic tensor."""
         self.dev = torch.device(device)
         self.nmma, self.lo = nmma, nmma == 3
         self.vae = vae
+        self.clip = clip
         self._boxes = {}
         self.unet = UNetEngine(sd, device, nmma=nmma, prefix=unet_prefix)
         self.W, self.F = {}, {}
@@ -159,10 +161,13 @@ class BackboneEngine:
         return out
 
     @torch.no_grad()
-    def extract(self, B, crop_hw=(512, 512), vae_taps=None, crops=None):
+    def extract(self, B, crop_hw=(512, 512), vae_taps=None, crops=None, clip_embed=None):
         """single_forward for a batch of B crops.  crops: normalised NHWC fp32 [B*h*w, 3] -> the VAE engine produces
-        latent + taps; otherwise they are given / synthetic.  The CLIP image embedding is synthetic (§8f-2)."""
+        latent + taps; otherwise they are given / synthetic.  clip_embed: [B, 768] from the CLIP image tower
+        (ldm.py:705); synthetic when no ClipVisualEngine is attached."""
         t = vae_taps if vae_taps is not None else self.taps_provider(B, crop_hw)
+        if clip_embed is not None:
+            t = dict(t, clip_embed=clip_embed)
         if crops is not None and self.vae is not None:
             enc = self.vae.encode(crops, B, crop_hw[0], crop_hw[1])
             lat, lh, lw = enc["latent"]
@@ -201,14 +206,17 @@ class BackboneEngine:
         boxes, short = self.crop_grid(h_img, w_img)
         nc = len(boxes)
         B = n_images * nc                                # crop batch, image-major: b = img * nc + crop
-        crops = None
-        if images_u8 is not None and self.vae is not None:
+        crops = clip_embed = None
+        if images_u8 is not None and (self.vae is not None or self.clip is not None):
             key = (n_images, h_img, w_img)
             if key not in self._boxes:
                 self._boxes[key] = torch.tensor([[i, y, x] for i in range(n_images) for (y, x) in boxes],
                                                 dtype=torch.int32).to(self.dev)
-            crops = ops.image_crops(images_u8, self._boxes[key], B, h_img, w_img, short, short)
-        feats = self.extract(B, (short, short), vae_taps, crops)
+            if self.vae is not None:
+                crops = ops.image_crops(images_u8, self._boxes[key], B, h_img, w_img, short, short)
+            if self.clip is not None:
+                clip_embed = self.clip.embed(images_u8, self._boxes[key], B, h_img, w_img, short, short)
+        feats = self.extract(B, (short, short), vae_taps, crops, clip_embed)
         if nc == 1 and short == h_img == w_img:
             return feats
         out = {}

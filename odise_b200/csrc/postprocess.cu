@@ -187,6 +187,128 @@ __global__ void panoptic_relabel_kernel(const int16_t* __restrict__ ids, const u
   }
 }
 
+
+// ---- MaskFormer.instance_inference (maskformer_model.py:344-380) ------------------------------------------------
+// top-k over the flattened [Q*K] class probabilities (void column dropped) by an 8-pass MSB radix select on the
+// unique 64-bit key (prob bits << 32 | ~flat index), then a bitonic sort of the <= 1024 winners: deterministic,
+// descending score, ties broken towards the lower flat index.  grid B, block 1024.
+__global__ void __launch_bounds__(1024)
+instance_topk_kernel(const float* __restrict__ probs, const uint8_t* __restrict__ is_thing, float* __restrict__ scores,
+                     int32_t* __restrict__ classes, int32_t* __restrict__ query_index, int32_t* __restrict__ valid, int Q,
+                     int K, int topk) {
+  __shared__ unsigned int hist[256];
+  __shared__ unsigned long long sel[1024];
+  __shared__ unsigned long long s_prefix;
+  __shared__ int s_remaining, s_count;
+  const int b = blockIdx.x, tid = threadIdx.x, n = Q * K, K1 = K + 1;
+  const float* pb = probs + (long long)b * Q * K1;
+  auto key_of = [&](int i) -> unsigned long long {
+    const float v = pb[(i / K) * K1 + (i % K)];
+    return ((unsigned long long)__float_as_uint(v) << 32) | (unsigned long long)(0xffffffffu - (unsigned)i);
+  };
+  const int k = topk < n ? topk : n;
+  if (tid == 0) { s_prefix = 0ull; s_remaining = k; s_count = 0; }
+  __syncthreads();
+  for (int pass = 7; pass >= 0; --pass) {
+    if (tid < 256) hist[tid] = 0u;
+    __syncthreads();
+    const unsigned long long prefix = s_prefix;
+    const unsigned long long hi_mask = pass == 7 ? 0ull : (~0ull << ((pass + 1) * 8));
+    for (int i = tid; i < n; i += 1024) {
+      const unsigned long long key = key_of(i);
+      if ((key & hi_mask) == prefix) atomicAdd(&hist[(unsigned)(key >> (pass * 8)) & 255u], 1u);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int rem = s_remaining, bin = 255;
+      for (; bin > 0; --bin) {
+        if ((int)hist[bin] >= rem) break;
+        rem -= (int)hist[bin];
+      }
+      s_remaining = rem;
+      s_prefix = prefix | ((unsigned long long)bin << (pass * 8));
+    }
+    __syncthreads();
+  }
+  const unsigned long long kth = s_prefix;      // the k-th largest key (keys are unique)
+  sel[tid] = 0ull;
+  __syncthreads();
+  for (int i = tid; i < n; i += 1024) {
+    const unsigned long long key = key_of(i);
+    if (key >= kth) sel[atomicAdd(&s_count, 1)] = key;
+  }
+  __syncthreads();
+  for (int sz = 2; sz <= 1024; sz <<= 1)         // bitonic sort, descending
+    for (int st = sz >> 1; st > 0; st >>= 1) {
+      const int j = tid ^ st;
+      if (j > tid) {
+        const unsigned long long a = sel[tid], c = sel[j];
+        const bool desc = (tid & sz) == 0;
+        if (desc ? (a < c) : (a > c)) { sel[tid] = c; sel[j] = a; }
+      }
+      __syncthreads();
+    }
+  if (tid < topk) {
+    const long long o = (long long)b * topk + tid;
+    if (tid < k) {
+      const unsigned long long key = sel[tid];
+      const int i = (int)(0xffffffffu - (unsigned)(key & 0xffffffffu));
+      const int c = i % K;
+      scores[o] = __uint_as_float((unsigned)(key >> 32));
+      classes[o] = c;
+      query_index[o] = i / K;
+      valid[o] = is_thing ? (int)is_thing[c] : 1;
+    } else {
+      scores[o] = 0.f; classes[o] = -1; query_index[o] = 0; valid[o] = 0;
+    }
+  }
+}
+
+// per (query, row chunk): sum of sigmoid(up) over up > 0 and the count; optional binary mask u8 [B, Q, H, W].
+// grid (chunks, Q, B), block 256; deterministic two-stage reduction (partials [B, Q, chunks, 2]).
+__global__ void __launch_bounds__(256)
+instance_mask_partial_kernel(const float* __restrict__ logits, uint8_t* __restrict__ masks, float* __restrict__ partial,
+                             int Q, int hs, int ws, int H, int W, int rows_per_chunk) {
+  __shared__ float red[2][8];
+  const int chunk = blockIdx.x, q = blockIdx.y, b = blockIdx.z, nchunks = gridDim.x;
+  const float* src = logits + ((long long)b * Q + q) * hs * ws;
+  const float sy = (float)hs / (float)H, sx = (float)ws / (float)W;
+  const int y0 = chunk * rows_per_chunk, y1 = min(H, y0 + rows_per_chunk);
+  float num = 0.f, den = 0.f;
+  for (int i = y0 * W + threadIdx.x; i < y1 * W; i += 256) {
+    const int oy = i / W, ox = i - oy * W;
+    const float lg = bilerp(src, hs, ws, oy, ox, sy, sx);
+    const bool on = lg > 0.f;
+    if (on) { num += 1.f / (1.f + expf(-lg)); den += 1.f; }
+    if (masks) masks[((long long)b * Q + q) * H * W + i] = on ? 1 : 0;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    num += __shfl_xor_sync(0xffffffffu, num, o);
+    den += __shfl_xor_sync(0xffffffffu, den, o);
+  }
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = num; red[1][threadIdx.x >> 5] = den; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f, c = 0.f;
+    for (int w = 0; w < 8; ++w) { a += red[0][w]; c += red[1][w]; }
+    float* o = partial + (((long long)b * Q + q) * nchunks + chunk) * 2;
+    o[0] = a; o[1] = c;
+  }
+}
+
+// scores[b, i] *= sum(sig * mask) / (sum(mask) + 1e-6) of query_index[b, i]
+__global__ void instance_finalize_kernel(const float* __restrict__ partial, const int32_t* __restrict__ query_index,
+                                         float* __restrict__ scores, int n, int topk, int Q, int nchunks) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int b = i / topk;
+  const float* p = partial + ((long long)b * Q + query_index[i]) * nchunks * 2;
+  float a = 0.f, c = 0.f;
+  for (int w = 0; w < nchunks; ++w) { a += p[2 * w]; c += p[2 * w + 1]; }
+  scores[i] *= a / (c + 1e-6f);
+}
+
 }  // namespace ob
 
 using namespace ob;
@@ -245,6 +367,34 @@ extern "C" int odise_panoptic_inference_f32(const float* logits, const float* sc
   int rb = (int)((npix + 255) / 256);
   if (rb > 148 * 8) rb = 148 * 8;
   panoptic_relabel_kernel<<<rb, 256, 0, st>>>(ids, fg, seg_of, pan, Q, (long long)H * W, B);
+  count_launch(3);
+  return (int)cudaGetLastError();
+}
+
+// instance_inference on the device.  probs [B*Q, K+1] (softmax incl. void; odise_query_scores_f32), logits [B, Q, hs, ws].
+// Outputs per image, sorted by class probability (descending): scores [B, topk] = class prob * mask score,
+// classes / query_index [B, topk], valid [B, topk] (= is_thing[class] when is_thing != NULL: the panoptic_on filter),
+// masks u8 [B, Q, H, W] (optional; the mask of instance i is masks[b, query_index[b, i]]).
+static inline int instance_chunks(int H) { return H >= 64 ? 16 : 1; }
+extern "C" long long odise_instance_ws_bytes(int B, int Q, int H, int W) {
+  (void)W;
+  return (long long)B * Q * instance_chunks(H) * 2 * sizeof(float) + 256;
+}
+
+extern "C" int odise_instance_inference_f32(const float* probs, const float* logits, const uint8_t* is_thing,
+                                            float* scores, int32_t* classes, int32_t* query_index, int32_t* valid,
+                                            uint8_t* masks, void* ws, int B, int Q, int K, int topk, int hs, int ws_,
+                                            int H, int W, void* stream) {
+  if (!probs || !logits || !scores || !classes || !query_index || !valid || !ws) return ODISE_ERR_ARG;
+  if (B <= 0 || Q <= 0 || K <= 0 || topk <= 0 || topk > 1024 || hs <= 0 || ws_ <= 0 || H <= 0 || W <= 0) return ODISE_ERR_ARG;
+  if ((long long)Q * K >= 0x7fffffffLL) return ODISE_ERR_ARG;
+  cudaStream_t st = STREAM(stream);
+  const int nchunks = instance_chunks(H), rows = (H + nchunks - 1) / nchunks;
+  float* partial = reinterpret_cast<float*>(ws);
+  instance_topk_kernel<<<B, 1024, 0, st>>>(probs, is_thing, scores, classes, query_index, valid, Q, K, topk);
+  instance_mask_partial_kernel<<<dim3(nchunks, Q, B), 256, 0, st>>>(logits, masks, partial, Q, hs, ws_, H, W, rows);
+  const int n = B * topk;
+  instance_finalize_kernel<<<(n + 255) / 256, 256, 0, st>>>(partial, query_index, scores, n, topk, Q, nchunks);
   count_launch(3);
   return (int)cudaGetLastError();
 }

@@ -14,20 +14,25 @@ from .backbone import BackboneEngine
 from .head import HeadEngine
 
 
-def full_param_list(with_vae=False):
-    return spec.unet_params() + spec.backbone_params() + spec.head_params() + (spec.vae_params() if with_vae else [])
+def full_param_list(with_vae=False, with_clip=False):
+    return (spec.unet_params() + spec.backbone_params() + spec.head_params() + (spec.vae_params() if with_vae else [])
+            + (spec.clip_visual_params() if with_clip else []))
 
 
 class ODISEEngine:
-    def __init__(self, sd, device, nmma=3, num_queries=100, with_vae=False):
+    def __init__(self, sd, device, nmma=3, num_queries=100, with_vae=False, with_clip=False):
         self.dev = torch.device(device)
         self.nmma = nmma
         vae = None
         if with_vae:                      # real KL-VAE taps instead of synthetic ones
             from .vae import VAEEngine
             vae = VAEEngine(sd, device, nmma=nmma)
-        self.with_vae = with_vae
-        self.backbone = BackboneEngine(sd, device, nmma=nmma, vae=vae)
+        clip = None
+        if with_clip:                     # real CLIP ViT-L/14-336 image embedding of every crop
+            from .clip import ClipVisualEngine
+            clip = ClipVisualEngine(sd, device, nmma=nmma)
+        self.with_vae, self.with_clip = with_vae, with_clip
+        self.backbone = BackboneEngine(sd, device, nmma=nmma, vae=vae, clip=clip)
         self.head = HeadEngine(sd, device, nmma=nmma, num_queries=num_queries)
         self.Q = num_queries
         self._graphs = {}
@@ -53,7 +58,7 @@ class ODISEEngine:
     @torch.no_grad()
     def step(self, n_images, H, W, vae_taps=None, images_u8=None):
         """One pass of the hot path for n_images resident images (eager). Returns device tensors."""
-        if images_u8 is None and self.with_vae:
+        if images_u8 is None and (self.with_vae or self.with_clip):
             images_u8 = self._image_buffer(n_images, H, W)
         feats = self.backbone.forward(n_images, H, W, vae_taps, images_u8)
         out = self.head.forward(feats, n_images, vocab_key=self.vocab_key)

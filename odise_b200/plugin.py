@@ -24,17 +24,20 @@ class B200FeatureExtractorBackbone(nn.Module):
     forward(img: [B, 3, H, W] in [0, 1], H, W % 64 == 0) -> {"s2".."s5": [B, 512, H/2^k, W/2^k]}."""
 
     def __init__(self, state_dict, device, out_features=("s2", "s3", "s4", "s5"), nmma=3, with_vae=True,
-                 clip_embed_fn=None):
+                 with_clip=True):
         super().__init__()
         vae = None
         if with_vae:
             from .vae import VAEEngine
             vae = VAEEngine(state_dict, device, nmma=nmma)
-        self.engine = BackboneEngine(state_dict, device, nmma=nmma, vae=vae)
+        clip = None
+        if with_clip:                            # ClipAdapter image tower (clip.py:177-231), weights `clip.visual.*`
+            from .clip import ClipVisualEngine
+            clip = ClipVisualEngine(state_dict, device, nmma=nmma)
+        self.engine = BackboneEngine(state_dict, device, nmma=nmma, vae=vae, clip=clip)
         self._out_features = list(out_features)
         self._out_feature_strides = {f"s{k}": 2 ** k for k in (2, 3, 4, 5)}
         self._out_feature_channels = {f"s{k}": 512 for k in (2, 3, 4, 5)}
-        self.clip_embed_fn = clip_embed_fn      # f-2: CLIP image tower; None -> seeded synthetic embedding
 
     @property
     def size_divisibility(self):

@@ -1,6 +1,6 @@
 """Device-side post-processing: the tail of CategoryODISE.forward without a clip_head
 (odise/modeling/meta_arch/odise.py:326-370) — bilinear mask upsample, MaskFormer.semantic_inference and
-MaskFormer.panoptic_inference (maskformer_model.py:280-342) with no host round trips: the reference syncs ~4x per
+MaskFormer.panoptic_inference / instance_inference (maskformer_model.py:280-380) with no host round trips: the reference syncs ~4x per
 query through `.item()`.  Output sizes must equal the padded input size (sem_seg_postprocess is then the identity)."""
 import torch
 
@@ -19,9 +19,13 @@ class PostProcessor:
         self.obj_thr, self.ov_thr = float(object_mask_threshold), float(overlap_threshold)
 
     @torch.no_grad()
-    def __call__(self, pred_logits, pred_masks, H, W, semantic=True, panoptic=True):
+    def __call__(self, pred_logits, pred_masks, H, W, semantic=True, panoptic=True, instance=False, topk=100,
+                 panoptic_on=True, instance_masks=True):
         """pred_logits [B, Q, K+1], pred_masks [B, Q, h, w] (device fp32) ->
-        dict(sem_seg [B, K, H, W], panoptic_seg int32 [B, H, W], seg_info int32 [B, Q, 3], n_segments int32 [B])."""
+        dict(sem_seg [B, K, H, W], panoptic_seg int32 [B, H, W], seg_info int32 [B, Q, 3], n_segments int32 [B]);
+        instance=True adds dict(instances=dict(scores, pred_classes, query_index, valid [B, topk], query_masks u8
+        [B, Q, H, W])): instance i of image b has the binary mask query_masks[b, query_index[b, i]] and is kept by the
+        reference's panoptic_on filter iff valid[b, i]."""
         B, Q, K1 = pred_logits.shape
         assert K1 == self.K + 1
         hs, ws = pred_masks.shape[-2:]
@@ -32,7 +36,8 @@ class PostProcessor:
         labels = torch.empty(B * Q, dtype=torch.int32, device=dev)
         keep = torch.empty(B * Q, dtype=torch.int32, device=dev)
         cl = pred_logits.contiguous()
-        _check(L.odise_query_scores_f32(_ptr(cl), None, _ptr(probs_t), _ptr(scores), _ptr(labels), _ptr(keep), B, Q, Qp,
+        probs = torch.empty(B * Q, K1, dtype=torch.float32, device=dev) if instance else None
+        _check(L.odise_query_scores_f32(_ptr(cl), _ptr(probs), _ptr(probs_t), _ptr(scores), _ptr(labels), _ptr(keep), B, Q, Qp,
                                         K1, self.obj_thr, _stream()), "query_scores")
         out = {}
         pm = pred_masks.contiguous()
@@ -55,6 +60,17 @@ class PostProcessor:
                                                   _ptr(pan), _ptr(seg_info), _ptr(nseg), _ptr(wsb), B, Q, self.K, hs, ws,
                                                   H, W, self.ov_thr, _stream()), "panoptic_inference")
             out.update(panoptic_seg=pan, seg_info=seg_info, n_segments=nseg)
+        if instance:
+            i_sc = torch.empty(B, topk, dtype=torch.float32, device=dev)
+            i_cl = torch.empty(B, topk, dtype=torch.int32, device=dev)
+            i_q = torch.empty(B, topk, dtype=torch.int32, device=dev)
+            i_ok = torch.empty(B, topk, dtype=torch.int32, device=dev)
+            qm = torch.empty(B, Q, H, W, dtype=torch.uint8, device=dev) if instance_masks else None
+            wsb = torch.empty(int(L.odise_instance_ws_bytes(B, Q, H, W)), dtype=torch.uint8, device=dev)
+            _check(L.odise_instance_inference_f32(_ptr(probs), _ptr(pm), _ptr(self.is_thing) if panoptic_on else None,
+                                                  _ptr(i_sc), _ptr(i_cl), _ptr(i_q), _ptr(i_ok), _ptr(qm), _ptr(wsb), B, Q,
+                                                  self.K, topk, hs, ws, H, W, _stream()), "instance_inference")
+            out["instances"] = dict(scores=i_sc, pred_classes=i_cl, query_index=i_q, valid=i_ok, query_masks=qm)
         out.update(scores=scores.view(B, Q), labels=labels.view(B, Q), keep=keep.view(B, Q))
         return out
 

@@ -31,7 +31,8 @@ def test_head_plugin_contract(cuda):
 def test_backbone_plugin_contract(cuda):
     from odise_b200 import spec
     from odise_b200.plugin import B200FeatureExtractorBackbone
-    sd = spec.synth_state_dict(spec.unet_params() + spec.backbone_params() + spec.vae_params(), seed=0)
+    sd = spec.synth_state_dict(spec.unet_params() + spec.backbone_params() + spec.vae_params() +
+                                 spec.clip_visual_params(), seed=0)
     bb = B200FeatureExtractorBackbone(sd, cuda)
     assert bb.size_divisibility == 64
     shp = bb.output_shape()

@@ -46,3 +46,34 @@ def test_postprocess(cuda, cfg):
         assert agree > 0.9995, agree          # ties at sigmoid == 0.5 / argmax rounding may flip isolated pixels
         n_nonempty += len(info) > 0
     assert n_nonempty > 0
+
+
+@pytest.mark.parametrize("cfg", [(4, 2, 20, 7, 24, 32, 4, 50), (5, 1, 100, 150, 64, 64, 4, 100), (6, 1, 5, 3, 16, 16, 2, 100)])
+def test_instance_inference(cuda, cfg):
+    """MaskFormer.instance_inference (maskformer_model.py:344-380): top-k (query, class) pairs, mask-weighted scores."""
+    from odise_b200.postprocess import PostProcessor
+    from oracle import postprocess as opp
+    seed, B, Q, K, h, w, up, topk = cfg
+    H, W = h * up, w * up
+    cls, masks = _case(seed, B, Q, K, h, w)
+    things = list(range(0, K, 2))
+    pp = PostProcessor(cuda, K, things)
+    out = pp(cls.to(cuda), masks.to(cuda), H, W, semantic=False, panoptic=False, instance=True, topk=topk)["instances"]
+    torch.cuda.synchronize()
+    k_eff = min(topk, Q * K)
+    for b in range(B):
+        up_masks = opp.upsample_masks(masks[b:b + 1], (H, W))[0]
+        ref = opp.instance_inference(cls[b], up_masks, K, things, topk=k_eff, panoptic_on=True)
+        ok = out["valid"][b].cpu().bool()
+        assert int(out["valid"][b, k_eff:].sum()) == 0
+        sc, pc, qi = out["scores"][b].cpu()[ok], out["pred_classes"][b].cpu()[ok], out["query_index"][b].cpu()[ok]
+        assert sc.numel() == ref["scores"].numel()
+        # the reference's top-k is unsorted: compare as sets ordered by (class, score)
+        o1 = sorted(range(sc.numel()), key=lambda i: (int(pc[i]), float(sc[i])))
+        o2 = sorted(range(sc.numel()), key=lambda i: (int(ref["pred_classes"][i]), float(ref["scores"][i])))
+        assert [int(pc[i]) for i in o1] == [int(ref["pred_classes"][i]) for i in o2]
+        assert torch.allclose(sc[o1], ref["scores"][o2], rtol=2e-4, atol=1e-6)
+        gm = out["query_masks"][b].cpu()[qi.long()][o1].float()
+        agree = (gm == ref["pred_masks"][o2]).float().mean().item()
+        assert agree > 0.9999, agree
+        assert torch.isin(pc, torch.tensor(things, dtype=pc.dtype)).all()
