@@ -178,30 +178,46 @@ __global__ void gn_apply_kernel(const float* __restrict__ x, long long ldx, cons
   }
   const float* xb = x + (long long)b * x_bs + c;
   const int p0 = blockIdx.x * pix_per_block, p1 = min(HW, p0 + pix_per_block);
-  for (int pix = p0 + pl; pix < p1; pix += PL) {
-    const float4 v = *reinterpret_cast<const float4*>(xb + (long long)pix * ldx);
+  auto finish = [&](float4 v, float4 r4, float4 prev, int pix) {
     const float in[4] = {v.x, v.y, v.z, v.w};
     float o[4];
 #pragma unroll
     for (int t = 0; t < 4; ++t) o[t] = fmaf((in[t] - mu[t]) * rs[t], ga[t], be[t]);   // torch order
-    if (res) {   // BottleneckBlock: relu(gn(conv3) + shortcut); res is dense [B*HW, C]
-      const float4 r4 = *reinterpret_cast<const float4*>(res + ((long long)b * HW + pix) * ldres + c);
-      o[0] += r4.x; o[1] += r4.y; o[2] += r4.z; o[3] += r4.w;
-    }
+    if (res) { o[0] += r4.x; o[1] += r4.y; o[2] += r4.z; o[3] += r4.w; }   // BottleneckBlock: relu(gn(conv3) + shortcut)
     if (act != ODISE_ACT_NONE) {
 #pragma unroll
       for (int t = 0; t < 4; ++t) o[t] = act_apply(o[t], act);
     }
     float4 ov = make_float4(o[0], o[1], o[2], o[3]);
     if (y) {
-      float4* yp = reinterpret_cast<float4*>(y + (long long)b * y_bs + (long long)pix * ldy + c);
-      if (accumulate) { const float4 prev = *yp; ov.x += prev.x; ov.y += prev.y; ov.z += prev.z; ov.w += prev.w; }
-      *yp = ov;
+      if (accumulate) { ov.x += prev.x; ov.y += prev.y; ov.z += prev.z; ov.w += prev.w; }
+      *reinterpret_cast<float4*>(y + (long long)b * y_bs + (long long)pix * ldy + c) = ov;
     }
     if (hi) {
       const long long o_ = (long long)b * o_bs + (long long)pix * ldo + c;
       store_split4(hi + o_, lo ? lo + o_ : nullptr, ov);
     }
+  };
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  const bool acc = y && accumulate;
+  int pix = p0 + pl;
+  for (; pix + 3 * PL < p1; pix += 4 * PL) {   // all loads of 4 pixels in flight before the first use
+    float4 v[4], r4[4], pv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int px = pix + u * PL;
+      v[u] = *reinterpret_cast<const float4*>(xb + (long long)px * ldx);
+      r4[u] = res ? *reinterpret_cast<const float4*>(res + ((long long)b * HW + px) * ldres + c) : z4;
+      pv[u] = acc ? *reinterpret_cast<const float4*>(y + (long long)b * y_bs + (long long)px * ldy + c) : z4;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) finish(v[u], r4[u], pv[u], pix + u * PL);
+  }
+  for (; pix < p1; pix += PL) {
+    const float4 v = *reinterpret_cast<const float4*>(xb + (long long)pix * ldx);
+    const float4 r4 = res ? *reinterpret_cast<const float4*>(res + ((long long)b * HW + pix) * ldres + c) : z4;
+    const float4 pv = acc ? *reinterpret_cast<const float4*>(y + (long long)b * y_bs + (long long)pix * ldy + c) : z4;
+    finish(v, r4, pv, pix);
   }
 }
 
