@@ -282,6 +282,25 @@ int odise_instance_inference_f32(const float* probs, const float* logits, const 
                                  int32_t* classes, int32_t* query_index, int32_t* valid, uint8_t* masks, void* ws, int B,
                                  int Q, int K, int topk, int hs, int ws_, int H, int W, void* stream);
 
+/* MaskCLIP front-end (odise/modeling/meta_arch/clip.py:284-339) and the open-vocabulary merge (odise.py:1506-1536,
+ * :300-323).
+ * preprocess: whole image [N,3,H,W] (u8 0..255 or f32 in [0,1]) -> bilinear (align_corners=False) S x S, CLIP
+ *   mean/std, NHWC fp32 [N*S*S, 3].
+ * bits: mask logits [B,Q,hm,wm] -> attention bits of the Q mask tokens in odise_attention_tc's layout: a token
+ *   sequence of Tq rows per image whose rows row0..row0+Q-1 are the mask tokens; bits [B, Tq, ceil(((S/P)^2+1)/32)]
+ *   (key 0 = class token, always on; key 1+p = patch p, on iff the max over its PxP window of the mask upsampled to
+ *   S x S has sigmoid >= 0.5); row_any [B, Tq] = 1 on mask-token rows, 0 elsewhere (those rows ignore the bits).
+ * merge: cat_logits [rows, K+1] (category head, void last), clip_logits [rows, K] (row stride ld_clip), overlap u8 [K]
+ *   (class also named in the training vocabulary) -> out [rows, K+1] = log(cat[softmax(e) * (1 - p_void), p_void] +
+ *   1e-8), e_k = (1-a_k) log softmax(cat[:K])_k + a_k log softmax(clip)_k, a_k = alpha if overlap[k] else beta;
+ *   open_logits [rows, K] = e (optional). */
+int odise_maskclip_preprocess(const void* img, int img_is_u8, float* out, int N, int H, int W, int S, void* stream);
+int odise_maskclip_bits_f32(const float* mask_logits, uint32_t* bits, int32_t* row_any, int B, int Q, int hm, int wm,
+                            int S, int P, int Tq, int row0, void* stream);
+int odise_open_vocab_merge_f32(const float* cat_logits, const float* clip_logits, long long ld_clip,
+                               const uint8_t* overlap, float alpha, float beta, float* out, float* open_logits, int rows,
+                               int K, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

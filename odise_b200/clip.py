@@ -53,19 +53,28 @@ class ClipVisualEngine:
     def _gemm(self, a, name, **kw):
         return lib.gemm(a, self.W[name], nmma=self.nmma, bias=self.F.get(name + ".b"), **kw)
 
-    @torch.no_grad()
-    def embed(self, img, boxes_dev, n_crops, H, W, ch, cw):
-        """img: device uint8 / float32 [N, 3, H, W]; boxes [n_crops, 3] int32 -> image_embed fp32 [n_crops, 768]."""
-        dev, B, Wd, T, TS = self.dev, n_crops, self.width, self.T, self.TS
-        x = ops.clip_preprocess(img, boxes_dev, B, H, W, ch, cw, self.image)
+    def _tokens(self, x, B, n_extra):
+        """normalised NHWC image [B*S*S, 3] -> pre-ln_pre token matrix [B*TS, width]: per image row 0 = class token,
+        rows 1..576 = patches (+ positional embedding), rows 577..577+n_extra-1 = mask tokens (copies of the class
+        row: ln_pre acts per row, so copying before it equals the reference's copy after it, clip.py:271-274)."""
+        dev, Wd, T = self.dev, self.width, self.T
+        TS = (T + n_extra + 7) // 8 * 8
         patches = ops.patchify_split(x, B, self.image, self.patch, lo=self.lo)
         tok = torch.zeros(B * TS, Wd, dtype=torch.float32, device=dev)
-        # patch embedding + positional embedding written straight into rows 1..576 of every image's token block
         lib.gemm(patches, self.W["conv1"], M=T - 1, N=Wd, K=patches.cols, nmma=self.nmma, batch=B,
                  a_bs=(T - 1) * patches.ld, residual=self.F["pos_patches"], ld_res=Wd, res_bs=0,
                  out=tok[1:], ld_out=Wd, out_bs=TS * Wd)
-        # class rows: class_embedding + positional_embedding[0]
         ops.copy2d(self.F["cls_row"].expand(B, Wd), tok.view(B, TS * Wd)[:, :Wd])
+        if n_extra:
+            # mask-token rows: broadcast the class row over [B, n_extra] rows in one strided copy per image block
+            src = self.F["cls_row"].expand(n_extra, Wd)
+            for b in range(B):
+                ops.copy2d(src, tok[b * TS + T: b * TS + T + n_extra])
+        return tok, TS
+
+    def _tower(self, tok, B, TS, bits=None, row_any=None):
+        """ln_pre + the 24 residual attention blocks on [B*TS, width]; keys = the first 577 rows of every image."""
+        dev, Wd, T = self.dev, self.width, self.T
         h, _ = ops.layer_norm(tok, self.F["ln_pre.g"], self.F["ln_pre.b"], want_f32=True, want_planes=False, lo=self.lo)
         M = B * TS
         d = Wd // self.heads
@@ -77,7 +86,7 @@ class ClipVisualEngine:
             vt = Planes.empty(Wd, M, dev, lo=self.lo)
             lib.gemm(self.W[n + "v"], y, nmma=self.nmma, bias_m=self.F[n + "v.b"], out_planes=vt)
             _, o = ops.attention_tc(qk.col_slice(0, Wd), qk.col_slice(Wd, Wd), vt, B, self.heads, d, TS, T, d ** -0.5,
-                                    self.nmma, tk_stride=TS)
+                                    self.nmma, tk_stride=TS, mask_bits=bits, row_any=row_any)
             h2 = ops.empty(M, Wd, dev)
             self._gemm(o, n + "o", residual=h, out=h2)
             _, y2 = ops.layer_norm(h2, self.F[n + "ln_2.g"], self.F[n + "ln_2.b"], lo=self.lo)
@@ -85,8 +94,80 @@ class ClipVisualEngine:
             self._gemm(y2, n + "fc", act=ACT_QUICKGELU, out_planes=u)
             h = ops.empty(M, Wd, dev)
             self._gemm(u, n + "pr", residual=h2, out=h)
+        return h
+
+    @torch.no_grad()
+    def embed(self, img, boxes_dev, n_crops, H, W, ch, cw):
+        """ClipAdapter.embed_image (clip.py:225-231) of every crop.
+        img: device uint8 / float32 [N, 3, H, W]; boxes [n_crops, 3] int32 -> image_embed fp32 [n_crops, 768]."""
+        B, Wd = n_crops, self.width
+        x = ops.clip_preprocess(img, boxes_dev, B, H, W, ch, cw, self.image)
+        tok, TS = self._tokens(x, B, 0)
+        h = self._tower(tok, B, TS)
         cls = h.view(B, TS * Wd)[:, :Wd]                                       # token 0 of every image (strided rows)
         _, c = ops.layer_norm(cls, self.F["ln_post.g"], self.F["ln_post.b"], lo=self.lo)
-        out = ops.empty(B, self.W["proj"].rows, dev)
+        out = ops.empty(B, self.W["proj"].rows, self.dev)
         lib.gemm(c, self.W["proj"], nmma=self.nmma, out=out)
+        return out
+
+    @torch.no_grad()
+    def mask_embed(self, img, mask_logits, N, H, W):
+        """MaskCLIP.get_mask_embed (clip.py:325-339): img [N,3,H,W] (u8 / f32 in [0,1]), mask logits [N,Q,hm,wm]
+        -> fp32 [N*Q, 768].  The Q mask tokens are rows 577.. of each image's token block; their attention mask
+        is 1 bit per (token, key) built straight from the low-resolution logits (odise_maskclip_bits_f32)."""
+        Wd, T = self.width, self.T
+        Q, hm, wm = mask_logits.shape[1:]
+        x = ops.maskclip_preprocess(img, N, H, W, self.image)
+        tok, TS = self._tokens(x, N, Q)
+        bits, row_any = ops.maskclip_bits(mask_logits.contiguous(), N, Q, hm, wm, self.image, self.patch, TS, T)
+        h = self._tower(tok, N, TS, bits, row_any)
+        _, c = ops.layer_norm(h, self.F["ln_post.g"], self.F["ln_post.b"], lo=self.lo)
+        E = self.W["proj"].rows
+        out = ops.empty(N * Q, E, self.dev)
+        lib.gemm(c.row_slice(T, Q), self.W["proj"], M=Q, nmma=self.nmma, batch=N, a_bs=TS * c.ld, out=out, ld_out=E,
+                 out_bs=Q * E)
+        return out
+
+
+class MaskClipHead:
+    """PoolingCLIPHead + the clip_head branch of CategoryODISE.forward (odise.py:1469-1542, :292-323) on the device:
+    MaskCLIP mask embeddings x CLIP text bank -> per-class max over synonym prompts -> geometric ensemble with the
+    category head (alpha for classes of the training vocabulary, beta for novel ones) -> void merge -> log-probs."""
+
+    def __init__(self, visual, alpha=0.3, beta=0.7, logit_scale=100.0):
+        self.visual, self.dev = visual, visual.dev
+        self.nmma, self.lo = visual.nmma, visual.lo
+        self.alpha, self.beta = float(alpha), float(beta)
+        self.logit_scale = float(min(logit_scale, 100.0))            # clamp(exp(clip.logit_scale), max=100), clip.py:247
+        self._vocab = {}
+
+    def set_vocabulary(self, key, text_bank, group_sizes, overlapping):
+        """text_bank: raw CLIP text embeddings of every prompt [K', 768] (get_and_cache_test_text_embed);
+        overlapping[k]: class k shares a name with the training vocabulary (odise.py:1483-1493)."""
+        tb = text_bank.to(self.dev, torch.float32).contiguous()
+        gs = torch.zeros(len(group_sizes) + 1, dtype=torch.int32)
+        gs[1:] = torch.as_tensor(group_sizes, dtype=torch.int32).cumsum(0)
+        self._vocab[key] = dict(te_p=ops.l2_normalize_split(tb, lo=self.lo), gs=gs.to(self.dev), K=len(group_sizes),
+                                Kp=tb.shape[0],
+                                ov=torch.as_tensor(overlapping).to(torch.uint8).to(self.dev).contiguous())
+
+    @torch.no_grad()
+    def forward(self, key, img, N, H, W, pred_masks, cat_logits, want_open=False):
+        """pred_masks [N,Q,hm,wm] logits, cat_logits [N,Q,K+1] -> dict(pred_logits [N,Q,K+1] merged log-probs,
+        mask_embed [N*Q,768], mask_pred_open_logits [N*Q,K] (row stride K+1), pred_open_logits (optional))."""
+        v = self._vocab[key]
+        Q, K = pred_masks.shape[1], v["K"]
+        rows = N * Q
+        me = self.visual.mask_embed(img, pred_masks, N, H, W)
+        me_p = ops.l2_normalize_split(me, lo=self.lo)
+        sims = ops.empty(rows, v["Kp"], self.dev)
+        lib.gemm(me_p, v["te_p"], nmma=self.nmma, alpha=self.logit_scale, out=sims)
+        if not hasattr(self, "_zero") or self._zero.shape[0] < rows:
+            self._zero = torch.zeros(rows, 1, dtype=torch.float32, device=self.dev)
+        clip_logits = ops.class_max(sims, v["gs"], self._zero, rows, K)         # [rows, K+1], last column unused
+        cl = cat_logits.contiguous().view(rows, K + 1)
+        merged, op = ops.open_vocab_merge(cl, clip_logits, K + 1, v["ov"], self.alpha, self.beta, rows, K, want_open)
+        out = dict(pred_logits=merged.view(N, Q, K + 1), mask_embed=me, mask_pred_open_logits=clip_logits)
+        if want_open:
+            out["pred_open_logits"] = op.view(N, Q, K)
         return out

@@ -284,3 +284,32 @@ def patchify_split(x, B, S, P, lo=True):
     p = Planes.empty(B * G * G, Kpad, x.device, lo=lo, ld=Kpad)
     _check(load().odise_patchify_split_f32(_ptr(x), _ptr(p.hi), _ptr(p.lo), B, S, P, Kpad, _stream()), "patchify")
     return p
+
+
+def maskclip_preprocess(img, N, H, W, S=336):
+    """whole image [N,3,H,W] (u8 0..255 / f32 in [0,1]) -> bilinear S x S + CLIP normalisation, NHWC [N*S*S, 3]."""
+    if img.dtype not in (torch.uint8, torch.float32):
+        raise lib.OdiseError("maskclip_preprocess: uint8 or float32 image expected")
+    out = torch.empty(N * S * S, 3, dtype=torch.float32, device=img.device)
+    _check(load().odise_maskclip_preprocess(_ptr(img), 1 if img.dtype == torch.uint8 else 0, _ptr(out), N, H, W, S,
+                                            _stream()), "maskclip_preprocess")
+    return out
+
+
+def maskclip_bits(mask_logits, B, Q, hm, wm, S, P, Tq, row0):
+    """-> (bits uint32 [B, Tq, words], row_any int32 [B, Tq]) for odise_attention_tc (clip.py:291-321)."""
+    G = S // P
+    words = (G * G + 1 + 31) // 32
+    bits = torch.zeros(B, Tq, words, dtype=torch.int32, device=mask_logits.device)
+    row_any = torch.empty(B, Tq, dtype=torch.int32, device=mask_logits.device)
+    _check(load().odise_maskclip_bits_f32(_ptr(mask_logits), _ptr(bits), _ptr(row_any), B, Q, hm, wm, S, P, Tq, row0,
+                                          _stream()), "maskclip_bits")
+    return bits, row_any
+
+
+def open_vocab_merge(cat_logits, clip_logits, ld_clip, overlap_u8, alpha, beta, rows, K, want_open=False):
+    out = torch.empty(rows, K + 1, dtype=torch.float32, device=cat_logits.device)
+    op = torch.empty(rows, K, dtype=torch.float32, device=cat_logits.device) if want_open else None
+    _check(load().odise_open_vocab_merge_f32(_ptr(cat_logits), _ptr(clip_logits), ld_clip, _ptr(overlap_u8), alpha, beta,
+                                             _ptr(out), _ptr(op), rows, K, _stream()), "open_vocab_merge")
+    return out, op

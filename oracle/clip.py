@@ -34,9 +34,9 @@ class ResidualAttentionBlock(nn.Module):
         self.mlp.add_module("gelu", QuickGELU())
         self.mlp.add_module("c_proj", nn.Linear(4 * d, d))
 
-    def forward(self, x):                      # [L, N, D]
+    def forward(self, x, attn_mask=None):      # [L, N, D]; bool attn_mask: True = may NOT attend
         y = self.ln_1(x)
-        x = x + self.attn(y, y, y, need_weights=False)[0]
+        x = x + self.attn(y, y, y, need_weights=False, attn_mask=attn_mask)[0]
         return x + self.mlp(self.ln_2(x))
 
 
@@ -45,9 +45,9 @@ class Transformer(nn.Module):
         super().__init__()
         self.resblocks = nn.ModuleList([ResidualAttentionBlock(width, heads) for _ in range(layers)])
 
-    def forward(self, x):
+    def forward(self, x, attn_mask=None):
         for r in self.resblocks:
-            x = r(x)
+            x = r(x, attn_mask)
         return x
 
 
@@ -94,3 +94,74 @@ def encode_image(visual, image):
 def embed_image(visual, crop01):
     """ClipAdapter.embed_image with normalize=False (clip.py:225-231, ldm.py:652): crop in [0, 1] -> [B, out_dim]."""
     return encode_image(visual, preprocess(crop01, visual.image_size)).float()
+
+
+# ---------------------------------------------------------------------------------------------------- MaskCLIP
+# MaskCLIP (clip.py:239-361): Q extra "mask tokens" (copies of the class token after ln_pre) ride through the frozen
+# ViT; nobody attends to them, and mask token q attends to the class token and to the patches its mask touches.
+# Pinned: tests/test_oracle_cpu.py runs the reference's MaskCLIP methods verbatim on these modules.
+
+def mask_clip_forward(visual, x, attn_mask, num_mask_tokens):
+    """MaskCLIP._mask_clip_forward (clip.py:252-282): normalised image [B,3,S,S] -> [B, Q, out_dim]."""
+    x = visual.conv1(x)
+    x = x.reshape(x.shape[0], x.shape[1], -1).permute(0, 2, 1)
+    x = torch.cat([visual.class_embedding.to(x.dtype) + torch.zeros(x.shape[0], 1, x.shape[-1], dtype=x.dtype), x], dim=1)
+    x = visual.ln_pre(x + visual.positional_embedding.to(x.dtype)).permute(1, 0, 2)
+    x = torch.cat([x[0:1].expand(num_mask_tokens, -1, -1), x], dim=0)
+    x = visual.transformer(x, attn_mask).permute(1, 0, 2)
+    x = visual.ln_post(x[:, :num_mask_tokens, :])
+    return torch.einsum("nld,dc->nlc", x, visual.proj)
+
+
+def mask_attention_mask(visual, mask_logits):
+    """encode_image_with_mask's mask construction (clip.py:291-321): mask logits [B, Q, S, S] (already at the CLIP
+    resolution) -> bool [B*heads, Q+1+G*G, Q+1+G*G], True = blocked."""
+    B, Q = mask_logits.shape[:2]
+    patch_mask = F.max_pool2d(mask_logits.sigmoid(), kernel_size=visual.conv1.kernel_size, stride=visual.conv1.stride)
+    blocked = (patch_mask < 0.5).reshape(B, Q, -1)
+    n_img = visual.positional_embedding.shape[0] - 1
+    n_all = Q + 1 + n_img
+    am = torch.zeros(n_all, n_all, dtype=torch.bool)
+    am[:, :Q] = True
+    am = am.unsqueeze(0).repeat_interleave(B, dim=0)
+    am[:, :Q, -n_img:] = blocked
+    heads = visual.conv1.out_channels // 64
+    return am.unsqueeze(1).expand(-1, heads, -1, -1).reshape(B * heads, n_all, n_all)
+
+
+def get_mask_embed(visual, image01, mask_logits):
+    """MaskCLIP.get_mask_embed (clip.py:325-339): image in [0,1] at any size, mask logits [B, Q, h, w] -> [B, Q, out]."""
+    S = visual.image_size
+    image = F.interpolate(image01, size=(S, S), mode="bilinear", align_corners=False)
+    mask = F.interpolate(mask_logits, size=(S, S), mode="bilinear", align_corners=False)
+    image = preprocess(image, S)                     # Resize(S) of an SxS tensor is the identity; Normalize remains
+    return mask_clip_forward(visual, image, mask_attention_mask(visual, mask), mask_logits.shape[1])
+
+
+def maskclip_pred_logits(mask_embed, text_embed, group_sizes, logit_scale):
+    """MaskCLIP.pred_logits (clip.py:341-351) + ensemble_logits_with_labels (helper.py:79-109, "max").
+    logit_scale = clamp(exp(clip.logit_scale), max=100) (clip.py:247-250)."""
+    lg = torch.einsum("bqc,nc->bqn", F.normalize(mask_embed, dim=-1), F.normalize(text_embed, dim=-1)) * logit_scale
+    out, o = [], 0
+    for n in group_sizes:
+        out.append(lg[..., o:o + n].max(dim=-1).values)
+        o += n
+    return torch.stack(out, dim=-1)
+
+
+def pooling_clip_ensemble(pred_open_logits, mask_pred_open_logits, overlapping, alpha, beta):
+    """PoolingCLIPHead.forward, normalize_logits=True branch (odise.py:1506-1536): geometric ensemble of the two class
+    distributions with exponent alpha for classes seen in training (overlapping = 1) and beta for novel ones."""
+    ov = overlapping.to(pred_open_logits.dtype)
+    p, m = pred_open_logits.softmax(dim=-1), mask_pred_open_logits.softmax(dim=-1)
+    base = (p ** (1 - alpha) * m ** alpha).log() * ov
+    novel = (p ** (1 - beta) * m ** beta).log() * (1 - ov)
+    return base + novel
+
+
+def merge_with_void(pred_logits, open_logits):
+    """CategoryODISE.forward, clip_head without bg labels (odise.py:300-323): class distribution from the ensemble,
+    void probability from the category head -> log-probabilities [B, Q, K+1]."""
+    p_void = F.softmax(pred_logits, dim=-1)[..., -1:]
+    cls = F.softmax(open_logits, dim=-1) * (1 - p_void)
+    return torch.log(torch.cat([cls, p_void], dim=-1) + 1e-8)

@@ -49,3 +49,84 @@ def test_clip_image_embed(cuda):
     torch.cuda.synchronize()
     assert got.shape == (2, 768)
     assert _rel(got.cpu(), want) < 1e-3, _rel(got.cpu(), want)
+
+
+def test_maskclip_preprocess_and_bits(cuda):
+    import torch.nn.functional as F
+    from odise_b200 import ops
+    from oracle import clip as oclip
+    g = torch.Generator().manual_seed(11)
+    img = torch.rand(2, 3, 320, 448, generator=g)
+    got = ops.maskclip_preprocess(img.to(cuda), 2, 320, 448, 336).view(2, 336, 336, 3).permute(0, 3, 1, 2).cpu()
+    want = oclip.preprocess(F.interpolate(img, size=(336, 336), mode="bilinear", align_corners=False), 336)
+    assert (got - want).abs().max() < 2e-5
+    u8 = torch.randint(0, 256, (1, 3, 1024, 1024), generator=g, dtype=torch.uint8)
+    got = ops.maskclip_preprocess(u8.to(cuda), 1, 1024, 1024, 336).view(1, 336, 336, 3).permute(0, 3, 1, 2).cpu()
+    want = oclip.preprocess(F.interpolate(u8.float() / 255.0, size=(336, 336), mode="bilinear", align_corners=False), 336)
+    assert (got - want).abs().max() < 2e-5
+    # attention bits of the mask tokens vs the reference's bool mask (True = blocked)
+    with torch.device("meta"):
+        v = oclip.VisionTransformer()
+    B, Q, T, TS = 2, 9, 577, 592
+    masks = torch.randn(B, Q, 64, 80, generator=g) * 2 - 1.5
+    masks[1, 3] = -4.0                                                     # touches no patch: only the class key stays
+    am = oclip.mask_attention_mask(v, F.interpolate(masks, size=(336, 336), mode="bilinear", align_corners=False))
+    am = am.view(B, 16, Q + T, Q + T)[:, 0, :Q, Q:]                          # [B, Q, 577] blocked flags of mask rows
+    bits, row_any = ops.maskclip_bits(masks.to(cuda), B, Q, 64, 80, 336, 14, TS, T)
+    bits, row_any = bits.cpu(), row_any.cpu()
+    assert row_any[:, T:T + Q].eq(1).all() and row_any[:, :T].eq(0).all() and row_any[:, T + Q:].eq(0).all()
+    keys = torch.arange(T)
+    on = ((bits[:, T:T + Q][..., keys // 32] >> (keys % 32)) & 1).bool()
+    assert torch.equal(on, ~am)
+    assert on[1, 3].sum() == 1 and on[..., 0].all()
+
+
+def test_open_vocab_merge(cuda):
+    from odise_b200 import ops
+    from oracle import clip as oclip
+    g = torch.Generator().manual_seed(12)
+    rows, K = 37, 150
+    cat = torch.randn(rows, K + 1, generator=g) * 6
+    clip = torch.randn(rows, K + 1, generator=g) * 8                       # last column = padding (row stride K+1)
+    ov = (torch.rand(K, generator=g) < 0.5)
+    merged, op = ops.open_vocab_merge(cat.to(cuda), clip.to(cuda), K + 1, ov.to(torch.uint8).to(cuda), 0.3, 0.7, rows, K,
+                                      want_open=True)
+    ens = oclip.pooling_clip_ensemble(cat[:, :K].double(), clip[:, :K].double(), ov.long(), 0.3, 0.7)
+    want = oclip.merge_with_void(cat.double(), ens)
+    assert (op.cpu().double() - ens).abs().max() < 1e-4
+    assert (merged.cpu().double() - want).abs().max() < 1e-4
+
+
+def test_maskclip_head(cuda):
+    """MaskCLIP.get_mask_embed + pred_logits + PoolingCLIPHead ensemble + void merge vs the oracle (full ViT-L/14-336)."""
+    from odise_b200 import spec
+    from odise_b200.clip import ClipVisualEngine, MaskClipHead
+    from oracle import clip as oclip
+    sd = spec.synth_state_dict(spec.clip_visual_params(), seed=5)
+    with torch.device("meta"):
+        v = oclip.VisionTransformer()
+    v.load_state_dict({k[len(spec.CLIP_PREFIX):]: t for k, t in sd.items()}, assign=True)
+    v.eval()
+    g = torch.Generator().manual_seed(13)
+    N, Q, K = 1, 12, 6
+    img = torch.rand(N, 3, 512, 512, generator=g)
+    yy, xx = torch.meshgrid(torch.arange(128).float(), torch.arange(128).float(), indexing="ij")
+    masks = torch.stack([(20 + 4 * q - ((yy - 10 * q) ** 2 + (xx - 64) ** 2).sqrt()) * 0.5 for q in range(Q)])[None]
+    masks = masks + torch.randn(N, Q, 128, 128, generator=g) * 0.2
+    sizes = [2, 1, 3, 1, 1, 2]
+    text = torch.randn(sum(sizes), 768, generator=g)
+    cat = torch.randn(N, Q, K + 1, generator=g) * 3
+    ov = torch.tensor([1, 0, 1, 1, 0, 0])
+    with torch.no_grad():
+        me = oclip.get_mask_embed(v, img, masks)
+        lg = oclip.maskclip_pred_logits(me, text, sizes, 100.0)
+        want = oclip.merge_with_void(cat, oclip.pooling_clip_ensemble(cat[..., :-1], lg, ov, 0.3, 0.7))
+    eng = ClipVisualEngine(sd, cuda, nmma=3)
+    head = MaskClipHead(eng, alpha=0.3, beta=0.7, logit_scale=100.0)
+    head.set_vocabulary("v", text, sizes, ov)
+    out = head.forward("v", img.to(cuda), N, 512, 512, masks.to(cuda), cat.to(cuda))
+    torch.cuda.synchronize()
+    assert _rel(out["mask_embed"].view(N, Q, -1).cpu(), me) < 1e-3, _rel(out["mask_embed"].view(N, Q, -1).cpu(), me)
+    got_lg = out["mask_pred_open_logits"].view(N, Q, K + 1)[..., :K].cpu()
+    assert (got_lg - lg).abs().max() < 2e-2          # logits are 100 * cos-sim: 2e-4 of their scale
+    assert (out["pred_logits"].cpu() - want).abs().max() < 2e-2

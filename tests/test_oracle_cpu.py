@@ -209,3 +209,58 @@ def test_reference_clip_glue_runs_on_oracle_visual():
     fake = types.SimpleNamespace(clip=types.SimpleNamespace(visual=v))
     emb_ref, _ = rc.ClipAdapter._encode_image(fake, img)
     assert torch.allclose(emb_ref, oclip.encode_image(v, img), rtol=1e-5, atol=1e-6)
+
+
+@needs_ref
+@torch.no_grad()
+def test_reference_maskclip_runs_on_oracle_visual():
+    """MaskCLIP.get_mask_embed / pred_logits (clip.py:252-351) executed verbatim on the oracle VisionTransformer."""
+    import importlib
+    from oracle import clip as oclip
+    refshim.install()
+    rc = importlib.import_module("odise.modeling.meta_arch.clip")
+    torch.manual_seed(1)
+    v = oclip.VisionTransformer(image_size=56, patch=14, width=128, layers=2, heads=2, out_dim=32).eval()
+    for p in v.parameters():
+        torch.nn.init.normal_(p, std=0.1)
+    img = torch.rand(2, 3, 96, 96)
+    masks = torch.randn(2, 5, 24, 24) * 3
+    masks[0, 0] = -5.0                                         # a query whose mask touches no patch at all
+    fake = types.SimpleNamespace(clip=types.SimpleNamespace(visual=v), image_size=(56, 56),
+                                 clip_preprocess=lambda im: oclip.preprocess(im, 56), logit_scale=torch.tensor(37.0))
+    fake._mask_clip_forward = lambda *a: rc.MaskCLIP._mask_clip_forward(fake, *a)
+    fake.encode_image_with_mask = lambda *a: rc.MaskCLIP.encode_image_with_mask(fake, *a)
+    ref = rc.MaskCLIP.get_mask_embed(fake, img, masks)
+    got = oclip.get_mask_embed(v, img, masks)
+    assert ref.shape == (2, 5, 32) and torch.allclose(ref, got, rtol=1e-5, atol=1e-6)
+    text = torch.randn(7, 32)
+    labels = [["a", "b"], ["c"], ["d", "e", "f"], ["g"]]
+    lr = rc.MaskCLIP.pred_logits(fake, ref, text, labels)
+    lo = oclip.maskclip_pred_logits(got, text, [len(l) for l in labels], fake.logit_scale)
+    assert torch.allclose(lr, lo, rtol=1e-5, atol=1e-5)
+
+
+@needs_ref
+@torch.no_grad()
+def test_reference_pooling_clip_head_ensemble():
+    """PoolingCLIPHead.forward (odise.py:1469-1542) run verbatim with a stubbed MaskCLIP == oracle ensemble."""
+    from oracle import clip as oclip
+    refshim.install()
+    import importlib
+    ro = importlib.import_module("odise.modeling.meta_arch.odise")
+    torch.manual_seed(2)
+    test_labels = [["cat", "kitty"], ["unicorn"], ["dog"], ["spaceship", "rocket"]]
+    train_labels = [["cat"], ["dog", "puppy"], ["tree"]]
+    cat_logits, clip_logits = torch.randn(2, 6, 4) * 4, torch.randn(2, 6, 4) * 4
+    fake = types.SimpleNamespace(training=False, test_labels=test_labels, train_labels=train_labels, prompt="photo",
+                                 with_bg=False, bg_labels=None, alpha=0.3, beta=0.7, normalize_logits=True,
+                                 get_and_cache_test_text_embed=lambda labels: None,
+                                 clip=lambda im, m, t, l: {"mask_pred_open_logits": clip_logits})
+    out = ro.PoolingCLIPHead.forward(fake, {"pred_open_logits": cat_logits.clone(), "images": torch.zeros(1),
+                                            "pred_masks": None})
+    ov = torch.tensor([1, 0, 1, 0])
+    got = oclip.pooling_clip_ensemble(cat_logits, clip_logits, ov, 0.3, 0.7)
+    assert torch.allclose(out["pred_open_logits"], got, rtol=1e-6, atol=1e-6)
+    full = torch.randn(2, 6, 5)
+    merged = oclip.merge_with_void(full, got)
+    assert torch.allclose(merged.exp().sum(-1), torch.ones(2, 6) + 5e-8, atol=1e-5)
