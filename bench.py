@@ -140,6 +140,8 @@ class CpuHotPath:
                 vis = oclip.VisionTransformer()
             vis.load_state_dict({k[len(spec.CLIP_PREFIX):]: v for k, v in sd_c.items()}, assign=True)
             self.vis = vis.eval()
+            self.img_full = torch.rand(1, 3, size, size, generator=g)
+            self.ov = torch.tensor([(k % 2) == 0 for k in range(VOCABS[vocab][0])]).long()
 
     @torch.no_grad()
     def sample(self):
@@ -156,12 +158,17 @@ class CpuHotPath:
         mf, _, ms = m2f.pixel_decoder(self.sd_h, self.feats, "sem_seg_head.pixel_decoder.")
         out, _ = m2f.transformer_decoder(self.sd_h, ms, mf, "sem_seg_head.predictor.")
         te, ne = m2f.category_embed(self.sd_h, self.bank, self.null)
-        m2f.cal_pred_logits(out["mask_embed"], te, ne, out["logit_scale"], self.sizes)
+        lg = m2f.cal_pred_logits(out["mask_embed"], te, ne, out["logit_scale"], self.sizes)
+        if self.full:                 # clip_head branch (odise.py:292-323): MaskCLIP over the whole image + ensemble
+            oc = self.oclip
+            me = oc.get_mask_embed(self.vis, self.img_full, out["pred_masks"])
+            cl = oc.maskclip_pred_logits(me, self.bank, self.sizes, 100.0)
+            oc.merge_with_void(lg, oc.pooling_clip_ensemble(lg[..., :-1], cl, self.ov, 0.3, 0.7))
         t_head = time.perf_counter() - t0
         ips = 1.0 / (self.crops * t_unet + t_head)
         return dict(value=ips, unit="images/s", cores=self.n, kind="port",
                     sample=f"1 crop (512^2) through {'CLIP ViT-L/14 image tower + VAE enc + UNet + full VAE dec' if self.full else 'the UNet'} as the "
-                           f"reference executes it ({t_unet:.2f} s) + 1 image head at {self.size}^2 "
+                           f"reference executes it ({t_unet:.2f} s) + 1 image head{' + MaskCLIP' if self.full else ''} at {self.size}^2 "
                            f"({t_head:.2f} s); images/s = 1/({self.crops}*t_crop + t_head); fp32 torch CPU, "
                            f"{self.n} threads of {os.cpu_count()}")
 
@@ -295,11 +302,12 @@ def main():
         "config": {"workload": f"ODISE(label) hot path, batch {B}/GPU x {S}x{S}, {crops} crops/image, {args.vocab} "
                                f"({ncls} classes / {npr} prompts), Q=100",
                    "stages": ("CLIP ViT-L/14-336 image tower on every crop, KL-VAE encoder + truncated decoder (taps), "
-                              if args.full else "") +
+                              if args.full else "") + ("MaskCLIP (100 mask tokens/image through the ViT) + alpha/beta "
+                              "ensemble + void merge, " if args.full else "") +
                              "implicit-captioner front, q_sample, SD-v1 UNet feature pass (4 taps), 8 projections, "
                              "MSDeformAttn pixel decoder, 9-layer masked-attention decoder, CLIP-text scoring, "
                              "NCCL all-gather of logits",
-                   "not_in_path": ("nothing of the per-image pass: CLIP image tower and KL-VAE taps ARE executed; the CLIP "
+                   "not_in_path": ("nothing of the per-image pass: CLIP image tower, KL-VAE taps and MaskCLIP ARE executed; the CLIP "
                                    "TEXT bank of the vocabulary is precomputed per vocabulary (as in the reference)")
                                   if args.full else
                                   ("KL-VAE encoder/decoder taps and CLIP image embedding enter as seeded synthetic "

@@ -7,6 +7,8 @@
 One process per GPU; images shard over ranks with a single NCCL all-gather of the final logits (reference analogue:
 d2 evaluator gather).  A step at fixed (batch, H, W) is captured once into a CUDA graph and replayed.
 """
+import math
+
 import torch
 
 from . import lib, ops, spec
@@ -20,7 +22,10 @@ def full_param_list(with_vae=False, with_clip=False):
 
 
 class ODISEEngine:
-    def __init__(self, sd, device, nmma=3, num_queries=100, with_vae=False, with_clip=False):
+    def __init__(self, sd, device, nmma=3, num_queries=100, with_vae=False, with_clip=False, with_clip_head=None,
+                 alpha=0.3, beta=0.7):
+        """with_clip: CLIP ViT-L/14-336 image tower (implicit captioner input, §8f-2); with_clip_head (default = with_clip):
+        MaskCLIP + PoolingCLIPHead ensemble (odise_with_label.py: alpha 0.3, beta 0.7) on the same frozen tower."""
         self.dev = torch.device(device)
         self.nmma = nmma
         vae = None
@@ -32,6 +37,12 @@ class ODISEEngine:
             from .clip import ClipVisualEngine
             clip = ClipVisualEngine(sd, device, nmma=nmma)
         self.with_vae, self.with_clip = with_vae, with_clip
+        self.clip_head = None
+        if with_clip_head if with_clip_head is not None else with_clip:
+            from .clip import MaskClipHead
+            assert clip is not None, "the MaskCLIP head shares the CLIP image tower: with_clip=True required"
+            self.clip_head = MaskClipHead(clip, alpha=alpha, beta=beta,
+                                          logit_scale=math.exp(float(sd.get("clip.logit_scale", math.log(100.0)))))
         self.backbone = BackboneEngine(sd, device, nmma=nmma, vae=vae, clip=clip)
         self.head = HeadEngine(sd, device, nmma=nmma, num_queries=num_queries)
         self.Q = num_queries
@@ -39,11 +50,18 @@ class ODISEEngine:
         self.vocab_key = None
         self.launches_per_step = None
 
-    def set_vocabulary(self, key, text_bank, null_bank, group_sizes, thing_ids=None):
+    def set_vocabulary(self, key, text_bank, null_bank, group_sizes, thing_ids=None, clip_text_bank=None,
+                       overlapping=None):
         """OpenPanopticInference / CategoryEmbed.test_labels analogue (pano_wrapper.py:58-68, odise.py:1281-1307):
         the vocabulary is a [K', 768] CLIP text bank + per-class prompt counts (+ which classes are "things" for
-        the panoptic merge, metadata.thing_dataset_id_to_contiguous_id in the reference)."""
+        the panoptic merge, metadata.thing_dataset_id_to_contiguous_id in the reference).  With a MaskCLIP head:
+        clip_text_bank = the raw CLIP text embeddings of the same prompts (default: text_bank), overlapping[k] = class k
+        shares a name with the training vocabulary (odise.py:1483-1493; default: every other class)."""
         self.head.set_vocabulary(key, text_bank, null_bank, group_sizes)
+        if self.clip_head is not None:
+            K = len(group_sizes)
+            ov = overlapping if overlapping is not None else [(k % 2) == 0 for k in range(K)]
+            self.clip_head.set_vocabulary(key, clip_text_bank if clip_text_bank is not None else text_bank, group_sizes, ov)
         self.vocab_key = key
         from .postprocess import PostProcessor
         K = len(group_sizes)
@@ -69,6 +87,11 @@ class ODISEEngine:
                    mask_pooled_features=last["mask_pooled_features"].view(n_images, self.Q, -1))
         if "pred_logits" in out:
             res["pred_logits"] = out["pred_logits"]
+            if self.clip_head is not None:        # odise.py:292-323: MaskCLIP ensemble replaces the class scores
+                ch = self.clip_head.forward(self.vocab_key, images_u8, n_images, H, W, res["pred_masks"], out["pred_logits"])
+                res["pred_logits_category"] = out["pred_logits"]
+                res["pred_logits"] = ch["pred_logits"]
+                res["clip_mask_embed"] = ch["mask_embed"]
         res["aux"] = out["heads"][:-1]
         return res
 

@@ -98,3 +98,42 @@ class B200MaskFormerHead(nn.Module):
 
     def layers(self, features, mask=None):
         return self.forward(features, mask)
+
+
+class B200PoolingCLIPHead(nn.Module):
+    """Drop-in for PoolingCLIPHead (odise.py:1420-1542), inference only, normalize_logits=True, no bg labels:
+    forward(outputs) pops "pred_open_logits" [B, Q, K] and returns {"pred_open_logits": ensemble logits [B, Q, K]}
+    from outputs["images"] ([B, 3, H, W] in [0, 1]) and outputs["pred_masks"].  The vocabulary (CLIP text embeddings of
+    the prompts, prompt counts per class, overlap with the training vocabulary) is set with set_vocabulary()."""
+
+    def __init__(self, state_dict, device, alpha=0.35, beta=0.65, nmma=3, visual=None):
+        super().__init__()
+        from .clip import ClipVisualEngine, MaskClipHead
+        self.visual = visual if visual is not None else ClipVisualEngine(state_dict, device, nmma=nmma)
+        import math
+        self.engine = MaskClipHead(self.visual, alpha=alpha, beta=beta,
+                                   logit_scale=math.exp(float(state_dict.get("clip.logit_scale", math.log(100.0)))))
+        self.alpha, self.beta = alpha, beta
+
+    @property
+    def with_bg(self):
+        return False
+
+    def set_vocabulary(self, text_embed, group_sizes, overlapping):
+        self.engine.set_vocabulary("test", text_embed, group_sizes, overlapping)
+
+    @torch.no_grad()
+    def forward(self, outputs, targets=None):
+        assert not self.training, "PoolingCLIPHead only supports inference"
+        assert targets is None and "test" in self.engine._vocab
+        open_logits = outputs.pop("pred_open_logits")
+        img, masks = outputs["images"], outputs["pred_masks"]
+        if not img.is_cuda:
+            raise RuntimeError("B200PoolingCLIPHead: CUDA tensors required (no CPU path)")
+        B, Q, K = open_logits.shape
+        # the device kernel takes the category logits with a void column; it only enters the merged output, which the
+        # plugin surface does not return (the caller merges, odise.py:300-323)
+        cat = torch.cat([open_logits.float(), torch.zeros(B, Q, 1, device=img.device)], dim=-1)
+        r = self.engine.forward("test", img.contiguous().float(), B, img.shape[2], img.shape[3], masks.float(), cat,
+                                want_open=True)
+        return {"pred_open_logits": r["pred_open_logits"]}

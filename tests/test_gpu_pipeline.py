@@ -1,0 +1,97 @@
+"""End-to-end GPU parity of the assembled pipeline (odise_b200/pipeline.py::ODISEEngine) against the oracle pieces
+composed the way the reference composes them:
+  LdmImplicitCaptionerExtractor.forward (ldm.py:697-718) -> LdmExtractor.forward (ldm.py:543-613)
+  -> FeatureExtractorBackbone.forward_features (feature_extractor.py:157-179), then the clip_head branch of
+  CategoryODISE.forward (odise.py:292-323).  One 512^2 image = one crop, full-size SD-v1 / ViT-L/14-336 / KL-VAE."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    return ((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30)).item()
+
+
+@pytest.fixture(scope="module")
+def world(cuda):
+    from odise_b200 import spec
+    from odise_b200.pipeline import ODISEEngine, full_param_list, synthetic_vocabulary
+    sd = spec.synth_state_dict(full_param_list(with_vae=True, with_clip=True), seed=0)
+    eng = ODISEEngine(sd, cuda, nmma=3, with_vae=True, with_clip=True)
+    bank, null, sizes = synthetic_vocabulary(20, 31)
+    clip_bank = torch.randn(31, 768, generator=torch.Generator().manual_seed(77))
+    ov = [(k % 3) == 0 for k in range(20)]
+    eng.set_vocabulary("v20", bank, null, sizes, clip_text_bank=clip_bank, overlapping=ov)
+    img = torch.randint(0, 256, (1, 3, 512, 512), generator=torch.Generator().manual_seed(5), dtype=torch.uint8)
+    return dict(sd=sd, eng=eng, img=img, bank=bank, null=null, sizes=sizes, clip_bank=clip_bank, ov=ov)
+
+
+@torch.no_grad()
+def test_backbone_end_to_end(cuda, world):
+    """uint8 image -> s2..s5 through VAE taps, CLIP image embedding, implicit captioner, UNet taps, projections."""
+    from odise_b200 import spec
+    from oracle import clip as oclip, ldm, m2f
+    sd, eng, img = world["sd"], world["eng"], world["img"]
+    got = eng.backbone.forward(1, 512, 512, images_u8=img.to(cuda))
+    torch.cuda.synchronize()
+
+    def load(cls, prefix):
+        with torch.device("meta"):
+            m = cls()
+        m.load_state_dict({k[len(prefix):]: v for k, v in sd.items() if k.startswith(prefix)}, assign=True)
+        return m.eval()
+    unet, vae, vis = load(ldm.UNetModel, spec.UNET_PREFIX), load(ldm.AutoencoderKL, spec.VAE_PREFIX), load(oclip.VisionTransformer, spec.CLIP_PREFIX)
+    img01 = img.float() / 255.0
+    e = "backbone.feature_extractor."
+    lin = torch.nn.functional.linear
+    emb = oclip.embed_image(vis, img01)                                                        # ldm.py:705
+    uncond = torch.randn(1, 77, 768, generator=torch.Generator().manual_seed(17))              # BackboneEngine default
+    ctx = uncond + torch.tanh(sd[e + "alpha_cond"]) * (
+        lin(emb, sd[e + "clip_project.linear.weight"], sd[e + "clip_project.linear.bias"]).unsqueeze(1)
+        + sd[e + "clip_project.positional_embedding"])
+    cemb = torch.tanh(sd[e + "alpha_cond_time_embed"]) * (
+        lin(emb, sd[e + "time_embed_project.linear.weight"], sd[e + "time_embed_project.linear.bias"]).unsqueeze(1)
+        + sd[e + "time_embed_project.positional_embedding"])
+    lat, ef = ldm.encoder_features(vae, (img01 - 0.5) / 0.5)
+    uf = ldm.unet_features(unet, ldm.q_sample_t0(lat, ldm.shared_noise()), ctx, cemb[:, 0])
+    df = ldm.decoder_features(vae, lat)
+    want = m2f.forward_features(sd, [*ef, *uf, *df], (512, 512))
+    for k, w in want.items():
+        t, h, ww = got[k]
+        r = _rel(t.view(1, h, ww, 512).permute(0, 3, 1, 2).cpu(), w)
+        assert r < 1e-3, (k, r)
+
+
+@torch.no_grad()
+def test_step_graph_and_clip_head(cuda, world):
+    """eager step == CUDA-graph replay == infer(); the merged class scores equal the oracle's clip_head branch applied
+    to the engine's own category logits / mask logits (the decoder's hard thresholds make a fully independent CPU
+    run discontinuous: the decoder itself is covered teacher-forced in test_gpu_head.py)."""
+    from odise_b200 import spec
+    from oracle import clip as oclip
+    sd, eng, img = world["sd"], world["eng"], world["img"]
+    dimg = img.to(cuda)
+    a = eng.step(1, 512, 512, images_u8=dimg)
+    torch.cuda.synchronize()
+    assert a["pred_logits"].shape == (1, 100, 21) and a["pred_masks"].shape == (1, 100, 128, 128)
+    assert torch.isfinite(a["pred_logits"]).all()
+    assert (a["pred_logits"].exp().sum(-1) - 1).abs().max() < 1e-3         # log-probabilities (+ 21e-8)
+    ea = {k: a[k].clone() for k in ("pred_logits", "pred_masks", "pred_logits_category")}
+    host = eng.infer(img.pin_memory())                                      # graph capture + replay, H2D/D2H inside
+    assert torch.equal(host["pred_logits"], ea["pred_logits"].cpu())
+    assert torch.equal(host["pred_masks"], ea["pred_masks"].cpu())
+    with torch.device("meta"):
+        vis = oclip.VisionTransformer()
+    vis.load_state_dict({k[len(spec.CLIP_PREFIX):]: v for k, v in sd.items() if k.startswith(spec.CLIP_PREFIX)}, assign=True)
+    cat, masks = ea["pred_logits_category"].cpu(), ea["pred_masks"].cpu()
+    me = oclip.get_mask_embed(vis.eval(), img.float() / 255.0, masks)
+    lg = oclip.maskclip_pred_logits(me, world["clip_bank"], world["sizes"], 100.0)
+    want = oclip.merge_with_void(cat, oclip.pooling_clip_ensemble(cat[..., :-1], lg, torch.tensor(world["ov"]).long(), 0.3, 0.7))
+    # a patch whose pooled mask value sits within rounding of the 0.5 threshold may flip one attention bit of one
+    # query: require every query but (at most) two to match tightly
+    err = (ea["pred_logits"].cpu() - want).abs().amax(-1)[0]
+    assert (err < 3e-2).sum() >= 98, err
+    # post-processing on the merged scores runs end to end
+    post = eng.postprocess(a, 512, 512)
+    assert post["sem_seg"].shape == (1, 20, 512, 512) and post["panoptic_seg"].shape == (1, 512, 512)
