@@ -6,6 +6,7 @@
 // ldm GEGLU, ldm Upsample (nearest x2), F.interpolate (feature_extractor.py:165, msdeformattn.py:349),
 // torch.cat skip concat (ldm.py:485), crop paste (feature_extractor.py:243-248), F.normalize + per-class max
 // (odise.py:181-207, helper.py:96-100), MaskPooling threshold / normalise (odise.py:945-959).
+#include <cstdlib>
 #include "ptx.cuh"
 #include "odise_b200.h"
 #include "launch_count.h"
@@ -221,11 +222,95 @@ __global__ void gn_apply_kernel(const float* __restrict__ x, long long ldx, cons
   }
 }
 
+// Lean variant for the common case (no residual / accumulate, C % 8 == 0): thread = fixed channel OCTET, 32-byte loads,
+// 16-byte plane stores, two pixels in flight, <= 64 registers so that 4 x 256 threads stay resident per SM; the grid is
+// exactly one resident wave (grid-stride over pixel chunks).
+__device__ __forceinline__ void store_split8(__nv_bfloat16* hi, __nv_bfloat16* lo, const float* v) {
+  __align__(16) __nv_bfloat16 h[8];
+  __align__(16) __nv_bfloat16 l[8];
+#pragma unroll
+  for (int t = 0; t < 8; ++t) split_bf16(v[t], h[t], l[t]);
+  *reinterpret_cast<uint4*>(hi) = *reinterpret_cast<const uint4*>(h);
+  if (lo) *reinterpret_cast<uint4*>(lo) = *reinterpret_cast<const uint4*>(l);
+}
+
+__global__ void __launch_bounds__(256, 4)
+gn_apply8_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ mean,
+                 const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ beta,
+                 int act, float* __restrict__ y, long long ldy, __nv_bfloat16* __restrict__ hi,
+                 __nv_bfloat16* __restrict__ lo, long long ldo, int HW, int C, int G, long long x_bs, long long y_bs,
+                 long long o_bs, int pix_per_block) {
+  const int b = blockIdx.y;
+  const int C8 = C >> 3, cpg = C / G;
+  const int PL = blockDim.x / C8;
+  const int q = threadIdx.x % C8, pl = threadIdx.x / C8;
+  if (pl >= PL) return;
+  const int c = q * 8;
+  // an octet touches at most two groups (launcher guarantees cpg % 4 == 0 or cpg >= 8): the first nb channels use g0
+  const int g0 = c / cpg, g1 = min(g0 + 1, G - 1);
+  const int nb = min(8, (g0 + 1) * cpg - c);
+  const float mu0 = __ldg(mean + b * G + g0), rs0 = __ldg(rstd + b * G + g0);
+  const float mu1 = __ldg(mean + b * G + g1), rs1 = __ldg(rstd + b * G + g1);
+  float ga[8], be[8];
+#pragma unroll
+  for (int t = 0; t < 8; ++t) { ga[t] = __ldg(gamma + c + t); be[t] = __ldg(beta + c + t); }
+  const float* xb = x + (long long)b * x_bs + c;
+  const int p0 = blockIdx.x * pix_per_block, p1 = min(HW, p0 + pix_per_block);
+  auto finish = [&](const float4& v0, const float4& v1, int pix) {
+    float o[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+    for (int t = 0; t < 8; ++t)
+      o[t] = fmaf((o[t] - (t < nb ? mu0 : mu1)) * (t < nb ? rs0 : rs1), ga[t], be[t]);   // torch order
+    if (act != ODISE_ACT_NONE) {
+#pragma unroll
+      for (int t = 0; t < 8; ++t) o[t] = act_apply(o[t], act);
+    }
+    if (y) {
+      float4* yp = reinterpret_cast<float4*>(y + (long long)b * y_bs + (long long)pix * ldy + c);
+      yp[0] = make_float4(o[0], o[1], o[2], o[3]);
+      yp[1] = make_float4(o[4], o[5], o[6], o[7]);
+    }
+    if (hi) {
+      const long long o_ = (long long)b * o_bs + (long long)pix * ldo + c;
+      store_split8(hi + o_, lo ? lo + o_ : nullptr, o);
+    }
+  };
+  int pix = p0 + pl;
+  for (; pix + PL < p1; pix += 2 * PL) {
+    const float4* s0 = reinterpret_cast<const float4*>(xb + (long long)pix * ldx);
+    const float4* s1 = reinterpret_cast<const float4*>(xb + (long long)(pix + PL) * ldx);
+    const float4 v00 = s0[0], v01 = s0[1], v10 = s1[0], v11 = s1[1];
+    finish(v00, v01, pix);
+    finish(v10, v11, pix + PL);
+  }
+  if (pix < p1) {
+    const float4* s0 = reinterpret_cast<const float4*>(xb + (long long)pix * ldx);
+    const float4 v00 = s0[0], v01 = s0[1];
+    finish(v00, v01, pix);
+  }
+}
+
 static int launch_gn_apply(const float* x, long long ldx, const float* mean, const float* rstd, const float* gamma,
                            const float* beta, int act, float* y, long long ldy, __nv_bfloat16* hi,
                            __nv_bfloat16* lo, long long ldo, int B, int HW, int C, int G, long long x_bs,
                            long long y_bs, long long o_bs, const float* res, long long ldres, int accumulate,
                            cudaStream_t stream) {
+  const int cpg_ = C / G;
+  static const bool force_quad = getenv("ODISE_GN_QUAD") != nullptr;   // A/B switch for tools/gn_probe.py
+  if (!force_quad && !res && !accumulate && C % 8 == 0 && C / 8 <= 256 && (cpg_ % 4 == 0 || cpg_ >= 8) && ldx % 4 == 0 && x_bs % 4 == 0 && (!y || (ldy % 4 == 0 && y_bs % 4 == 0)) &&
+      (!hi || (ldo % 8 == 0 && o_bs % 8 == 0))) {
+    const int C8 = C / 8;
+    const int PL = 256 / C8;
+    const int threads = C8 * PL;
+    int chunks = (4 * 148 + B - 1) / B;          // one resident wave: 4 blocks per SM
+    if (chunks > (HW + 2 * PL - 1) / (2 * PL)) chunks = (HW + 2 * PL - 1) / (2 * PL);
+    if (chunks < 1) chunks = 1;
+    const int ppb = (HW + chunks - 1) / chunks;
+    chunks = (HW + ppb - 1) / ppb;
+    gn_apply8_kernel<<<dim3(chunks, B), threads, 0, stream>>>(x, ldx, mean, rstd, gamma, beta, act, y, ldy, hi, lo, ldo, HW,
+                                                             C, G, x_bs, y_bs, o_bs, ppb);
+    return (int)cudaGetLastError();
+  }
   const int C4 = C / 4;
   if (C4 > 1024) return ODISE_ERR_UNSUPPORTED;
   int PL = 256 / C4;
