@@ -301,6 +301,11 @@ int odise_open_vocab_merge_f32(const float* cat_logits, const float* clip_logits
                                const uint8_t* overlap, float alpha, float beta, float* out, float* open_logits, int rows,
                                int K, void* stream);
 
+/* out[i, :] = src[idx[i], :] (+ add[i % add_period, :]) — token-embedding lookup + positional embedding of the CLIP text
+ * towers (clip.py:139-140), and the EOT-row gather (clip.py:150). */
+int odise_gather_rows_f32(const float* src, long long lds, const int32_t* idx, const float* add, long long ld_add,
+                          int add_period, float* out, long long ldo, long long rows, int cols, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

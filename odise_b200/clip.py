@@ -13,6 +13,54 @@ from .lib import Planes
 from .ops import ACT_QUICKGELU
 
 
+class _ResBlocks:
+    """`layers` open_clip ResidualAttentionBlocks (x += attn(ln_1 x); x += c_proj(QuickGELU(c_fc(ln_2 x)))) as operand
+    planes + the loop that runs them on a token matrix [B*TS, width] whose first Tk rows per image are the keys."""
+
+    def __init__(self, sd, prefix, device, nmma, width, layers, heads):
+        self.dev, self.nmma, self.lo = torch.device(device), nmma, nmma == 3
+        self.width, self.layers, self.heads = width, layers, heads
+        f = lambda t: t.to(self.dev, torch.float32).contiguous()
+        pl = lambda w: lib.split(f(w), lo=self.lo)
+        self.W, self.F = {}, {}
+        for i in range(layers):
+            q = f"{prefix}transformer.resblocks.{i}."
+            n = f"l{i}."
+            w, b = sd[q + "attn.in_proj_weight"], sd[q + "attn.in_proj_bias"]
+            self.W[n + "qk"], self.F[n + "qk.b"] = pl(w[:2 * width]), f(b[:2 * width])
+            self.W[n + "v"], self.F[n + "v.b"] = pl(w[2 * width:]), f(b[2 * width:])
+            self.W[n + "o"], self.F[n + "o.b"] = pl(sd[q + "attn.out_proj.weight"]), f(sd[q + "attn.out_proj.bias"])
+            self.W[n + "fc"], self.F[n + "fc.b"] = pl(sd[q + "mlp.c_fc.weight"]), f(sd[q + "mlp.c_fc.bias"])
+            self.W[n + "pr"], self.F[n + "pr.b"] = pl(sd[q + "mlp.c_proj.weight"]), f(sd[q + "mlp.c_proj.bias"])
+            for ln in ("ln_1", "ln_2"):
+                self.F[n + ln + ".g"], self.F[n + ln + ".b"] = f(sd[q + ln + ".weight"]), f(sd[q + ln + ".bias"])
+
+    def _gemm(self, a, name, **kw):
+        return lib.gemm(a, self.W[name], nmma=self.nmma, bias=self.F.get(name + ".b"), **kw)
+
+    def run(self, h, B, TS, Tk, bits=None, row_any=None):
+        dev, Wd = self.dev, self.width
+        M = B * TS
+        d = Wd // self.heads
+        for i in range(self.layers):
+            n = f"l{i}."
+            _, y = ops.layer_norm(h, self.F[n + "ln_1.g"], self.F[n + "ln_1.b"], lo=self.lo)
+            qk = Planes.empty(M, 2 * Wd, dev, lo=self.lo)
+            self._gemm(y, n + "qk", out_planes=qk)
+            vt = Planes.empty(Wd, M, dev, lo=self.lo)
+            lib.gemm(self.W[n + "v"], y, nmma=self.nmma, bias_m=self.F[n + "v.b"], out_planes=vt)
+            _, o = ops.attention_tc(qk.col_slice(0, Wd), qk.col_slice(Wd, Wd), vt, B, self.heads, d, TS, Tk, d ** -0.5,
+                                    self.nmma, tk_stride=TS, mask_bits=bits, row_any=row_any)
+            h2 = ops.empty(M, Wd, dev)
+            self._gemm(o, n + "o", residual=h, out=h2)
+            _, y2 = ops.layer_norm(h2, self.F[n + "ln_2.g"], self.F[n + "ln_2.b"], lo=self.lo)
+            u = Planes.empty(M, 4 * Wd, dev, lo=self.lo)
+            self._gemm(y2, n + "fc", act=ACT_QUICKGELU, out_planes=u)
+            h = ops.empty(M, Wd, dev)
+            self._gemm(u, n + "pr", residual=h2, out=h)
+        return h
+
+
 class ClipVisualEngine:
     def __init__(self, sd, device, nmma=3, prefix=spec.CLIP_PREFIX, width=1024, layers=24, heads=16, patch=14, image=336):
         self.dev = torch.device(device)
@@ -36,22 +84,9 @@ class ClipVisualEngine:
         self.F["pos_patches"] = f(pos[1:])                                   # [576, width]
         self.F["cls_row"] = f((g("class_embedding").float() + pos[0]).view(1, width))
         self.F["ln_pre.g"], self.F["ln_pre.b"] = f(g("ln_pre.weight")), f(g("ln_pre.bias"))
-        for i in range(layers):
-            q = f"transformer.resblocks.{i}."
-            n = f"l{i}."
-            w, b = g(q + "attn.in_proj_weight"), g(q + "attn.in_proj_bias")
-            self.W[n + "qk"], self.F[n + "qk.b"] = pl(w[:2 * width]), f(b[:2 * width])
-            self.W[n + "v"], self.F[n + "v.b"] = pl(w[2 * width:]), f(b[2 * width:])
-            self.W[n + "o"], self.F[n + "o.b"] = pl(g(q + "attn.out_proj.weight")), f(g(q + "attn.out_proj.bias"))
-            self.W[n + "fc"], self.F[n + "fc.b"] = pl(g(q + "mlp.c_fc.weight")), f(g(q + "mlp.c_fc.bias"))
-            self.W[n + "pr"], self.F[n + "pr.b"] = pl(g(q + "mlp.c_proj.weight")), f(g(q + "mlp.c_proj.bias"))
-            for ln in ("ln_1", "ln_2"):
-                self.F[n + ln + ".g"], self.F[n + ln + ".b"] = f(g(q + ln + ".weight")), f(g(q + ln + ".bias"))
+        self.blocks = _ResBlocks(sd, prefix, device, nmma, width, layers, heads)
         self.F["ln_post.g"], self.F["ln_post.b"] = f(g("ln_post.weight")), f(g("ln_post.bias"))
         self.W["proj"] = pl(g("proj").t())                                   # x @ proj == x @ (proj^T)^T
-
-    def _gemm(self, a, name, **kw):
-        return lib.gemm(a, self.W[name], nmma=self.nmma, bias=self.F.get(name + ".b"), **kw)
 
     def _tokens(self, x, B, n_extra):
         """normalised NHWC image [B*S*S, 3] -> pre-ln_pre token matrix [B*TS, width]: per image row 0 = class token,
@@ -74,27 +109,8 @@ class ClipVisualEngine:
 
     def _tower(self, tok, B, TS, bits=None, row_any=None):
         """ln_pre + the 24 residual attention blocks on [B*TS, width]; keys = the first 577 rows of every image."""
-        dev, Wd, T = self.dev, self.width, self.T
         h, _ = ops.layer_norm(tok, self.F["ln_pre.g"], self.F["ln_pre.b"], want_f32=True, want_planes=False, lo=self.lo)
-        M = B * TS
-        d = Wd // self.heads
-        for i in range(self.layers):
-            n = f"l{i}."
-            _, y = ops.layer_norm(h, self.F[n + "ln_1.g"], self.F[n + "ln_1.b"], lo=self.lo)
-            qk = Planes.empty(M, 2 * Wd, dev, lo=self.lo)
-            self._gemm(y, n + "qk", out_planes=qk)
-            vt = Planes.empty(Wd, M, dev, lo=self.lo)
-            lib.gemm(self.W[n + "v"], y, nmma=self.nmma, bias_m=self.F[n + "v.b"], out_planes=vt)
-            _, o = ops.attention_tc(qk.col_slice(0, Wd), qk.col_slice(Wd, Wd), vt, B, self.heads, d, TS, T, d ** -0.5,
-                                    self.nmma, tk_stride=TS, mask_bits=bits, row_any=row_any)
-            h2 = ops.empty(M, Wd, dev)
-            self._gemm(o, n + "o", residual=h, out=h2)
-            _, y2 = ops.layer_norm(h2, self.F[n + "ln_2.g"], self.F[n + "ln_2.b"], lo=self.lo)
-            u = Planes.empty(M, 4 * Wd, dev, lo=self.lo)
-            self._gemm(y2, n + "fc", act=ACT_QUICKGELU, out_planes=u)
-            h = ops.empty(M, Wd, dev)
-            self._gemm(u, n + "pr", residual=h2, out=h)
-        return h
+        return self.blocks.run(h, B, TS, self.T, bits, row_any)
 
     @torch.no_grad()
     def embed(self, img, boxes_dev, n_crops, H, W, ch, cw):
@@ -171,3 +187,70 @@ class MaskClipHead:
         if want_open:
             out["pred_open_logits"] = op.view(N, Q, K)
         return out
+
+
+class ClipTextEngine:
+    """CLIP text tower on the device (f-4 text-bank builder): ClipAdapter._encode_text / open_clip CLIP.encode_text
+    (odise/modeling/meta_arch/clip.py:138-152, :29-73) for the vocabulary's prompt bank, and — with the SD-v1
+    `cond_stage_model` weights renamed by spec.hf_text_to_openai and project=False — ldm's FrozenCLIPEmbedder, whose
+    output for "" is `uncond_inputs` (ldm.py:116).  Token ids come from the caller (the BPE vocabulary file is not part
+    of this repo); ctx 77 is padded to 80 rows per prompt, the causal mask is 1 bit per (query, key)."""
+
+    def __init__(self, sd, device, nmma=3, prefix=spec.CLIP_TEXT_PREFIX, width=768, layers=12, heads=12, ctx=77, project=True):
+        self.dev = torch.device(device)
+        self.nmma, self.lo = nmma, nmma == 3
+        self.width, self.ctx = width, ctx
+        self.TS = (ctx + 7) // 8 * 8
+        f = lambda t: t.to(self.dev, torch.float32).contiguous()
+        self.table = f(sd[prefix + "token_embedding.weight"])
+        self.pos = torch.zeros(self.TS, width, dtype=torch.float32, device=self.dev)
+        self.pos[:ctx] = f(sd[prefix + "positional_embedding"])
+        self.blocks = _ResBlocks(sd, prefix, device, nmma, width, layers, heads)
+        self.ln_g, self.ln_b = f(sd[prefix + "ln_final.weight"]), f(sd[prefix + "ln_final.bias"])
+        self.proj = lib.split(f(sd[prefix + "text_projection"].t()), lo=self.lo) if project else None
+        words = (ctx + 31) // 32
+        q = torch.arange(self.TS).view(-1, 1, 1)
+        key = (torch.arange(words).view(1, -1, 1) * 32 + torch.arange(32).view(1, 1, -1))
+        allowed = ((key <= q) & (key < ctx)).to(torch.int64)                       # causal: query i sees keys <= i
+        self._row_bits = (allowed << torch.arange(32).view(1, 1, -1)).sum(-1)      # [TS, words] as uint32 values
+        self._row_bits = torch.where(self._row_bits >= 2 ** 31, self._row_bits - 2 ** 32, self._row_bits).to(torch.int32)
+        self._row_any = (torch.arange(self.TS) < ctx).to(torch.int32)
+
+    @torch.no_grad()
+    def encode(self, token_ids):
+        """token_ids int [N, ctx] (host or device) -> (text_embed fp32 [N, out] or None, encodings fp32 [N, ctx, width])."""
+        N = token_ids.shape[0]
+        assert token_ids.shape[1] == self.ctx
+        TS, Wd, dev = self.TS, self.width, self.dev
+        ids = torch.zeros(N, TS, dtype=torch.int32)
+        ids[:, :self.ctx] = token_ids.cpu().to(torch.int32)
+        h = ops.gather_rows(self.table, ids.view(-1).to(dev), add=self.pos, add_period=TS)
+        bits = self._row_bits.unsqueeze(0).expand(N, -1, -1).contiguous().to(dev)
+        row_any = self._row_any.unsqueeze(0).expand(N, -1).contiguous().to(dev)
+        h = self.blocks.run(h, N, TS, self.ctx, bits, row_any)
+        x, xp = ops.layer_norm(h, self.ln_g, self.ln_b, want_f32=True, want_planes=self.proj is not None, lo=self.lo)
+        enc = x.view(N, TS, Wd)[:, :self.ctx]
+        if self.proj is None:
+            return None, enc
+        eot = (token_ids.cpu().argmax(dim=-1) + torch.arange(N) * TS).to(torch.int32).to(dev)      # clip.py:150
+        rows = ops.gather_rows(x, eot)
+        out = ops.empty(N, self.proj.rows, dev)
+        lib.gemm(ops.split(rows, lo=self.lo), self.proj, nmma=self.nmma, out=out)
+        return out, enc
+
+
+def build_text_bank(text_engine, token_ids, batch=256):
+    """build_clip_text_embed (clip.py:29-73): prompts are encoded in chunks of 256 -> raw text embeddings [K', 768]."""
+    outs = [text_engine.encode(token_ids[i:i + batch])[0] for i in range(0, token_ids.shape[0], batch)]
+    return torch.cat(outs)
+
+
+EMPTY_PROMPT_IDS = [49406] + [49407] * 76          # "<|startoftext|>" + "<|endoftext|>" padding: the tokens of ""
+
+
+def uncond_inputs(sd, device, nmma=3):
+    """LdmExtractor `uncond_inputs` = ldm.embed_text([""]) (ldm.py:116): the SD-v1 text encoder applied to the empty
+    prompt -> [1, 77, 768], from the `cond_stage_model.*` weights of an sd-v1 checkpoint."""
+    conv = spec.hf_text_to_openai(sd, dst_prefix="sd_text.")
+    eng = ClipTextEngine(conv, device, nmma=nmma, prefix="sd_text.", project=False)
+    return eng.encode(torch.tensor([EMPTY_PROMPT_IDS]))[1].contiguous()

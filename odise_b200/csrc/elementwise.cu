@@ -799,6 +799,20 @@ __global__ void clip_preprocess_kernel(const T* __restrict__ img, float* __restr
   }
 }
 
+// out[i, :] = src[idx[i], :] (+ add[i % add_period, :]): token-embedding lookup + positional embedding, EOT-row gather
+__global__ void gather_rows_kernel(const float* __restrict__ src, long long lds, const int32_t* __restrict__ idx,
+                                   const float* __restrict__ add, long long ld_add, int add_period,
+                                   float* __restrict__ out, long long ldo, long long rows, int cols) {
+  const long long total = rows * cols;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / cols;
+    const int c = (int)(i - r * cols);
+    float v = src[(long long)idx[r] * lds + c];
+    if (add) v += add[(r % add_period) * ld_add + c];
+    out[r * ldo + c] = v;
+  }
+}
+
 // non-overlapping P x P patches of an NHWC image [B, S, S, 3] -> (hi, lo) rows [B*G*G, Kpad], k = c*P*P + ky*P + kx
 // (the layout of visual.conv1.weight.reshape(width, 3*P*P); clip.py:179)
 __global__ void patchify_split_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi,
@@ -1172,6 +1186,15 @@ extern "C" int odise_patchify_split_f32(const float* x, void* hi, void* lo, int 
   const int G = S / P;
   patchify_split_kernel<<<grid_for((long long)B * G * G * Kpad, 256), 256, 0, STREAM(stream)>>>(x, BF(hi), BF(lo), B, S,
                                                                                             P, Kpad);
+  count_launch(1);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int odise_gather_rows_f32(const float* src, long long lds, const int32_t* idx, const float* add, long long ld_add,
+                                     int add_period, float* out, long long ldo, long long rows, int cols, void* stream) {
+  if (!src || !idx || !out || rows <= 0 || cols <= 0 || (add && add_period <= 0)) return ODISE_ERR_ARG;
+  gather_rows_kernel<<<grid_for(rows * cols, 256), 256, 0, STREAM(stream)>>>(src, lds, idx, add, ld_add, add_period, out, ldo,
+                                                                          rows, cols);
   count_launch(1);
   return (int)cudaGetLastError();
 }

@@ -313,3 +313,12 @@ def open_vocab_merge(cat_logits, clip_logits, ld_clip, overlap_u8, alpha, beta, 
     _check(load().odise_open_vocab_merge_f32(_ptr(cat_logits), _ptr(clip_logits), ld_clip, _ptr(overlap_u8), alpha, beta,
                                              _ptr(out), _ptr(op), rows, K, _stream()), "open_vocab_merge")
     return out, op
+
+
+def gather_rows(src, idx, add=None, add_period=1):
+    """out[i] = src[idx[i]] (+ add[i % add_period]); src fp32 [n, cols], idx int32 [rows]."""
+    rows, cols = idx.numel(), src.shape[1]
+    out = empty(rows, cols, src.device)
+    _check(load().odise_gather_rows_f32(_ptr(src), src.stride(0), _ptr(idx), _ptr(add), add.stride(0) if add is not None else 0,
+                                        add_period, _ptr(out), cols, rows, cols, _stream()), "gather_rows")
+    return out

@@ -270,6 +270,62 @@ def clip_visual_params(prefix=CLIP_PREFIX, width=1024, layers=24, patch=14, imag
     return ps
 
 
+CLIP_TEXT_PREFIX = "clip."
+SD_TEXT_PREFIX = "cond_stage_model.transformer.text_model."
+
+
+def clip_text_params(prefix=CLIP_TEXT_PREFIX, width=768, layers=12, vocab=49408, ctx=77, out_dim=768):
+    """open_clip CLIP text tower (ViT-L-14-336 "openai"), OpenAI parameter names — what build_clip_text_embed /
+    ClipAdapter._encode_text run (odise/modeling/meta_arch/clip.py:29-73, :138-152)."""
+    ps = [(prefix + "token_embedding.weight", (vocab, width), "pos"), (prefix + "positional_embedding", (ctx, width), "pos")]
+    for i in range(layers):
+        q = f"{prefix}transformer.resblocks.{i}."
+        ps += [(q + "ln_1.weight", (width,), "gamma"), (q + "ln_1.bias", (width,), "beta"),
+               (q + "attn.in_proj_weight", (3 * width, width), "w"), (q + "attn.in_proj_bias", (3 * width,), "b"),
+               (q + "attn.out_proj.weight", (width, width), "w"), (q + "attn.out_proj.bias", (width,), "b"),
+               (q + "ln_2.weight", (width,), "gamma"), (q + "ln_2.bias", (width,), "beta"),
+               (q + "mlp.c_fc.weight", (4 * width, width), "w"), (q + "mlp.c_fc.bias", (4 * width,), "b"),
+               (q + "mlp.c_proj.weight", (width, 4 * width), "w"), (q + "mlp.c_proj.bias", (width,), "b")]
+    ps += [(prefix + "ln_final.weight", (width,), "gamma"), (prefix + "ln_final.bias", (width,), "beta"),
+           (prefix + "text_projection", (width, out_dim), "proj"), (prefix + "logit_scale", (), "logit_scale")]
+    return ps
+
+
+def sd_text_params(prefix=SD_TEXT_PREFIX, width=768, layers=12, vocab=49408, ctx=77):
+    """SD-v1 `cond_stage_model` (ldm FrozenCLIPEmbedder = HF CLIPTextModel openai/clip-vit-large-patch14), HF parameter
+    names as stored in sd-v1-*.ckpt; produces `uncond_inputs` = last_hidden_state of "" (ldm.py:116)."""
+    ps = [(prefix + "embeddings.token_embedding.weight", (vocab, width), "pos"),
+          (prefix + "embeddings.position_embedding.weight", (ctx, width), "pos")]
+    for i in range(layers):
+        q = f"{prefix}encoder.layers.{i}."
+        ps += [(q + "layer_norm1.weight", (width,), "gamma"), (q + "layer_norm1.bias", (width,), "beta")]
+        for n in ("q_proj", "k_proj", "v_proj", "out_proj"):
+            ps += [(q + f"self_attn.{n}.weight", (width, width), "w"), (q + f"self_attn.{n}.bias", (width,), "b")]
+        ps += [(q + "layer_norm2.weight", (width,), "gamma"), (q + "layer_norm2.bias", (width,), "beta"),
+               (q + "mlp.fc1.weight", (4 * width, width), "w"), (q + "mlp.fc1.bias", (4 * width,), "b"),
+               (q + "mlp.fc2.weight", (width, 4 * width), "w"), (q + "mlp.fc2.bias", (width,), "b")]
+    ps += [(prefix + "final_layer_norm.weight", (width,), "gamma"), (prefix + "final_layer_norm.bias", (width,), "beta")]
+    return ps
+
+
+def hf_text_to_openai(sd, src_prefix=SD_TEXT_PREFIX, dst_prefix="sd_text."):
+    """HF CLIPTextModel names -> OpenAI CLIP names (q/k/v concatenated into in_proj), so one engine serves both."""
+    out = {dst_prefix + "token_embedding.weight": sd[src_prefix + "embeddings.token_embedding.weight"],
+           dst_prefix + "positional_embedding": sd[src_prefix + "embeddings.position_embedding.weight"],
+           dst_prefix + "ln_final.weight": sd[src_prefix + "final_layer_norm.weight"],
+           dst_prefix + "ln_final.bias": sd[src_prefix + "final_layer_norm.bias"]}
+    i = 0
+    while f"{src_prefix}encoder.layers.{i}.layer_norm1.weight" in sd:
+        s, d = f"{src_prefix}encoder.layers.{i}.", f"{dst_prefix}transformer.resblocks.{i}."
+        for a, b in (("layer_norm1", "ln_1"), ("layer_norm2", "ln_2"), ("self_attn.out_proj", "attn.out_proj"),
+                     ("mlp.fc1", "mlp.c_fc"), ("mlp.fc2", "mlp.c_proj")):
+            out[d + b + ".weight"], out[d + b + ".bias"] = sd[s + a + ".weight"], sd[s + a + ".bias"]
+        out[d + "attn.in_proj_weight"] = torch.cat([sd[s + f"self_attn.{n}.weight"] for n in ("q_proj", "k_proj", "v_proj")])
+        out[d + "attn.in_proj_bias"] = torch.cat([sd[s + f"self_attn.{n}.bias"] for n in ("q_proj", "k_proj", "v_proj")])
+        i += 1
+    return out
+
+
 def msda_offset_bias(M=8, L=3, P=4):
     """MSDeformAttn._reset_parameters directional grid (ops/modules/ms_deform_attn.py:66-74)."""
     thetas = torch.arange(M, dtype=torch.float32) * (2.0 * math.pi / M)

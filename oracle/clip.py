@@ -165,3 +165,30 @@ def merge_with_void(pred_logits, open_logits):
     p_void = F.softmax(pred_logits, dim=-1)[..., -1:]
     cls = F.softmax(open_logits, dim=-1) * (1 - p_void)
     return torch.log(torch.cat([cls, p_void], dim=-1) + 1e-8)
+
+
+# ---------------------------------------------------------------------------------------------------- text tower
+# CLIP text tower (open_clip 2.0.2 `CLIP.encode_text`; glue vendored as ClipAdapter._encode_text, clip.py:138-152 —
+# pinned in tests/test_oracle_cpu.py).  The same module with the projection skipped restates SD-v1's
+# `cond_stage_model` (ldm FrozenCLIPEmbedder -> HF CLIPTextModel.last_hidden_state; parameter names differ only).
+
+class TextTransformer(nn.Module):
+    def __init__(self, vocab=49408, ctx=77, width=768, layers=12, heads=12, out_dim=768):
+        super().__init__()
+        self.token_embedding = nn.Embedding(vocab, width)
+        self.positional_embedding = nn.Parameter(torch.zeros(ctx, width))
+        self.transformer = Transformer(width, layers, heads)
+        self.ln_final = nn.LayerNorm(width)
+        self.text_projection = nn.Parameter(torch.zeros(width, out_dim))
+        self.logit_scale = nn.Parameter(torch.zeros(()))
+        mask = torch.empty(ctx, ctx).fill_(float("-inf")).triu_(1)          # open_clip build_attention_mask
+        self.register_buffer("attn_mask", mask, persistent=False)
+
+
+def encode_text(model, text):
+    """ClipAdapter._encode_text (clip.py:138-152): token ids [N, ctx] -> (text_embed [N, out], encodings [N, ctx, width]);
+    the embedding is read at the EOT position = argmax of the ids."""
+    x = model.token_embedding(text) + model.positional_embedding
+    x = model.transformer(x.permute(1, 0, 2), attn_mask=model.attn_mask).permute(1, 0, 2)
+    x = model.ln_final(x)
+    return x[torch.arange(x.shape[0]), text.argmax(dim=-1)] @ model.text_projection, x

@@ -130,3 +130,41 @@ def test_maskclip_head(cuda):
     got_lg = out["mask_pred_open_logits"].view(N, Q, K + 1)[..., :K].cpu()
     assert (got_lg - lg).abs().max() < 2e-2          # logits are 100 * cos-sim: 2e-4 of their scale
     assert (out["pred_logits"].cpu() - want).abs().max() < 2e-2
+
+
+def test_clip_text_tower_and_uncond(cuda):
+    """CLIP text tower (open_clip names) vs oracle.encode_text (== ClipAdapter._encode_text, pinned), and the SD-v1
+    cond_stage_model (HF names) producing uncond_inputs for the empty prompt (ldm.py:116)."""
+    from odise_b200 import spec
+    from odise_b200.clip import ClipTextEngine, build_text_bank, uncond_inputs, EMPTY_PROMPT_IDS
+    from oracle import clip as oclip
+    sd = spec.synth_state_dict(spec.clip_text_params(), seed=8)
+    with torch.device("meta"):
+        m = oclip.TextTransformer()
+    m.load_state_dict({k[len(spec.CLIP_TEXT_PREFIX):]: v for k, v in sd.items()}, assign=True)
+    m.attn_mask = torch.empty(77, 77).fill_(float("-inf")).triu_(1)
+    m.eval()
+    g = torch.Generator().manual_seed(4)
+    ids = torch.zeros(5, 77, dtype=torch.int64)
+    for i, n in enumerate((2, 5, 9, 30, 77)):                               # prompt lengths incl. BOS/EOT; 77 = full
+        ids[i, :n] = torch.randint(1000, 40000, (n,), generator=g)
+        ids[i, 0], ids[i, n - 1] = 49406, 49407
+    with torch.no_grad():
+        emb, enc = oclip.encode_text(m, ids)
+    eng = ClipTextEngine(sd, cuda, nmma=3)
+    got_emb, got_enc = eng.encode(ids)
+    torch.cuda.synchronize()
+    assert _rel(got_emb.cpu(), emb) < 1e-3 and _rel(got_enc.cpu(), enc) < 1e-3
+    assert torch.equal(build_text_bank(eng, ids, batch=2).cpu(), got_emb.cpu())
+    # SD text encoder: HF parameter names, no projection
+    hf = spec.synth_state_dict(spec.sd_text_params(), seed=9)
+    conv = spec.hf_text_to_openai(hf, dst_prefix="")
+    with torch.device("meta"):
+        t = oclip.TextTransformer()
+    t.load_state_dict(conv, assign=True, strict=False)
+    t.attn_mask = m.attn_mask
+    t.text_projection = torch.nn.Parameter(torch.zeros(768, 768))
+    with torch.no_grad():
+        _, want = oclip.encode_text(t.eval(), torch.tensor([EMPTY_PROMPT_IDS]))
+    got = uncond_inputs(hf, cuda)
+    assert got.shape == (1, 77, 768) and _rel(got.cpu(), want) < 1e-3

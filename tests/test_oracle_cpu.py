@@ -264,3 +264,37 @@ def test_reference_pooling_clip_head_ensemble():
     full = torch.randn(2, 6, 5)
     merged = oclip.merge_with_void(full, got)
     assert torch.allclose(merged.exp().sum(-1), torch.ones(2, 6) + 5e-8, atol=1e-5)
+
+
+def test_clip_text_inventory_matches_oracle_module():
+    from oracle import clip as oclip
+    with torch.device("meta"):
+        t = oclip.TextTransformer()
+    got = {n[len(spec.CLIP_TEXT_PREFIX):]: tuple(s) for n, s, _ in spec.clip_text_params()}
+    assert got == {k: tuple(v.shape) for k, v in t.state_dict().items()}
+    # the SD-v1 cond_stage_model (HF names) maps onto the same module minus projection / logit_scale
+    hf = spec.synth_state_dict(spec.sd_text_params(width=64, layers=2, vocab=100), 0)
+    conv = spec.hf_text_to_openai(hf, dst_prefix="")
+    small = oclip.TextTransformer(vocab=100, width=64, layers=2, heads=2, out_dim=64)
+    missing = set(small.state_dict()) - set(conv)
+    assert missing == {"text_projection", "logit_scale"} and not (set(conv) - set(small.state_dict()))
+
+
+@needs_ref
+@torch.no_grad()
+def test_reference_encode_text_runs_on_oracle_text_tower():
+    """ClipAdapter._encode_text (clip.py:138-152) executed verbatim on the oracle TextTransformer == oracle.encode_text."""
+    import importlib
+    from oracle import clip as oclip
+    refshim.install()
+    rc = importlib.import_module("odise.modeling.meta_arch.clip")
+    torch.manual_seed(3)
+    m = oclip.TextTransformer(vocab=50, ctx=9, width=64, layers=2, heads=2, out_dim=32).eval()
+    for p in m.parameters():
+        torch.nn.init.normal_(p, std=0.1)
+    ids = torch.randint(1, 40, (3, 9))
+    ids[0, 4], ids[1, 8], ids[2, 2] = 49, 49, 49                          # EOT = highest id
+    fake = types.SimpleNamespace(clip=m)
+    emb_ref, enc_ref = rc.ClipAdapter._encode_text(fake, ids)
+    emb, enc = oclip.encode_text(m, ids)
+    assert torch.allclose(emb_ref, emb, rtol=1e-5, atol=1e-6) and torch.allclose(enc_ref, enc, rtol=1e-5, atol=1e-6)
