@@ -106,7 +106,7 @@ def assemble(ldm=None, clip=None, odise=None):
 
 
 def expected_params(with_vae=True, with_clip=True, with_text=True):
-    ps = spec.unet_params() + spec.backbone_params() + spec.head_params()
+    ps = spec.unet_params() + spec.backbone_params() + spec.head_params() + [("category_head.null_embed", (1, 768), "pos")]
     if with_vae:
         ps += spec.vae_params()
     if with_clip:

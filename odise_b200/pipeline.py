@@ -23,7 +23,7 @@ def full_param_list(with_vae=False, with_clip=False):
 
 class ODISEEngine:
     def __init__(self, sd, device, nmma=3, num_queries=100, with_vae=False, with_clip=False, with_clip_head=None,
-                 alpha=0.3, beta=0.7):
+                 alpha=0.3, beta=0.7, uncond=None):
         """with_clip: CLIP ViT-L/14-336 image tower (implicit captioner input, §8f-2); with_clip_head (default = with_clip):
         MaskCLIP + PoolingCLIPHead ensemble (odise_with_label.py: alpha 0.3, beta 0.7) on the same frozen tower."""
         self.dev = torch.device(device)
@@ -43,7 +43,10 @@ class ODISEEngine:
             assert clip is not None, "the MaskCLIP head shares the CLIP image tower: with_clip=True required"
             self.clip_head = MaskClipHead(clip, alpha=alpha, beta=beta,
                                           logit_scale=math.exp(float(sd.get("clip.logit_scale", math.log(100.0)))))
-        self.backbone = BackboneEngine(sd, device, nmma=nmma, vae=vae, clip=clip)
+        self.backbone = BackboneEngine(sd, device, nmma=nmma, vae=vae, clip=clip, uncond=uncond)
+        self.text = None                  # ClipTextEngine, built on demand (set_vocabulary_from_tokens)
+        self._sd_text = {k: v for k, v in sd.items() if k.startswith(spec.CLIP_TEXT_PREFIX) and not k.startswith(spec.CLIP_PREFIX)}
+        self._null_embed = sd.get("category_head.null_embed")
         self.head = HeadEngine(sd, device, nmma=nmma, num_queries=num_queries)
         self.Q = num_queries
         self._graphs = {}
@@ -66,6 +69,37 @@ class ODISEEngine:
         from .postprocess import PostProcessor
         K = len(group_sizes)
         self.post = PostProcessor(self.dev, K, thing_ids if thing_ids is not None else range(0, K, 2), nmma=self.nmma)
+
+    @classmethod
+    def from_checkpoints(cls, ldm_path, odise_path, clip_path, device, trusted=False, **kw):
+        """The reference's three downloads (sd-v1-3.ckpt, OpenAI CLIP ViT-L-14-336, odise_*.pth) -> a ready engine:
+        weights verified against the spec inventory, `uncond_inputs` computed by the SD text encoder (ldm.py:116)."""
+        from . import checkpoint
+        from .clip import uncond_inputs
+        sd, _ = checkpoint.load_reference_checkpoints(ldm_path, odise_path, clip_path, trusted=trusted)
+        nmma = kw.get("nmma", 3)
+        un = uncond_inputs(sd, device, nmma=nmma).cpu()
+        return cls(sd, device, with_vae=True, with_clip=True, uncond=un, **kw)
+
+    @torch.no_grad()
+    def set_vocabulary_from_tokens(self, key, token_ids, group_sizes, null_token_ids=None, thing_ids=None, overlapping=None):
+        """CategoryEmbed.get_and_cache_test_text_embed (odise.py:1281-1288): tokenised prompts [K', 77] (all synonyms of
+        all classes, class-major) -> CLIP text bank on the device -> set_vocabulary.  The null embedding is the
+        checkpoint's `category_head.null_embed` parameter, or the text embedding of `null_token_ids` ("" at init)."""
+        from .clip import ClipTextEngine, build_text_bank
+        if self.text is None:
+            if not self._sd_text:
+                raise lib.OdiseError("no CLIP text tower weights (`clip.token_embedding.weight`, ...) in the state dict")
+            self.text = ClipTextEngine(self._sd_text, self.dev, nmma=self.nmma)
+        bank = build_text_bank(self.text, token_ids)
+        if self._null_embed is not None:
+            null = self._null_embed.view(1, -1)
+        elif null_token_ids is not None:
+            null = self.text.encode(null_token_ids.view(1, -1))[0]
+        else:
+            raise lib.OdiseError("no category_head.null_embed in the state dict and no null_token_ids given")
+        self.set_vocabulary(key, bank, null, group_sizes, thing_ids=thing_ids, clip_text_bank=bank, overlapping=overlapping)
+        return bank
 
     @torch.no_grad()
     def postprocess(self, out, H, W, semantic=True, panoptic=True):

@@ -95,3 +95,32 @@ def test_step_graph_and_clip_head(cuda, world):
     # post-processing on the merged scores runs end to end
     post = eng.postprocess(a, 512, 512)
     assert post["sem_seg"].shape == (1, 20, 512, 512) and post["panoptic_seg"].shape == (1, 512, 512)
+
+
+@torch.no_grad()
+def test_vocabulary_from_tokens(cuda, world):
+    """tokenised prompts -> CLIP text bank on the device -> category + MaskCLIP vocabularies (odise.py:1281-1288)."""
+    from odise_b200 import spec
+    from oracle import clip as oclip
+    eng = world["eng"]
+    tsd = spec.synth_state_dict(spec.clip_text_params(), seed=8)
+    eng._sd_text, eng.text = tsd, None
+    eng._null_embed = torch.randn(1, 768, generator=torch.Generator().manual_seed(3))
+    g = torch.Generator().manual_seed(6)
+    sizes = [2, 1, 1, 3]
+    ids = torch.zeros(sum(sizes), 77, dtype=torch.int64)
+    for i in range(ids.shape[0]):
+        n = 3 + i
+        ids[i, :n] = torch.randint(1000, 40000, (n,), generator=g)
+        ids[i, 0], ids[i, n - 1] = 49406, 49407
+    bank = eng.set_vocabulary_from_tokens("tok4", ids, sizes, thing_ids=[0, 2], overlapping=[1, 0, 0, 1])
+    with torch.device("meta"):
+        m = oclip.TextTransformer()
+    m.load_state_dict({k[len(spec.CLIP_TEXT_PREFIX):]: v for k, v in tsd.items()}, assign=True)
+    m.attn_mask = torch.empty(77, 77).fill_(float("-inf")).triu_(1)
+    want, _ = oclip.encode_text(m.eval(), ids)
+    assert _rel(bank.cpu(), want) < 1e-3
+    out = eng.step(1, 512, 512, images_u8=world["img"].to(cuda))
+    assert out["pred_logits"].shape == (1, 100, 5) and torch.isfinite(out["pred_logits"]).all()
+    eng.set_vocabulary("v20", world["bank"], world["null"], world["sizes"], clip_text_bank=world["clip_bank"],
+                       overlapping=world["ov"])
