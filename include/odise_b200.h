@@ -257,8 +257,12 @@ int odise_class_max_f32(const float* sims, long long ld_sims, const int32_t* gro
  * Post-processing on the device (odise.py:326-370; maskformer_model.py:280-342) — no host syncs.
  * upsample: bilinear (align_corners=False) of mask logits [B, Q, hs, ws] to (H, W), sigmoid, written pixel-major as
  *   (hi, lo) planes [B*H*W, Qpad] (operand of the semantic GEMM) and optionally the upsampled logits up_f32 [B,Q,H,W]. */
+/* geom (optional, all three post-processing calls): sem_seg_postprocess (detectron2 modeling/postprocessing.py, called
+ * at odise.py:343-347 with sem_seg_postprocess_before_inference=True).  NULL: output (H, W) == padded input size.
+ * Otherwise the logits are resampled [hs, ws] -> (pad_h, pad_w) -> crop (img_h, img_w) -> (H, W), both bilinear. */
+typedef struct { int pad_h, pad_w, img_h, img_w; } odise_postprocess_geom;
 int odise_upsample_sigmoid_split_f32(const float* logits, void* hi, void* lo, float* up_f32, int B, int Q, int Qpad,
-                                     int hs, int ws, int H, int W, void* stream);
+                                     int hs, int ws, int H, int W, const odise_postprocess_geom* geom, void* stream);
 /* softmax over the K+1 class logits of every query: probs [B*Q, K1] (optional), probs_t [B, K, Qpad] (optional,
  * transposed without the void class, pad columns untouched: pre-zero it), max prob, argmax (first among ties),
  * keep = (label != K) && (score > threshold)   (maskformer_model.py:287-290) */
@@ -270,7 +274,7 @@ long long odise_panoptic_ws_bytes(int B, int Q, int H, int W);
 int odise_panoptic_inference_f32(const float* logits, const float* scores, const int32_t* labels, const int32_t* keep,
                                  const uint8_t* is_thing, int32_t* pan, int32_t* seg_info, int32_t* n_segments,
                                  void* ws, int B, int Q, int K, int hs, int ws_, int H, int W, double overlap_thr,
-                                 void* stream);
+                                 const odise_postprocess_geom* geom, void* stream);
 
 /* MaskFormer.instance_inference (maskformer_model.py:344-380) on the device: top-k over the flattened [Q*K] class
  * probabilities (probs [B*Q, K+1] from odise_query_scores_f32; void column dropped), sorted by probability
@@ -280,7 +284,8 @@ int odise_panoptic_inference_f32(const float* logits, const float* scores, const
 long long odise_instance_ws_bytes(int B, int Q, int H, int W);
 int odise_instance_inference_f32(const float* probs, const float* logits, const uint8_t* is_thing, float* scores,
                                  int32_t* classes, int32_t* query_index, int32_t* valid, uint8_t* masks, void* ws, int B,
-                                 int Q, int K, int topk, int hs, int ws_, int H, int W, void* stream);
+                                 int Q, int K, int topk, int hs, int ws_, int H, int W,
+                                 const odise_postprocess_geom* geom, void* stream);
 
 /* MaskCLIP front-end (odise/modeling/meta_arch/clip.py:284-339) and the open-vocabulary merge (odise.py:1506-1536,
  * :300-323).

@@ -26,21 +26,52 @@ __device__ __forceinline__ float bilerp(const float* __restrict__ src, int Hs, i
   return hy * (hx * src[y0 * Ws + x0] + lx * src[y0 * Ws + x1]) + ly * (hx * src[y1 * Ws + x0] + lx * src[y1 * Ws + x1]);
 }
 
+// Output-pixel sampler of the mask logits.  One stage: [hs, ws] -> (H, W) bilinear (odise.py:326-331, output == padded
+// input size).  Two stages (sem_seg_postprocess, detectron2 modeling/postprocessing.py, called at odise.py:343-347):
+// [hs, ws] -> (pad_h, pad_w), crop to the un-padded (img_h, img_w), bilinear again to the requested (H, W); the
+// 4 stage-2 neighbours are evaluated on the fly, the [Q, pad_h, pad_w] field is never written.
+struct Sampler {
+  int hs, ws, two, img_h, img_w;
+  float sy1, sx1, sy2, sx2;
+};
+static Sampler make_sampler(int hs, int ws, int H, int W, const odise_postprocess_geom* g) {
+  Sampler s{};
+  s.hs = hs; s.ws = ws;
+  if (g) {
+    s.two = 1; s.img_h = g->img_h; s.img_w = g->img_w;
+    s.sy1 = (float)hs / (float)g->pad_h; s.sx1 = (float)ws / (float)g->pad_w;
+    s.sy2 = (float)g->img_h / (float)H; s.sx2 = (float)g->img_w / (float)W;
+  } else {
+    s.sy1 = (float)hs / (float)H; s.sx1 = (float)ws / (float)W;
+  }
+  return s;
+}
+__device__ __forceinline__ float sample(const float* __restrict__ src, const Sampler& s, int oy, int ox) {
+  if (!s.two) return bilerp(src, s.hs, s.ws, oy, ox, s.sy1, s.sx1);
+  const float fy = fmaxf((oy + 0.5f) * s.sy2 - 0.5f, 0.f), fx = fmaxf((ox + 0.5f) * s.sx2 - 0.5f, 0.f);
+  const int y0 = (int)fy, x0 = (int)fx;
+  const int y1 = y0 + (y0 < s.img_h - 1 ? 1 : 0), x1 = x0 + (x0 < s.img_w - 1 ? 1 : 0);
+  const float ly = fy - y0, lx = fx - x0, hy = 1.f - ly, hx = 1.f - lx;
+  const float v00 = bilerp(src, s.hs, s.ws, y0, x0, s.sy1, s.sx1), v01 = bilerp(src, s.hs, s.ws, y0, x1, s.sy1, s.sx1);
+  const float v10 = bilerp(src, s.hs, s.ws, y1, x0, s.sy1, s.sx1), v11 = bilerp(src, s.hs, s.ws, y1, x1, s.sy1, s.sx1);
+  return hy * (hx * v00 + lx * v01) + ly * (hx * v10 + lx * v11);
+}
+
 // grid (W/32, H, B); block (32 x-pixels, 8): each y-thread strides over queries; smem transpose -> q-fastest writes
 __global__ void __launch_bounds__(256)
 upsample_sigmoid_split_kernel(const float* __restrict__ logits, __nv_bfloat16* __restrict__ hi,
-                              __nv_bfloat16* __restrict__ lo, float* __restrict__ up_f32, int Q, int Qpad, int hs,
-                              int ws, int H, int W) {
+                              __nv_bfloat16* __restrict__ lo, float* __restrict__ up_f32, int Q, int Qpad, int H, int W,
+                              Sampler sp) {
   __shared__ float tile[32][33];   // [q within chunk][x]
   const int b = blockIdx.z, oy = blockIdx.y, ox0 = blockIdx.x * 32;
-  const float sy = (float)hs / (float)H, sx = (float)ws / (float)W;
+  const int hs = sp.hs, ws = sp.ws;
   const int tx = threadIdx.x, ty = threadIdx.y;
   for (int q0 = 0; q0 < Qpad; q0 += 32) {
     for (int qq = ty; qq < 32; qq += 8) {
       const int q = q0 + qq, ox = ox0 + tx;
       float v = 0.f;
       if (q < Q && ox < W) {
-        const float lg = bilerp(logits + ((long long)b * Q + q) * hs * ws, hs, ws, oy, ox, sy, sx);
+        const float lg = sample(logits + ((long long)b * Q + q) * hs * ws, sp, oy, ox);
         if (up_f32) up_f32[(((long long)b * Q + q) * H + oy) * W + ox] = lg;
         v = 1.f / (1.f + expf(-lg));
       }
@@ -108,12 +139,12 @@ __global__ void __launch_bounds__(256)
 panoptic_argmax_kernel(const float* __restrict__ logits, const float* __restrict__ scores,
                        const int32_t* __restrict__ keep, int16_t* __restrict__ ids, uint8_t* __restrict__ fg,
                        int32_t* __restrict__ area, int32_t* __restrict__ orig, int32_t* __restrict__ inter, int Q,
-                       int hs, int ws, int H, int W) {
+                       int H, int W, Sampler sp) {
   extern __shared__ int32_t cnt[];   // [3][Q]
   const int b = blockIdx.y;
   for (int i = threadIdx.x; i < 3 * Q; i += blockDim.x) cnt[i] = 0;
   __syncthreads();
-  const float sy = (float)hs / (float)H, sx = (float)ws / (float)W;
+  const int hs = sp.hs, ws = sp.ws;
   const long long npix = (long long)H * W;
   for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < npix; p += (long long)gridDim.x * blockDim.x) {
     const int oy = (int)(p / W), ox = (int)(p - (long long)oy * W);
@@ -122,7 +153,7 @@ panoptic_argmax_kernel(const float* __restrict__ logits, const float* __restrict
     bool bfg = false;
     for (int q = 0; q < Q; ++q) {
       if (!keep[b * Q + q]) continue;      // warp-uniform
-      const float lg = bilerp(logits + ((long long)b * Q + q) * hs * ws, hs, ws, oy, ox, sy, sx);
+      const float lg = sample(logits + ((long long)b * Q + q) * hs * ws, sp, oy, ox);
       const float s = 1.f / (1.f + expf(-lg));
       const bool f = s >= 0.5f;
       if (f) atomicAdd(&cnt[Q + q], 1);
@@ -268,16 +299,15 @@ instance_topk_kernel(const float* __restrict__ probs, const uint8_t* __restrict_
 // grid (chunks, Q, B), block 256; deterministic two-stage reduction (partials [B, Q, chunks, 2]).
 __global__ void __launch_bounds__(256)
 instance_mask_partial_kernel(const float* __restrict__ logits, uint8_t* __restrict__ masks, float* __restrict__ partial,
-                             int Q, int hs, int ws, int H, int W, int rows_per_chunk) {
+                             int Q, int H, int W, int rows_per_chunk, Sampler sp) {
   __shared__ float red[2][8];
   const int chunk = blockIdx.x, q = blockIdx.y, b = blockIdx.z, nchunks = gridDim.x;
-  const float* src = logits + ((long long)b * Q + q) * hs * ws;
-  const float sy = (float)hs / (float)H, sx = (float)ws / (float)W;
+  const float* src = logits + ((long long)b * Q + q) * sp.hs * sp.ws;
   const int y0 = chunk * rows_per_chunk, y1 = min(H, y0 + rows_per_chunk);
   float num = 0.f, den = 0.f;
   for (int i = y0 * W + threadIdx.x; i < y1 * W; i += 256) {
     const int oy = i / W, ox = i - oy * W;
-    const float lg = bilerp(src, hs, ws, oy, ox, sy, sx);
+    const float lg = sample(src, sp, oy, ox);
     const bool on = lg > 0.f;
     if (on) { num += 1.f / (1.f + expf(-lg)); den += 1.f; }
     if (masks) masks[((long long)b * Q + q) * H * W + i] = on ? 1 : 0;
@@ -314,13 +344,19 @@ __global__ void instance_finalize_kernel(const float* __restrict__ partial, cons
 using namespace ob;
 #define STREAM(s) reinterpret_cast<cudaStream_t>(s)
 
+static int geom_bad(const odise_postprocess_geom* g) {
+  return g && (g->pad_h <= 0 || g->pad_w <= 0 || g->img_h <= 0 || g->img_w <= 0 || g->img_h > g->pad_h || g->img_w > g->pad_w);
+}
+
 extern "C" int odise_upsample_sigmoid_split_f32(const float* logits, void* hi, void* lo, float* up_f32, int B, int Q,
-                                                int Qpad, int hs, int ws, int H, int W, void* stream) {
-  if (!logits || !hi || B <= 0 || Q <= 0 || Qpad < Q || hs <= 0 || ws <= 0 || H <= 0 || W <= 0) return ODISE_ERR_ARG;
+                                                int Qpad, int hs, int ws, int H, int W,
+                                                const odise_postprocess_geom* geom, void* stream) {
+  if (!logits || !hi || B <= 0 || Q <= 0 || Qpad < Q || hs <= 0 || ws <= 0 || H <= 0 || W <= 0 || geom_bad(geom))
+    return ODISE_ERR_ARG;
   dim3 grid((W + 31) / 32, H, B), block(32, 8);
   upsample_sigmoid_split_kernel<<<grid, block, 0, STREAM(stream)>>>(logits, reinterpret_cast<__nv_bfloat16*>(hi),
                                                                     reinterpret_cast<__nv_bfloat16*>(lo), up_f32, Q, Qpad,
-                                                                    hs, ws, H, W);
+                                                                    H, W, make_sampler(hs, ws, H, W, geom));
   count_launch(1);
   return (int)cudaGetLastError();
 }
@@ -346,8 +382,10 @@ extern "C" long long odise_panoptic_ws_bytes(int B, int Q, int H, int W) {
 extern "C" int odise_panoptic_inference_f32(const float* logits, const float* scores, const int32_t* labels,
                                             const int32_t* keep, const uint8_t* is_thing, int32_t* pan,
                                             int32_t* seg_info, int32_t* n_segments, void* ws, int B, int Q, int K,
-                                            int hs, int ws_, int H, int W, double overlap_thr, void* stream) {
-  if (!logits || !scores || !labels || !keep || !is_thing || !pan || !seg_info || !n_segments || !ws) return ODISE_ERR_ARG;
+                                            int hs, int ws_, int H, int W, double overlap_thr,
+                                            const odise_postprocess_geom* geom, void* stream) {
+  if (!logits || !scores || !labels || !keep || !is_thing || !pan || !seg_info || !n_segments || !ws || geom_bad(geom))
+    return ODISE_ERR_ARG;
   if (B <= 0 || Q <= 0 || Q > 32767 || K <= 0 || K * 4 > 48 * 1024) return ODISE_ERR_ARG;
   cudaStream_t st = STREAM(stream);
   const long long npix = (long long)B * H * W;
@@ -361,7 +399,7 @@ extern "C" int odise_panoptic_inference_f32(const float* logits, const float* sc
   int blocks = (int)(((long long)H * W + 255) / 256);
   if (blocks > 148 * 4) blocks = 148 * 4;
   panoptic_argmax_kernel<<<dim3(blocks, B), 256, 3 * Q * sizeof(int32_t), st>>>(logits, scores, keep, ids, fg, area, orig,
-                                                                            inter, Q, hs, ws_, H, W);
+                                                                            inter, Q, H, W, make_sampler(hs, ws_, H, W, geom));
   panoptic_assign_kernel<<<B, 32, K * sizeof(int32_t), st>>>(keep, labels, area, orig, inter, is_thing, seg_of, seg_info,
                                                           n_segments, Q, K, overlap_thr);
   int rb = (int)((npix + 255) / 256);
@@ -384,15 +422,16 @@ extern "C" long long odise_instance_ws_bytes(int B, int Q, int H, int W) {
 extern "C" int odise_instance_inference_f32(const float* probs, const float* logits, const uint8_t* is_thing,
                                             float* scores, int32_t* classes, int32_t* query_index, int32_t* valid,
                                             uint8_t* masks, void* ws, int B, int Q, int K, int topk, int hs, int ws_,
-                                            int H, int W, void* stream) {
-  if (!probs || !logits || !scores || !classes || !query_index || !valid || !ws) return ODISE_ERR_ARG;
+                                            int H, int W, const odise_postprocess_geom* geom, void* stream) {
+  if (!probs || !logits || !scores || !classes || !query_index || !valid || !ws || geom_bad(geom)) return ODISE_ERR_ARG;
   if (B <= 0 || Q <= 0 || K <= 0 || topk <= 0 || topk > 1024 || hs <= 0 || ws_ <= 0 || H <= 0 || W <= 0) return ODISE_ERR_ARG;
   if ((long long)Q * K >= 0x7fffffffLL) return ODISE_ERR_ARG;
   cudaStream_t st = STREAM(stream);
   const int nchunks = instance_chunks(H), rows = (H + nchunks - 1) / nchunks;
   float* partial = reinterpret_cast<float*>(ws);
   instance_topk_kernel<<<B, 1024, 0, st>>>(probs, is_thing, scores, classes, query_index, valid, Q, K, topk);
-  instance_mask_partial_kernel<<<dim3(nchunks, Q, B), 256, 0, st>>>(logits, masks, partial, Q, hs, ws_, H, W, rows);
+  instance_mask_partial_kernel<<<dim3(nchunks, Q, B), 256, 0, st>>>(logits, masks, partial, Q, H, W, rows,
+                                                                          make_sampler(hs, ws_, H, W, geom));
   const int n = B * topk;
   instance_finalize_kernel<<<(n + 255) / 256, 256, 0, st>>>(partial, query_index, scores, n, topk, Q, nchunks);
   count_launch(3);

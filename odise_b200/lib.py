@@ -102,11 +102,11 @@ _SIGS = {
     "odise_softmax_split_f32": [c_void_p, c_longlong, c_void_p, c_void_p, c_longlong, c_longlong, c_int, c_int,
                                 c_float, c_void_p],
     "odise_upsample_sigmoid_split_f32": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
-                                         c_int, c_void_p],
+                                         c_int, c_void_p, c_void_p],
     "odise_query_scores_f32": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                c_float, c_void_p],
-    "odise_panoptic_inference_f32": [c_void_p] * 9 + [c_int] * 7 + [ctypes.c_double, c_void_p],
-    "odise_instance_inference_f32": [c_void_p] * 9 + [c_int] * 8 + [c_void_p],
+    "odise_panoptic_inference_f32": [c_void_p] * 9 + [c_int] * 7 + [ctypes.c_double, c_void_p, c_void_p],
+    "odise_instance_inference_f32": [c_void_p] * 9 + [c_int] * 8 + [c_void_p, c_void_p],
     "odise_gather_rows_f32": [c_void_p, c_longlong, c_void_p, c_void_p, c_longlong, c_int, c_void_p, c_longlong, c_longlong,
                               c_int, c_void_p],
     "odise_maskclip_preprocess": [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
@@ -170,6 +170,11 @@ def _req(t, dtype, name):
     if t.dtype != dtype:
         raise OdiseError(f"{name}: expected {dtype}, got {t.dtype}")
     return t
+
+
+class PostprocessGeom(ctypes.Structure):
+    """odise_postprocess_geom (include/odise_b200.h): padded size and un-padded image size of sem_seg_postprocess."""
+    _fields_ = [("pad_h", c_int), ("pad_w", c_int), ("img_h", c_int), ("img_w", c_int)]
 
 
 class Planes:

@@ -102,9 +102,11 @@ class ODISEEngine:
         return bank
 
     @torch.no_grad()
-    def postprocess(self, out, H, W, semantic=True, panoptic=True):
-        """semantic / panoptic inference on the device (odise.py:335-370 without a clip_head)."""
-        return self.post(out["pred_logits"], out["pred_masks"], H, W, semantic=semantic, panoptic=panoptic)
+    def postprocess(self, out, H, W, semantic=True, panoptic=True, instance=False, padded_size=None, image_size=None):
+        """semantic / panoptic / instance inference on the device (odise.py:326-370).  (H, W) = requested output size;
+        padded_size / image_size as in sem_seg_postprocess when the output is not the padded input itself."""
+        return self.post(out["pred_logits"], out["pred_masks"], H, W, semantic=semantic, panoptic=panoptic,
+                         instance=instance, padded_size=padded_size, image_size=image_size)
 
     # ------------------------------------------------------------------------------------------- device step
     @torch.no_grad()

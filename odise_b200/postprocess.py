@@ -1,7 +1,9 @@
 """Device-side post-processing: the tail of CategoryODISE.forward without a clip_head
 (odise/modeling/meta_arch/odise.py:326-370) — bilinear mask upsample, MaskFormer.semantic_inference and
 MaskFormer.panoptic_inference / instance_inference (maskformer_model.py:280-380) with no host round trips: the reference syncs ~4x per
-query through `.item()`.  Output sizes must equal the padded input size (sem_seg_postprocess is then the identity)."""
+query through `.item()`.  sem_seg_postprocess (crop to the un-padded image, bilinear resize to the requested output size;
+sem_seg_postprocess_before_inference=True in every ODISE config) is folded into the samplers of the three kernels."""
+import ctypes
 import torch
 
 from . import lib, ops
@@ -20,16 +22,25 @@ class PostProcessor:
 
     @torch.no_grad()
     def __call__(self, pred_logits, pred_masks, H, W, semantic=True, panoptic=True, instance=False, topk=100,
-                 panoptic_on=True, instance_masks=True):
+                 panoptic_on=True, instance_masks=True, padded_size=None, image_size=None):
         """pred_logits [B, Q, K+1], pred_masks [B, Q, h, w] (device fp32) ->
         dict(sem_seg [B, K, H, W], panoptic_seg int32 [B, H, W], seg_info int32 [B, Q, 3], n_segments int32 [B]);
         instance=True adds dict(instances=dict(scores, pred_classes, query_index, valid [B, topk], query_masks u8
         [B, Q, H, W])): instance i of image b has the binary mask query_masks[b, query_index[b, i]] and is kept by the
-        reference's panoptic_on filter iff valid[b, i]."""
+        reference's panoptic_on filter iff valid[b, i].
+        (H, W): output size ("height"/"width" of the request).  padded_size / image_size: the padded network input and the
+        un-padded image inside it (images.tensor.shape[-2:], images.image_sizes[i]; odise.py:326-347); omit both when
+        (H, W) is the padded input size itself."""
         B, Q, K1 = pred_logits.shape
         assert K1 == self.K + 1
         hs, ws = pred_masks.shape[-2:]
         dev, L = self.dev, load()
+        geom = None
+        if padded_size is not None or image_size is not None:
+            ph, pw = padded_size if padded_size is not None else (H, W)
+            ih, iw = image_size if image_size is not None else (ph, pw)
+            if (ph, pw, ih, iw) != (H, W, H, W):
+                geom = ctypes.byref(lib.PostprocessGeom(int(ph), int(pw), int(ih), int(iw)))
         Qp = (Q + 7) // 8 * 8
         probs_t = torch.zeros(B * self.K, Qp, dtype=torch.float32, device=dev) if semantic else None
         scores = torch.empty(B * Q, dtype=torch.float32, device=dev)
@@ -44,7 +55,7 @@ class PostProcessor:
         if semantic:
             sig = Planes.empty(B * H * W, Qp, dev, lo=self.lo, ld=Qp)
             _check(L.odise_upsample_sigmoid_split_f32(_ptr(pm), _ptr(sig.hi), _ptr(sig.lo), None, B, Q, Qp, hs, ws, H, W,
-                                                      _stream()), "upsample_sigmoid")
+                                                      geom, _stream()), "upsample_sigmoid")
             # sem[b] = P_b^T [K, Q] @ sig_b^T [Q, HW]: swapped-operand GEMM writes the reference's [K, H, W] layout
             ptp = ops.split(probs_t, lo=self.lo)
             sem = torch.empty(B, self.K, H * W, dtype=torch.float32, device=dev)
@@ -58,7 +69,7 @@ class PostProcessor:
             wsb = torch.empty(int(L.odise_panoptic_ws_bytes(B, Q, H, W)), dtype=torch.uint8, device=dev)
             _check(L.odise_panoptic_inference_f32(_ptr(pm), _ptr(scores), _ptr(labels), _ptr(keep), _ptr(self.is_thing),
                                                   _ptr(pan), _ptr(seg_info), _ptr(nseg), _ptr(wsb), B, Q, self.K, hs, ws,
-                                                  H, W, self.ov_thr, _stream()), "panoptic_inference")
+                                                  H, W, self.ov_thr, geom, _stream()), "panoptic_inference")
             out.update(panoptic_seg=pan, seg_info=seg_info, n_segments=nseg)
         if instance:
             i_sc = torch.empty(B, topk, dtype=torch.float32, device=dev)
@@ -69,7 +80,7 @@ class PostProcessor:
             wsb = torch.empty(int(L.odise_instance_ws_bytes(B, Q, H, W)), dtype=torch.uint8, device=dev)
             _check(L.odise_instance_inference_f32(_ptr(probs), _ptr(pm), _ptr(self.is_thing) if panoptic_on else None,
                                                   _ptr(i_sc), _ptr(i_cl), _ptr(i_q), _ptr(i_ok), _ptr(qm), _ptr(wsb), B, Q,
-                                                  self.K, topk, hs, ws, H, W, _stream()), "instance_inference")
+                                                  self.K, topk, hs, ws, H, W, geom, _stream()), "instance_inference")
             out["instances"] = dict(scores=i_sc, pred_classes=i_cl, query_index=i_q, valid=i_ok, query_masks=qm)
         out.update(scores=scores.view(B, Q), labels=labels.view(B, Q), keep=keep.view(B, Q))
         return out

@@ -14,6 +14,13 @@ def upsample_masks(mask_pred, size):
     return F.interpolate(mask_pred, size=size, mode="bilinear", align_corners=False)
 
 
+def sem_seg_postprocess(result, img_size, output_height, output_width):
+    """detectron2 v0.6 modeling/postprocessing.py::sem_seg_postprocess (un-vendored; restated, unpinned): crop the padded
+    prediction to the image, bilinear resize to the requested size.  result [C, Hpad, Wpad]."""
+    result = result[:, : img_size[0], : img_size[1]].expand(1, -1, -1, -1)
+    return F.interpolate(result, size=(output_height, output_width), mode="bilinear", align_corners=False)[0]
+
+
 def semantic_inference(mask_cls, mask_pred):
     """maskformer_model.py:280-284.  mask_cls [Q, K+1], mask_pred [Q, H, W] logits -> [K, H, W]."""
     mask_cls = F.softmax(mask_cls, dim=-1)[..., :-1]

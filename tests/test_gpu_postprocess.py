@@ -77,3 +77,30 @@ def test_instance_inference(cuda, cfg):
         agree = (gm == ref["pred_masks"][o2]).float().mean().item()
         assert agree > 0.9999, agree
         assert torch.isin(pc, torch.tensor(things, dtype=pc.dtype)).all()
+
+
+def test_postprocess_with_padding_and_resize(cuda):
+    """odise.py:326-347: masks upsampled to the padded input, cropped to the image, resized to the dataset's original
+    size (sem_seg_postprocess) BEFORE semantic / panoptic / instance inference."""
+    from odise_b200.postprocess import PostProcessor
+    from oracle import postprocess as opp
+    B, Q, K, h, w = 1, 30, 11, 40, 48                       # padded input 160 x 192, image 150 x 171, output 97 x 111
+    pad, img, outsz = (160, 192), (150, 171), (97, 111)
+    cls, masks = _case(9, B, Q, K, h, w)
+    things = list(range(0, K, 2))
+    pp = PostProcessor(cuda, K, things)
+    out = pp(cls.to(cuda), masks.to(cuda), outsz[0], outsz[1], instance=True, topk=50, padded_size=pad, image_size=img)
+    torch.cuda.synchronize()
+    up = opp.sem_seg_postprocess(opp.upsample_masks(masks, pad)[0], img, *outsz)
+    sem = opp.semantic_inference(cls[0], up)
+    got = out["sem_seg"][0].cpu()
+    assert got.shape == (K, *outsz)
+    assert ((got.double() - sem.double()).abs().max() / sem.abs().max()).item() < 1e-4
+    pan, info = opp.panoptic_inference(cls[0], up, K, things)
+    assert info == pp.segments_info(out["seg_info"], out["n_segments"])[0] and len(info) > 0
+    assert (out["panoptic_seg"][0].cpu() == pan).float().mean().item() > 0.999
+    ref = opp.instance_inference(cls[0], up, K, things, topk=50, panoptic_on=True)
+    ok = out["instances"]["valid"][0].cpu().bool()
+    sc = out["instances"]["scores"][0].cpu()[ok]
+    assert sc.numel() == ref["scores"].numel()
+    assert torch.allclose(sc.sort().values, ref["scores"].sort().values, rtol=3e-4, atol=1e-6)
