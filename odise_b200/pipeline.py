@@ -110,8 +110,10 @@ class ODISEEngine:
 
     # ------------------------------------------------------------------------------------------- device step
     @torch.no_grad()
-    def step(self, n_images, H, W, vae_taps=None, images_u8=None):
-        """One pass of the hot path for n_images resident images (eager). Returns device tensors."""
+    def step(self, n_images, H, W, vae_taps=None, images_u8=None, clip_images=None):
+        """One pass of the hot path for n_images resident images (eager). Returns device tensors.
+        clip_images: what MaskCLIP looks at when it differs from the network input — the reference feeds it the batch
+        padded only to its own maximum size, not to size_divisibility (odise.py:240-246)."""
         if images_u8 is None and (self.with_vae or self.with_clip):
             images_u8 = self._image_buffer(n_images, H, W)
         feats = self.backbone.forward(n_images, H, W, vae_taps, images_u8)
@@ -124,7 +126,9 @@ class ODISEEngine:
         if "pred_logits" in out:
             res["pred_logits"] = out["pred_logits"]
             if self.clip_head is not None:        # odise.py:292-323: MaskCLIP ensemble replaces the class scores
-                ch = self.clip_head.forward(self.vocab_key, images_u8, n_images, H, W, res["pred_masks"], out["pred_logits"])
+                ci = clip_images if clip_images is not None else images_u8
+                ch = self.clip_head.forward(self.vocab_key, ci, n_images, ci.shape[2], ci.shape[3], res["pred_masks"],
+                                            out["pred_logits"])
                 res["pred_logits_category"] = out["pred_logits"]
                 res["pred_logits"] = ch["pred_logits"]
                 res["clip_mask_embed"] = ch["mask_embed"]

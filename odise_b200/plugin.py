@@ -137,3 +137,57 @@ class B200PoolingCLIPHead(nn.Module):
         r = self.engine.forward("test", img.contiguous().float(), B, img.shape[2], img.shape[3], masks.float(), cat,
                                 want_open=True)
         return {"pred_open_logits": r["pred_open_logits"]}
+
+
+class B200CategoryODISE(nn.Module):
+    """Drop-in for the eval branch of CategoryODISE.forward (odise.py:209-246, :282-370): a list of
+    {"image": uint8 [3, h, w] (0..255), "height": H_out, "width": W_out} in, a list of
+    {"sem_seg": [K, H_out, W_out], "panoptic_seg": (int32 [H_out, W_out], segments_info), "instances": {...}} out.
+    Batching follows detectron2's ImageList.from_tensors: images are top-left aligned in a zero-padded batch whose size
+    is the per-batch maximum rounded up to size_divisibility (64) for the network, and un-rounded for MaskCLIP.
+    `engine` is an ODISEEngine with a vocabulary set (set_vocabulary / set_vocabulary_from_tokens)."""
+
+    def __init__(self, engine, size_divisibility=64, semantic_on=True, panoptic_on=True, instance_on=True,
+                 test_topk_per_image=100):
+        super().__init__()
+        self.engine = engine
+        self.size_divisibility = size_divisibility
+        self.semantic_on, self.panoptic_on, self.instance_on = semantic_on, panoptic_on, instance_on
+        self.test_topk_per_image = test_topk_per_image
+
+    @torch.no_grad()
+    def forward(self, batched_inputs):
+        assert not self.training, "B200CategoryODISE is inference only"
+        eng, dev = self.engine, self.engine.dev
+        imgs = [x["image"] for x in batched_inputs]
+        sizes = [(int(im.shape[-2]), int(im.shape[-1])) for im in imgs]
+        mh, mw = max(s[0] for s in sizes), max(s[1] for s in sizes)
+        d = self.size_divisibility
+        ph, pw = (mh + d - 1) // d * d, (mw + d - 1) // d * d
+        n = len(imgs)
+        net = torch.zeros(n, 3, ph, pw, dtype=torch.uint8, device=dev)
+        for i, im in enumerate(imgs):
+            if im.dtype != torch.uint8:
+                raise RuntimeError('"image" must be uint8 CHW in 0..255 (detectron2 DatasetMapper format)')
+            net[i, :, :sizes[i][0], :sizes[i][1]] = im.to(dev, non_blocking=True)
+        clip_in = net[:, :, :mh, :mw].contiguous() if (mh, mw) != (ph, pw) else net
+        out = eng.step(n, ph, pw, images_u8=net, clip_images=clip_in)
+        results = []
+        for i, x in enumerate(batched_inputs):
+            H, W = int(x.get("height", sizes[i][0])), int(x.get("width", sizes[i][1]))
+            post = eng.post(out["pred_logits"][i:i + 1], out["pred_masks"][i:i + 1], H, W, semantic=self.semantic_on,
+                            panoptic=self.panoptic_on, instance=self.instance_on, topk=self.test_topk_per_image,
+                            panoptic_on=self.panoptic_on, padded_size=(ph, pw), image_size=sizes[i])
+            r = {}
+            if self.semantic_on:
+                r["sem_seg"] = post["sem_seg"][0]
+            if self.panoptic_on:
+                r["panoptic_seg"] = (post["panoptic_seg"][0], eng.post.segments_info(post["seg_info"], post["n_segments"])[0])
+            if self.instance_on:
+                ins = post["instances"]
+                keep = ins["valid"][0].bool()
+                qi = ins["query_index"][0][keep].long()
+                r["instances"] = dict(pred_masks=ins["query_masks"][0][qi], scores=ins["scores"][0][keep],
+                                      pred_classes=ins["pred_classes"][0][keep].long(), image_size=(H, W))
+            results.append(r)
+        return results

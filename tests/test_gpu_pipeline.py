@@ -124,3 +124,37 @@ def test_vocabulary_from_tokens(cuda, world):
     assert out["pred_logits"].shape == (1, 100, 5) and torch.isfinite(out["pred_logits"]).all()
     eng.set_vocabulary("v20", world["bank"], world["null"], world["sizes"], clip_text_bank=world["clip_bank"],
                        overlapping=world["ov"])
+
+
+@torch.no_grad()
+def test_category_odise_plugin_ragged_batch(cuda, world):
+    """B200CategoryODISE: two images of different, non-64-divisible sizes in one batch, outputs at the datasets' original
+    sizes; checked against the oracle post-processing applied to the engine's own logits."""
+    from odise_b200.plugin import B200CategoryODISE
+    from oracle import postprocess as opp
+    eng = world["eng"]
+    g = torch.Generator().manual_seed(21)
+    ims = [torch.randint(0, 256, (3, 500, 620), generator=g, dtype=torch.uint8),
+           torch.randint(0, 256, (3, 470, 640), generator=g, dtype=torch.uint8)]
+    req = [dict(image=ims[0], height=250, width=310), dict(image=ims[1], height=600, width=817)]
+    model = B200CategoryODISE(eng).eval()
+    res = model(req)
+    torch.cuda.synchronize()
+    assert len(res) == 2
+    assert res[0]["sem_seg"].shape == (20, 250, 310) and res[1]["sem_seg"].shape == (20, 600, 817)
+    assert res[0]["panoptic_seg"][0].shape == (250, 310) and res[1]["panoptic_seg"][0].shape == (600, 817)
+    # re-run the network part to get the raw outputs the plugin post-processed (padded batch 512 x 640)
+    net = torch.zeros(2, 3, 512, 640, dtype=torch.uint8)
+    net[0, :, :500, :620], net[1, :, :470, :640] = ims[0], ims[1]
+    out = eng.step(2, 512, 640, images_u8=net.to(cuda), clip_images=net[:, :, :500, :640].contiguous().to(cuda))
+    things = list(range(0, 20, 2))
+    for i, (r, rq) in enumerate(zip(res, req)):
+        cls, masks = out["pred_logits"][i].cpu(), out["pred_masks"][i:i + 1].cpu()
+        up = opp.sem_seg_postprocess(opp.upsample_masks(masks, (512, 640))[0], ims[i].shape[-2:], rq["height"], rq["width"])
+        sem = opp.semantic_inference(cls, up)
+        assert ((r["sem_seg"].cpu().double() - sem.double()).abs().max() / sem.abs().max()).item() < 1e-3
+        pan, info = opp.panoptic_inference(cls, up, 20, things)
+        assert r["panoptic_seg"][1] == info
+        assert (r["panoptic_seg"][0].cpu() == pan).float().mean().item() > 0.999
+        ins = r["instances"]
+        assert ins["pred_masks"].shape[1:] == (rq["height"], rq["width"]) and ins["scores"].numel() == ins["pred_classes"].numel()
