@@ -96,3 +96,24 @@ elif which == "clip":
         fn = lambda: lib.gemm(me, te, alpha=14.2857, out=out)
         ms = timeit(fn)
         print(f"clip match [{rows},256]x[{kp},256]^T: {ms*1000:.1f} us, {2.0*rows*kp*256/ms/1e9:.2f} TFLOP/s")
+elif which == "clipattn":
+    # CLIP ViT-L/14-336 self-attention of 16 crops: 16 heads x d=64, 577 tokens (584 rows per image)
+    B, heads, d, T, TS = 16, 16, 64, 577, 584
+    qk = lib.split(torch.randn(B * TS, 2 * heads * d, device=dev))
+    vt = lib.split(torch.randn(heads * d, B * TS, device=dev))
+    fn = lambda: ops.attention_tc(qk.col_slice(0, heads * d), qk.col_slice(heads * d, heads * d), vt, B, heads, d, TS, T,
+                                  d ** -0.5, 3, tk_stride=TS)
+    ms = timeit(fn, 5)
+    fl = 4.0 * B * heads * TS * T * d
+    print(f"attn_tc d=64 T=577 B=16: {ms*1000:.1f} us, {fl/ms/1e9:.1f} TFLOP/s algorithmic, {3*fl/ms/1e9:.1f} MMA-TFLOP/s issued")
+elif which == "clipmlp":
+    # CLIP MLP c_fc: [16*584, 1024] x [4096, 1024]^T with bias + QuickGELU + (hi, lo) plane epilogue
+    M, K, N = 16 * 584, 1024, 4096
+    a = lib.split(torch.randn(M, K, device=dev))
+    w = lib.split(torch.randn(N, K, device=dev) * 0.03)
+    bias = torch.randn(N, device=dev)
+    u = lib.Planes.empty(M, N, dev)
+    fn = lambda: lib.gemm(a, w, bias=bias, act=4, out_planes=u)
+    ms = timeit(fn)
+    fl = 2.0 * M * N * K
+    print(f"clip c_fc {M}x{N}x{K}: {ms*1000:.1f} us, {fl/ms/1e9:.1f} TFLOP/s algorithmic, {3*fl/ms/1e9:.1f} MMA-TFLOP/s")
