@@ -29,6 +29,7 @@ struct GemmParams {
   int M, N, K, batch;
   int a_batched, b_batched;
   int conv, C, H, W, bw, bh, bb;   // H, W: OUTPUT spatial dims of the conv
+  int nseg;                        // > 1: the 128 pixels of a tile are fetched as nseg row segments of bw pixels
   int cstride, cpad;               // conv stride (1 | 2) and low-side zero padding (0 | 1)
   int tiles_m, tiles_n, splits, kblocks;
   float alpha;
@@ -231,9 +232,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
           if (p.conv) {
             const int tap = kb / cpk, cc = kb - tap * cpk;
             const int kh = tap / 3, kw = tap - kh * 3;
-            const int cx = w0 * p.cstride + kw - p.cpad, cy = h0 * p.cstride + kh - p.cpad;
-            tma_load_4d(st, &tmAh, &full[stage], cc * 64, cx, cy, b0);
-            if (NMMA == 3) tma_load_4d(st + Cfg::A_BYTES, &tmAl, &full[stage], cc * 64, cx, cy, b0);
+            if (p.nseg == 1) {
+              const int cx = w0 * p.cstride + kw - p.cpad, cy = h0 * p.cstride + kh - p.cpad;
+              tma_load_4d(st, &tmAh, &full[stage], cc * 64, cx, cy, b0);
+              if (NMMA == 3) tma_load_4d(st + Cfg::A_BYTES, &tmAl, &full[stage], cc * 64, cx, cy, b0);
+            } else {
+              // widths that are neither a divisor nor a multiple of 128: raster-consecutive segments of
+              // bw = gcd(W, 128) pixels never straddle an image row; each lands on its 8-row-aligned slice of the tile
+              const int hw = p.H * p.W;
+              for (int sg = 0; sg < p.nseg; ++sg) {
+                const int m = m0 + sg * p.bw;
+                const int bi = m / hw, rem = m - bi * hw;
+                const int hi_ = rem / p.W, wi = rem - hi_ * p.W;
+                const int cx = wi * p.cstride + kw - p.cpad, cy = hi_ * p.cstride + kh - p.cpad;
+                uint8_t* sa = st + sg * p.bw * 128;
+                tma_load_4d(sa, &tmAh, &full[stage], cc * 64, cx, cy, bi);
+                if (NMMA == 3) tma_load_4d(sa + Cfg::A_BYTES, &tmAl, &full[stage], cc * 64, cx, cy, bi);
+              }
+            }
           } else {
             const int za = p.a_batched ? z : 0;
             tma_load_3d(st, &tmAh, &full[stage], kb * 64, m0, za);
@@ -616,16 +632,24 @@ extern "C" int odise_gemm_bf16(const odise_gemm_desc* d, void* stream_v) {
     const int hw = p.H * p.W;
     if (d->M % hw) return ODISE_ERR_ARG;
     const int B = d->M / hw;
-    if (p.W >= 128) {
-      if (p.W % 128) return ODISE_ERR_ARG;
+    p.nseg = 1;
+    bool boxed = false;
+    if (p.W % 128 == 0) {
       p.bw = 128; p.bh = 1; p.bb = 1;
-    } else {
-      if (128 % p.W) return ODISE_ERR_ARG;
+      boxed = true;
+    } else if (128 % p.W == 0) {
       p.bw = p.W;
       p.bh = 128 / p.W < p.H ? 128 / p.W : p.H;
-      if (p.H % p.bh) return ODISE_ERR_ARG;
-      if (128 % (p.bw * p.bh)) return ODISE_ERR_ARG;
-      p.bb = 128 / (p.bw * p.bh);
+      if (p.H % p.bh == 0 && 128 % (p.bw * p.bh) == 0) {
+        p.bb = 128 / (p.bw * p.bh);
+        boxed = true;
+      }
+    }
+    if (!boxed) {                       // general widths (e.g. 160 = 640 / 4): segmented fetch
+      int g = p.W, r = 128;
+      while (r) { const int t = g % r; g = r; r = t; }
+      if (g % 8) return ODISE_ERR_UNSUPPORTED;
+      p.bw = g; p.bh = 1; p.bb = 1; p.nseg = 128 / g;
     }
     const long long pix = d->lda;  // elements between consecutive pixels (>= C: channel slices of wider buffers)
     if (pix < p.C || pix % 8) return ODISE_ERR_ALIGN;

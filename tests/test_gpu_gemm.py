@@ -76,7 +76,9 @@ def test_gemm_batched_and_splitk(cuda):
 
 @pytest.mark.parametrize("nmma", [3, 1])
 @pytest.mark.parametrize("shape", [(2, 64, 64, 64, 128), (3, 8, 8, 128, 64), (2, 16, 16, 320, 320), (1, 32, 32, 192, 100),
-                                   (1, 128, 128, 64, 64), (1, 4, 256, 64, 32)])
+                                   (1, 128, 128, 64, 64), (1, 4, 256, 64, 32),
+                                   # widths that neither divide nor are multiples of 128 (segmented fetch), e.g. 640 / 4
+                                   (2, 24, 160, 64, 64), (1, 10, 40, 128, 96), (3, 7, 96, 64, 32), (1, 6, 8, 64, 64)])
 def test_conv3x3_implicit(cuda, nmma, shape):
     """F.conv2d(x, w, padding=1) on NCHW == implicit GEMM on NHWC with k = (kh*3+kw)*C + c."""
     from odise_b200 import lib
@@ -126,7 +128,8 @@ def test_gemm_geglu_fused(cuda, M):
 
 
 @pytest.mark.parametrize("mode", [1, 2])
-@pytest.mark.parametrize("shape", [(2, 64, 64, 64, 96), (1, 16, 16, 320, 320), (3, 8, 8, 128, 64), (1, 256, 256, 64, 64), (1, 512, 512, 128, 32)])
+@pytest.mark.parametrize("shape", [(2, 64, 64, 64, 96), (1, 16, 16, 320, 320), (3, 8, 8, 128, 64), (1, 256, 256, 64, 64), (1, 512, 512, 128, 32),
+                                   (2, 12, 160, 64, 64), (1, 20, 48, 128, 64)])
 def test_conv3x3_stride2_implicit(cuda, mode, shape):
     """stride-2 3x3 conv as a strided implicit GEMM: mode 1 = pad (1,1) (ldm Downsample), mode 2 = F.pad(0,1,0,1) + no pad (VAE)."""
     from odise_b200 import lib
