@@ -51,6 +51,19 @@ struct GemmParams {
   float* partial;  // [splits][batch][M][N] when splits > 1
 };
 
+// exact-erf GELU with erf from Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7, i.e. fp32 rounding level): one ex2, one
+// rcp and six FMAs instead of libdevice's two-branch erff; used by the fused GEGLU epilogue (ldm GEGLU = F.gelu).
+__device__ __forceinline__ float gelu_erf_fast(float v) {
+  const float x = fabsf(v) * 0.70710678118654752f;
+  const float t = __frcp_rn(fmaf(0.3275911f, x, 1.f));
+  float pl = fmaf(1.061405429f, t, -1.453152027f);
+  pl = fmaf(pl, t, 1.421413741f);
+  pl = fmaf(pl, t, -0.284496736f);
+  pl = fmaf(pl, t, 0.254829592f);
+  const float er = 1.f - pl * t * exp2f(-1.4426950408889634f * x * x);   // erf(|v| / sqrt 2)
+  return 0.5f * v * (1.f + copysignf(er, v));
+}
+
 __device__ __forceinline__ float apply_act(float v, int act) {
   if (act == ODISE_ACT_RELU) return fmaxf(v, 0.f);
   if (act == ODISE_ACT_SILU) return v / (1.f + __expf(-v));
@@ -380,19 +393,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
             if (p.geglu) {
               // ldm GEGLU fused: lanes with even cq hold 4 `a` values, their xor-1 partner the 4 gates of the same
               // channels (weight rows were quad-interleaved at load time); output planes have N/2 columns
-              float gt[4];
-#pragma unroll
-              for (int j = 0; j < 4; ++j) gt[j] = __shfl_xor_sync(0xffffffffu, e[j], 1);
-              if ((cq & 1) == 0) {
-                __align__(8) __nv_bfloat16 h[4];
-                __align__(8) __nv_bfloat16 l[4];
-#pragma unroll
-                for (int t = 0; t < 4; ++t) split_bf16(e[t] * apply_act(gt[t], ODISE_ACT_GELU), h[t], l[t]);
-                const long long og = (long long)z * p.h_bs + (long long)(m_base + it * 8 + rsub) * p.ldh +
-                                     ((n0 + c0) >> 1) + (cq >> 1) * 4;
-                *reinterpret_cast<uint2*>(p.Dh + og) = *reinterpret_cast<const uint2*>(h);
-                if (p.Dl) *reinterpret_cast<uint2*>(p.Dl + og) = *reinterpret_cast<const uint2*>(l);
-              }
+              // both partners work: the even lane finishes channels 0,1 of the quad, the odd lane channels 2,3
+              const bool odd = cq & 1;
+              const float r0 = __shfl_xor_sync(0xffffffffu, odd ? e[0] : e[2], 1);
+              const float r1 = __shfl_xor_sync(0xffffffffu, odd ? e[1] : e[3], 1);
+              const float a0 = odd ? r0 : e[0], a1 = odd ? r1 : e[1];
+              const float g0 = odd ? e[2] : r0, g1 = odd ? e[3] : r1;
+              __nv_bfloat16 h0, l0, h1, l1;
+              split_bf16(a0 * gelu_erf_fast(g0), h0, l0);
+              split_bf16(a1 * gelu_erf_fast(g1), h1, l1);
+              const long long og = (long long)z * p.h_bs + (long long)(m_base + it * 8 + rsub) * p.ldh +
+                                   ((n0 + c0) >> 1) + (cq >> 1) * 4 + (odd ? 2 : 0);
+              *reinterpret_cast<__nv_bfloat162*>(p.Dh + og) = __halves2bfloat162(h0, h1);
+              if (p.Dl) *reinterpret_cast<__nv_bfloat162*>(p.Dl + og) = __halves2bfloat162(l0, l1);
               continue;
             }
             if (p.act != ODISE_ACT_NONE) {
@@ -443,7 +456,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
                   __align__(8) __nv_bfloat16 h[4];
                   __align__(8) __nv_bfloat16 l[4];
 #pragma unroll
-                  for (int t = 0; t < 4; ++t) split_bf16(e[t] * apply_act(gt[t], ODISE_ACT_GELU), h[t], l[t]);
+                  for (int t = 0; t < 4; ++t) split_bf16(e[t] * gelu_erf_fast(gt[t]), h[t], l[t]);
                   const long long og = (long long)z * p.h_bs + (long long)m * p.ldh + ((n0 + c0) >> 1) + (cq >> 1) * 4;
                   *reinterpret_cast<uint2*>(p.Dh + og) = *reinterpret_cast<const uint2*>(h);
                   if (p.Dl) *reinterpret_cast<uint2*>(p.Dl + og) = *reinterpret_cast<const uint2*>(l);
@@ -562,18 +575,34 @@ static int launch_cfg(const CUtensorMap& ah, const CUtensorMap& al, const CUtens
   return (int)cudaGetLastError();
 }
 
-static int pick_bn(int M, int N, int batch, int forced) {
+static int pick_bn(int M, int N, int K, int batch, int forced, bool conv) {
   if (forced == 64 || forced == 128 || forced == 160 || forced == 256) return forced;
   const int cands[4] = {256, 160, 128, 64};
-  const double eff[4] = {1.0, 1.0, 1.0, 1.45};  // BN=64 is smem-bandwidth bound on the A re-read
   const long long tm = (M + 127) / 128;
   double best = 1e30;
   int best_bn = 128;
+  if (conv) {   // implicit convs (K >= 576) are MMA bound at every width: balance waves only
+    const double eff[4] = {1.0, 1.0, 1.0, 1.45};  // BN=64 is smem-bandwidth bound on the A re-read
+    for (int i = 0; i < 4; ++i) {
+      const int bn = cands[i];
+      const long long tiles = tm * ((N + bn - 1) / bn) * batch;
+      const long long waves = (tiles + num_sms() - 1) / num_sms();
+      const double cost = (double)waves * bn * eff[i] + 0.02 * bn;  // mild bias toward smaller tiles on ties
+      if (cost < best) { best = cost; best_bn = bn; }
+    }
+    return best_bn;
+  }
+  // plain GEMMs: per-tile time = max(MMA, epilogue) + fixed fill/drain.  Measured on B200 (tools/gemm_one.py): the
+  // epilogue of a 128-wide tile costs as much as K ~ 480 of MMA with 8 epilogue warps (BN 64/128/256) and K ~ 960 with
+  // the 4 warps of BN = 160; wider tiles re-read less of A (BN = 256 ~10 % faster than 128 at equal waves).
+  const double mma_eff[4] = {0.90, 0.95, 1.0, 1.45};
+  const double epi_k[4] = {480.0, 960.0, 480.0, 480.0};
   for (int i = 0; i < 4; ++i) {
     const int bn = cands[i];
     const long long tiles = tm * ((N + bn - 1) / bn) * batch;
     const long long waves = (tiles + num_sms() - 1) / num_sms();
-    const double cost = (double)waves * bn * eff[i] + 0.02 * bn;  // mild bias toward smaller tiles on ties
+    const double mma = (double)bn * K * mma_eff[i], epi = (double)bn * epi_k[i];
+    const double cost = (double)waves * ((mma > epi ? mma : epi) + 20000.0);
     if (cost < best) { best = cost; best_bn = bn; }
   }
   return best_bn;
@@ -672,7 +701,7 @@ extern "C" int odise_gemm_bf16(const odise_gemm_desc* d, void* stream_v) {
     rc = encode_map(&al, d->nmma == 3 ? d->a_lo : d->a_hi, 3, dims, str, box);
     if (rc) return rc;
   }
-  const int BN = pick_bn(d->M, d->N, d->batch, d->force_bn);
+  const int BN = pick_bn(d->M, d->N, d->K, d->batch, d->force_bn, d->conv3x3 != 0);
   {
     if (d->ldb % 8 || d->b_batch_stride % 8) return ODISE_ERR_ALIGN;
     const long long bs = d->b_batch_stride ? d->b_batch_stride : (long long)d->N * d->ldb;

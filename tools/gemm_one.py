@@ -1,4 +1,4 @@
-"""Single-shape GEMM runner for ncu captures: python tools/gemm_one.py M N K [planes|f32|both] [nmma] [bn]"""
+"""Single-shape GEMM runner for ncu captures: python tools/gemm_one.py M N K [planes|f32|both|geglu] [nmma] [bn]"""
 import os
 import sys
 
@@ -17,13 +17,16 @@ b = lib.split(torch.randn(N, K, device=dev) * 0.05)
 bias = torch.randn(N, device=dev)
 out = torch.empty(M, N, device=dev) if mode in ("f32", "both") else None
 outp = lib.Planes.empty(M, N, dev) if mode in ("planes", "both") else None
+kw = {}
+if mode == "geglu":
+    outp, kw = lib.Planes.empty(M, N // 2, dev), dict(geglu=True)
 for i in range(5):
-    lib.gemm(a, b, nmma=nmma, bias=bias, out=out, out_planes=outp, force_bn=bn)
+    lib.gemm(a, b, nmma=nmma, bias=bias, out=out, out_planes=outp, force_bn=bn, **kw)
 torch.cuda.synchronize()
 s, e = torch.cuda.Event(True), torch.cuda.Event(True)
 s.record()
 for i in range(10):
-    lib.gemm(a, b, nmma=nmma, bias=bias, out=out, out_planes=outp, force_bn=bn)
+    lib.gemm(a, b, nmma=nmma, bias=bias, out=out, out_planes=outp, force_bn=bn, **kw)
 e.record()
 torch.cuda.synchronize()
 ms = s.elapsed_time(e) / 10
