@@ -163,7 +163,11 @@ struct GemmCfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 256 /*barriers*/;
 };
 
-template <int BN, int NMMA>
+// EPI selects the compiled epilogue of the interior fast path (the runtime flags it excludes are guaranteed off by the
+// host dispatch): 0 = lean (alpha, bias, activation -> fp32 and/or planes), 1 = + row bias / bias_m / residual,
+// 2 = fused GEGLU.  ncu on the K = 320 FF1 GEMM showed ~190 of the 354 instructions of a chunk iteration were runtime
+// flag tests, predicated-off adds and parameter re-loads; the lean variant drops them.
+template <int BN, int NMMA, int EPI>
 __global__ void __launch_bounds__(GemmCfg<BN, NMMA>::THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
@@ -343,6 +347,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
       const bool interior = p.vec_ok && p.splits == 1 && (mt * 128 + 128 <= p.M) && (n0 + BN <= p.N);
       if (interior) {
         // fast path: whole tile in range, vector accesses; per-row offsets hoisted out of the column loop
+        constexpr bool EXTRA = EPI == 1, GEGLU = EPI == 2;
         long long oD[4], oR[4], oH[4];
         const float* rbp[4];
         float bm[4];
@@ -351,11 +356,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
           const long long m = m_base + it * 8 + rsub;
           const int nn = n0 + cq * 4;
           oD[it] = (long long)z * p.d_bs + m * p.ldd + nn;
-          oR[it] = (long long)z * p.res_bs + m * p.ldres + nn;
+          oR[it] = EXTRA ? (long long)z * p.res_bs + m * p.ldres + nn : 0;
           oH[it] = (long long)z * p.h_bs + m * p.ldh + nn;
-          rbp[it] = p.rowbias ? p.rowbias + (((long long)z * p.M + m) / p.rows_per_group) * p.rowbias_ld + nn : nullptr;
-          bm[it] = p.bias_m ? __ldg(p.bias_m + m) : 0.f;
+          rbp[it] = (EXTRA && p.rowbias)
+                        ? p.rowbias + (((long long)z * p.M + m) / p.rows_per_group) * p.rowbias_ld + nn : nullptr;
+          bm[it] = (EXTRA && p.bias_m) ? __ldg(p.bias_m + m) : 0.f;
         }
+        const bool has_bias = p.bias != nullptr, has_res = EXTRA && p.res != nullptr;
+        const bool to_f32 = p.D != nullptr, to_hi = p.Dh != nullptr, to_lo = p.Dl != nullptr;
+        const int act = p.act;
+        const float alpha = p.alpha;
 #pragma unroll 1
         for (int c0 = c_first; c0 < BN; c0 += c_step) {
           uint32_t v[16];
@@ -368,7 +378,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
                             __uint_as_float(v[4 * j + 3]));
           __syncwarp();
           float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (p.bias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c0 + cq * 4));
+          if (has_bias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c0 + cq * 4));
           float4 q[4];
 #pragma unroll
           for (int it = 0; it < 4; ++it) {
@@ -376,7 +386,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
             q[it] = *reinterpret_cast<const float4*>(stg + rr * 16 + ((cq ^ ((rr >> 1) & 3)) << 2));
           }
           float4 r4[4];
-          if (p.res) {
+          if (has_res) {
 #pragma unroll
             for (int it = 0; it < 4; ++it) r4[it] = *reinterpret_cast<const float4*>(p.res + oR[it] + c0);
           }
@@ -385,12 +395,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
             float e[4] = {q[it].x, q[it].y, q[it].z, q[it].w};
             const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
-            for (int j = 0; j < 4; ++j) e[j] = fmaf(e[j], p.alpha, bb[j] + bm[it]);
-            if (rbp[it]) {
+            for (int j = 0; j < 4; ++j) e[j] = fmaf(e[j], alpha, EXTRA ? bb[j] + bm[it] : bb[j]);
+            if (EXTRA && rbp[it]) {
               const float4 rb = __ldg(reinterpret_cast<const float4*>(rbp[it] + c0));
               e[0] += rb.x; e[1] += rb.y; e[2] += rb.z; e[3] += rb.w;
             }
-            if (p.geglu) {
+            if (GEGLU) {
               // ldm GEGLU fused: lanes with even cq hold 4 `a` values, their xor-1 partner the 4 gates of the same
               // channels (weight rows were quad-interleaved at load time); output planes have N/2 columns
               // both partners work: the even lane finishes channels 0,1 of the quad, the odd lane channels 2,3
@@ -405,22 +415,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
               const long long og = (long long)z * p.h_bs + (long long)(m_base + it * 8 + rsub) * p.ldh +
                                    ((n0 + c0) >> 1) + (cq >> 1) * 4 + (odd ? 2 : 0);
               *reinterpret_cast<__nv_bfloat162*>(p.Dh + og) = __halves2bfloat162(h0, h1);
-              if (p.Dl) *reinterpret_cast<__nv_bfloat162*>(p.Dl + og) = __halves2bfloat162(l0, l1);
+              if (to_lo) *reinterpret_cast<__nv_bfloat162*>(p.Dl + og) = __halves2bfloat162(l0, l1);
               continue;
             }
-            if (p.act != ODISE_ACT_NONE) {
+            if (act != ODISE_ACT_NONE) {
 #pragma unroll
-              for (int j = 0; j < 4; ++j) e[j] = apply_act(e[j], p.act);
+              for (int j = 0; j < 4; ++j) e[j] = apply_act(e[j], act);
             }
-            if (p.res) { e[0] += r4[it].x; e[1] += r4[it].y; e[2] += r4[it].z; e[3] += r4[it].w; }
-            if (p.D) *reinterpret_cast<float4*>(p.D + oD[it] + c0) = make_float4(e[0], e[1], e[2], e[3]);
-            if (p.Dh) {
-              __align__(8) __nv_bfloat16 h[4];
-              __align__(8) __nv_bfloat16 l[4];
-#pragma unroll
-              for (int t = 0; t < 4; ++t) split_bf16(e[t], h[t], l[t]);
-              *reinterpret_cast<uint2*>(p.Dh + oH[it] + c0) = *reinterpret_cast<const uint2*>(h);
-              if (p.Dl) *reinterpret_cast<uint2*>(p.Dl + oH[it] + c0) = *reinterpret_cast<const uint2*>(l);
+            if (has_res) { e[0] += r4[it].x; e[1] += r4[it].y; e[2] += r4[it].z; e[3] += r4[it].w; }
+            if (to_f32) *reinterpret_cast<float4*>(p.D + oD[it] + c0) = make_float4(e[0], e[1], e[2], e[3]);
+            if (to_hi) {
+              // packed conversions: hi = bf16x2(e), lo = bf16x2(e - float(hi))  (same values as split_bf16)
+              const __nv_bfloat162 h01 = __floats2bfloat162_rn(e[0], e[1]), h23 = __floats2bfloat162_rn(e[2], e[3]);
+              uint2 hv;
+              hv.x = *reinterpret_cast<const uint32_t*>(&h01);
+              hv.y = *reinterpret_cast<const uint32_t*>(&h23);
+              *reinterpret_cast<uint2*>(p.Dh + oH[it] + c0) = hv;
+              if (to_lo) {
+                const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
+                const __nv_bfloat162 l01 = __floats2bfloat162_rn(e[0] - f01.x, e[1] - f01.y);
+                const __nv_bfloat162 l23 = __floats2bfloat162_rn(e[2] - f23.x, e[3] - f23.y);
+                uint2 lv;
+                lv.x = *reinterpret_cast<const uint32_t*>(&l01);
+                lv.y = *reinterpret_cast<const uint32_t*>(&l23);
+                *reinterpret_cast<uint2*>(p.Dl + oH[it] + c0) = lv;
+              }
             }
           }
           __syncwarp();
@@ -558,20 +577,20 @@ int num_sms() {
   return n;
 }
 
-template <int BN, int NMMA>
+template <int BN, int NMMA, int EPI>
 static int launch_cfg(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl,
                       const GemmParams& p, cudaStream_t stream) {
   using Cfg = GemmCfg<BN, NMMA>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, NMMA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, NMMA, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
   const int total = p.tiles_m * p.tiles_n * p.splits * p.batch;
   const int grid = total < num_sms() ? total : num_sms();
-  gemm_tc_kernel<BN, NMMA><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(ah, al, bh, bl, p);
+  gemm_tc_kernel<BN, NMMA, EPI><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(ah, al, bh, bl, p);
   return (int)cudaGetLastError();
 }
 
@@ -740,7 +759,11 @@ extern "C" int odise_gemm_bf16(const odise_gemm_desc* d, void* stream_v) {
     rec.nmma = d->nmma; rec.splits = p.splits;
     cudaEventRecord(rec.a, stream);
   }
-#define ODISE_LAUNCH(BN_, NM_) rc = launch_cfg<BN_, NM_>(ah, al, bh, bl, p, stream)
+  const int epi = d->geglu ? 2 : ((d->residual || d->rowbias || d->bias_m) ? 1 : 0);
+#define ODISE_LAUNCH(BN_, NM_)                                                        \
+  rc = epi == 2   ? launch_cfg<BN_, NM_, 2>(ah, al, bh, bl, p, stream)                \
+       : epi == 1 ? launch_cfg<BN_, NM_, 1>(ah, al, bh, bl, p, stream)                \
+                  : launch_cfg<BN_, NM_, 0>(ah, al, bh, bl, p, stream)
   if (d->nmma == 3) {
     switch (BN) {
       case 64: ODISE_LAUNCH(64, 3); break;
