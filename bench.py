@@ -197,7 +197,7 @@ def run_reference(args):
         "config": {"workload": f"ODISE hot path, {args.size}x{args.size}, {args.vocab} ({npr} prompts), CPU oracle",
                    "note": "reference arm = CPU restatement (reference not installable: detectron2/ldm/open_clip absent)"},
         "cpu_baseline": info,
-        "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
 
 
 # ----------------------------------------------------------------------------------------------- our arm
@@ -336,7 +336,7 @@ def main():
             line["cpu_baseline"] = CpuHotPath(S, args.vocab, full=args.full).sample()
         except Exception as ex:  # noqa
             line["cpu_baseline"] = {"error": str(ex)}
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
