@@ -279,6 +279,23 @@ def main():
     eng.step(B, S, S)
     n_gemm, gemm_ms, gemm_flops = lib.profile_end()
     torch.cuda.synchronize()
+    # the north-star stage on its own: SD-v1 UNet feature pass (minimal pass, 0.740 TFLOP per 512^2 crop) on resident inputs
+    from odise_b200.backbone import SyntheticTaps
+    n_crops = B * ((S // 512) ** 2 if S > 512 else 1)
+    tp_ = SyntheticTaps(dev)(n_crops)
+    ctx_, cemb_ = eng.backbone.conditioning(tp_["clip_embed"], n_crops)
+    lat_, lh_, lw_ = tp_["latent"]
+    x_ = eng.backbone.q_sample(lat_, n_crops, lh_, lw_)
+    for _ in range(2):
+        eng.backbone.unet.forward(x_, n_crops, lh_, lw_, ctx_, cemb_)
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(True), torch.cuda.Event(True)
+    ev0.record()
+    for _ in range(3):
+        eng.backbone.unet.forward(x_, n_crops, lh_, lw_, ctx_, cemb_)
+    ev1.record()
+    torch.cuda.synchronize()
+    unet_ms = ev0.elapsed_time(ev1) / 3
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -329,7 +346,14 @@ def main():
                      "mma_kind": "tcgen05.mma kind::f16 (bf16 in, fp32 TMEM accumulate)" +
                                  (", 3 MMAs per k-step (bf16x3 split)" if nmma == 3 else ""),
                      "tensor_pipe_equiv_frac": achieved * nmma / pk["bf16_sustained"],
-                     "unet_frac_of_step": (UNET_TFLOP_PER_CROP * crops * B) / (gemm_flops / 1e12), "traffic": traffic},
+                     "unet_frac_of_step": (UNET_TFLOP_PER_CROP * crops * B) / (gemm_flops / 1e12), "traffic": traffic,
+                     "unet_feature_pass": {
+                         "ms": unet_ms, "crops": n_crops, "algorithmic_tflop": UNET_TFLOP_PER_CROP * n_crops,
+                         "achieved_tflops": UNET_TFLOP_PER_CROP * n_crops / (unet_ms / 1000.0),
+                         "frac_of_bf16_peak": UNET_TFLOP_PER_CROP * n_crops / (unet_ms / 1000.0) / pk["bf16_sustained"],
+                         "tensor_pipe_equiv_frac": nmma * UNET_TFLOP_PER_CROP * n_crops / (unet_ms / 1000.0) / pk["bf16_sustained"],
+                         "note": "whole UNet pass incl. GroupNorm / attention softmax / elementwise kernels, eager launches, "
+                                 "CUDA events; minimal pass FLOPs (output block 11 + out skipped)"}},
     }
     if not args.no_cpu_baseline:
         try:
