@@ -280,16 +280,23 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__
       mbar_wait(p_empty, (j & 1) ^ 1);
 #pragma unroll
       for (int cch = 0; cch < 8; ++cch) {
-        // packed conversions: hi = bf16x2(p), lo = bf16x2(p - float(hi))
+        // (hi, lo) planes of p >= 0.  bf16x3: hi = the upper 16 bits of p (truncation: one LOP3 instead of the
+        // pack / unpack round trip), lo = bf16_rn(p - hi) -> hi + lo = p to 2^-17 either way.  Plain bf16: hi = bf16_rn(p).
         uint32_t hw[4], lw[4];
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
           const float a0 = s[cch * 8 + 2 * t], a1 = s[cch * 8 + 2 * t + 1];
-          const __nv_bfloat162 h2 = __floats2bfloat162_rn(a0, a1);
-          const float2 hf = __bfloat1622float2(h2);
-          const __nv_bfloat162 l2 = __floats2bfloat162_rn(a0 - hf.x, a1 - hf.y);
-          hw[t] = *reinterpret_cast<const uint32_t*>(&h2);
-          lw[t] = *reinterpret_cast<const uint32_t*>(&l2);
+          if (NMMA == 3) {
+            const uint32_t b0 = __float_as_uint(a0), b1 = __float_as_uint(a1);
+            hw[t] = __byte_perm(b0, b1, 0x7632);
+            const __nv_bfloat162 l2 = __floats2bfloat162_rn(a0 - __uint_as_float(b0 & 0xffff0000u),
+                                                            a1 - __uint_as_float(b1 & 0xffff0000u));
+            lw[t] = *reinterpret_cast<const uint32_t*>(&l2);
+          } else {
+            const __nv_bfloat162 h2 = __floats2bfloat162_rn(a0, a1);
+            hw[t] = *reinterpret_cast<const uint32_t*>(&h2);
+            lw[t] = 0u;
+          }
         }
         const uint32_t off = sw128_offset(row, cch);
         *reinterpret_cast<uint4*>(sP + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
