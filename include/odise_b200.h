@@ -311,6 +311,11 @@ int odise_open_vocab_merge_f32(const float* cat_logits, const float* clip_logits
 int odise_gather_rows_f32(const float* src, long long lds, const int32_t* idx, const float* add, long long ld_add,
                           int add_period, float* out, long long ldo, long long rows, int cols, void* stream);
 
+/* Shared-memory carve-out policy of the current device (cudaDeviceSetCacheConfig): 1 = prefer the maximum shared-memory
+ * carve-out for every kernel so the SMs are not re-partitioned between elementwise kernels and the TMA-staged GEMMs;
+ * 0 = driver default. */
+int odise_set_carveout_policy(int prefer_shared);
+
 #ifdef __cplusplus
 }
 #endif

@@ -869,6 +869,12 @@ using namespace ob;
 
 extern "C" int odise_version(void) { return 100; }
 extern "C" long long odise_launch_count(void) { return g_launches.load(); }
+// Shared-memory carve-out policy of the current device: 1 = every kernel runs with the maximum shared-memory carve-out
+// (what the TMA-staged GEMM / attention kernels need), so the SMs are not re-partitioned between an elementwise kernel
+// and the GEMM that follows it; 0 = driver default (per-kernel choice).
+extern "C" int odise_set_carveout_policy(int prefer_shared) {
+  return (int)cudaDeviceSetCacheConfig(prefer_shared ? cudaFuncCachePreferShared : cudaFuncCachePreferNone);
+}
 
 extern "C" int odise_split_f32(const float* x, long long ldx, void* hi, void* lo, long long ldo, long long rows,
                                int cols, void* stream) {

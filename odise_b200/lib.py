@@ -107,6 +107,7 @@ _SIGS = {
                                c_float, c_void_p],
     "odise_panoptic_inference_f32": [c_void_p] * 9 + [c_int] * 7 + [ctypes.c_double, c_void_p, c_void_p],
     "odise_instance_inference_f32": [c_void_p] * 9 + [c_int] * 8 + [c_void_p, c_void_p],
+    "odise_set_carveout_policy": [c_int],
     "odise_gather_rows_f32": [c_void_p, c_longlong, c_void_p, c_void_p, c_longlong, c_int, c_void_p, c_longlong, c_longlong,
                               c_int, c_void_p],
     "odise_maskclip_preprocess": [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
