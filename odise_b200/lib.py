@@ -226,6 +226,40 @@ def split(x, out=None, lo=True):
     return out
 
 
+_WS = {}
+
+
+def workspace(nbytes, device):
+    """Grow-only scratch buffer per device for split-K partials (GEMMs of one stream run in order, so it is shared)."""
+    key = str(device)
+    if key not in _WS or _WS[key].numel() < nbytes:
+        _WS[key] = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+    return _WS[key]
+
+
+def auto_split(M, N, K, batch=1, sms=148):
+    """(force_bn, split_k) for GEMMs that cannot fill the GPU with output tiles alone (e.g. the 8x8 / 16x16 UNet levels:
+    M = 1024 -> 80 tiles of 128 x 128 on 148 SMs).  Cost model in units of K * BN per wave (tools/gemm_one.py), plus
+    ~6 us for the reduce launch; (0, 1) = leave it to the kernel's own heuristic."""
+    tm = (M + 127) // 128
+    kblocks = (K + 63) // 64
+    unit = 0.68 / (64 * 128)                      # us per (k element x output column) of a 128-row tile, bf16x3
+    best = (None, 1e30)
+    for bn in (128, 160, 256):
+        tiles = tm * ((N + bn - 1) // bn) * batch
+        for s in (1, 2, 3, 4):
+            if s > 1 and kblocks // s < 16:
+                continue
+            waves = (tiles * s + sms - 1) // sms
+            cost = waves * (K / s) * bn * unit
+            if s > 1:                             # reduce launch + the partial sums written and read back through HBM / L2
+                cost += 6.0 + 8.0 * s * M * N * batch / 5.0e6
+            if cost < best[1]:
+                best = ((bn, s), cost)
+    bn, s = best[0]
+    return (bn, s) if s > 1 else (0, 1)
+
+
 def gemm(a, b, *, M=None, N=None, K=None, nmma=3, batch=1, a_bs=0, b_bs=0, conv=None, alpha=1.0, bias=None, bias_m=None,
          rowbias=None, rows_per_group=1, act=ACT_NONE, residual=None, ld_res=None, res_bs=0, out=None, ld_out=None,
          out_bs=0, out_planes=None, outp_bs=0, split_k=1, workspace=None, force_bn=0, geglu=False, conv_mode=0):

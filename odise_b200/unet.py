@@ -142,6 +142,12 @@ class UNetEngine:
 
     # ------------------------------------------------------------------------------------------- primitives
     def _gemm(self, a, wname, bias=None, **kw):
+        if "conv" in kw and kw.get("conv_mode", 0) == 0:
+            # low-resolution levels cannot fill 148 SMs with output tiles: split K (lib.auto_split)
+            Mc, Nc, Kc = kw["M"], kw["N"], 9 * kw["conv"][0]
+            bn, sk = lib.auto_split(Mc, Nc, Kc)
+            if sk > 1:
+                kw.update(split_k=sk, force_bn=bn, workspace=lib.workspace(sk * Mc * Nc * 4, self.dev))
         return lib.gemm(a, self.W[wname], nmma=self.nmma, bias=self.F[bias] if bias else None, **kw)
 
     def _resblock(self, q, x, B, H, W, cin, cout, emb_all, dst):

@@ -149,3 +149,26 @@ def test_conv3x3_stride2_implicit(cuda, mode, shape):
     out = torch.empty(B * Ho * Wo, Co, device=cuda)
     lib.gemm(xp, wp, M=B * Ho * Wo, N=Co, conv=(C, H, W), conv_mode=mode, bias=bias, out=out)
     assert _rel(out, ref.permute(0, 2, 3, 1).reshape(B * Ho * Wo, Co)) < 2e-5
+
+
+@pytest.mark.parametrize("cfg", [(16, 8, 8, 1280, 1280, 160, 2), (16, 8, 8, 128, 192, 128, 4), (4, 16, 16, 640, 320, 256, 3)])
+def test_conv3x3_split_k_with_fused_epilogue(cuda, cfg):
+    """low-resolution UNet levels: implicit conv + split-K (lib.auto_split), epilogue (bias, time-embedding row bias,
+    residual) applied by the reduce kernel."""
+    from odise_b200 import lib
+    B, H, W, C, Co, bn, sk = cfg
+    g = torch.Generator().manual_seed(C + sk)
+    x = torch.randn(B, C, H, W, generator=g).to(cuda)
+    w = (torch.randn(Co, C, 3, 3, generator=g) / (3 * C ** 0.5)).to(cuda)
+    bias, emb = torch.randn(Co, generator=g).to(cuda), torch.randn(B, Co, generator=g).to(cuda)
+    res = torch.randn(B * H * W, Co, generator=g).to(cuda)
+    ref = F.conv2d(x.double(), w.double(), bias.double(), padding=1) + emb.double()[:, :, None, None]
+    ref = ref.permute(0, 2, 3, 1).reshape(B * H * W, Co) + res.double()
+    xp = lib.split(x.permute(0, 2, 3, 1).contiguous().view(B * H * W, C))
+    wp = lib.split(w.permute(0, 2, 3, 1).contiguous().view(Co, 9 * C))
+    out = torch.empty(B * H * W, Co, device=cuda)
+    M = B * H * W
+    lib.gemm(xp, wp, M=M, N=Co, conv=(C, H, W), bias=bias, rowbias=emb, rows_per_group=H * W, residual=res, out=out,
+             split_k=sk, force_bn=bn, workspace=lib.workspace(sk * M * Co * 4, cuda))
+    assert _rel(out, ref) < 2e-5
+    assert lib.auto_split(1024, 1280, 11520) == (160, 2) and lib.auto_split(65536, 320, 2880) == (0, 1)
