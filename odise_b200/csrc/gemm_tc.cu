@@ -601,7 +601,10 @@ static int pick_bn(int M, int N, int K, int batch, int forced, bool conv) {
   double best = 1e30;
   int best_bn = 128;
   if (conv) {   // implicit convs (K >= 576) are MMA bound at every width: balance waves only
-    const double eff[4] = {1.0, 1.0, 1.0, 1.45};  // BN=64 is smem-bandwidth bound on the A re-read
+    // 256-wide tiles move 25 % fewer operand bytes per FLOP from L2 into shared memory; on a power-capped board that is
+    // worth ~2.5 % of the whole step (A/B on one box: 172.6 vs 177.2 ms, SM clocks 1.68 vs 1.61 GHz).
+    // BN=64 is smem-bandwidth bound on the A re-read.
+    const double eff[4] = {0.95, 1.0, 1.0, 1.45};
     for (int i = 0; i < 4; ++i) {
       const int bn = cands[i];
       const long long tiles = tm * ((N + bn - 1) / bn) * batch;
