@@ -65,10 +65,22 @@ class ODISEEngine:
             K = len(group_sizes)
             ov = overlapping if overlapping is not None else [(k % 2) == 0 for k in range(K)]
             self.clip_head.set_vocabulary(key, clip_text_bank if clip_text_bank is not None else text_bank, group_sizes, ov)
-        self.vocab_key = key
         from .postprocess import PostProcessor
         K = len(group_sizes)
-        self.post = PostProcessor(self.dev, K, thing_ids if thing_ids is not None else range(0, K, 2), nmma=self.nmma)
+        if not hasattr(self, "_posts"):
+            self._posts = {}
+        self._posts[key] = PostProcessor(self.dev, K, thing_ids if thing_ids is not None else range(0, K, 2), nmma=self.nmma)
+        self.use_vocabulary(key)
+
+    def has_vocabulary(self, key):
+        return key in getattr(self, "_posts", {})
+
+    def use_vocabulary(self, key):
+        """Switch to a vocabulary that was set before (the reference caches text banks per label tuple, odise.py:1281-1288)."""
+        if not self.has_vocabulary(key):
+            raise lib.OdiseError(f"vocabulary {key!r} has not been set")
+        self.vocab_key = key
+        self.post = self._posts[key]
 
     @classmethod
     def from_checkpoints(cls, ldm_path, odise_path, clip_path, device, trusted=False, **kw):

@@ -148,12 +148,69 @@ class B200CategoryODISE(nn.Module):
     `engine` is an ODISEEngine with a vocabulary set (set_vocabulary / set_vocabulary_from_tokens)."""
 
     def __init__(self, engine, size_divisibility=64, semantic_on=True, panoptic_on=True, instance_on=True,
-                 test_topk_per_image=100):
+                 test_topk_per_image=100, tokenizer=None, train_labels=None, prompt="photo", metadata=None):
         super().__init__()
         self.engine = engine
         self.size_divisibility = size_divisibility
         self.semantic_on, self.panoptic_on, self.instance_on = semantic_on, panoptic_on, instance_on
         self.test_topk_per_image = test_topk_per_image
+        self.tokenizer, self.train_labels, self.prompt = tokenizer, train_labels, prompt
+        self.metadata = metadata
+        self.num_classes = None
+        self.test_labels = None
+
+    # ---- vocabulary protocol of OpenPanopticInference (odise/modeling/wrapper/pano_wrapper.py:36-68, odise.py:133-166)
+    def open_state_dict(self, destination=None, prefix=""):
+        d = OrderedDict() if destination is None else destination
+        d[prefix + "sem_seg_head.num_classes"] = self.num_classes
+        d[prefix + "metadata"] = self.metadata
+        d[prefix + "test_topk_per_image"] = self.test_topk_per_image
+        d[prefix + "semantic_on"] = self.semantic_on
+        d[prefix + "panoptic_on"] = self.panoptic_on
+        d[prefix + "instance_on"] = self.instance_on
+        d[prefix + "category_head.test_labels"] = self.test_labels
+        d[prefix + "clip_head.test_labels"] = self.test_labels
+        return d
+
+    def load_open_state_dict(self, state_dict):
+        """Same keys as open_state_dict().  New `test_labels` (list of synonym lists) build — or re-activate from the cache,
+        like get_and_cache_test_text_embed — the vocabulary on the device; `metadata.thing_dataset_id_to_contiguous_id`
+        names the "thing" classes of the panoptic merge (maskformer_model.py:318)."""
+        known = set(self.open_state_dict())
+        for k, v in state_dict.items():
+            if k not in known:
+                raise KeyError(f"{k} is not part of the open state dict")
+        g = state_dict.get
+        self.num_classes = g("sem_seg_head.num_classes", self.num_classes)
+        self.metadata = g("metadata", self.metadata)
+        self.test_topk_per_image = g("test_topk_per_image", self.test_topk_per_image)
+        self.semantic_on = g("semantic_on", self.semantic_on)
+        self.panoptic_on = g("panoptic_on", self.panoptic_on)
+        self.instance_on = g("instance_on", self.instance_on)
+        cat, clip = g("category_head.test_labels", self.test_labels), g("clip_head.test_labels", self.test_labels)
+        if "category_head.test_labels" in state_dict and "clip_head.test_labels" in state_dict and cat != clip:
+            raise ValueError("category_head and clip_head must share one test vocabulary")
+        labels = cat if "category_head.test_labels" in state_dict else clip
+        if labels is not None and labels != self.test_labels:
+            self._activate(labels)
+        self.test_labels = labels
+        for k, v in state_dict.items():                       # the reference asserts every key took (odise.py:166)
+            assert self.open_state_dict()[k] == v, f"{k} is not loaded correctly"
+
+    def _activate(self, labels):
+        from . import vocab
+        key = tuple(tuple(s) for s in labels)
+        if self.num_classes is not None and self.num_classes != len(labels):
+            raise ValueError(f"num_classes = {self.num_classes} but {len(labels)} test labels")
+        if self.engine.has_vocabulary(key):
+            self.engine.use_vocabulary(key)
+            return
+        if self.tokenizer is None:
+            raise RuntimeError("a new test vocabulary needs a tokenizer (odise_b200.vocab.SimpleTokenizer)")
+        things = None
+        if self.metadata is not None and hasattr(self.metadata, "thing_dataset_id_to_contiguous_id"):
+            things = sorted(self.metadata.thing_dataset_id_to_contiguous_id.values())
+        vocab.build_vocabulary(self.engine, self.tokenizer, key, labels, self.train_labels, things, self.prompt)
 
     @torch.no_grad()
     def forward(self, batched_inputs):

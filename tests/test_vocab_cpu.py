@@ -55,3 +55,61 @@ def test_bpe_tokenizer_mechanics():
     assert (ids.argmax(-1) == torch.tensor([2, 5])).all()                        # the EOT position clip.py:150 reads
     full = vocab.SimpleTokenizer(merges=[])
     assert full.tokenize("")[0, :2].tolist() == [full.sot_id, full.eot_id]
+
+
+def test_open_state_dict_protocol_swaps_vocabularies():
+    """OpenPanopticInference (pano_wrapper.py:36-68) saves the model's open state, loads its own, runs, restores: the
+    plugin must round-trip the same keys, build a vocabulary once per label tuple and re-activate cached ones."""
+    import types
+    from collections import OrderedDict
+    from odise_b200.plugin import B200CategoryODISE
+
+    class FakeEngine:                                           # records what the plugin asks of the engine
+        dev = "cpu"
+
+        def __init__(self):
+            self.vocabs, self.active, self.built = {}, None, []
+
+        def has_vocabulary(self, key):
+            return key in self.vocabs
+
+        def use_vocabulary(self, key):
+            self.active = key
+
+        def set_vocabulary_from_tokens(self, key, ids, sizes, thing_ids=None, overlapping=None):
+            self.vocabs[key] = dict(ids=ids, sizes=sizes, things=thing_ids, ov=overlapping)
+            self.built.append(key)
+            self.active = key
+
+    eng = FakeEngine()
+    tk = vocab.SimpleTokenizer(merges=["c a", "ca t</w>"])
+    meta_a = types.SimpleNamespace(thing_dataset_id_to_contiguous_id={7: 0, 9: 2})
+    model = B200CategoryODISE(eng, tokenizer=tk, train_labels=[["cat"], ["tree"]])
+    assert list(model.open_state_dict()) == ["sem_seg_head.num_classes", "metadata", "test_topk_per_image", "semantic_on",
+                                             "panoptic_on", "instance_on", "category_head.test_labels",
+                                             "clip_head.test_labels"]
+    la = [["cat", "kitty"], ["sky"], ["dog"]]
+    lb = [["tree"], ["car", "automobile"]]
+    wrap_a = OrderedDict([("sem_seg_head.num_classes", 3), ("metadata", meta_a), ("test_topk_per_image", 50),
+                          ("semantic_on", True), ("panoptic_on", True), ("instance_on", False),
+                          ("category_head.test_labels", la), ("clip_head.test_labels", la)])
+    saved = model.open_state_dict()
+    model.load_open_state_dict(wrap_a)
+    ka = tuple(tuple(s) for s in la)
+    assert eng.active == ka and eng.built == [ka]
+    v = eng.vocabs[ka]
+    assert v["sizes"] == [2, 1, 1] and v["things"] == [0, 2] and v["ov"] == [True, False, False]
+    assert v["ids"].shape == (4, 77) and v["ids"][0, 0] == tk.sot_id          # "a photo of a cat." ...
+    assert model.test_topk_per_image == 50 and model.instance_on is False and model.num_classes == 3
+    model.load_open_state_dict(OrderedDict([("sem_seg_head.num_classes", 2), ("category_head.test_labels", lb),
+                                            ("clip_head.test_labels", lb)]))
+    kb = tuple(tuple(s) for s in lb)
+    assert eng.active == kb and eng.built == [ka, kb] and eng.vocabs[kb]["ov"] == [True, False]
+    model.load_open_state_dict(wrap_a)                                         # cached: no rebuild
+    assert eng.active == ka and eng.built == [ka, kb]
+    with pytest.raises(KeyError):
+        model.load_open_state_dict({"backbone.whatever": 1})
+    with pytest.raises(ValueError):
+        model.load_open_state_dict({"sem_seg_head.num_classes": 5, "category_head.test_labels": [["x"]],
+                                    "clip_head.test_labels": [["x"]]})
+    assert saved["category_head.test_labels"] is None
