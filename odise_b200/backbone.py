@@ -16,8 +16,7 @@ import math
 import torch
 
 from . import lib, ops, spec
-from .lib import Planes
-from .ops import ACT_NONE, ACT_RELU
+from .ops import ACT_RELU
 from .unet import UNetEngine, CTX_T
 
 FEATURE_DIMS = spec.FEATURE_DIMS

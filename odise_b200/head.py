@@ -14,7 +14,7 @@ import torch
 
 from . import lib, ops
 from .lib import Planes
-from .ops import ACT_NONE, ACT_RELU
+from .ops import ACT_RELU
 
 M_HEADS, D_HEAD, N_POINTS, N_LEVELS = 8, 32, 4, 3
 

@@ -1,7 +1,5 @@
 """Thin typed wrappers over the C ABI used by the engines (unet.py, head.py).  Activations are token-major /
 NHWC fp32 matrices [rows, C]; GEMM operands are lib.Planes.  No torch math on the hot path: torch only allocates."""
-import math
-
 import torch
 
 from . import lib

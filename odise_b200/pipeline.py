@@ -11,7 +11,7 @@ import math
 
 import torch
 
-from . import lib, ops, spec
+from . import lib, spec
 from .backbone import BackboneEngine
 from .head import HeadEngine
 

@@ -9,8 +9,6 @@ concat buffer their mirror block will read, up-path blocks into the left half.
 
 All arithmetic runs in libodise_b200.so; torch only owns the memory.
 """
-import math
-
 import torch
 
 from . import lib, ops, spec

@@ -3,7 +3,6 @@ mounted; fixtures committed under tests/golden/ref_*.pt).  Unlike tests/test_ora
 so the oracle stays pinned on the GPU box too.  Inputs: oracle/cases.py (seeded)."""
 import os
 
-import pytest
 import torch
 
 from oracle import cases
