@@ -82,3 +82,25 @@ def test_t0_coefficients_and_spec_counts():
     n_train = sum(torch.Size(s).numel() for _, s, _ in spec.backbone_params() + spec.head_params())
     # README.md:89 of the reference: 28.1 M trainable parameters (ours excludes null_embed / criterion-free params)
     assert 27.5e6 < n_train < 28.5e6, n_train
+
+
+def test_auto_split_and_struct_layouts():
+    """host heuristics / ctypes mirrors that never touch the device."""
+    import ctypes
+    import re
+    from odise_b200 import lib
+    # split K only where output tiles alone cannot fill 148 SMs and the partial-sum traffic pays for itself
+    assert lib.auto_split(1024, 1280, 11520) == (160, 2)
+    assert lib.auto_split(65536, 320, 2880) == (0, 1) and lib.auto_split(4096, 640, 5760) == (0, 1)
+    assert lib.auto_split(256, 1280, 11520)[1] > 1
+    assert lib.auto_split(128, 64, 512) == (0, 1)                       # too few k-blocks to split
+    hdr = open(os.path.join(ROOT, "include", "odise_b200.h")).read()
+    m = re.search(r"typedef struct \{([^}]*)\} odise_postprocess_geom;", hdr)
+    fields = [f.strip(" ;") for f in m.group(1).replace("int", "").split(",")]
+    assert fields == [n for n, _ in lib.PostprocessGeom._fields_] and ctypes.sizeof(lib.PostprocessGeom) == 16
+    # the GEMM descriptor mirrors the header field by field
+    body = re.search(r"typedef struct odise_gemm_desc \{(.*?)\} odise_gemm_desc;", hdr, re.S)
+    names = []
+    for stmt in re.sub(r"/\*.*?\*/", "", body.group(1), flags=re.S).split(";"):
+        names += [re.findall(r"\w+", d)[-1] for d in stmt.split(",") if re.findall(r"\w+", d)]
+    assert names == [n for n, _ in lib.GemmDesc._fields_]
