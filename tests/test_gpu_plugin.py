@@ -44,3 +44,32 @@ def test_backbone_plugin_contract(cuda):
     assert all(torch.isfinite(v).all() for v in out.values())
     with pytest.raises(RuntimeError):
         bb(img.cpu())
+
+
+def test_pooling_clip_head_plugin(cuda):
+    """B200PoolingCLIPHead.forward(outputs) == PoolingCLIPHead.forward over MaskCLIP (odise.py:1469-1542) on a small ViT."""
+    from odise_b200 import spec
+    from odise_b200.clip import ClipVisualEngine
+    from odise_b200.plugin import B200PoolingCLIPHead
+    from oracle import clip as oclip
+    cfg = dict(width=128, layers=2, patch=14, image=56)
+    sd = spec.synth_state_dict(spec.clip_visual_params(out_dim=32, **cfg), 5)
+    vis = oclip.VisionTransformer(image_size=56, patch=14, width=128, layers=2, heads=2, out_dim=32).eval()
+    vis.load_state_dict({k[len(spec.CLIP_PREFIX):]: v for k, v in sd.items()})
+    g = torch.Generator().manual_seed(31)
+    img = torch.rand(2, 3, 64, 96, generator=g)
+    masks = torch.randn(2, 7, 16, 24, generator=g) * 3
+    sizes, ov = [2, 1, 2, 1], [1, 0, 0, 1]
+    text = torch.randn(sum(sizes), 32, generator=g)
+    open_logits = torch.randn(2, 7, 4, generator=g) * 3
+    with torch.no_grad():
+        lg = oclip.maskclip_pred_logits(oclip.get_mask_embed(vis, img, masks), text, sizes, 100.0)
+        want = oclip.pooling_clip_ensemble(open_logits, lg, torch.tensor(ov), 0.35, 0.65)
+    head = B200PoolingCLIPHead(sd, cuda, alpha=0.35, beta=0.65, visual=ClipVisualEngine(sd, cuda, nmma=3, heads=2, **cfg)).eval()
+    head.set_vocabulary(text, sizes, ov)
+    outputs = {"pred_open_logits": open_logits.to(cuda), "images": img.to(cuda), "pred_masks": masks.to(cuda)}
+    got = head(outputs)["pred_open_logits"]
+    assert "pred_open_logits" not in outputs                      # popped like the reference does
+    assert got.shape == (2, 7, 4) and (got.cpu() - want).abs().max() < 2e-2
+    with pytest.raises(RuntimeError):
+        head({"pred_open_logits": open_logits, "images": img, "pred_masks": masks})
