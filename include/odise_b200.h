@@ -185,6 +185,13 @@ int odise_image_crops_f32(const float* img, float* out, const int32_t* boxes, in
  * out NHWC fp32 [n_crops, S, S, 3]. */
 int odise_clip_preprocess(const void* img, int img_is_u8, float* out, const int32_t* boxes, int n_crops, int H, int W,
                           int ch, int cw, int S, void* stream);
+/* T.Resize(backbone_in_size, BICUBIC) of FeatureExtractorBackbone.single_forward (feature_extractor.py:73-76, :144): a
+ * square crop smaller than 512 x 512 is resized to S x S before the feature extractor sees it.  Same sampling as
+ * odise_clip_preprocess (bicubic A = -0.75, align_corners=False, no antialias, indices clamped to the crop), no
+ * normalisation, no clamping of the overshoot (float tensors are not clamped by torchvision); out is a float image
+ * batch NCHW [n_crops, 3, S, S] in (about) [0, 1] that re-enters odise_image_crops_f32 / odise_clip_preprocess. */
+int odise_crop_resize_bicubic(const void* img, int img_is_u8, float* out, const int32_t* boxes, int n_crops, int H, int W,
+                              int ch, int cw, int S, void* stream);
 /* P x P non-overlapping patches of NHWC [B, S, S, 3] -> (hi, lo) rows [B*(S/P)^2, Kpad] with k = c*P*P + ky*P + kx
  * (visual.conv1 as a GEMM, clip.py:179) */
 int odise_patchify_split_f32(const float* x, void* hi, void* lo, int B, int S, int P, int Kpad, void* stream);
@@ -195,11 +202,12 @@ int odise_nhwc_to_nchw_f32(const float* src, long long lds, float* dst, int B, i
 /* ------------------------------------------------------------------------------------------------------------
  * Fused flash attention on tcgen05 (UNet SpatialTransformer self- and cross-attention; ldm CrossAttention,
  * SURVEY.md App. A): out[b, t, h*d + j] = softmax_k(scale * q.k) v.
- * Operands are HEAD-PADDED (hi, lo) planes: head h occupies columns [h*HS, h*HS + d) with HS = 64 (d <= 48) or
- * 128 (d <= 80), pad columns zero:  q [B*Tq, heads*HS] (ldq), k [B*tk_stride, heads*HS] (ldk), and V TRANSPOSED
+ * Operands are HEAD-PADDED (hi, lo) planes: head h occupies columns [h*HS, h*HS + d) with HS = 64 (d <= 64),
+ * 128 (d <= 80) or 192 (d == 160: the 16x16 / 8x8 UNet levels), pad columns zero:  q [B*Tq, heads*HS] (ldq), k [B*tk_stride, heads*HS] (ldk), and V TRANSPOSED
  * vt [vt_rows >= heads*HS, ldvt >= B*tk_stride] with vt[h*HS + j][b*tk_stride + t] = v[b, t, h, j] (the projection
  * GEMM writes it directly by swapping its operands).  tk_stride >= Tk is the per-image row count of the key /
- * value planes (multiple of 8: TMA box starts must be 16-byte aligned); keys t >= Tk are masked out.  d % 8 == 0, d <= 80 (larger heads: odise_gemm_bf16 + odise_softmax_split_f32).
+ * value planes (multiple of 8: TMA box starts must be 16-byte aligned); keys t >= Tk are masked out.  d % 8 == 0 and
+ * d <= 80, or d == 160 (other head sizes: odise_gemm_bf16 + odise_softmax_split_f32, e.g. the VAE mid block's d = 512).
  * out fp32 and/or (hi, lo) planes, UNPADDED [B*Tq, heads*d] with row stride ldo.
  * mask_bits / row_any (optional, from odise_attn_mask_bits_f32): the Mask2Former decoder's masked cross-attention
  * (d = 32) on the same tensor-core kernel — key k of row (b, t) is dropped when its bit is 0 and row_any != 0. */

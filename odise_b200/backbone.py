@@ -57,7 +57,8 @@ class SyntheticTaps:
 
 
 class BackboneEngine:
-    def __init__(self, sd, device, nmma=3, prefix="backbone.", unet_prefix=spec.UNET_PREFIX, uncond=None, vae=None, clip=None):
+    def __init__(self, sd, device, nmma=3, prefix="backbone.", unet_prefix=spec.UNET_PREFIX, uncond=None, vae=None, clip=None,
+                 synthetic_uncond=False, backbone_in_size=512):
         """sd: state dict with `backbone.feature_projections.*`, `backbone.feature_extractor.*` and the UNet.
         uncond: the frozen text-encoder output for "" ([1, 77, 768]; ldm.py:116) — an input of the path.
         vae: optional VAEEngine; without it the VAE taps / latent are synthetic.
@@ -67,6 +68,8 @@ class BackboneEngine:
         self.vae = vae
         self.clip = clip
         self._boxes = {}
+        self._inv_cnt = {}
+        self.in_size = backbone_in_size            # FeatureExtractorBackbone(backbone_in_size=(512, 512))
         self.unet = UNetEngine(sd, device, nmma=nmma, prefix=unet_prefix)
         self.W, self.F = {}, {}
         f = lambda t: t.to(self.dev, torch.float32).contiguous()
@@ -88,7 +91,16 @@ class BackboneEngine:
         self.W["time_project"] = pl(sd[e + "time_embed_project.linear.weight"])
         self.F["time_project.b"] = f(sd[e + "time_embed_project.linear.bias"])
         if uncond is None:
-            uncond = torch.randn(1, CTX_T, 768, generator=torch.Generator().manual_seed(17))
+            # never condition a real checkpoint on noise.  With the SD text encoder in the state dict the
+            # empty-prompt embedding (ldm.py:116) is computed here; a seeded random stand-in is an explicit opt-in.
+            if any(k.startswith(spec.SD_TEXT_PREFIX) for k in sd):
+                from .clip import uncond_inputs
+                uncond = uncond_inputs(sd, device, nmma=nmma).cpu()
+            elif synthetic_uncond:
+                uncond = torch.randn(1, CTX_T, 768, generator=torch.Generator().manual_seed(17))
+            else:
+                raise lib.OdiseError("BackboneEngine: no `uncond` given and no cond_stage_model.* weights to compute it "
+                                     "from; pass synthetic_uncond=True for a seeded stand-in (benchmarks / tests)")
         # weight-only terms of cond = uncond + tanh(alpha) * (proj + pos)   (ldm.py:707-709)
         ta = torch.tanh(sd[e + "alpha_cond"].float())
         self.F["cond.ta"] = f(ta.view(CTX_T, 768))
@@ -98,8 +110,9 @@ class BackboneEngine:
         self.F["temb.a0"] = f(tt * sd[e + "time_embed_project.positional_embedding"].float().view(1, 1280))
         c0, c1 = t0_coefficients()
         self.c0 = c0
-        noise = torch.randn(1, 4, 64, 64, generator=torch.Generator().manual_seed(42))      # ldm.py:273-276
-        self.F["noise_c1"] = f((c1 * noise).permute(0, 2, 3, 1).reshape(64 * 64, 4))
+        self.c1 = c1
+        self._noise = torch.randn(1, 4, 64, 64, generator=torch.Generator().manual_seed(42))      # ldm.py:273-276
+        self._noise_c1 = {(64, 64): f((c1 * self._noise).permute(0, 2, 3, 1).reshape(64 * 64, 4))}
         self.taps_provider = SyntheticTaps(device)
 
     # ------------------------------------------------------------------------------------------- pieces
@@ -114,13 +127,20 @@ class BackboneEngine:
         cemb = ops.bcast_fma(self.F["temb.a0"], self.F["temb.ta"], tp, B, 1, 1280)
         return ctx, cemb
 
+    def shared_noise(self, h, w):
+        """sqrt(1 - abar_0) * shared noise for an h x w latent, NHWC [h*w, 4] on the device.  Latents other than 64 x 64
+        get the bicubic resize of the 64 x 64 noise (ldm.py:583-592: F.interpolate(mode="bicubic", align_corners=False));
+        a constant of (h, w), computed once on the host and cached."""
+        if (h, w) not in self._noise_c1:
+            n = torch.nn.functional.interpolate(self._noise, size=(h, w), mode="bicubic", align_corners=False)
+            self._noise_c1[(h, w)] = (self.c1 * n).permute(0, 2, 3, 1).reshape(h * w, 4).contiguous().to(self.dev)
+        return self._noise_c1[(h, w)]
+
     def q_sample(self, latent, B, h, w):
-        """x_t = sqrt(abar_0) * z + sqrt(1 - abar_0) * eps with the shared 64x64 noise (64x64 latents only)."""
-        if (h, w) != (64, 64):
-            raise lib.OdiseError("q_sample: only the 64x64 latent of a 512x512 crop is supported")
+        """x_t = sqrt(abar_0) * z + sqrt(1 - abar_0) * eps with the shared noise (gaussian_diffusion.py:275-292)."""
         x = ops.empty(B * h * w, 4, self.dev)
         ops.copy2d(latent, x, scale=self.c0)
-        y, _ = ops.add_split(x, self.F["noise_c1"], b_rows=h * w, want_f32=True, want_planes=False)
+        y, _ = ops.add_split(x, self.shared_noise(h, w), b_rows=h * w, want_f32=True, want_planes=False)
         return y
 
     def project(self, taps, B, crop_hw):
@@ -160,26 +180,32 @@ class BackboneEngine:
         return out
 
     @torch.no_grad()
-    def extract(self, B, crop_hw=(512, 512), vae_taps=None, crops=None, clip_embed=None):
-        """single_forward for a batch of B crops.  crops: normalised NHWC fp32 [B*h*w, 3] -> the VAE engine produces
+    def extract(self, B, crop_hw=(512, 512), vae_taps=None, crops=None, clip_embed=None, out_hw=None):
+        """single_forward for a batch of B crops.  out_hw: the crop size BEFORE T.Resize (input_image_size of
+        forward_features, feature_extractor.py:141-155): the projections run at out_hw / stride.  crops: normalised NHWC fp32 [B*h*w, 3] -> the VAE engine produces
         latent + taps; otherwise they are given / synthetic.  clip_embed: [B, 768] from the CLIP image tower
         (ldm.py:705); synthetic when no ClipVisualEngine is attached."""
         t = vae_taps if vae_taps is not None else self.taps_provider(B, crop_hw)
         if clip_embed is not None:
             t = dict(t, clip_embed=clip_embed)
         if crops is not None and self.vae is not None:
-            enc = self.vae.encode(crops, B, crop_hw[0], crop_hw[1])
+            with lib.nvtx("vae_encoder_taps"):
+                enc = self.vae.encode(crops, B, crop_hw[0], crop_hw[1])
             lat, lh, lw = enc["latent"]
-            dec = self.vae.decode_taps(lat, B, lh, lw)
+            with lib.nvtx("vae_decoder_taps"):
+                dec = self.vae.decode_taps(lat, B, lh, lw)
             t = dict(latent=enc["latent"], enc5=enc["enc5"], enc7=enc["enc7"], dec2=dec["dec2"], dec5=dec["dec5"],
                      clip_embed=t["clip_embed"])
-        ctx, cemb = self.conditioning(t["clip_embed"], B)
-        lat, lh, lw = t["latent"]
-        x = self.q_sample(lat, B, lh, lw)
-        u = self.unet.forward(x, B, lh, lw, ctx, cemb)
+        with lib.nvtx("implicit_captioner+q_sample"):
+            ctx, cemb = self.conditioning(t["clip_embed"], B)
+            lat, lh, lw = t["latent"]
+            x = self.q_sample(lat, B, lh, lw)
+        with lib.nvtx("unet_feature_pass"):
+            u = self.unet.forward(x, B, lh, lw, ctx, cemb)
         taps = dict(enc5=t["enc5"], enc7=t["enc7"], dec2=t["dec2"], dec5=t["dec5"],
                     unet2=u[0], unet5=u[1], unet8=u[2], unet11=u[3])
-        return self.project(taps, B, crop_hw)
+        with lib.nvtx("feature_projections"):
+            return self.project(taps, B, out_hw or crop_hw)
 
     # ------------------------------------------------------------------------------------------- sliding window
     @staticmethod
@@ -206,16 +232,31 @@ class BackboneEngine:
         nc = len(boxes)
         B = n_images * nc                                # crop batch, image-major: b = img * nc + crop
         crops = clip_embed = None
+        net = short                                          # side of what the feature extractor sees
         if images_u8 is not None and (self.vae is not None or self.clip is not None):
             key = (n_images, h_img, w_img)
             if key not in self._boxes:
                 self._boxes[key] = torch.tensor([[i, y, x] for i in range(n_images) for (y, x) in boxes],
                                                 dtype=torch.int32).to(self.dev)
+            src, bx, sh, sw = images_u8, self._boxes[key], h_img, w_img
+            if short != self.in_size:
+                # single_forward's image_preprocess = T.Resize((512, 512), BICUBIC) (feature_extractor.py:73-76, :144):
+                # crops of images whose short side is below 512 are upsampled before the extractor, so the latent is
+                # always 64 x 64; the features are brought back to crop / stride in project() (F.interpolate nearest)
+                net = self.in_size
+                src = ops.crop_resize_bicubic(images_u8, bx, B, h_img, w_img, short, short, net)
+                ikey = ("id", B)
+                if ikey not in self._boxes:
+                    self._boxes[ikey] = torch.tensor([[i, 0, 0] for i in range(B)], dtype=torch.int32).to(self.dev)
+                bx, sh, sw = self._boxes[ikey], net, net
             if self.vae is not None:
-                crops = ops.image_crops(images_u8, self._boxes[key], B, h_img, w_img, short, short)
+                crops = ops.image_crops(src, bx, B, sh, sw, net, net)
             if self.clip is not None:
-                clip_embed = self.clip.embed(images_u8, self._boxes[key], B, h_img, w_img, short, short)
-        feats = self.extract(B, (short, short), vae_taps, crops, clip_embed)
+                with lib.nvtx("clip_image_tower"):
+                    clip_embed = self.clip.embed(src, bx, B, sh, sw, net, net)
+        elif short != self.in_size and vae_taps is None:
+            net = self.in_size
+        feats = self.extract(B, (net, net), vae_taps, crops, clip_embed, out_hw=(short, short))
         if nc == 1 and short == h_img == w_img:
             return feats
         out = {}
@@ -223,9 +264,12 @@ class BackboneEngine:
             s = short // fh
             Hd, Wd = h_img // s, w_img // s
             dst = torch.zeros(n_images * Hd * Wd, 512, dtype=torch.float32, device=self.dev)
-            cnt = torch.zeros(Hd, Wd)
-            for ci, (y1, x1) in enumerate(boxes):
-                cnt[y1 // s:y1 // s + fh, x1 // s:x1 // s + fw] += 1
+            ckey = (n_images, h_img, w_img, s)
+            if ckey not in self._inv_cnt:                  # cached on the device: no H2D copy inside a graph capture
+                cnt = torch.zeros(Hd, Wd)
+                for ci, (y1, x1) in enumerate(boxes):
+                    cnt[y1 // s:y1 // s + fh, x1 // s:x1 // s + fw] += 1
+                self._inv_cnt[ckey] = (1.0 / cnt).reshape(-1).repeat(n_images).to(self.dev) if float(cnt.max()) > 1 else None
             for img in range(n_images):
                 for ci, (y1, x1) in enumerate(boxes):
                     b = img * nc + ci
@@ -233,8 +277,7 @@ class BackboneEngine:
                     d0 = (img * Hd + y1 // s) * Wd + x1 // s
                     dv = dst[d0:d0 + (fh - 1) * Wd + fw].as_strided((fh, fw * 512), (Wd * 512, 1))
                     ops.copy2d(src, dv, accumulate=True)
-            if float(cnt.max()) > 1:
-                inv = (1.0 / cnt).reshape(-1).repeat(n_images).to(self.dev)
-                ops.rowscale(dst, inv)
+            if self._inv_cnt[ckey] is not None:
+                ops.rowscale(dst, self._inv_cnt[ckey])
             out[k] = (dst, Hd, Wd)
         return out

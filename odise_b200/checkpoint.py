@@ -45,20 +45,21 @@ def _tensors(d):
 def _load(path, trusted):
     """torch.load restricted to tensors/containers unless the caller vouches for the file (pytorch-lightning
     checkpoints such as sd-v1-*.ckpt pickle callback objects and need trusted=True)."""
+    if trusted:
+        return torch.load(path, map_location="cpu", weights_only=False)
+    # detectron2-style checkpoints store some entries as numpy arrays: allow exactly the array constructors
     try:
-        if trusted:
-            return torch.load(path, map_location="cpu", weights_only=False)
-        # detectron2-style checkpoints store some entries as numpy arrays: allow exactly the array constructors
-        import numpy._core.multiarray as ma
+        import numpy._core.multiarray as ma            # numpy >= 2
+    except ImportError:
+        import numpy.core.multiarray as ma             # numpy 1.x
+    try:
         allow = [ma._reconstruct, ma.scalar, np.ndarray, np.dtype] + [type(np.dtype(t)) for t in
                  (np.float16, np.float32, np.float64, np.int32, np.int64, np.uint8, np.bool_)]
         with torch.serialization.safe_globals(allow):
             return torch.load(path, map_location="cpu", weights_only=True)
-    except Exception as e:  # noqa
-        if not trusted:
-            raise CheckpointError(f"{path}: not loadable with weights_only=True ({type(e).__name__}: {e}); "
-                                  f"pass trusted=True if the file comes from a source you trust") from e
-        raise
+    except Exception as e:  # noqa  (unpickling errors only: import problems above surface as themselves)
+        raise CheckpointError(f"{path}: not loadable with weights_only=True ({type(e).__name__}: {e}); "
+                              f"pass trusted=True if the file comes from a source you trust") from e
 
 
 def read_ldm_checkpoint(path, trusted=False):
@@ -75,10 +76,16 @@ def read_clip_checkpoint(path, trusted=False):
     """OpenAI CLIP weights: TorchScript archive (what open_clip downloads for pretrained="openai") or a state dict.
     -> keys under `clip.` (`clip.visual.*`, `clip.transformer.*`, `clip.token_embedding.weight`, ...)."""
     sd = None
-    try:
-        sd = torch.jit.load(path, map_location="cpu").state_dict()
-    except Exception:  # noqa
-        ck = _load(path, trusted)
+    if trusted:       # a TorchScript archive executes code on load: only for files the caller vouches for
+        try:
+            sd = torch.jit.load(path, map_location="cpu").state_dict()
+        except Exception:  # noqa
+            sd = None
+    if sd is None:
+        try:
+            ck = _load(path, trusted)
+        except CheckpointError as e:
+            raise CheckpointError(f"{e} (OpenAI's CLIP download is a TorchScript archive: it needs trusted=True)") from e
         sd = ck.get("state_dict", ck) if isinstance(ck, dict) else ck.state_dict()
     sd = _tensors(sd)
     if "visual.conv1.weight" not in sd:

@@ -36,16 +36,20 @@ __device__ __forceinline__ float fast_exp2(float x) {
   return y;
 }
 
-template <int DP, int NMMA>
+// DP = width of the P V product one CTA computes (= TMEM / register accumulator width); QK = contraction width of
+// Q K^T (head dim padded to 16).  QK > DP: the head's V columns are split over QK / DP CTAs that each recompute S
+// (head dim 160 of the 16x16 / 8x8 UNet levels: QK = 160, DP = 80, two CTAs per (tile, head)) — 160 fp32 accumulators
+// per thread next to the 64 scores would not fit the register file.
+template <int DP, int NMMA, int QK = DP>
 struct AttnCfg {
-  static constexpr int NC = (DP + 63) / 64;          // 64-column chunks per head
+  static constexpr int NC = (QK + 63) / 64;          // 64-column chunks per head
   static constexpr int HS = NC * 64;                 // head stride in q / k planes
   static constexpr int NP = (NMMA == 3) ? 2 : 1;
   static constexpr int BK = 64;                      // keys per block
-  static constexpr int STAGES = 2;                           // K stages
+  static constexpr int STAGES = (NC >= 3) ? 1 : 2;           // K stages (three chunks: shared memory allows one)
   // d = 40: one V stage + 256 TMEM columns so that TWO CTAs fit per SM (softmax of one overlaps the MMAs of the other)
-  static constexpr int VSTAGES = (DP <= 48) ? 1 : 2;
-  static constexpr int CTAS_PER_SM = (DP <= 48) ? 2 : 1;   // DP = 64 misses two CTAs by 512 B of shared memory
+  static constexpr int VSTAGES = (DP <= 48 || NC >= 3) ? 1 : 2;
+  static constexpr int CTAS_PER_SM = (DP <= 48 && NC == 1) ? 2 : 1;   // DP = 64 misses two CTAs by 512 B of shared memory
   static constexpr int Q_BYTES = NC * NP * 128 * 128;       // [chunk][plane][128 rows x 128 B]
   static constexpr int K_BYTES = NC * NP * BK * 128;        // per stage
   static constexpr int V_TILE = DP * 128;                   // one plane: DP rows x 64 tokens
@@ -56,13 +60,13 @@ struct AttnCfg {
   static constexpr int TMEM_COLS = (DP <= 64) ? 256 : 512;  // S: 2 x 64 @ 0, O: 2 x OSTRIDE @ 128
 };
 
-template <int DP, int NMMA>
-__global__ void __launch_bounds__(192, AttnCfg<DP, NMMA>::CTAS_PER_SM)
+template <int DP, int NMMA, int QK = DP>
+__global__ void __launch_bounds__(192, AttnCfg<DP, NMMA, QK>::CTAS_PER_SM)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ CUtensorMap tmQl,
                const __grid_constant__ CUtensorMap tmKh, const __grid_constant__ CUtensorMap tmKl,
                const __grid_constant__ CUtensorMap tmVh, const __grid_constant__ CUtensorMap tmVl,
                const AttnParams p) {
-  using Cfg = AttnCfg<DP, NMMA>;
+  using Cfg = AttnCfg<DP, NMMA, QK>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;
@@ -84,7 +88,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
+  constexpr int VPARTS = QK > DP ? QK / DP : 1;        // CTAs sharing one head (each owns DP columns of V / of the output)
+  const int q0 = blockIdx.x * 128, h = blockIdx.y / VPARTS, vpart = blockIdx.y % VPARTS, b = blockIdx.z;
   const int nblk = (p.Tk + Cfg::BK - 1) / Cfg::BK;
 
   if (warp == 0 && lane == 0) {
@@ -118,8 +123,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__
         if (NMMA == 3) tma_load_3d(sQ + (c * Cfg::NP + 1) * 16384, &tmQl, q_full, h * Cfg::HS + c * 64, b * p.Tq + q0, 0);
       }
       auto load_k = [&](int j) {
-        const int st = j & 1;
-        mbar_wait(&k_empty[st], ((j >> 1) & 1) ^ 1);
+        const int st = j % Cfg::STAGES;
+        mbar_wait(&k_empty[st], ((j / Cfg::STAGES) & 1) ^ 1);
         mbar_arrive_expect_tx(&k_full[st], Cfg::K_BYTES);
         uint8_t* kd = sK + st * Cfg::K_BYTES;
         for (int c = 0; c < Cfg::NC; ++c) {
@@ -135,8 +140,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__
         mbar_wait(&v_empty[sv], ((j / Cfg::VSTAGES) & 1) ^ 1);
         mbar_arrive_expect_tx(&v_full[sv], Cfg::V_BYTES);
         uint8_t* vd = sV + sv * Cfg::V_BYTES;
-        tma_load_3d(vd, &tmVh, &v_full[sv], b * p.TkS + j * 64, h * Cfg::HS, 0);
-        if (NMMA == 3) tma_load_3d(vd + Cfg::V_TILE, &tmVl, &v_full[sv], b * p.TkS + j * 64, h * Cfg::HS, 0);
+        tma_load_3d(vd, &tmVh, &v_full[sv], b * p.TkS + j * 64, h * Cfg::HS + vpart * DP, 0);
+        if (NMMA == 3)
+          tma_load_3d(vd + Cfg::V_TILE, &tmVl, &v_full[sv], b * p.TkS + j * 64, h * Cfg::HS + vpart * DP, 0);
       }
     }
   } else if (warp == 1) {
@@ -144,14 +150,15 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__
       // ---------------------------------------------------------------- MMA issuer
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64);
       constexpr uint32_t idesc_o = umma_idesc_bf16(128, DP);
-      constexpr int KS = DP / 16;
+      constexpr int KS = QK / 16;
       auto issue_s = [&](int j) {
-        const int st = j & 1;
-        mbar_wait(&k_full[st], (j >> 1) & 1);
+        const int st = j & 1;                      // S buffer in TMEM
+        const int sk = j % Cfg::STAGES;            // K stage in shared memory
+        mbar_wait(&k_full[sk], (j / Cfg::STAGES) & 1);
         mbar_wait(&s_empty[st], ((j >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + st * 64;
-        const uint32_t kq = smem_u32(sQ), kk = smem_u32(sK + st * Cfg::K_BYTES);
+        const uint32_t kq = smem_u32(sQ), kk = smem_u32(sK + sk * Cfg::K_BYTES);
 #pragma unroll
         for (int ks = 0; ks < KS; ++ks) {
           const int c = ks >> 2, off = (ks & 3) * 32;
@@ -165,7 +172,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__
             umma_bf16(d_tmem, ql, kh, idesc_s, 1u);
           }
         }
-        umma_commit(&k_empty[st]);
+        umma_commit(&k_empty[sk]);
         umma_commit(&s_full[st]);
       };
       mbar_wait(q_full, 0);
@@ -312,18 +319,19 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__
     const int q = q0 + row;
     if (q < p.Tq) {
       const float inv = 1.f / l;
-      const long long o = ((long long)b * p.Tq + q) * p.ldo + (long long)h * p.d;
+      const int dpart = p.d / VPARTS;              // columns of the head this CTA owns
+      const long long o = ((long long)b * p.Tq + q) * p.ldo + (long long)h * p.d + vpart * dpart;
       if (p.out) {
 #pragma unroll
         for (int i = 0; i < DP; i += 4)
-          if (i < p.d)
+          if (i < dpart)
             *reinterpret_cast<float4*>(p.out + o + i) =
                 make_float4(acc[i] * inv, acc[i + 1] * inv, acc[i + 2] * inv, acc[i + 3] * inv);
       }
       if (p.out_hi) {
 #pragma unroll
         for (int i = 0; i < DP; i += 8) {
-          if (i < p.d) {
+          if (i < dpart) {
             __align__(16) __nv_bfloat16 hi[8];
             __align__(16) __nv_bfloat16 lo[8];
 #pragma unroll
@@ -372,18 +380,19 @@ static int attn_map(CUtensorMap* tm, const void* base, long long cols, long long
   return r == CUDA_SUCCESS ? ODISE_OK : ODISE_ERR_TENSORMAP;
 }
 
-template <int DP, int NMMA>
+template <int DP, int NMMA, int QK = DP>
 static int attn_launch(const CUtensorMap* m, const AttnParams& p, cudaStream_t stream) {
-  using Cfg = AttnCfg<DP, NMMA>;
+  using Cfg = AttnCfg<DP, NMMA, QK>;
+  static_assert(Cfg::SMEM_BYTES <= 232448, "attention tile does not fit shared memory");
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel<DP, NMMA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel<DP, NMMA, QK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
-  dim3 grid((p.Tq + 127) / 128, p.heads, p.B);
-  attn_tc_kernel<DP, NMMA><<<grid, 192, Cfg::SMEM_BYTES, stream>>>(m[0], m[1], m[2], m[3], m[4], m[5], p);
+  dim3 grid((p.Tq + 127) / 128, p.heads * (QK > DP ? QK / DP : 1), p.B);
+  attn_tc_kernel<DP, NMMA, QK><<<grid, 192, Cfg::SMEM_BYTES, stream>>>(m[0], m[1], m[2], m[3], m[4], m[5], p);
   return (int)cudaGetLastError();
 }
 
@@ -409,9 +418,10 @@ extern "C" int odise_attention_tc(const void* q_hi, const void* q_lo, long long 
   if (mask_bits && !row_any) return ODISE_ERR_ARG;
   int DP;
   if (d <= 32) DP = 32; else if (d <= 48) DP = 48; else if (d <= 64) DP = 64; else if (d <= 80) DP = 80;
+  else if (d == 160) DP = 160;      // SD-v1 16x16 / 8x8 levels: Q K^T over 160, P V split into two 80-column halves
   else return ODISE_ERR_UNSUPPORTED;
   if (d % 8) return ODISE_ERR_UNSUPPORTED;
-  const int HS = DP <= 64 ? 64 : 128;
+  const int HS = DP <= 64 ? 64 : (DP <= 80 ? 128 : 192);
   if (ldq % 8 || ldk % 8 || ldvt % 8 || ldq < (long long)heads * HS || ldk < (long long)heads * HS ||
       vt_rows < (long long)heads * HS || ldvt < (long long)B * TkS)
     return ODISE_ERR_ALIGN;
@@ -422,8 +432,9 @@ extern "C" int odise_attention_tc(const void* q_hi, const void* q_lo, long long 
   if ((rc = attn_map(&m[1], nmma == 3 ? q_lo : q_hi, (long long)heads * HS, (long long)B * Tq, ldq, 64, 128))) return rc;
   if ((rc = attn_map(&m[2], k_hi, (long long)heads * HS, (long long)B * TkS, ldk, 64, 64))) return rc;
   if ((rc = attn_map(&m[3], nmma == 3 ? k_lo : k_hi, (long long)heads * HS, (long long)B * TkS, ldk, 64, 64))) return rc;
-  if ((rc = attn_map(&m[4], vt_hi, (long long)B * TkS, vt_rows, ldvt, 64, DP))) return rc;
-  if ((rc = attn_map(&m[5], nmma == 3 ? vt_lo : vt_hi, (long long)B * TkS, vt_rows, ldvt, 64, DP))) return rc;
+  const int vbox = DP == 160 ? 80 : DP;
+  if ((rc = attn_map(&m[4], vt_hi, (long long)B * TkS, vt_rows, ldvt, 64, vbox))) return rc;
+  if ((rc = attn_map(&m[5], nmma == 3 ? vt_lo : vt_hi, (long long)B * TkS, vt_rows, ldvt, 64, vbox))) return rc;
   AttnParams p{};
   p.B = B; p.heads = heads; p.d = d; p.Tq = Tq; p.Tk = Tk; p.TkS = TkS;
   p.scale_log2 = scale * 1.4426950408889634f;
@@ -433,6 +444,7 @@ extern "C" int odise_attention_tc(const void* q_hi, const void* q_lo, long long 
   if (DP == 32) rc = nmma == 3 ? attn_launch<32, 3>(m, p, stream) : attn_launch<32, 1>(m, p, stream);
   else if (DP == 64) rc = nmma == 3 ? attn_launch<64, 3>(m, p, stream) : attn_launch<64, 1>(m, p, stream);
   else if (DP == 48) rc = nmma == 3 ? attn_launch<48, 3>(m, p, stream) : attn_launch<48, 1>(m, p, stream);
+  else if (DP == 160) rc = nmma == 3 ? attn_launch<80, 3, 160>(m, p, stream) : attn_launch<80, 1, 160>(m, p, stream);
   else rc = nmma == 3 ? attn_launch<80, 3>(m, p, stream) : attn_launch<80, 1>(m, p, stream);
   if (rc) return rc;
   count_launch(1);

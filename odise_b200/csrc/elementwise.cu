@@ -758,7 +758,9 @@ __global__ void image_crops_f32_kernel(const float* __restrict__ img, float* __r
 __device__ __forceinline__ float cubic1(float x, float A) { return ((A + 2.f) * x - (A + 3.f)) * x * x + 1.f; }
 __device__ __forceinline__ float cubic2(float x, float A) { return ((A * x - 5.f * A) * x + 8.f * A) * x - 4.f * A; }
 
-template <typename T>
+// PLANAR = true writes NCHW [n_crops, 3, S, S] (the crop re-enters the pipeline as an image batch: T.Resize of
+// FeatureExtractorBackbone.single_forward, feature_extractor.py:73-76,144) instead of NHWC.
+template <typename T, bool PLANAR = false>
 __global__ void clip_preprocess_kernel(const T* __restrict__ img, float* __restrict__ out,
                                        const int32_t* __restrict__ boxes, int n_crops, int H, int W, int ch, int cw,
                                        int S, float in_scale, float m0, float m1, float m2, float s0, float s1,
@@ -794,7 +796,8 @@ __global__ void clip_preprocess_kernel(const T* __restrict__ img, float* __restr
         }
         acc += wy[a] * row;
       }
-      out[i * 3 + c] = (acc - mean[c]) / stdv[c];
+      if (PLANAR) out[((long long)b * 3 + c) * S * S + (long long)oy * S + ox] = acc;
+      else out[i * 3 + c] = (acc - mean[c]) / stdv[c];
     }
   }
 }
@@ -1183,6 +1186,21 @@ extern "C" int odise_clip_preprocess(const void* img, int img_is_u8, float* out,
   else
     clip_preprocess_kernel<float><<<blocks, 256, 0, STREAM(stream)>>>(reinterpret_cast<const float*>(img), out, boxes,
                                                                       n_crops, H, W, ch, cw, S, 1.f, m0, m1, m2, s0, s1, s2);
+  count_launch(1);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int odise_crop_resize_bicubic(const void* img, int img_is_u8, float* out, const int32_t* boxes, int n_crops,
+                                         int H, int W, int ch, int cw, int S, void* stream) {
+  if (!img || !out || !boxes || n_crops <= 0 || H <= 0 || W <= 0 || ch <= 0 || cw <= 0 || S <= 0) return ODISE_ERR_ARG;
+  if (ch != cw) return ODISE_ERR_UNSUPPORTED;
+  const int blocks = grid_for((long long)n_crops * S * S, 256);
+  if (img_is_u8)
+    clip_preprocess_kernel<uint8_t, true><<<blocks, 256, 0, STREAM(stream)>>>(
+        reinterpret_cast<const uint8_t*>(img), out, boxes, n_crops, H, W, ch, cw, S, 1.f / 255.f, 0, 0, 0, 1, 1, 1);
+  else
+    clip_preprocess_kernel<float, true><<<blocks, 256, 0, STREAM(stream)>>>(
+        reinterpret_cast<const float*>(img), out, boxes, n_crops, H, W, ch, cw, S, 1.f, 0, 0, 0, 1, 1, 1);
   count_launch(1);
   return (int)cudaGetLastError();
 }

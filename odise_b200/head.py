@@ -95,11 +95,16 @@ class HeadEngine:
         # decoder
         C = 256
         self.dec_level_embed = sd[dp + "level_embed.weight"].float()
+        # num_feature_levels of the decoder (mask2former_transformer_decoder.py:296: 3 in every ODISE config; the C4
+        # microbench of BASELINE.json runs 4 scales) and the query count come from the weights
+        self.n_lvl = int(self.dec_level_embed.shape[0])
         self.F["query_embed"] = self._f(sd[dp + "query_embed.weight"])
         self.query_feat = sd[dp + "query_feat.weight"].float()
-        for lvl in range(3):   # K / V projections of the layers that read level lvl, concatenated along N and
+        if self.query_feat.shape[0] != self.Q:
+            raise lib.OdiseError(f"num_queries = {self.Q} but query_feat has {self.query_feat.shape[0]} rows")
+        for lvl in range(self.n_lvl):   # K / V projections of the layers that read level lvl, concatenated along N and
             # head-padded 32 -> 64 columns per head (zero rows): the operands of the tcgen05 attention kernel
-            ids = [i for i in range(self.n_dec) if i % 3 == lvl]
+            ids = [i for i in range(self.n_dec) if i % self.n_lvl == lvl]
             pad = lambda w: ops.head_pad_rows(w, M_HEADS, D_HEAD, 64)
             padb = lambda b: ops.head_pad_rows(b.view(-1, 1), M_HEADS, D_HEAD, 64).view(-1)
             wk = torch.cat([pad(sd[f"{dp}transformer_cross_attention_layers.{i}.multihead_attn.in_proj_weight"][C:2 * C]) for i in ids])
@@ -224,6 +229,32 @@ class HeadEngine:
         lib.gemm(self.W["pd.mask_features"], y2_p, nmma=self.nmma, bias_m=self.F["pd.mask_features.b"], out_planes=mft_p)
         return dict(memory=src, memory_p=src_p, shapes=shapes, geo=g, mf_p=mf_p, mft_p=mft_p, mf=mf, mask_hw=(h2, w2))
 
+    @torch.no_grad()
+    def pd_from_tensors(self, multi_scale, mask_features):
+        """The decoder's inputs from the plugin boundary (ODISEMultiScaleMaskedTransformerDecoder.forward(x, mask_features),
+        odise.py:642-660): x = 3 NCHW maps [B, 256, h, w] (coarse -> fine), mask_features NCHW [B, 256, H/4, W/4]
+        -> the dict transformer_decoder() consumes (token-major memory of the levels, mask features as GEMM operands)."""
+        dev = self.dev
+        B = mask_features.shape[0]
+        shapes = [(int(t.shape[2]), int(t.shape[3])) for t in multi_scale]
+        g = self._geometry(B, shapes)
+        S, starts = g["S"], g["starts"]
+        mem = ops.empty(B * S, 256, dev)
+        for i, t in enumerate(multi_scale):
+            h, w = shapes[i]
+            lvl = ops.nchw_to_nhwc(t.float())
+            ops.copy2d(lvl.view(B, h * w * 256), mem.view(B, S * 256)[:, starts[i] * 256:(starts[i] + h * w) * 256])
+        h2, w2 = int(mask_features.shape[2]), int(mask_features.shape[3])
+        HW = h2 * w2
+        mf = ops.nchw_to_nhwc(mask_features.float())                       # [B*HW, 256]
+        mf_p = ops.split(mf, lo=self.lo)
+        mft = ops.empty(256, B * HW, dev)                                  # [C, B*HW]: image z at column offset z*HW
+        src = mask_features.float().contiguous().view(B, 256, HW)
+        for z in range(B):
+            ops.copy2d(src[z], mft[:, z * HW:(z + 1) * HW])
+        mft_p = ops.split(mft, lo=self.lo)
+        return dict(memory=mem, memory_p=None, shapes=shapes, geo=g, mf_p=mf_p, mft_p=mft_p, mf=mf, mask_hw=(h2, w2))
+
     # ------------------------------------------------------------------------------------------- decoder
     def _mlp3(self, x_p, base, rows, out_f32):
         a = Planes.empty(rows, 256, self.dev, lo=self.lo)
@@ -287,14 +318,18 @@ class HeadEngine:
         _, vin_p = ops.add_split(mem, g["dec_lvl"], b_rows=S, lo=self.lo)
         K, V = [], []
         CP = M_HEADS * 64                      # head-padded width of one layer's K / V
+        nl = self.n_lvl
+        if len(shapes) != nl:
+            raise lib.OdiseError(f"the decoder has {nl} feature levels, got {len(shapes)} maps")
         for lvl, (h, w) in enumerate(shapes):
             hw = h * w
-            k = Planes.empty(B * hw, 3 * CP, dev, lo=self.lo)            # [B*hw, 3 layers x 8 heads x 64]
-            lib.gemm(kin_p.row_slice(starts[lvl], hw), self.W[f"dec.k{lvl}"], M=hw, N=3 * CP, K=256, nmma=self.nmma,
+            nk = self.W[f"dec.k{lvl}"].rows // CP                         # layers reading this level (i % nl == lvl)
+            k = Planes.empty(B * hw, nk * CP, dev, lo=self.lo)           # [B*hw, nk layers x 8 heads x 64]
+            lib.gemm(kin_p.row_slice(starts[lvl], hw), self.W[f"dec.k{lvl}"], M=hw, N=nk * CP, K=256, nmma=self.nmma,
                      batch=B, a_bs=S * kin_p.ld, bias=self.F[f"dec.k{lvl}.b"], out_planes=k, outp_bs=hw * k.ld)
-            # V^T [3*CP, B*hw]: swapped operands, image z lands at column offset z*hw
-            vt = Planes.empty(3 * CP, B * hw, dev, lo=self.lo)
-            lib.gemm(self.W[f"dec.v{lvl}"], vin_p.row_slice(starts[lvl], hw), M=3 * CP, N=hw, K=256, nmma=self.nmma,
+            # V^T [nk*CP, B*hw]: swapped operands, image z lands at column offset z*hw
+            vt = Planes.empty(nk * CP, B * hw, dev, lo=self.lo)
+            lib.gemm(self.W[f"dec.v{lvl}"], vin_p.row_slice(starts[lvl], hw), M=nk * CP, N=hw, K=256, nmma=self.nmma,
                      batch=B, b_bs=S * vin_p.ld, bias_m=self.F[f"dec.v{lvl}.b"], out_planes=vt, outp_bs=hw)
             K.append(k)
             V.append(vt)
@@ -306,7 +341,7 @@ class HeadEngine:
         scale = D_HEAD ** -0.5
         qe = self.F["query_embed"]
         for i in range(self.n_dec):
-            lvl, slot = i % 3, i // 3
+            lvl, slot = i % nl, i // nl
             hw = shapes[lvl][0] * shapes[lvl][1]
             n = f"dec.l{i}."
             # masked cross-attention (mask2former_transformer_decoder.py:98-110, odise.py:683-692)
@@ -334,7 +369,7 @@ class HeadEngine:
             t = ops.empty(B * Q, 256, dev)
             self._gemm(f_p, n + "f2", residual=output, out=t)
             output, _ = self._ln(t, n + "fn", want_f32=True, want_planes=False)
-            nxt = shapes[(i + 1) % 3] if i + 1 < self.n_dec else None
+            nxt = shapes[(i + 1) % nl] if i + 1 < self.n_dec else None
             res, bits, row_any = self._pred_head(output, pd, B, nxt, fm(i + 1))
             heads.append(res)
         return heads
@@ -371,9 +406,12 @@ class HeadEngine:
 
     @torch.no_grad()
     def forward(self, feats, B, vocab_key=None, want_mask_features_f32=False):
-        pd = self.pixel_decoder(feats, B, want_mask_features_f32)
-        heads = self.transformer_decoder(pd, B)
+        with lib.nvtx("pixel_decoder"):
+            pd = self.pixel_decoder(feats, B, want_mask_features_f32)
+        with lib.nvtx("masked_attention_decoder"):
+            heads = self.transformer_decoder(pd, B)
         out = dict(heads=heads, pd=pd)
         if vocab_key is not None:
-            out["pred_logits"] = self.score(heads[-1]["mask_embed"], vocab_key).view(B, self.Q, -1)
+            with lib.nvtx("clip_text_scoring"):
+                out["pred_logits"] = self.score(heads[-1]["mask_embed"], vocab_key).view(B, self.Q, -1)
         return out

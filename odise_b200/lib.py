@@ -85,6 +85,7 @@ _SIGS = {
     "odise_image_crops_u8_f32": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
     "odise_image_crops_f32": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
     "odise_clip_preprocess": [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p],
+    "odise_crop_resize_bicubic": [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p],
     "odise_patchify_split_f32": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     "odise_nchw_to_nhwc_f32": [c_void_p, c_void_p, c_longlong, c_int, c_int, c_int, c_void_p],
     "odise_nhwc_to_nchw_f32": [c_void_p, c_longlong, c_void_p, c_int, c_int, c_int, c_void_p],
@@ -260,6 +261,20 @@ def auto_split(M, N, K, batch=1, sms=148):
     return (bn, s) if s > 1 else (0, 1)
 
 
+def conv_ok(H, W):
+    """Can odise_gemm_bf16 run a 3x3 conv with OUTPUT size H x W as an implicit GEMM (gemm_tc.cu host checks)?  Widths whose
+    gcd with the 128-pixel tile is below 8 (e.g. 12, 6: latents of crops that are not 512^2) take the materialised
+    im2col path instead."""
+    import math
+    if W % 128 == 0:
+        return True
+    if 128 % W == 0:
+        bh = min(128 // W, H)
+        if H % bh == 0 and 128 % (W * bh) == 0:
+            return True
+    return math.gcd(W, 128) % 8 == 0
+
+
 def gemm(a, b, *, M=None, N=None, K=None, nmma=3, batch=1, a_bs=0, b_bs=0, conv=None, alpha=1.0, bias=None, bias_m=None,
          rowbias=None, rows_per_group=1, act=ACT_NONE, residual=None, ld_res=None, res_bs=0, out=None, ld_out=None,
          out_bs=0, out_planes=None, outp_bs=0, split_k=1, workspace=None, force_bn=0, geglu=False, conv_mode=0):
@@ -325,6 +340,20 @@ def msda_forward(value, spatial_shapes, level_start_index, sampling_locations, a
                                          _ptr(attention_weights), _ptr(out), N, S, M, D, L, Lq, P, _stream()),
            "odise_msda_forward_f32")
     return out
+
+
+class nvtx:
+    """NVTX range around a pipeline stage (SURVEY.md §5 tracing): visible in nsys / ncu --nvtx timelines, free otherwise."""
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        torch.cuda.nvtx.range_push(self.name)
+
+    def __exit__(self, *exc):
+        torch.cuda.nvtx.range_pop()
+        return False
 
 
 def profile_begin():

@@ -167,6 +167,8 @@ def head_stride(d):
         return 64
     if d <= 80:
         return 128
+    if d == 160:  # SD-v1 16x16 / 8x8 levels: Q K^T over three 64-column chunks, P V in two 80-column halves
+        return 192
     return None   # unfused path
 
 
@@ -273,6 +275,16 @@ def clip_preprocess(img, boxes_dev, n_crops, H, W, ch, cw, S=336):
         raise lib.OdiseError("clip_preprocess: uint8 or float32 image expected")
     _check(load().odise_clip_preprocess(_ptr(img), 1 if img.dtype == torch.uint8 else 0, _ptr(out), _ptr(boxes_dev),
                                         n_crops, H, W, ch, cw, S, _stream()), "clip_preprocess")
+    return out
+
+
+def crop_resize_bicubic(img, boxes_dev, n_crops, H, W, ch, cw, S=512):
+    """T.Resize((S, S), BICUBIC) of every crop -> float image batch NCHW [n_crops, 3, S, S] (feature_extractor.py:73-76)."""
+    if img.dtype not in (torch.uint8, torch.float32):
+        raise lib.OdiseError("crop_resize_bicubic: uint8 or float32 image expected")
+    out = torch.empty(n_crops, 3, S, S, dtype=torch.float32, device=img.device)
+    _check(load().odise_crop_resize_bicubic(_ptr(img), 1 if img.dtype == torch.uint8 else 0, _ptr(out), _ptr(boxes_dev),
+                                            n_crops, H, W, ch, cw, S, _stream()), "crop_resize_bicubic")
     return out
 
 

@@ -23,7 +23,7 @@ def full_param_list(with_vae=False, with_clip=False):
 
 class ODISEEngine:
     def __init__(self, sd, device, nmma=3, num_queries=100, with_vae=False, with_clip=False, with_clip_head=None,
-                 alpha=0.3, beta=0.7, uncond=None):
+                 alpha=0.3, beta=0.7, uncond=None, synthetic_uncond=False):
         """with_clip: CLIP ViT-L/14-336 image tower (implicit captioner input, §8f-2); with_clip_head (default = with_clip):
         MaskCLIP + PoolingCLIPHead ensemble (odise_with_label.py: alpha 0.3, beta 0.7) on the same frozen tower."""
         self.dev = torch.device(device)
@@ -43,7 +43,8 @@ class ODISEEngine:
             assert clip is not None, "the MaskCLIP head shares the CLIP image tower: with_clip=True required"
             self.clip_head = MaskClipHead(clip, alpha=alpha, beta=beta,
                                           logit_scale=math.exp(float(sd.get("clip.logit_scale", math.log(100.0)))))
-        self.backbone = BackboneEngine(sd, device, nmma=nmma, vae=vae, clip=clip, uncond=uncond)
+        self.backbone = BackboneEngine(sd, device, nmma=nmma, vae=vae, clip=clip, uncond=uncond,
+                                       synthetic_uncond=synthetic_uncond)
         self.text = None                  # ClipTextEngine, built on demand (set_vocabulary_from_tokens)
         self._sd_text = {k: v for k, v in sd.items() if k.startswith(spec.CLIP_TEXT_PREFIX) and not k.startswith(spec.CLIP_PREFIX)}
         self._null_embed = sd.get("category_head.null_embed")
@@ -58,19 +59,33 @@ class ODISEEngine:
         """OpenPanopticInference / CategoryEmbed.test_labels analogue (pano_wrapper.py:58-68, odise.py:1281-1307):
         the vocabulary is a [K', 768] CLIP text bank + per-class prompt counts (+ which classes are "things" for
         the panoptic merge, metadata.thing_dataset_id_to_contiguous_id in the reference).  With a MaskCLIP head:
-        clip_text_bank = the raw CLIP text embeddings of the same prompts (default: text_bank), overlapping[k] = class k
-        shares a name with the training vocabulary (odise.py:1483-1493; default: every other class)."""
+        clip_text_bank = the CLIP text embeddings of the PoolingCLIPHead prompts ("a photo of a {}.": odise.py:1428,1475 —
+        NOT the category head's raw class names, odise.py:1225), overlapping[k] = class k shares a name with the training
+        vocabulary (odise.py:1483-1493).  thing_ids / overlapping have no defaults: a silently wrong thing/stuff split or
+        alpha/beta assignment changes the results (synthetic runs: set_synthetic_vocabulary)."""
+        K = len(group_sizes)
+        if thing_ids is None:
+            raise lib.OdiseError("set_vocabulary: thing_ids is required (metadata.thing_dataset_id_to_contiguous_id "
+                                 "values; pass () for a stuff-only vocabulary)")
+        if self.clip_head is not None and (overlapping is None or clip_text_bank is None):
+            raise lib.OdiseError("set_vocabulary: the MaskCLIP head needs `clip_text_bank` (prompted labels) and "
+                                 "`overlapping` (vocab.overlapping_mask(test_labels, train_labels))")
         self.head.set_vocabulary(key, text_bank, null_bank, group_sizes)
         if self.clip_head is not None:
-            K = len(group_sizes)
-            ov = overlapping if overlapping is not None else [(k % 2) == 0 for k in range(K)]
-            self.clip_head.set_vocabulary(key, clip_text_bank if clip_text_bank is not None else text_bank, group_sizes, ov)
+            self.clip_head.set_vocabulary(key, clip_text_bank, group_sizes, list(overlapping))
         from .postprocess import PostProcessor
-        K = len(group_sizes)
         if not hasattr(self, "_posts"):
             self._posts = {}
-        self._posts[key] = PostProcessor(self.dev, K, thing_ids if thing_ids is not None else range(0, K, 2), nmma=self.nmma)
+        self._posts[key] = PostProcessor(self.dev, K, thing_ids, nmma=self.nmma)
         self.use_vocabulary(key)
+
+    def set_synthetic_vocabulary(self, key, n_classes, n_prompts, seed=11):
+        """Benchmarks / tests only: seeded random text banks (category bank and an independent MaskCLIP bank), every
+        other class a "thing", every other class "seen in training"."""
+        bank, null, sizes = synthetic_vocabulary(n_classes, n_prompts, seed)
+        clip_bank = torch.randn(n_prompts, 768, generator=torch.Generator().manual_seed(seed + 66))
+        self.set_vocabulary(key, bank, null, sizes, thing_ids=list(range(0, n_classes, 2)), clip_text_bank=clip_bank,
+                            overlapping=[(k % 2) == 0 for k in range(n_classes)])
 
     def has_vocabulary(self, key):
         return key in getattr(self, "_posts", {})
@@ -94,10 +109,13 @@ class ODISEEngine:
         return cls(sd, device, with_vae=True, with_clip=True, uncond=un, **kw)
 
     @torch.no_grad()
-    def set_vocabulary_from_tokens(self, key, token_ids, group_sizes, null_token_ids=None, thing_ids=None, overlapping=None):
+    def set_vocabulary_from_tokens(self, key, token_ids, group_sizes, null_token_ids=None, thing_ids=None, overlapping=None,
+                                   clip_token_ids=None):
         """CategoryEmbed.get_and_cache_test_text_embed (odise.py:1281-1288): tokenised prompts [K', 77] (all synonyms of
-        all classes, class-major) -> CLIP text bank on the device -> set_vocabulary.  The null embedding is the
-        checkpoint's `category_head.null_embed` parameter, or the text embedding of `null_token_ids` ("" at init)."""
+        all classes, class-major) -> CLIP text bank on the device -> set_vocabulary.  clip_token_ids: the same labels under
+        the PoolingCLIPHead prompt (odise.py:1475) — a second bank; None = same tokens (caption model: both 'photo').
+        The null embedding is the checkpoint's `category_head.null_embed` parameter, or the text embedding of
+        `null_token_ids` ("" at init)."""
         from .clip import ClipTextEngine, build_text_bank
         if self.text is None:
             if not self._sd_text:
@@ -110,7 +128,8 @@ class ODISEEngine:
             null = self.text.encode(null_token_ids.view(1, -1))[0]
         else:
             raise lib.OdiseError("no category_head.null_embed in the state dict and no null_token_ids given")
-        self.set_vocabulary(key, bank, null, group_sizes, thing_ids=thing_ids, clip_text_bank=bank, overlapping=overlapping)
+        clip_bank = bank if clip_token_ids is None else build_text_bank(self.text, clip_token_ids)
+        self.set_vocabulary(key, bank, null, group_sizes, thing_ids=thing_ids, clip_text_bank=clip_bank, overlapping=overlapping)
         return bank
 
     @torch.no_grad()
@@ -139,12 +158,23 @@ class ODISEEngine:
             res["pred_logits"] = out["pred_logits"]
             if self.clip_head is not None:        # odise.py:292-323: MaskCLIP ensemble replaces the class scores
                 ci = clip_images if clip_images is not None else images_u8
-                ch = self.clip_head.forward(self.vocab_key, ci, n_images, ci.shape[2], ci.shape[3], res["pred_masks"],
-                                            out["pred_logits"])
+                with lib.nvtx("maskclip_ensemble"):
+                    ch = self.clip_head.forward(self.vocab_key, ci, n_images, ci.shape[2], ci.shape[3], res["pred_masks"],
+                                                out["pred_logits"])
                 res["pred_logits_category"] = out["pred_logits"]
                 res["pred_logits"] = ch["pred_logits"]
                 res["clip_mask_embed"] = ch["mask_embed"]
         res["aux"] = out["heads"][:-1]
+        return res
+
+    @torch.no_grad()
+    def step_full(self, n_images, H, W, images_u8=None, semantic=True, panoptic=True, instance=True, topk=100):
+        """step() + the inference heads of CategoryODISE.forward (odise.py:326-370: semantic / panoptic / instance
+        inference at the input resolution) — what the metric "panoptic inference" times.  All on the device."""
+        res = self.step(n_images, H, W, images_u8=images_u8)
+        with lib.nvtx("semantic_panoptic_instance_inference"):
+            res["post"] = self.post(res["pred_logits"], res["pred_masks"], H, W, semantic=semantic, panoptic=panoptic,
+                                    instance=instance, topk=topk)
         return res
 
     def _image_buffer(self, n_images, H, W):
@@ -152,50 +182,67 @@ class ODISEEngine:
         if not hasattr(self, "_img_dev") or tuple(self._img_dev.shape) != shp:
             g = torch.Generator().manual_seed(99)
             self._img_dev = torch.randint(0, 256, shp, generator=g, dtype=torch.uint8).to(self.dev)
-            self._host_logits = None
         return self._img_dev
 
-    def capture(self, n_images, H, W):
-        """Warm up eagerly, then capture the step into a CUDA graph (static shapes, static buffers)."""
-        key = (n_images, H, W, self.vocab_key)
+    def capture(self, n_images, H, W, post=False):
+        """Warm up eagerly, then capture the step into a CUDA graph (static shapes, static buffers).
+        post=True captures step_full (network + semantic / panoptic / instance inference)."""
+        key = (n_images, H, W, self.vocab_key, bool(post))
         if key in self._graphs:
             return self._graphs[key]
+        fn = self.step_full if post else self.step
         s = torch.cuda.Stream(device=self.dev)
         s.wait_stream(torch.cuda.current_stream(self.dev))
         with torch.cuda.stream(s):
             for _ in range(2):
-                self.step(n_images, H, W)
+                fn(n_images, H, W)
         torch.cuda.current_stream(self.dev).wait_stream(s)
         torch.cuda.synchronize(self.dev)
         before = lib.launch_count()
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
-            out = self.step(n_images, H, W)
+            out = fn(n_images, H, W)
         self.launches_per_step = lib.launch_count() - before
         self._graphs[key] = (g, out)
         return self._graphs[key]
 
     # ------------------------------------------------------------------------------------------- user API
     @torch.no_grad()
-    def infer(self, images_u8_pinned, use_graph=True):
-        """End-to-end call on a host batch: uint8 [B, 3, H, W] in pinned memory -> host dict
-        (pred_logits [B, Q, K+1], pred_masks [B, Q, H/4, W/4]).  H2D and D2H inside."""
+    def infer(self, images_u8_pinned, use_graph=True, outputs="raw"):
+        """End-to-end call on a host batch: uint8 [B, 3, H, W] in pinned memory -> host dict.  H2D and D2H inside.
+        outputs="raw": pred_logits [B, Q, K+1] + pred_masks [B, Q, H/4, W/4] (the network outputs);
+        outputs="panoptic": the inference results at the input resolution — panoptic_seg int32 [B, H, W], seg_info
+        [B, Q, 3] + n_segments [B], semantic label map uint8/int16 is NOT shipped (the [K, H, W] score tensor stays on the
+        device like in the reference), instance scores / classes / query index [B, topk], plus pred_logits."""
         B, _, H, W = images_u8_pinned.shape
         self._image_buffer(B, H, W).copy_(images_u8_pinned, non_blocking=True)
-        if not hasattr(self, "_host_logits"):
-            self._host_logits = None
+        post = outputs == "panoptic"
         if use_graph:
-            g, out = self.capture(B, H, W)
+            g, out = self.capture(B, H, W, post=post)
             g.replay()
         else:
-            out = self.step(B, H, W, images_u8=self._img_dev)
-        if self._host_logits is None:
-            self._host_logits = torch.empty(out["pred_logits"].shape, dtype=torch.float32).pin_memory()
-            self._host_masks = torch.empty(out["pred_masks"].shape, dtype=torch.float32).pin_memory()
-        self._host_logits.copy_(out["pred_logits"], non_blocking=True)
-        self._host_masks.copy_(out["pred_masks"], non_blocking=True)
+            out = (self.step_full if post else self.step)(B, H, W, images_u8=self._img_dev)
+        if post:
+            src = dict(pred_logits=out["pred_logits"], panoptic_seg=out["post"]["panoptic_seg"],
+                       seg_info=out["post"]["seg_info"], n_segments=out["post"]["n_segments"])
+            if "instances" in out["post"]:
+                ins = out["post"]["instances"]
+                src.update(instance_scores=ins["scores"], instance_classes=ins["pred_classes"],
+                           instance_query=ins["query_index"], instance_valid=ins["valid"])
+        else:
+            src = dict(pred_logits=out["pred_logits"], pred_masks=out["pred_masks"])
+        hk = (outputs, B, H, W, self.vocab_key)
+        if getattr(self, "_host_key", None) != hk:
+            self._host = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in src.items()}
+            self._host_key = hk
+        for k, v in src.items():
+            self._host[k].copy_(v, non_blocking=True)
         torch.cuda.current_stream(self.dev).synchronize()
-        return dict(pred_logits=self._host_logits, pred_masks=self._host_masks)
+        return dict(self._host)
+
+    def d2h_bytes(self):
+        """bytes infer() last copied back per call"""
+        return int(sum(v.numel() * v.element_size() for v in getattr(self, "_host", {}).values()))
 
 
 def gather_logits(local_logits):

@@ -216,7 +216,7 @@ def pixel_decoder_params(prefix="sem_seg_head.pixel_decoder.", n_layers=6, C=256
     return ps
 
 
-def decoder_params(prefix="sem_seg_head.predictor.", n_layers=9, C=256, ffn=2048, Q=100):
+def decoder_params(prefix="sem_seg_head.predictor.", n_layers=9, C=256, ffn=2048, Q=100, n_levels=3):
     ps = []
     for i in range(n_layers):
         for nm, attn in ((f"transformer_self_attention_layers.{i}", "self_attn"),
@@ -231,7 +231,7 @@ def decoder_params(prefix="sem_seg_head.predictor.", n_layers=9, C=256, ffn=2048
                (q + "norm.weight", (C,), "gamma"), (q + "norm.bias", (C,), "beta")]
     ps += [(prefix + "decoder_norm.weight", (C,), "gamma"), (prefix + "decoder_norm.bias", (C,), "beta"),
            (prefix + "query_feat.weight", (Q, C), "emb"), (prefix + "query_embed.weight", (Q, C), "emb"),
-           (prefix + "level_embed.weight", (3, C), "emb")]
+           (prefix + "level_embed.weight", (n_levels, C), "emb")]
     for base in ("mask_embed.", "post_mask_embed.mask_embed.1."):
         for j in range(3):
             ps += [(f"{prefix}{base}layers.{j}.weight", (C, C), "w"), (f"{prefix}{base}layers.{j}.bias", (C,), "b")]

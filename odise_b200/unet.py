@@ -151,18 +151,28 @@ class UNetEngine:
     def _resblock(self, q, x, B, H, W, cin, cout, emb_all, dst):
         """x: fp32 view [B*H*W, cin]; dst: fp32 view [B*H*W, cout] (may be a column slice of a concat buffer)."""
         M = B * H * W
-        _, a1 = ops.group_norm(x, B, H * W, self.F[q + "gn1.g"], self.F[q + "gn1.b"], 1e-5, ACT_SILU, lo=self.lo)
+        imp = lib.conv_ok(H, W)          # False: map width the implicit-GEMM TMA boxes cannot tile -> materialised im2col
+        y1, a1 = ops.group_norm(x, B, H * W, self.F[q + "gn1.g"], self.F[q + "gn1.b"], 1e-5, ACT_SILU, lo=self.lo,
+                                want_f32=not imp, want_planes=imp)
         eo, ec = self.emb_off[q]
         h = ops.empty(M, cout, self.dev)
-        self._gemm(a1, q + "conv1", q + "conv1.b", M=M, N=cout, conv=(cin, H, W), rowbias=emb_all[:, eo:eo + ec],
-                   rows_per_group=H * W, out=h)
-        _, a2 = ops.group_norm(h, B, H * W, self.F[q + "gn2.g"], self.F[q + "gn2.b"], 1e-5, ACT_SILU, lo=self.lo)
+        if imp:
+            self._gemm(a1, q + "conv1", q + "conv1.b", M=M, N=cout, conv=(cin, H, W), rowbias=emb_all[:, eo:eo + ec],
+                       rows_per_group=H * W, out=h)
+        else:
+            self._gemm(ops.im2col3x3_split(y1, B, H, W, lo=self.lo)[0], q + "conv1", q + "conv1.b",
+                       rowbias=emb_all[:, eo:eo + ec], rows_per_group=H * W, out=h)
+        y2, a2 = ops.group_norm(h, B, H * W, self.F[q + "gn2.g"], self.F[q + "gn2.b"], 1e-5, ACT_SILU, lo=self.lo,
+                                want_f32=not imp, want_planes=imp)
         if cin != cout:
             skip = ops.empty(M, cout, self.dev)
             self._gemm(ops.split(x, lo=self.lo), q + "skip", q + "skip.b", out=skip)
         else:
             skip = x
-        self._gemm(a2, q + "conv2", q + "conv2.b", M=M, N=cout, conv=(cout, H, W), residual=skip, out=dst)
+        if imp:
+            self._gemm(a2, q + "conv2", q + "conv2.b", M=M, N=cout, conv=(cout, H, W), residual=skip, out=dst)
+        else:
+            self._gemm(ops.im2col3x3_split(y2, B, H, W, lo=self.lo)[0], q + "conv2", q + "conv2.b", residual=skip, out=dst)
         return dst
 
     def _attention(self, t, a, xq, kv_src, B, T, Tk, ch, TkS=None):
@@ -285,8 +295,12 @@ class UNetEngine:
             elif kind == "down":
                 # ldm Downsample = conv3x3 stride 2 pad 1: strided implicit GEMM (TMA element strides), no im2col
                 cdim = layers[0][1]
-                self._gemm(ops.split(cur, lo=self.lo), q + "0.conv", q + "0.conv.b", M=B * (ch_ // 2) * (cw_ // 2),
-                           N=cdim, conv=(cdim, ch_, cw_), conv_mode=1, out=dst)
+                if lib.conv_ok(ch_ // 2, cw_ // 2):
+                    self._gemm(ops.split(cur, lo=self.lo), q + "0.conv", q + "0.conv.b", M=B * (ch_ // 2) * (cw_ // 2),
+                               N=cdim, conv=(cdim, ch_, cw_), conv_mode=1, out=dst)
+                else:
+                    self._gemm(ops.im2col3x3_split(cur, B, ch_, cw_, stride=2, lo=self.lo)[0], q + "0.conv", q + "0.conv.b",
+                               out=dst)
                 ch_, cw_ = ch_ // 2, cw_ // 2
             else:
                 _, cin, cout = layers[0]
@@ -327,7 +341,12 @@ class UNetEngine:
                 t = t_out
                 k += 1
             if k < len(layers) and layers[k][0] == "up":
-                up = ops.upsample2x_split(t, B, hh, ww, lo=self.lo)
-                self._gemm(up, f"{q}{k}.conv", f"{q}{k}.conv.b", M=B * 4 * hh * ww, N=cout, conv=(cout, 2 * hh, 2 * ww),
-                           out=dst)
+                if lib.conv_ok(2 * hh, 2 * ww):
+                    up = ops.upsample2x_split(t, B, hh, ww, lo=self.lo)
+                    self._gemm(up, f"{q}{k}.conv", f"{q}{k}.conv.b", M=B * 4 * hh * ww, N=cout,
+                               conv=(cout, 2 * hh, 2 * ww), out=dst)
+                else:
+                    up = ops.resize_nhwc(t, B, hh, ww, 2 * hh, 2 * ww, bilinear=False)
+                    self._gemm(ops.im2col3x3_split(up, B, 2 * hh, 2 * ww, lo=self.lo)[0], f"{q}{k}.conv", f"{q}{k}.conv.b",
+                               out=dst)
         return taps

@@ -141,11 +141,23 @@ class SimpleTokenizer:
         return out
 
 
-def build_vocabulary(engine, tokenizer, key, test_labels, train_labels=None, thing_ids=None, prompt="photo"):
+def vocabulary_prompts(test_labels, category_prompt=None, clip_prompt="photo"):
+    """The two prompt sets of one test vocabulary: CategoryEmbed scores against prompt_labels(labels, None) = the raw
+    class names (odise.py:1225, :1302; mask_generator_with_label.py builds CategoryEmbed without a prompt), PoolingCLIPHead
+    against prompt_labels(labels, "photo") (odise.py:1428, :1475).  The caption model (CLIPOpenClassEmbed /
+    WordEmbed, odise.py:1026) uses "photo" for both.  -> (flat category prompts, flat clip prompts, group sizes)"""
+    cat, clip = prompt_labels(test_labels, category_prompt), prompt_labels(test_labels, clip_prompt)
+    return [p for syn in cat for p in syn], [p for syn in clip for p in syn], [len(s) for s in cat]
+
+
+def build_vocabulary(engine, tokenizer, key, test_labels, train_labels=None, thing_ids=None, category_prompt=None,
+                     clip_prompt="photo"):
     """CategoryEmbed.forward eval branch + PoolingCLIPHead's label handling (odise.py:1298-1307, :1476-1497): class synonym
-    lists -> prompts -> token ids -> CLIP text bank on the device -> engine vocabulary.  Returns the text bank."""
-    prompts = prompt_labels(test_labels, prompt)
-    flat = [p for syn in prompts for p in syn]
-    ids = tokenizer.tokenize(flat)
+    lists -> the two prompt sets -> token ids -> two CLIP text banks on the device -> engine vocabulary.
+    train_labels (PoolingCLIPHead.train_labels, default in the reference: the COCO panoptic prompt-engineered label file)
+    decides which classes take exponent alpha; it is required whenever the engine has a MaskCLIP head."""
+    cat, clip, sizes = vocabulary_prompts(test_labels, category_prompt, clip_prompt)
     ov = overlapping_mask(test_labels, train_labels) if train_labels is not None else None
-    return engine.set_vocabulary_from_tokens(key, ids, [len(s) for s in prompts], thing_ids=thing_ids, overlapping=ov)
+    clip_ids = None if clip == cat else tokenizer.tokenize(clip)
+    return engine.set_vocabulary_from_tokens(key, tokenizer.tokenize(cat), sizes, thing_ids=thing_ids, overlapping=ov,
+                                             clip_token_ids=clip_ids)

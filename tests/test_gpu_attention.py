@@ -12,7 +12,8 @@ def _rel(a, b):
 
 @pytest.mark.parametrize("nmma", [3, 1])
 @pytest.mark.parametrize("cfg", [(2, 8, 40, 256, 256), (1, 8, 40, 1024, 1024), (2, 8, 80, 256, 256), (3, 8, 40, 128, 77),
-                                 (2, 8, 80, 64, 77), (1, 4, 80, 64, 64), (2, 2, 40, 200, 130), (1, 8, 40, 4096, 4096)])
+                                 (2, 8, 80, 64, 77), (1, 4, 80, 64, 64), (2, 2, 40, 200, 130), (1, 8, 40, 4096, 4096),
+                                 (2, 8, 160, 256, 256), (3, 8, 160, 64, 64), (2, 8, 160, 256, 77), (1, 3, 160, 144, 144)])
 def test_attention_tc(cuda, nmma, cfg):
     from odise_b200 import lib, ops
     B, heads, d, Tq, Tk = cfg

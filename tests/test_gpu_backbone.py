@@ -16,7 +16,7 @@ def bb(cuda):
     from odise_b200 import spec
     from odise_b200.backbone import BackboneEngine
     sd = spec.synth_state_dict(spec.unet_params() + spec.backbone_params(), seed=0)
-    return sd, BackboneEngine(sd, cuda, nmma=3)
+    return sd, BackboneEngine(sd, cuda, nmma=3, synthetic_uncond=True)
 
 
 def test_conditioning_and_q_sample(cuda, bb):

@@ -18,11 +18,11 @@ def world(cuda):
     from odise_b200 import spec
     from odise_b200.pipeline import ODISEEngine, full_param_list, synthetic_vocabulary
     sd = spec.synth_state_dict(full_param_list(with_vae=True, with_clip=True), seed=0)
-    eng = ODISEEngine(sd, cuda, nmma=3, with_vae=True, with_clip=True)
+    eng = ODISEEngine(sd, cuda, nmma=3, with_vae=True, with_clip=True, synthetic_uncond=True)
     bank, null, sizes = synthetic_vocabulary(20, 31)
     clip_bank = torch.randn(31, 768, generator=torch.Generator().manual_seed(77))
     ov = [(k % 3) == 0 for k in range(20)]
-    eng.set_vocabulary("v20", bank, null, sizes, clip_text_bank=clip_bank, overlapping=ov)
+    eng.set_vocabulary("v20", bank, null, sizes, thing_ids=list(range(0, 20, 2)), clip_text_bank=clip_bank, overlapping=ov)
     img = torch.randint(0, 256, (1, 3, 512, 512), generator=torch.Generator().manual_seed(5), dtype=torch.uint8)
     return dict(sd=sd, eng=eng, img=img, bank=bank, null=null, sizes=sizes, clip_bank=clip_bank, ov=ov)
 
@@ -122,8 +122,8 @@ def test_vocabulary_from_tokens(cuda, world):
     assert _rel(bank.cpu(), want) < 1e-3
     out = eng.step(1, 512, 512, images_u8=world["img"].to(cuda))
     assert out["pred_logits"].shape == (1, 100, 5) and torch.isfinite(out["pred_logits"]).all()
-    eng.set_vocabulary("v20", world["bank"], world["null"], world["sizes"], clip_text_bank=world["clip_bank"],
-                       overlapping=world["ov"])
+    eng.set_vocabulary("v20", world["bank"], world["null"], world["sizes"], thing_ids=list(range(0, 20, 2)),
+                       clip_text_bank=world["clip_bank"], overlapping=world["ov"])
 
 
 @torch.no_grad()
@@ -158,3 +158,152 @@ def test_category_odise_plugin_ragged_batch(cuda, world):
         assert (r["panoptic_seg"][0].cpu() == pan).float().mean().item() > 0.999
         ins = r["instances"]
         assert ins["pred_masks"].shape[1:] == (rq["height"], rq["width"]) and ins["scores"].numel() == ins["pred_classes"].numel()
+
+
+# ------------------------------------------------------------------------------------------------ round-2 parity closure
+def _nchw(t, h, w):
+    return t.view(-1, h, w, 512).permute(0, 3, 1, 2).cpu()
+
+
+UNCOND17 = lambda: torch.randn(1, 77, 768, generator=torch.Generator().manual_seed(17))      # synthetic_uncond=True
+
+
+@torch.no_grad()
+def test_c1_end_to_end_mask_logits_and_class_scores(cuda, world):
+    """BASELINE.json configs[0] / BASELINE.md §4 as stated: ONE 512 x 512 image, Q = 100, 20-class vocabulary; FINAL mask
+    logits and FINAL class scores of the whole pipeline vs the composed oracle within 1e-3 (max |a-b| / max |b|, one global
+    norm per tensor).  The three hard thresholds of the path (attention mask sigmoid < 0.5, odise.py:772; MaskPooling mask > 0,
+    odise.py:951; MaskCLIP patch mask >= 0.5, clip.py:291-321) are teacher-forced with the ORACLE's mask logits — everything
+    continuous is computed independently by both sides from the uint8 image — and the un-forced decisions are compared
+    separately as a bit-flip rate."""
+    from oracle import clip as oclip, compose, m2f
+    sd, eng, img = world["sd"], world["eng"], world["img"]
+    mods = compose.load_modules(sd)
+    img01 = img.float() / 255.0
+    feats = compose.slide_forward(sd, mods, img01, UNCOND17())
+    mf, _, ms = m2f.pixel_decoder(sd, feats, "sem_seg_head.pixel_decoder.")
+    ref, ref_masks = m2f.transformer_decoder(sd, ms, mf, "sem_seg_head.predictor.")
+    te, ne = m2f.category_embed(sd, world["bank"], world["null"])
+    cat_ref = m2f.cal_pred_logits(ref["mask_embed"], te, ne, ref["logit_scale"], world["sizes"])
+    me = oclip.get_mask_embed(mods["vis"], img01, ref["pred_masks"])
+    lg = oclip.maskclip_pred_logits(me, world["clip_bank"], world["sizes"], 100.0)
+    want_cls = oclip.merge_with_void(cat_ref, oclip.pooling_clip_ensemble(cat_ref[..., :-1], lg, torch.tensor(world["ov"]).long(), 0.3, 0.7))
+    # engine, thresholds forced to the oracle's decisions
+    dimg = img.to(cuda)
+    eng.use_vocabulary("v20")
+    f_e = eng.backbone.forward(1, 512, 512, images_u8=dimg)
+    pd = eng.head.pixel_decoder(f_e, 1)
+    forced = [m.reshape(1, 100, -1).contiguous().to(cuda) for m in ref_masks]
+    heads = eng.head.transformer_decoder(pd, 1, forced_masks=forced)
+    cat = eng.head.score(heads[-1]["mask_embed"], "v20").view(1, 100, -1)
+    got = eng.clip_head.forward("v20", dimg, 1, 512, 512, ref["pred_masks"].to(cuda).contiguous(), cat)
+    torch.cuda.synchronize()
+    e_mask = _rel(heads[-1]["pred_masks"].view_as(ref["pred_masks"]).cpu(), ref["pred_masks"])
+    e_cat = _rel(cat.cpu(), cat_ref)
+    e_cls = _rel(got["pred_logits"].cpu(), want_cls)
+    # un-forced run: how many discrete decisions differ (reported, bounded loosely: they are discontinuities, not errors)
+    out = eng.step(1, 512, 512, images_u8=dimg)
+    flips = [((h["pred_masks"].view_as(r).cpu() > 0) != (r > 0)).float().mean().item()
+             for h, r in zip(out["aux"] + [dict(pred_masks=out["pred_masks"])], ref_masks)]
+    print(f"C1 end to end: final mask logits rel {e_mask:.2e}, category scores rel {e_cat:.2e}, merged class scores rel "
+          f"{e_cls:.2e}; un-forced sign flips per head {['%.1e' % f for f in flips]}")
+    assert e_mask < 1e-3 and e_cat < 1e-3 and e_cls < 1e-3, (e_mask, e_cat, e_cls)
+    assert max(flips) < 1e-2
+
+
+@torch.no_grad()
+def test_full_size_batch4_1024_paste(cuda, world):
+    """B = 4 x 1024^2 (BASELINE.json configs[1] shape): the real 4-crop paste with real VAE / CLIP / UNet taps.  The
+    oracle runs ONE of the four images (4 crops on the host cores); the other three are checked against the engine's own
+    single-image result (batch composition must not change an image's features)."""
+    from oracle import compose
+    sd, eng = world["sd"], world["eng"]
+    g = torch.Generator().manual_seed(77)
+    imgs = torch.randint(0, 256, (4, 3, 1024, 1024), generator=g, dtype=torch.uint8)
+    got = eng.backbone.forward(4, 1024, 1024, images_u8=imgs.to(cuda))
+    torch.cuda.synchronize()
+    got = {k: _nchw(t, h, w) for k, (t, h, w) in got.items()}
+    want = compose.slide_forward(sd, compose.load_modules(sd), imgs[2:3].float() / 255.0, UNCOND17())
+    for k, w_ in want.items():
+        assert got[k].shape == (4, 512, 1024 // 2 ** int(k[1]), 1024 // 2 ** int(k[1]))
+        assert _rel(got[k][2:3], w_) < 1e-3, (k, _rel(got[k][2:3], w_))
+    one = eng.backbone.forward(1, 1024, 1024, images_u8=imgs[1:2].to(cuda))
+    torch.cuda.synchronize()
+    for k, (t, h, w) in one.items():
+        assert _rel(got[k][1:2], _nchw(t, h, w)) < 1e-5, k
+
+
+@torch.no_grad()
+def test_1280_nine_overlapping_crops(cuda, world):
+    """1280 x 1280 (BASELINE.json configs[4]): 3 x 3 crops of 512 with stride 512 clamped to the border -> overlaps of 256
+    pixels, paste-add + count + divide (feature_extractor.py:197-250)."""
+    from odise_b200.backbone import BackboneEngine
+    from oracle import compose
+    sd, eng = world["sd"], world["eng"]
+    boxes, short = BackboneEngine.crop_grid(1280, 1280)
+    assert short == 512 and boxes == [(y, x) for y in (0, 512, 768) for x in (0, 512, 768)]
+    img = torch.randint(0, 256, (1, 3, 1280, 1280), generator=torch.Generator().manual_seed(78), dtype=torch.uint8)
+    got = eng.backbone.forward(1, 1280, 1280, images_u8=img.to(cuda))
+    torch.cuda.synchronize()
+    want = compose.slide_forward(sd, compose.load_modules(sd), img.float() / 255.0, UNCOND17())
+    for k, w_ in want.items():
+        t, h, w = got[k]
+        assert _rel(_nchw(t, h, w), w_) < 1e-3, (k, _rel(_nchw(t, h, w), w_))
+
+
+@torch.no_grad()
+def test_short_side_below_512(cuda, world):
+    """A 384 x 640 image: two overlapping 384^2 crops, each bicubic-resized to 512^2 before the extractor
+    (single_forward's T.Resize, feature_extractor.py:73-76,144) and brought back by the nearest resize of forward_features;
+    then the whole engine runs on it (round 1 raised here)."""
+    from oracle import compose
+    sd, eng = world["sd"], world["eng"]
+    img = torch.randint(0, 256, (1, 3, 384, 640), generator=torch.Generator().manual_seed(79), dtype=torch.uint8)
+    got = eng.backbone.forward(1, 384, 640, images_u8=img.to(cuda))
+    torch.cuda.synchronize()
+    want = compose.slide_forward(sd, compose.load_modules(sd), img.float() / 255.0, UNCOND17())
+    for k, w_ in want.items():
+        t, h, w = got[k]
+        assert (h, w) == tuple(w_.shape[-2:]) and _rel(_nchw(t, h, w), w_) < 1e-3, (k, _rel(_nchw(t, h, w), w_))
+    eng.use_vocabulary("v20")
+    out = eng.step_full(1, 384, 640, images_u8=img.to(cuda))
+    assert out["pred_masks"].shape == (1, 100, 96, 160) and out["post"]["panoptic_seg"].shape == (1, 384, 640)
+    assert torch.isfinite(out["pred_logits"]).all()
+
+
+@torch.no_grad()
+def test_latent_other_than_64(cuda, world):
+    """LdmExtractor at a latent that is not 64 x 64 (ldm.py:583-592: the shared noise is bicubic-resized): a 384^2 crop
+    WITHOUT the backbone's resize -> 48 x 48 latent, UNet levels 48 / 24 / 12 / 6 (the last two take the materialised
+    im2col path: their widths cannot be tiled by the implicit-GEMM TMA boxes)."""
+    from odise_b200 import spec
+    from oracle import ldm
+    eng = world["eng"]
+    sd = world["sd"]
+    with torch.device("meta"):
+        unet = ldm.UNetModel()
+    unet.load_state_dict({k[len(spec.UNET_PREFIX):]: v for k, v in sd.items() if k.startswith(spec.UNET_PREFIX)}, assign=True)
+    g = torch.Generator().manual_seed(80)
+    lat, ctx, cemb = torch.randn(1, 4, 48, 48, generator=g), torch.randn(1, 77, 768, generator=g), torch.randn(1, 1280, generator=g) * 0.5
+    want = ldm.unet_features(unet.eval(), ldm.q_sample_t0(lat, ldm.shared_noise((48, 48))), ctx, cemb)
+    bb = eng.backbone
+    x = bb.q_sample(lat.permute(0, 2, 3, 1).reshape(-1, 4).contiguous().to(cuda), 1, 48, 48)
+    taps = bb.unet.forward(x, 1, 48, 48, ctx.view(77, 768).to(cuda), cemb.to(cuda))
+    torch.cuda.synchronize()
+    for (t, h, w), r in zip(taps, want):
+        assert _rel(t.view(1, h, w, -1).permute(0, 3, 1, 2).cpu(), r) < 1e-3
+
+
+@torch.no_grad()
+def test_ade847_vocabulary_scoring(cuda, world):
+    """K = 847 classes / K' = 1342 prompts (BASELINE.json configs[4]): cal_pred_logits + per-class max at full size."""
+    from odise_b200.pipeline import synthetic_vocabulary
+    from oracle import m2f
+    sd, eng = world["sd"], world["eng"]
+    bank, null, sizes = synthetic_vocabulary(847, 1342)
+    eng.head.set_vocabulary("ade847", bank, null, sizes)
+    me = torch.randn(400, 256, generator=torch.Generator().manual_seed(81))
+    te, ne = m2f.category_embed(sd, bank, null)
+    want = m2f.cal_pred_logits(me.view(4, 100, 256), te, ne, torch.tensor(eng.head.logit_scale), sizes)
+    got = eng.head.score(me.to(cuda), "ade847").view(4, 100, -1).cpu()
+    assert got.shape == (4, 100, 848) and _rel(got, want) < 1e-3

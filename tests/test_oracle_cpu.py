@@ -1,5 +1,6 @@
 """CPU tests that PIN the oracle (oracle/) against the reference's own code imported from /root/reference
 (skipped where that tree is absent, i.e. on the GPU box) and check the parameter inventory of odise_b200/spec.py."""
+import os
 import types
 
 import pytest
@@ -298,3 +299,42 @@ def test_reference_encode_text_runs_on_oracle_text_tower():
     emb_ref, enc_ref = rc.ClipAdapter._encode_text(fake, ids)
     emb, enc = oclip.encode_text(m, ids)
     assert torch.allclose(emb_ref, emb, rtol=1e-5, atol=1e-6) and torch.allclose(enc_ref, enc, rtol=1e-5, atol=1e-6)
+
+
+@needs_ref
+def test_plugin_surface_matches_reference_modules():
+    """the B200 plugin classes take the constructor keywords the LazyConfigs pass
+    (configs/common/models/odise_with_label.py:16-29, mask_generator_with_label.py:29-66) and expect exactly the state-dict
+    keys of the reference modules they replace."""
+    import inspect
+    from odise_b200 import plugin
+    m = refshim.modules()
+    pd, dec = _ref_head(m)
+    head = plugin.B200MaskFormerHead(num_classes=133, device="cpu")
+    want = {"pixel_decoder." + k for k in pd.state_dict()} | {"predictor." + k for k in dec.state_dict()}
+    assert set(head.expected_keys()) == want
+    for mine, ref in ((plugin.B200MSDeformAttnPixelDecoder, m.MSDeformAttnPixelDecoder),
+                      (plugin.B200ODISEMultiScaleMaskedTransformerDecoder, m.ODISEMultiScaleMaskedTransformerDecoder),
+                      (plugin.B200PooledMaskEmbed, m.PooledMaskEmbed), (plugin.B200PseudoClassEmbed, m.PseudoClassEmbed)):
+        ref_kw = [p for c in ref.__mro__ if c.__module__.startswith(("odise", "mask2former"))
+                  for p in inspect.signature(c.__init__).parameters if p not in ("self", "kwargs", "args")]
+        mine_kw = set(inspect.signature(mine.__init__).parameters)
+        assert set(ref_kw) <= mine_kw, (mine.__name__, set(ref_kw) - mine_kw)
+    # the two config files' keyword sets, parsed from the files themselves
+    cfg = open(os.path.join(refshim.REF, "configs/common/models/odise_with_label.py")).read()
+    bb_kw = {"feature_extractor", "out_features", "use_checkpoint", "slide_training"}
+    assert all(k + "=" in cfg for k in bb_kw)
+    assert bb_kw <= set(inspect.signature(plugin.B200FeatureExtractorBackbone.__init__).parameters)
+    fe_kw = {"encoder_block_indices", "unet_block_indices", "decoder_block_indices", "steps", "learnable_time_embed",
+             "num_timesteps", "clip_model_name"}
+    assert all(k + "=" in cfg for k in fe_kw)
+    assert fe_kw <= set(inspect.signature(plugin.B200LdmImplicitCaptionerExtractor.__init__).parameters)
+    fe = plugin.B200LdmImplicitCaptionerExtractor(frozen_state_dict={}, device="cpu")
+    bb = plugin.B200FeatureExtractorBackbone(fe, ["s2", "s3", "s4", "s5"], use_checkpoint=True, slide_training=True)
+    got = set(bb.expected_keys())
+    assert {k for k in got if k.startswith("feature_extractor.")} == {
+        "feature_extractor." + k for k in ("clip_project.linear.weight", "clip_project.linear.bias",
+                                           "clip_project.positional_embedding", "alpha_cond",
+                                           "time_embed_project.linear.weight", "time_embed_project.linear.bias",
+                                           "time_embed_project.positional_embedding", "alpha_cond_time_embed")}
+    assert len([k for k in got if k.startswith("feature_projections.")]) == 8 * 9 + 4 * 3   # 4 of 8 blocks have a shortcut

@@ -76,8 +76,10 @@ def test_open_state_dict_protocol_swaps_vocabularies():
         def use_vocabulary(self, key):
             self.active = key
 
-        def set_vocabulary_from_tokens(self, key, ids, sizes, thing_ids=None, overlapping=None):
-            self.vocabs[key] = dict(ids=ids, sizes=sizes, things=thing_ids, ov=overlapping)
+        clip_head = object()                                    # the engine has a MaskCLIP head
+
+        def set_vocabulary_from_tokens(self, key, ids, sizes, thing_ids=None, overlapping=None, clip_token_ids=None):
+            self.vocabs[key] = dict(ids=ids, sizes=sizes, things=thing_ids, ov=overlapping, clip_ids=clip_token_ids)
             self.built.append(key)
             self.active = key
 
@@ -99,7 +101,11 @@ def test_open_state_dict_protocol_swaps_vocabularies():
     assert eng.active == ka and eng.built == [ka]
     v = eng.vocabs[ka]
     assert v["sizes"] == [2, 1, 1] and v["things"] == [0, 2] and v["ov"] == [True, False, False]
-    assert v["ids"].shape == (4, 77) and v["ids"][0, 0] == tk.sot_id          # "a photo of a cat." ...
+    assert v["ids"].shape == (4, 77) and v["ids"][0, 0] == tk.sot_id
+    # category bank = raw class names (CategoryEmbed prompt=None), MaskCLIP bank = "a photo of a {}." (PoolingCLIPHead)
+    assert v["ids"][0].tolist()[:3] == [tk.sot_id, tk.encoder["cat</w>"], tk.eot_id]
+    assert v["clip_ids"].shape == (4, 77) and torch.equal(v["clip_ids"], tk.tokenize(
+        ["a photo of a cat.", "a photo of a kitty.", "a photo of a sky.", "a photo of a dog."]))
     assert model.test_topk_per_image == 50 and model.instance_on is False and model.num_classes == 3
     model.load_open_state_dict(OrderedDict([("sem_seg_head.num_classes", 2), ("category_head.test_labels", lb),
                                             ("clip_head.test_labels", lb)]))
@@ -113,3 +119,30 @@ def test_open_state_dict_protocol_swaps_vocabularies():
         model.load_open_state_dict({"sem_seg_head.num_classes": 5, "category_head.test_labels": [["x"]],
                                     "clip_head.test_labels": [["x"]]})
     assert saved["category_head.test_labels"] is None
+    # no silent defaults: a new vocabulary without train_labels / metadata is an error, not an alternating pattern
+    bare = B200CategoryODISE(FakeEngine(), tokenizer=tk)
+    with pytest.raises(RuntimeError):
+        bare.load_open_state_dict({"category_head.test_labels": la, "clip_head.test_labels": la})
+    bare.metadata = meta_a
+    with pytest.raises(RuntimeError):
+        bare.load_open_state_dict({"category_head.test_labels": la, "clip_head.test_labels": la})
+
+
+@needs_ref
+def test_prompts_of_the_two_heads_match_reference():
+    """in the label model the category head scores against the RAW class names (CategoryEmbed
+    prompt=None, odise.py:1225; configs/common/models/mask_generator_with_label.py passes none) and only PoolingCLIPHead
+    uses "a photo of a {}." (odise.py:1428).  Pinned on the reference's own defaults and prompt function."""
+    import inspect
+    od = refshim.modules().odise_module
+    assert inspect.signature(od.CategoryEmbed.__init__).parameters["prompt"].default is None
+    assert inspect.signature(od.PoolingCLIPHead.__init__).parameters["prompt"].default == "photo"
+    cfg = open("/root/reference/configs/common/models/mask_generator_with_label.py").read()
+    assert "prompt=" not in cfg.split("category_head=")[1].split("clip_head=")[0]
+    assert "clip_head=L(PoolingCLIPHead)()" in cfg
+    labels = vocab.read_label_file(os.path.join(LABELS, "ade20k_150_with_prompt_eng.txt"))
+    cat, clip, sizes = vocab.vocabulary_prompts(labels)
+    want_cat = od.prompt_labels(labels, inspect.signature(od.CategoryEmbed.__init__).parameters["prompt"].default)
+    want_clip = od.prompt_labels(labels, inspect.signature(od.PoolingCLIPHead.__init__).parameters["prompt"].default)
+    assert cat == [p for s_ in want_cat for p in s_] and clip == [p for s_ in want_clip for p in s_]
+    assert sizes == [len(s_) for s_ in labels] and len(cat) == len(clip) == 403 and cat != clip

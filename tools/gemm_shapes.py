@@ -17,9 +17,9 @@ from odise_b200.pipeline import ODISEEngine, full_param_list, synthetic_vocabula
 full = "--full" in sys.argv
 nmma = 1 if "--bf16" in sys.argv else 3
 dev = torch.device("cuda:0")
-eng = ODISEEngine(spec.synth_state_dict(full_param_list(with_vae=full, with_clip=full), 0), dev, nmma=nmma, with_vae=full,
+eng = ODISEEngine(spec.synth_state_dict(full_param_list(with_vae=full, with_clip=full), 0), dev, synthetic_uncond=True, nmma=nmma, with_vae=full,
                   with_clip=full)
-eng.set_vocabulary("ade150", *synthetic_vocabulary(150, 403))
+eng.set_synthetic_vocabulary("ade150", 150, 403)
 for _ in range(2):
     eng.step(4, 1024, 1024)
 torch.cuda.synchronize()

@@ -18,10 +18,10 @@ ap.add_argument("--full", action="store_true", help="include the VAE (f-1) and C
 a = ap.parse_args()
 dev = torch.device("cuda:0")
 sd = spec.synth_state_dict(full_param_list(with_vae=a.full, with_clip=a.full), 0)
-eng = ODISEEngine(sd, dev, nmma=3 if a.precision == "bf16x3" else 1, with_vae=a.full, with_clip=a.full)
-eng.set_vocabulary("ade150", *synthetic_vocabulary(150, 403))
+eng = ODISEEngine(sd, dev, nmma=3 if a.precision == "bf16x3" else 1, synthetic_uncond=True, with_vae=a.full, with_clip=a.full)
+eng.set_synthetic_vocabulary("ade150", 150, 403)
 n0 = lib.launch_count()
 for i in range(a.iters):
-    eng.step(a.batch, a.size, a.size)
+    eng.step_full(a.batch, a.size, a.size)
     torch.cuda.synchronize()
     print("iter", i, "launches so far", lib.launch_count() - n0, flush=True)

@@ -13,9 +13,9 @@ from odise_b200.pipeline import ODISEEngine, full_param_list, synthetic_vocabula
 
 full = "--hot-path-only" not in sys.argv
 dev = torch.device("cuda:0")
-eng = ODISEEngine(spec.synth_state_dict(full_param_list(with_vae=full, with_clip=full), 0), dev, nmma=3, with_vae=full,
+eng = ODISEEngine(spec.synth_state_dict(full_param_list(with_vae=full, with_clip=full), 0), dev, synthetic_uncond=True, nmma=3, with_vae=full,
                   with_clip=full)
-eng.set_vocabulary("ade150", *synthetic_vocabulary(150, 403))
+eng.set_synthetic_vocabulary("ade150", 150, 403)
 g, out = eng.capture(4, 1024, 1024)
 for _ in range(3):
     g.replay()
