@@ -91,6 +91,12 @@ typedef struct odise_gemm_desc {
                                         M = B * (H/stride) * (W/stride) */
   int geglu;                         /* 1: N = 2*Nh, weight rows quad-interleaved (a0-3, g0-3, a4-7, g4-7, ...):
                                         out planes [M, Nh] = a * gelu(gate)  (ldm GEGLU fused into FF1) */
+  float* gn_partial;                 /* optional: GroupNorm statistics of the OUTPUT computed in the epilogue (the
+                                        producer side of the fused conv + GN + SiLU of ldm ResBlock): per (32-row segment,
+                                        column) a record (shift, S1, S2) at gn_partial[seg * gn_seg_stride +
+                                        {0,1,2} * gn_plane_stride + n], seg = (z*M + m) / 32.  Needs M % 32 == 0, split_k <= 1.
+                                        Merged per (image, group) by odise_groupnorm_finalize_seg_f32. */
+  long long gn_seg_stride; long long gn_plane_stride;
 } odise_gemm_desc;
 int odise_gemm_bf16(const odise_gemm_desc* desc, void* stream);
 /* optional per-launch timing of odise_gemm_bf16 (CUDA events on the launch stream; not for use under graph capture):
@@ -116,6 +122,12 @@ int odise_groupnorm_stats_bs_f32(const float* x, long long ldx, long long x_bs, 
 long long odise_groupnorm_ws_floats(int B, int HW, int C, int G);
 int odise_groupnorm_stats_ws_f32(const float* x, long long ldx, long long x_bs, float* ws, float* mean, float* rstd,
                                  int B, int HW, int C, int G, float eps, void* stream);
+/* mean / rstd [B, G] from the per-(32-row segment, channel) records an odise_gemm_bf16 epilogue left in `partial`
+ * (desc.gn_partial; rows of image b are segments [b*HW/32, (b+1)*HW/32), HW % 32 == 0; channel c at column c of each of
+ * the three planes): Chan's parallel-variance merge in double, fixed order -> deterministic.  Replaces the statistics pass
+ * over the activation (odise_groupnorm_stats_ws_f32) when the activation was produced by our own GEMM. */
+int odise_groupnorm_finalize_seg_f32(const float* partial, long long seg_stride, long long plane_stride, float* mean,
+                                     float* rstd, int B, int HW, int C, int G, float eps, void* stream);
 /* y = act(gn(x) * gamma + beta): writes fp32 (optional) and (hi, lo) planes (optional). act: NONE/SILU/RELU.
  * The *_bs variants take explicit per-image strides (elements; 0 = dense) so a level can be read from / written
  * into the level-concatenated [B, S, C] token matrix of the pixel decoder (msdeformattn.py:61-78). */

@@ -156,19 +156,22 @@ class BackboneEngine:
             M = B * th * tw
             n = f"p{idx}."
             x_p = ops.split(x, lo=self.lo)
-            t1 = ops.empty(M, 128, self.dev)
-            lib.gemm(x_p, self.W[n + "c1"], nmma=self.nmma, out=t1)
-            _, a1 = ops.group_norm(t1, B, th * tw, self.F[n + "conv1.g"], self.F[n + "conv1.b"], 1e-5, ACT_RELU, lo=self.lo)
-            t2 = ops.empty(M, 128, self.dev)
-            lib.gemm(a1, self.W[n + "c2"], M=M, N=128, nmma=self.nmma, conv=(128, th, tw), out=t2)
-            _, a2 = ops.group_norm(t2, B, th * tw, self.F[n + "conv2.g"], self.F[n + "conv2.b"], 1e-5, ACT_RELU, lo=self.lo)
-            t3 = ops.empty(M, 512, self.dev)
-            lib.gemm(a2, self.W[n + "c3"], nmma=self.nmma, out=t3)
+            # every conv leaves the GroupNorm records of its output in its epilogue (lib.GnStats): no statistics passes
+            t1, s1 = ops.empty(M, 128, self.dev), lib.GnStats(M, 128, self.dev)
+            lib.gemm(x_p, self.W[n + "c1"], nmma=self.nmma, out=t1, gn=s1)
+            _, a1 = ops.group_norm(t1, B, th * tw, self.F[n + "conv1.g"], self.F[n + "conv1.b"], 1e-5, ACT_RELU, lo=self.lo,
+                                   stats=s1)
+            t2, s2 = ops.empty(M, 128, self.dev), lib.GnStats(M, 128, self.dev)
+            lib.gemm(a1, self.W[n + "c2"], M=M, N=128, nmma=self.nmma, conv=(128, th, tw), out=t2, gn=s2)
+            _, a2 = ops.group_norm(t2, B, th * tw, self.F[n + "conv2.g"], self.F[n + "conv2.b"], 1e-5, ACT_RELU, lo=self.lo,
+                                   stats=s2)
+            t3, s3 = ops.empty(M, 512, self.dev), lib.GnStats(M, 512, self.dev)
+            lib.gemm(a2, self.W[n + "c3"], nmma=self.nmma, out=t3, gn=s3)
             if FEATURE_DIMS[idx] != 512:
-                sc = ops.empty(M, 512, self.dev)
-                lib.gemm(x_p, self.W[n + "sc"], nmma=self.nmma, out=sc)
+                sc, ss = ops.empty(M, 512, self.dev), lib.GnStats(M, 512, self.dev)
+                lib.gemm(x_p, self.W[n + "sc"], nmma=self.nmma, out=sc, gn=ss)
                 sc, _ = ops.group_norm(sc, B, th * tw, self.F[n + "sc.g"], self.F[n + "sc.b"], 1e-5, want_f32=True,
-                                       want_planes=False)
+                                       want_planes=False, stats=ss)
             else:
                 sc = x
             key = f"s{int(math.log2(s))}"
@@ -176,7 +179,7 @@ class BackboneEngine:
             if first:
                 out[key] = (ops.empty(M, 512, self.dev), th, tw)
             ops.group_norm_res(t3, B, th * tw, self.F[n + "conv3.g"], self.F[n + "conv3.b"], 1e-5, sc, ACT_RELU,
-                               out[key][0], accumulate=not first)
+                               out[key][0], accumulate=not first, stats=s3)
         return out
 
     @torch.no_grad()

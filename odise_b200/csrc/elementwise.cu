@@ -404,6 +404,55 @@ __global__ void gn_finalize_kernel(const float* __restrict__ x, long long x_bs, 
   }
 }
 
+// merge of the (shift, S1, S2) records a GEMM epilogue wrote per (32-row segment, channel): one block per (image, group);
+// pass 1: mean of the segment means, pass 2: M2 = sum(M2_r + 32 (mean_r - mean)^2)  (Chan et al.), both in double with a
+// fixed reduction order (strided per-thread sums -> warp shuffles -> 8 warp partials) -> bit-reproducible
+__global__ void __launch_bounds__(256)
+gn_finalize_seg_kernel(const float* __restrict__ part, long long seg_stride, long long plane, float* __restrict__ mean,
+                       float* __restrict__ rstd, int HW, int C, int G, float eps) {
+  __shared__ double red[8];
+  __shared__ double bc;
+  const int b = blockIdx.x / G, g = blockIdx.x % G, cpg = C / G;
+  const int nseg = HW >> 5;
+  const int total = nseg * cpg;
+  const float* base = part + (long long)b * nseg * seg_stride + g * cpg;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  auto block_sum = [&](double v) {
+    v = warp_sum_d(v);
+    __syncthreads();
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0;
+      for (int w = 0; w < 8; ++w) t += red[w];
+      bc = t;
+    }
+    __syncthreads();
+    return bc;
+  };
+  double sm = 0;
+  for (int i = threadIdx.x; i < total; i += 256) {
+    const int sg = i / cpg, c = i - sg * cpg;
+    const float* r = base + (long long)sg * seg_stride + c;
+    sm += (double)r[0] + (double)r[plane] * (1.0 / 32.0);
+  }
+  const double mu = block_sum(sm) / (double)total;
+  double m2 = 0;
+  for (int i = threadIdx.x; i < total; i += 256) {
+    const int sg = i / cpg, c = i - sg * cpg;
+    const float* r = base + (long long)sg * seg_stride + c;
+    const double s1 = r[plane], s2 = r[2 * plane];
+    const double mr = (double)r[0] + s1 * (1.0 / 32.0);
+    m2 += (s2 - s1 * s1 * (1.0 / 32.0)) + 32.0 * (mr - mu) * (mr - mu);
+  }
+  double var = block_sum(m2) / ((double)total * 32.0);
+  if (threadIdx.x == 0) {
+    if (var < 0) var = 0;
+    mean[blockIdx.x] = (float)mu;
+    rstd[blockIdx.x] = (float)(1.0 / sqrt(var + (double)eps));
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- LayerNorm
 // one warp per row, row cached in registers (cols <= 4096)
 template <int MAXV>
@@ -1161,6 +1210,15 @@ extern "C" int odise_groupnorm_stats_ws_f32(const float* x, long long ldx, long 
   gn_partial_kernel<<<B * nchunk, threads, smem, STREAM(stream)>>>(x, ldx, xbs, ws, HW, C, G, nchunk, ppc);
   gn_finalize_kernel<<<(B * G + 7) / 8, 256, 0, STREAM(stream)>>>(x, xbs, ws, mean, rstd, B, HW, C, G, nchunk, eps);
   count_launch(2);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int odise_groupnorm_finalize_seg_f32(const float* partial, long long seg_stride, long long plane_stride,
+                                                float* mean, float* rstd, int B, int HW, int C, int G, float eps,
+                                                void* stream) {
+  if (!partial || !mean || !rstd || B <= 0 || HW <= 0 || C <= 0 || G <= 0 || C % G || HW % 32) return ODISE_ERR_ARG;
+  gn_finalize_seg_kernel<<<B * G, 256, 0, STREAM(stream)>>>(partial, seg_stride, plane_stride, mean, rstd, HW, C, G, eps);
+  count_launch(1);
   return (int)cudaGetLastError();
 }
 

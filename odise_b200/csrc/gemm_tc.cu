@@ -49,7 +49,57 @@ struct GemmParams {
   int geglu;   // N = 2*Nh with quad-interleaved (a, gate) columns: out[:, j] = a_j * gelu(g_j) -> planes [M, Nh]
   int vec_ok;  // all epilogue pointers / leading dims allow 16-byte vector access
   float* partial;  // [splits][batch][M][N] when splits > 1
+  // GroupNorm statistics of the OUTPUT, fused into the epilogue (the consumer's torch.nn.GroupNorm, ldm ResBlock
+  // in_layers[0] / out_layers[0], call sites ldm.py:481-489): per (32-row segment, column) a record (shift, S1, S2) with
+  // shift = the segment's first row, S1 = sum(x - shift), S2 = sum((x - shift)^2) over the 32 rows.  Layout
+  // gnp[seg * gnp_seg + {0,1,2} * gnp_plane + column]; odise_groupnorm_finalize_seg_f32 merges them per (image, group)
+  // in fixed order (Chan's formula, double) -> no atomics, bit-reproducible, no second pass over the activation.
+  float* gnp;
+  long long gnp_seg, gnp_plane;
 };
+
+// 4 columns x the 4 rows a lane owns -> per-column (shift, S1, S2) of the warp's 32 rows; lanes 0..3 (rsub == 0) hold
+// the result.  `first`: this call carries the rows it = 0 (row 0 of the segment sits in lanes 0..3).
+struct GnAcc {
+  float sh[4], s1[4], s2[4];
+};
+__device__ __forceinline__ void gn_acc_rows(GnAcc& a, const float (&e)[4], bool first, int lane) {
+  if (first) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      a.sh[j] = __shfl_sync(0xffffffffu, e[j], lane & 3);
+      a.s1[j] = 0.f; a.s2[j] = 0.f;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float d = e[j] - a.sh[j];
+    a.s1[j] += d;
+    a.s2[j] = fmaf(d, d, a.s2[j]);
+  }
+}
+__device__ __forceinline__ void gn_acc_store(GnAcc& a, const GemmParams& p, long long seg, int col, int valid, int lane) {
+#pragma unroll
+  for (int o = 4; o < 32; o <<= 1) {        // fixed-order butterfly over the 8 row-lanes sharing a column quad
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      a.s1[j] += __shfl_xor_sync(0xffffffffu, a.s1[j], o);
+      a.s2[j] += __shfl_xor_sync(0xffffffffu, a.s2[j], o);
+    }
+  }
+  if ((lane >> 2) == 0 && valid > 0) {
+    float* q = p.gnp + seg * p.gnp_seg + col;
+    if (valid == 4 && ((p.gnp_plane | p.gnp_seg) & 3) == 0 && ((reinterpret_cast<uintptr_t>(q) & 15) == 0)) {
+      *reinterpret_cast<float4*>(q) = make_float4(a.sh[0], a.sh[1], a.sh[2], a.sh[3]);
+      *reinterpret_cast<float4*>(q + p.gnp_plane) = make_float4(a.s1[0], a.s1[1], a.s1[2], a.s1[3]);
+      *reinterpret_cast<float4*>(q + 2 * p.gnp_plane) = make_float4(a.s2[0], a.s2[1], a.s2[2], a.s2[3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (j < valid) { q[j] = a.sh[j]; q[p.gnp_plane + j] = a.s1[j]; q[2 * p.gnp_plane + j] = a.s2[j]; }
+    }
+  }
+}
 
 // exact-erf GELU with erf from Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7, i.e. fp32 rounding level): one ex2, one
 // rcp and six FMAs instead of libdevice's two-branch erff; used by the fused GEGLU epilogue (ldm GEGLU = F.gelu).
@@ -73,7 +123,8 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 }
 
 // epilogue for 4 consecutive columns [n, n+4) of row m (n % 4 == 0); `valid` = how many of them exist (N tail)
-__device__ __forceinline__ void epilogue_quad(const GemmParams& p, int z, int m, int n, int valid, float4 a4) {
+__device__ __forceinline__ void epilogue_quad(const GemmParams& p, int z, int m, int n, int valid, float4 a4,
+                                              float* final_vals = nullptr) {
   float acc[4] = {a4.x, a4.y, a4.z, a4.w};
   const bool vec = (valid == 4) && p.vec_ok;
   if (p.alpha != 1.f) {
@@ -117,6 +168,10 @@ __device__ __forceinline__ void epilogue_quad(const GemmParams& p, int z, int m,
 #pragma unroll
       for (int j = 0; j < 4; ++j) if (j < valid) acc[j] += r[j];
     }
+  }
+  if (final_vals) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) final_vals[j] = acc[j];
   }
   if (p.D) {
     float* d = p.D + (long long)z * p.d_bs + (long long)m * p.ldd + n;
@@ -366,9 +421,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
         const bool to_f32 = p.D != nullptr, to_hi = p.Dh != nullptr, to_lo = p.Dl != nullptr;
         const int act = p.act;
         const float alpha = p.alpha;
+        const bool has_gn = !GEGLU && p.gnp != nullptr;
+        const long long gn_seg = ((long long)z * p.M + m_base) >> 5;
 #pragma unroll 1
         for (int c0 = c_first; c0 < BN; c0 += c_step) {
           uint32_t v[16];
+          GnAcc gacc;
           tmem_ld16(t_row + c0, v);
           tmem_ld_wait();
 #pragma unroll
@@ -423,6 +481,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
               for (int j = 0; j < 4; ++j) e[j] = apply_act(e[j], act);
             }
             if (has_res) { e[0] += r4[it].x; e[1] += r4[it].y; e[2] += r4[it].z; e[3] += r4[it].w; }
+            if (has_gn) gn_acc_rows(gacc, e, it == 0, lane);
             if (to_f32) *reinterpret_cast<float4*>(p.D + oD[it] + c0) = make_float4(e[0], e[1], e[2], e[3]);
             if (to_hi) {
               // packed conversions: hi = bf16x2(e), lo = bf16x2(e - float(hi))  (same values as split_bf16)
@@ -442,6 +501,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
               }
             }
           }
+          if (has_gn) gn_acc_store(gacc, p, gn_seg, n0 + c0 + cq * 4, 4, lane);
           __syncwarp();
         }
       } else {
@@ -459,6 +519,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
               *reinterpret_cast<float4*>(stg + lane * 16 + ((j ^ ((lane >> 1) & 3)) << 2)) = q4;
             }
             __syncwarp();
+            // fused GroupNorm statistics on edge tiles: whole 32-row segments only (M % 32 == 0 is checked on the host)
+            const bool gn_here = p.gnp != nullptr && !p.geglu && p.splits == 1 && m_base < p.M;
+            GnAcc gacc;
 #pragma unroll 1
             for (int it = 0; it < 4; ++it) {
               const int rr = it * 8 + rsub;
@@ -482,6 +545,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
                 }
                 continue;
               }
+              float fin[4] = {0.f, 0.f, 0.f, 0.f};
               if (m < p.M && n < p.N) {
                 const int valid = min(4, p.N - n);
                 if (p.splits > 1) {
@@ -490,9 +554,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
 #pragma unroll
                   for (int j = 0; j < 4; ++j) if (j < valid) dst[j] = e[j];
                 } else {
-                  epilogue_quad(p, z, m, n, valid, q4);
+                  epilogue_quad(p, z, m, n, valid, q4, fin);
                 }
               }
+              if (gn_here) gn_acc_rows(gacc, fin, it == 0, lane);      // warp-uniform: all lanes shuffle
+            }
+            if (gn_here) {
+              const int n = n0 + c0 + cq * 4;
+              gn_acc_store(gacc, p, ((long long)z * p.M + m_base) >> 5, n, n < p.N ? min(4, p.N - n) : 0, lane);
             }
             __syncwarp();
           }
@@ -655,6 +724,12 @@ extern "C" int odise_gemm_bf16(const odise_gemm_desc* d, void* stream_v) {
   p.ldh = d->ld_out_bf16; p.h_bs = d->out_bf16_batch_stride;
   p.act = d->act;
   p.geglu = d->geglu;
+  if (d->gn_partial) {
+    // whole 32-row segments, final values produced by this kernel (no split-K second pass, no GEGLU re-pairing)
+    if (d->M % 32 || d->split_k > 1 || d->geglu || d->gn_seg_stride <= 0 || d->gn_plane_stride <= 0)
+      return ODISE_ERR_UNSUPPORTED;
+    p.gnp = d->gn_partial; p.gnp_seg = d->gn_seg_stride; p.gnp_plane = d->gn_plane_stride;
+  }
 
   // vector epilogue paths need 16-byte alignment; otherwise the kernel takes the scalar path
   {

@@ -158,6 +158,12 @@ __device__ __forceinline__ uint32_t sw128_offset(uint32_t r, uint32_t chunk16) {
   return r * 128u + ((chunk16 ^ (r & 7u)) << 4);
 }
 
+// same with an fp16 A operand and a bf16 B operand (kind::f16 takes the two formats independently: a_format bits [7,10)
+// = 0 F16 / 1 BF16, b_format bits [10,13)): the attention kernel's P (fp16, one plane) x V (bf16 hi / lo planes)
+__host__ __device__ constexpr uint32_t umma_idesc_f16a_bf16b(uint32_t m, uint32_t n) {
+  return (1u << 4) | (0u << 7) | (1u << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
+}
+
 // fp32 -> (hi, lo) bf16 pair with hi + lo ~= x to ~16 mantissa bits (the "bf16x3" operand split)
 __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
   hi = __float2bfloat16_rn(x);

@@ -185,10 +185,10 @@ class HeadEngine:
         src = ops.empty(B * S, 256, dev)
         for i, n in enumerate(names):
             x, h, w = feats[n]
-            t = ops.empty(B * h * w, 256, dev)
-            self._gemm(ops.split(x, lo=self.lo), f"pd.in{i}", out=t)
+            t, ts = ops.empty(B * h * w, 256, dev), lib.GnStats(B * h * w, 256, dev)
+            self._gemm(ops.split(x, lo=self.lo), f"pd.in{i}", out=t, gn=ts)
             ops.group_norm(t, B, h * w, self.F[f"pd.in{i}.gn.g"], self.F[f"pd.in{i}.gn.be"], 1e-5, want_planes=False,
-                           y=src[starts[i]:], ldy=256, y_bs=S * 256)
+                           y=src[starts[i]:], ldy=256, y_bs=S * 256, stats=ts)
         src_p = ops.split(src, lo=self.lo)
         for l in range(self.n_enc):
             n = f"pd.l{l}."
@@ -212,15 +212,16 @@ class HeadEngine:
         # FPN level on s2 (msdeformattn.py:343-351)
         x2, h2, w2 = feats["s2"]
         h3, w3 = shapes[2]
-        lat = ops.empty(B * h2 * w2, 256, dev)
-        self._gemm(ops.split(x2, lo=self.lo), "pd.adapter", bias=False, out=lat)
+        lat, lat_s = ops.empty(B * h2 * w2, 256, dev), lib.GnStats(B * h2 * w2, 256, dev)
+        self._gemm(ops.split(x2, lo=self.lo), "pd.adapter", bias=False, out=lat, gn=lat_s)
         cur, _ = ops.group_norm(lat, B, h2 * w2, self.F["pd.adapter.gn.g"], self.F["pd.adapter.gn.be"], 1e-5,
-                                want_f32=True, want_planes=False)
+                                want_f32=True, want_planes=False, stats=lat_s)
         ops.resize_nhwc(src[starts[2]:], B, h3, w3, h2, w2, True, dst=cur, accumulate=True, src_bs=S * 256)
-        conv = ops.empty(B * h2 * w2, 256, dev)
-        self._gemm(ops.split(cur, lo=self.lo), "pd.layer", bias=False, M=B * h2 * w2, N=256, conv=(256, h2, w2), out=conv)
+        conv, conv_s = ops.empty(B * h2 * w2, 256, dev), lib.GnStats(B * h2 * w2, 256, dev)
+        self._gemm(ops.split(cur, lo=self.lo), "pd.layer", bias=False, M=B * h2 * w2, N=256, conv=(256, h2, w2), out=conv,
+                   gn=conv_s)
         _, y2_p = ops.group_norm(conv, B, h2 * w2, self.F["pd.layer.gn.g"], self.F["pd.layer.gn.be"], 1e-5, ACT_RELU,
-                                 lo=self.lo)
+                                 lo=self.lo, stats=conv_s)
         HW = h2 * w2
         mf_p = Planes.empty(B * HW, 256, dev, lo=self.lo)                 # [B*HW, C]: B operand of the mask einsum
         mf = ops.empty(B * HW, 256, dev) if want_mask_features_f32 else None

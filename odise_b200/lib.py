@@ -38,6 +38,7 @@ class GemmDesc(ctypes.Structure):
         ("bias_m", c_void_p),
         ("conv_mode", c_int),
         ("geglu", c_int),
+        ("gn_partial", c_void_p), ("gn_seg_stride", c_longlong), ("gn_plane_stride", c_longlong),
     ]
 
 
@@ -55,6 +56,8 @@ _SIGS = {
                                   c_void_p],
     "odise_groupnorm_apply_f32": [c_void_p, c_longlong, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
                                   c_longlong, c_void_p, c_void_p, c_longlong, c_int, c_int, c_int, c_int, c_void_p],
+    "odise_groupnorm_finalize_seg_f32": [c_void_p, c_longlong, c_longlong, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                         c_float, c_void_p],
     "odise_groupnorm_stats_bs_f32": [c_void_p, c_longlong, c_longlong, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                      c_float, c_void_p],
     "odise_groupnorm_stats_ws_f32": [c_void_p, c_longlong, c_longlong, c_void_p, c_void_p, c_void_p, c_int, c_int,
@@ -214,6 +217,40 @@ class Planes:
                       self.ld)
 
 
+class GnStats:
+    """Per-(32-row segment, channel) GroupNorm records of an fp32 activation [rows, C], filled by the epilogues of the GEMMs
+    that produce the activation (possibly several: the two halves of a skip concat write disjoint column ranges of one
+    buffer, see cols()) and merged by ops.group_norm().  `missing` (shared by all views of a buffer) is set by a producer that
+    could not fill its columns (split-K, ragged rows): group_norm() then falls back to the stand-alone statistics pass."""
+
+    __slots__ = ("t", "rows", "C", "Ctot", "col", "_flag")
+
+    def __init__(self, rows, C, device, _root=None, _col=0):
+        self.rows, self.C, self.col = rows, C, _col
+        if _root is None:
+            self._flag = [rows % 32 != 0]
+            self.Ctot = C
+            self.t = None if self._flag[0] else torch.empty(rows // 32, 3, C, dtype=torch.float32, device=device)
+        else:
+            self._flag, self.Ctot, self.t = _root._flag, _root.Ctot, _root.t
+
+    @property
+    def missing(self):
+        return self._flag[0]
+
+    @missing.setter
+    def missing(self, v):
+        self._flag[0] = bool(v)
+
+    def cols(self, c0, C):
+        """records of columns [c0, c0 + C) of the same activation buffer"""
+        return GnStats(self.rows, C, None, _root=self, _col=self.col + c0)
+
+    @property
+    def ptr(self):
+        return self.t.data_ptr() + 4 * self.col
+
+
 def split(x, out=None, lo=True):
     """fp32 [rows, cols] (last dim contiguous) -> Planes."""
     _req(x, torch.float32, "x")
@@ -277,7 +314,7 @@ def conv_ok(H, W):
 
 def gemm(a, b, *, M=None, N=None, K=None, nmma=3, batch=1, a_bs=0, b_bs=0, conv=None, alpha=1.0, bias=None, bias_m=None,
          rowbias=None, rows_per_group=1, act=ACT_NONE, residual=None, ld_res=None, res_bs=0, out=None, ld_out=None,
-         out_bs=0, out_planes=None, outp_bs=0, split_k=1, workspace=None, force_bn=0, geglu=False, conv_mode=0):
+         out_bs=0, out_planes=None, outp_bs=0, split_k=1, workspace=None, force_bn=0, geglu=False, conv_mode=0, gn=None):
     """out[z] = epi(alpha * A[z] @ B[z]^T).  a, b: Planes (K-major).  conv = (C, H, W) for implicit 3x3."""
     d = GemmDesc()
     d.M = M if M is not None else a.rows
@@ -313,6 +350,12 @@ def gemm(a, b, *, M=None, N=None, K=None, nmma=3, batch=1, a_bs=0, b_bs=0, conv=
             raise OdiseError("gemm: split_k needs a workspace of %d bytes" % need)
         d.workspace, d.workspace_bytes = _ptr(workspace), workspace.numel() * workspace.element_size()
     d.force_bn = force_bn
+    if gn is not None:        # GroupNorm records of the output (a GnStats view of the output's columns)
+        if split_k > 1 or gn.missing or d.M % 32 or gn.C != d.N or gn.rows != d.M * batch:
+            gn.missing = True
+        else:
+            d.gn_partial = gn.ptr
+            d.gn_seg_stride, d.gn_plane_stride = 3 * gn.Ctot, gn.Ctot
     d.geglu = 1 if geglu else 0
     d.conv_mode = conv_mode
     _check(load().odise_gemm_bf16(ctypes.byref(d), _stream()), "odise_gemm_bf16")

@@ -22,17 +22,27 @@ def _gn_stats(L, x, ldx, x_bs, mean, rstd, B, HW, C, G, eps):
                                           _stream()), "groupnorm_stats")
 
 
+def _gn_stats_any(L, x, ldx, x_bs, mean, rstd, B, HW, C, G, eps, stats):
+    """statistics from the producer epilogues' records when they exist, else the stand-alone pass over x"""
+    if stats is not None and not stats.missing and stats.C == C and stats.rows == B * HW and HW % 32 == 0 and x_bs == 0:
+        _check(L.odise_groupnorm_finalize_seg_f32(stats.ptr, 3 * stats.Ctot, stats.Ctot, _ptr(mean), _ptr(rstd), B, HW, C, G,
+                                                  eps, _stream()), "groupnorm_finalize_seg")
+    else:
+        _gn_stats(L, x, ldx, x_bs, mean, rstd, B, HW, C, G, eps)
+
+
 def group_norm(x, B, HW, gamma, beta, eps, act=ACT_NONE, G=32, want_f32=False, want_planes=True, lo=True, ldx=None,
-               x_bs=0, y=None, ldy=None, y_bs=0, planes=None, o_bs=0):
+               x_bs=0, y=None, ldy=None, y_bs=0, planes=None, o_bs=0, stats=None):
     """x [B*HW, C] (row stride ldx, per-image stride x_bs) -> (y fp32 | None, planes | None).
-    y / planes may be given (with explicit strides) to write into a slice of a larger buffer."""
+    y / planes may be given (with explicit strides) to write into a slice of a larger buffer.
+    stats: lib.GnStats filled by the GEMM epilogues that produced x (no statistics pass over x then)."""
     C = gamma.numel()
     ldx = ldx or x.stride(0)
     dev = x.device
     mean = torch.empty(B * G, dtype=torch.float32, device=dev)
     rstd = torch.empty(B * G, dtype=torch.float32, device=dev)
     L = load()
-    _gn_stats(L, x, ldx, x_bs, mean, rstd, B, HW, C, G, eps)
+    _gn_stats_any(L, x, ldx, x_bs, mean, rstd, B, HW, C, G, eps, stats)
     if y is None and want_f32:
         y = empty(B * HW, C, dev)
     if y is not None and ldy is None:
@@ -232,14 +242,14 @@ def class_max(sims, group_start, null_sim, rows, n_classes):
     return out
 
 
-def group_norm_res(x, B, HW, gamma, beta, eps, res, act, y, accumulate, G=32):
+def group_norm_res(x, B, HW, gamma, beta, eps, res, act, y, accumulate, G=32, stats=None):
     """y (+)= act(gn(x) + res); x, res, y dense [B*HW, C] fp32."""
     C = gamma.numel()
     dev = x.device
     mean = torch.empty(B * G, dtype=torch.float32, device=dev)
     rstd = torch.empty(B * G, dtype=torch.float32, device=dev)
     L = load()
-    _gn_stats(L, x, x.stride(0), 0, mean, rstd, B, HW, C, G, eps)
+    _gn_stats_any(L, x, x.stride(0), 0, mean, rstd, B, HW, C, G, eps, stats)
     _check(L.odise_groupnorm_apply_res_f32(_ptr(x), x.stride(0), _ptr(mean), _ptr(rstd), _ptr(gamma), _ptr(beta),
                                            _ptr(res), res.stride(0) if res is not None else 0, act, _ptr(y),
                                            y.stride(0), 1 if accumulate else 0, None, None, 0, B, HW, C, G, _stream()),

@@ -148,31 +148,36 @@ class UNetEngine:
                 kw.update(split_k=sk, force_bn=bn, workspace=lib.workspace(sk * Mc * Nc * 4, self.dev))
         return lib.gemm(a, self.W[wname], nmma=self.nmma, bias=self.F[bias] if bias else None, **kw)
 
-    def _resblock(self, q, x, B, H, W, cin, cout, emb_all, dst):
-        """x: fp32 view [B*H*W, cin]; dst: fp32 view [B*H*W, cout] (may be a column slice of a concat buffer)."""
+    def _resblock(self, q, x, B, H, W, cin, cout, emb_all, dst, xs=None, ds=None):
+        """x: fp32 view [B*H*W, cin]; dst: fp32 view [B*H*W, cout] (may be a column slice of a concat buffer).
+        xs / ds: lib.GnStats views of x / dst — the GroupNorm statistics travel with the activations: every GEMM that
+        writes an activation a GroupNorm will read leaves the per-segment records in its epilogue (conv + GN fusion, producer
+        side), so in_layers[0] / out_layers[0] never re-read the activation for its statistics."""
         M = B * H * W
         imp = lib.conv_ok(H, W)          # False: map width the implicit-GEMM TMA boxes cannot tile -> materialised im2col
         y1, a1 = ops.group_norm(x, B, H * W, self.F[q + "gn1.g"], self.F[q + "gn1.b"], 1e-5, ACT_SILU, lo=self.lo,
-                                want_f32=not imp, want_planes=imp)
+                                want_f32=not imp, want_planes=imp, stats=xs)
         eo, ec = self.emb_off[q]
         h = ops.empty(M, cout, self.dev)
+        hs = lib.GnStats(M, cout, self.dev)
         if imp:
             self._gemm(a1, q + "conv1", q + "conv1.b", M=M, N=cout, conv=(cin, H, W), rowbias=emb_all[:, eo:eo + ec],
-                       rows_per_group=H * W, out=h)
+                       rows_per_group=H * W, out=h, gn=hs)
         else:
             self._gemm(ops.im2col3x3_split(y1, B, H, W, lo=self.lo)[0], q + "conv1", q + "conv1.b",
-                       rowbias=emb_all[:, eo:eo + ec], rows_per_group=H * W, out=h)
+                       rowbias=emb_all[:, eo:eo + ec], rows_per_group=H * W, out=h, gn=hs)
         y2, a2 = ops.group_norm(h, B, H * W, self.F[q + "gn2.g"], self.F[q + "gn2.b"], 1e-5, ACT_SILU, lo=self.lo,
-                                want_f32=not imp, want_planes=imp)
+                                want_f32=not imp, want_planes=imp, stats=hs)
         if cin != cout:
             skip = ops.empty(M, cout, self.dev)
             self._gemm(ops.split(x, lo=self.lo), q + "skip", q + "skip.b", out=skip)
         else:
             skip = x
         if imp:
-            self._gemm(a2, q + "conv2", q + "conv2.b", M=M, N=cout, conv=(cout, H, W), residual=skip, out=dst)
+            self._gemm(a2, q + "conv2", q + "conv2.b", M=M, N=cout, conv=(cout, H, W), residual=skip, out=dst, gn=ds)
         else:
-            self._gemm(ops.im2col3x3_split(y2, B, H, W, lo=self.lo)[0], q + "conv2", q + "conv2.b", residual=skip, out=dst)
+            self._gemm(ops.im2col3x3_split(y2, B, H, W, lo=self.lo)[0], q + "conv2", q + "conv2.b", residual=skip, out=dst,
+                       gn=ds)
         return dst
 
     def _attention(self, t, a, xq, kv_src, B, T, Tk, ch, TkS=None):
@@ -223,11 +228,11 @@ class UNetEngine:
                      out_planes=o.col_slice(h * d, d), outp_bs=T * o.ld)
         return o
 
-    def _st(self, q, x, B, H, W, ch, ctx, dst):
+    def _st(self, q, x, B, H, W, ch, ctx, dst, xs=None, ds=None):
         T = H * W
         M = B * T
         t = q + "transformer_blocks.0."
-        _, xn = ops.group_norm(x, B, T, self.F[q + "norm.g"], self.F[q + "norm.b"], 1e-6, ACT_NONE, lo=self.lo)
+        _, xn = ops.group_norm(x, B, T, self.F[q + "norm.g"], self.F[q + "norm.b"], 1e-6, ACT_NONE, lo=self.lo, stats=xs)
         h = ops.empty(M, ch, self.dev)
         self._gemm(xn, q + "proj_in", q + "proj_in.b", out=h)
         _, n1 = ops.layer_norm(h, self.F[t + "norm1.g"], self.F[t + "norm1.b"], lo=self.lo)
@@ -243,7 +248,7 @@ class UNetEngine:
         self._gemm(n3, t + "ff1", t + "ff1.b", out_planes=gg, geglu=True)
         h4p = Planes.empty(M, ch, self.dev, lo=self.lo)
         self._gemm(gg, t + "ff2", t + "ff2.b", residual=h3, out_planes=h4p)
-        self._gemm(h4p, q + "proj_out", q + "proj_out.b", residual=x, out=dst)
+        self._gemm(h4p, q + "proj_out", q + "proj_out.b", residual=x, out=dst, gn=ds)
         return dst
 
     # ------------------------------------------------------------------------------------------- forward
@@ -275,49 +280,53 @@ class UNetEngine:
             sizes.append((h_, w_, cout))
         # cat[i] = input of output block i = [h (left) | skip hs[11 - i] (right)]
         ch_in = [l[0][1] for l in self.out]                      # channels of the concat
-        cat = []
+        cat, cst = [], []
         for i in range(12):
             hh, ww, cs = sizes[11 - i]
             cat.append((torch.empty(B * hh * ww, ch_in[i], dtype=torch.float32, device=dev), ch_in[i] - cs, hh, ww))
+            cst.append(lib.GnStats(B * hh * ww, ch_in[i], dev))   # GroupNorm records of the whole concat [h | skip]
 
-        def skip_view(j):   # where down-path output j lives
+        def skip_view(j):   # where down-path output j lives (+ the matching columns of the statistics records)
             buf, cl, hh, ww = cat[11 - j]
-            return buf[:, cl:]
+            return buf[:, cl:], cst[11 - j].cols(cl, buf.shape[1] - cl)
 
-        cur, ch_, cw_ = None, H, W
+        cur, cur_s, ch_, cw_ = None, None, H, W
         for j, layers in enumerate(self.inp):
             q = f"input_blocks.{j}."
-            dst = skip_view(j)
+            dst, dst_s = skip_view(j)
             kind = layers[0][0]
             if kind == "conv_in":
                 cols, _, _ = ops.im2col3x3_split(x, B, H, W, lo=self.lo)
-                self._gemm(cols, q + "0.conv", q + "0.conv.b", out=dst)
+                self._gemm(cols, q + "0.conv", q + "0.conv.b", out=dst, gn=dst_s)
             elif kind == "down":
                 # ldm Downsample = conv3x3 stride 2 pad 1: strided implicit GEMM (TMA element strides), no im2col
                 cdim = layers[0][1]
                 if lib.conv_ok(ch_ // 2, cw_ // 2):
                     self._gemm(ops.split(cur, lo=self.lo), q + "0.conv", q + "0.conv.b", M=B * (ch_ // 2) * (cw_ // 2),
-                               N=cdim, conv=(cdim, ch_, cw_), conv_mode=1, out=dst)
+                               N=cdim, conv=(cdim, ch_, cw_), conv_mode=1, out=dst, gn=dst_s)
                 else:
                     self._gemm(ops.im2col3x3_split(cur, B, ch_, cw_, stride=2, lo=self.lo)[0], q + "0.conv", q + "0.conv.b",
-                               out=dst)
+                               out=dst, gn=dst_s)
                 ch_, cw_ = ch_ // 2, cw_ // 2
             else:
                 _, cin, cout = layers[0]
                 if len(layers) == 1:
-                    self._resblock(q + "0.", cur, B, ch_, cw_, cin, cout, emb_all, dst)
+                    self._resblock(q + "0.", cur, B, ch_, cw_, cin, cout, emb_all, dst, cur_s, dst_s)
                 else:
                     tmp = ops.empty(B * ch_ * cw_, cout, dev)
-                    self._resblock(q + "0.", cur, B, ch_, cw_, cin, cout, emb_all, tmp)
-                    self._st(q + "1.", tmp, B, ch_, cw_, cout, ctx, dst)
-            cur = dst
+                    tmp_s = lib.GnStats(B * ch_ * cw_, cout, dev)
+                    self._resblock(q + "0.", cur, B, ch_, cw_, cin, cout, emb_all, tmp, cur_s, tmp_s)
+                    self._st(q + "1.", tmp, B, ch_, cw_, cout, ctx, dst, tmp_s, dst_s)
+            cur, cur_s = dst, dst_s
         # middle block -> left part of cat[0]
         c = self.mid[0][1]
-        t1 = ops.empty(B * ch_ * cw_, c, dev)
-        self._resblock("middle_block.0.", cur, B, ch_, cw_, c, c, emb_all, t1)
-        t2 = ops.empty(B * ch_ * cw_, c, dev)
-        self._st("middle_block.1.", t1, B, ch_, cw_, c, ctx, t2)
-        self._resblock("middle_block.2.", t2, B, ch_, cw_, c, c, emb_all, cat[0][0][:, :cat[0][1]])
+        Mm = B * ch_ * cw_
+        t1, t1s = ops.empty(Mm, c, dev), lib.GnStats(Mm, c, dev)
+        self._resblock("middle_block.0.", cur, B, ch_, cw_, c, c, emb_all, t1, cur_s, t1s)
+        t2, t2s = ops.empty(Mm, c, dev), lib.GnStats(Mm, c, dev)
+        self._st("middle_block.1.", t1, B, ch_, cw_, c, ctx, t2, t1s, t2s)
+        self._resblock("middle_block.2.", t2, B, ch_, cw_, c, c, emb_all, cat[0][0][:, :cat[0][1]], t2s,
+                       cst[0].cols(0, cat[0][1]))
 
         taps = []
         for i in range(12):
@@ -329,24 +338,24 @@ class UNetEngine:
             layers = self.out[i]
             q = f"output_blocks.{i}."
             nbuf, ncl, nh, nw = cat[i + 1]
-            dst = nbuf[:, :ncl]
+            dst, dst_s = nbuf[:, :ncl], cst[i + 1].cols(0, ncl)
             _, cin, cout = layers[0]
             last_is_res = len(layers) == 1
-            t = dst if last_is_res else ops.empty(B * hh * ww, cout, dev)
-            self._resblock(q + "0.", buf, B, hh, ww, cin, cout, emb_all, t)
+            t, ts = (dst, dst_s) if last_is_res else (ops.empty(B * hh * ww, cout, dev), lib.GnStats(B * hh * ww, cout, dev))
+            self._resblock(q + "0.", buf, B, hh, ww, cin, cout, emb_all, t, cst[i], ts)
             k = 1
             if k < len(layers) and layers[k][0] == "st":
-                t_out = dst if k == len(layers) - 1 else ops.empty(B * hh * ww, cout, dev)
-                self._st(f"{q}{k}.", t, B, hh, ww, cout, ctx, t_out)
+                t_out, to_s = (dst, dst_s) if k == len(layers) - 1 else (ops.empty(B * hh * ww, cout, dev), None)
+                self._st(f"{q}{k}.", t, B, hh, ww, cout, ctx, t_out, ts, to_s)
                 t = t_out
                 k += 1
             if k < len(layers) and layers[k][0] == "up":
                 if lib.conv_ok(2 * hh, 2 * ww):
                     up = ops.upsample2x_split(t, B, hh, ww, lo=self.lo)
                     self._gemm(up, f"{q}{k}.conv", f"{q}{k}.conv.b", M=B * 4 * hh * ww, N=cout,
-                               conv=(cout, 2 * hh, 2 * ww), out=dst)
+                               conv=(cout, 2 * hh, 2 * ww), out=dst, gn=dst_s)
                 else:
                     up = ops.resize_nhwc(t, B, hh, ww, 2 * hh, 2 * ww, bilinear=False)
                     self._gemm(ops.im2col3x3_split(up, B, 2 * hh, 2 * ww, lo=self.lo)[0], f"{q}{k}.conv", f"{q}{k}.conv.b",
-                               out=dst)
+                               out=dst, gn=dst_s)
         return taps

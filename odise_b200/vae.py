@@ -90,26 +90,30 @@ class VAEEngine:
     def _gn(self, x, B, HW, name, act, **kw):
         return ops.group_norm(x, B, HW, self.F[name + ".g"], self.F[name + ".be"], 1e-6, act, lo=self.lo, **kw)
 
-    def _res(self, n, x, B, H, W, cin, cout):
+    def _res(self, n, x, B, H, W, cin, cout, xs=None):
+        """ldm ResnetBlock.  xs: GroupNorm records of x left by its producer's epilogue (lib.GnStats) or None;
+        returns (out, records of out)."""
         M = B * H * W
-        _, a1 = self._gn(x, B, H * W, n + "n1", ACT_SILU)
+        _, a1 = self._gn(x, B, H * W, n + "n1", ACT_SILU, stats=xs)
         h = ops.empty(M, cout, self.dev)
-        self._gemm(a1, n + "c1", M=M, N=cout, conv=(cin, H, W), out=h)
-        _, a2 = self._gn(h, B, H * W, n + "n2", ACT_SILU)
+        hs = lib.GnStats(M, cout, self.dev)
+        self._gemm(a1, n + "c1", M=M, N=cout, conv=(cin, H, W), out=h, gn=hs)
+        _, a2 = self._gn(h, B, H * W, n + "n2", ACT_SILU, stats=hs)
         if cin != cout:
             skip = ops.empty(M, cout, self.dev)
             self._gemm(ops.split(x, lo=self.lo), n + "sc", out=skip)
         else:
             skip = x
         out = ops.empty(M, cout, self.dev)
-        self._gemm(a2, n + "c2", M=M, N=cout, conv=(cout, H, W), residual=skip, out=out)
-        return out
+        os_ = lib.GnStats(M, cout, self.dev)
+        self._gemm(a2, n + "c2", M=M, N=cout, conv=(cout, H, W), residual=skip, out=out, gn=os_)
+        return out, os_
 
-    def _attn(self, n, x, B, H, W):
+    def _attn(self, n, x, B, H, W, xs=None):
         """ldm AttnBlock: single head, d = C = 512, softmax(q k^T / sqrt(C)) v, 1x1 projections with bias."""
         T, C = H * W, 512
         M = B * T
-        _, xn = self._gn(x, B, T, n + "n", ACT_NONE)
+        _, xn = self._gn(x, B, T, n + "n", ACT_NONE, stats=xs)
         qk = Planes.empty(M, 2 * C, self.dev, lo=self.lo)
         self._gemm(xn, n + "qk", out_planes=qk)
         vt = Planes.empty(C, M, self.dev, lo=self.lo)
@@ -121,15 +125,17 @@ class VAEEngine:
         o = Planes.empty(M, C, self.dev, lo=self.lo)
         lib.gemm(P, vt, M=T, N=C, K=T, nmma=self.nmma, batch=B, a_bs=T * P.ld, b_bs=T, out_planes=o, outp_bs=T * o.ld)
         out = ops.empty(M, C, self.dev)
-        self._gemm(o, n + "o", residual=x, out=out)
-        return out
+        os_ = lib.GnStats(M, C, self.dev)
+        self._gemm(o, n + "o", residual=x, out=out, gn=os_)
+        return out, os_
 
     @torch.no_grad()
     def encode(self, img, B, H, W):
         """img: NHWC fp32 [B*H*W, 3], already (x - 0.5) / 0.5.  Returns dict(latent, enc5, enc7) of (tensor, h, w)."""
         cols, _, _ = ops.im2col3x3_split(img, B, H, W, lo=self.lo)
         h = ops.empty(B * H * W, 128, self.dev)
-        self._gemm(cols, "e.conv_in", out=h)
+        hs = lib.GnStats(B * H * W, 128, self.dev)
+        self._gemm(cols, "e.conv_in", out=h, gn=hs)
         taps = {}
         ch, cw = H, W
         for idx, (n, cin, cout, lvl) in enumerate(self.enc_blocks):
@@ -137,19 +143,20 @@ class VAEEngine:
                 taps["enc5"] = (h, ch, cw)
             if idx == 7:
                 taps["enc7"] = (h, ch, cw)
-            h = self._res(n, h, B, ch, cw, cin, cout)
+            h, hs = self._res(n, h, B, ch, cw, cin, cout, hs)
             if idx % 2 == 1 and lvl != 3:
                 # ldm Downsample (with_conv): F.pad(x, (0,1,0,1)) then conv3x3 stride 2, no padding
                 # strided implicit GEMM: conv_mode 2 = stride 2 with zero padding on the high side only
                 d = ops.empty(B * (ch // 2) * (cw // 2), cout, self.dev)
+                hs = lib.GnStats(B * (ch // 2) * (cw // 2), cout, self.dev)
                 self._gemm(ops.split(h, lo=self.lo), f"e.d{lvl}.down", M=B * (ch // 2) * (cw // 2), N=cout,
-                           conv=(cout, ch, cw), conv_mode=2, out=d)
+                           conv=(cout, ch, cw), conv_mode=2, out=d, gn=hs)
                 ch, cw = ch // 2, cw // 2
                 h = d
-        h = self._res("e.m1.", h, B, ch, cw, 512, 512)
-        h = self._attn("e.ma.", h, B, ch, cw)
-        h = self._res("e.m2.", h, B, ch, cw, 512, 512)
-        _, a = self._gn(h, B, ch * cw, "e.norm_out", ACT_SILU)
+        h, hs = self._res("e.m1.", h, B, ch, cw, 512, 512, hs)
+        h, hs = self._attn("e.ma.", h, B, ch, cw, hs)
+        h, hs = self._res("e.m2.", h, B, ch, cw, 512, 512, hs)
+        _, a = self._gn(h, B, ch * cw, "e.norm_out", ACT_SILU, stats=hs)
         mom_p = Planes.empty(B * ch * cw, 8, self.dev, lo=self.lo)
         self._gemm(a, "e.conv_out", M=B * ch * cw, N=8, conv=(512, ch, cw), out_planes=mom_p)
         # quant_conv (1x1, 8 -> 8); posterior mean = first 4 channels; latent = 0.18215 * mean (ldm.py:461-465)
@@ -171,18 +178,20 @@ class VAEEngine:
         self._gemm(ops.split(z8, lo=self.lo), "post_quant", out=pq)
         cols, _, _ = ops.im2col3x3_split(pq, B, h, w, lo=self.lo)
         x = ops.empty(B * h * w, 512, self.dev)
-        self._gemm(cols, "d.conv_in", out=x)
-        x = self._res("d.m1.", x, B, h, w, 512, 512)
-        x = self._attn("d.ma.", x, B, h, w)
-        x = self._res("d.m2.", x, B, h, w, 512, 512)
-        x = self._res("d.u3.b0.", x, B, h, w, 512, 512)
-        x = self._res("d.u3.b1.", x, B, h, w, 512, 512)
+        xs = lib.GnStats(B * h * w, 512, self.dev)
+        self._gemm(cols, "d.conv_in", out=x, gn=xs)
+        x, xs = self._res("d.m1.", x, B, h, w, 512, 512, xs)
+        x, xs = self._attn("d.ma.", x, B, h, w, xs)
+        x, xs = self._res("d.m2.", x, B, h, w, 512, 512, xs)
+        x, xs = self._res("d.u3.b0.", x, B, h, w, 512, 512, xs)
+        x, xs = self._res("d.u3.b1.", x, B, h, w, 512, 512, xs)
         taps = {"dec2": (x, h, w)}
-        x = self._res("d.u3.b2.", x, B, h, w, 512, 512)
+        x, xs = self._res("d.u3.b2.", x, B, h, w, 512, 512, xs)
         up = ops.upsample2x_split(x, B, h, w, lo=self.lo)
         y = ops.empty(B * 4 * h * w, 512, self.dev)
-        self._gemm(up, "d.u3.up", M=B * 4 * h * w, N=512, conv=(512, 2 * h, 2 * w), out=y)
-        y = self._res("d.u2.b0.", y, B, 2 * h, 2 * w, 512, 512)
-        y = self._res("d.u2.b1.", y, B, 2 * h, 2 * w, 512, 512)
+        ys = lib.GnStats(B * 4 * h * w, 512, self.dev)
+        self._gemm(up, "d.u3.up", M=B * 4 * h * w, N=512, conv=(512, 2 * h, 2 * w), out=y, gn=ys)
+        y, ys = self._res("d.u2.b0.", y, B, 2 * h, 2 * w, 512, 512, ys)
+        y, _ = self._res("d.u2.b1.", y, B, 2 * h, 2 * w, 512, 512, ys)
         taps["dec5"] = (y, 2 * h, 2 * w)
         return taps

@@ -172,3 +172,77 @@ def test_conv3x3_split_k_with_fused_epilogue(cuda, cfg):
              split_k=sk, force_bn=bn, workspace=lib.workspace(sk * M * Co * 4, cuda))
     assert _rel(out, ref) < 2e-5
     assert lib.auto_split(1024, 1280, 11520) == (160, 2) and lib.auto_split(65536, 320, 2880) == (0, 1)
+
+
+def _gn_ref(x, B, HW, G, eps):
+    xx = x.double().view(B, HW, G, -1).permute(0, 2, 1, 3).reshape(B, G, -1)
+    return xx.mean(-1).reshape(-1), 1.0 / torch.sqrt(xx.var(-1, unbiased=False) + eps).reshape(-1)
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(B=2, HW=1024, N=320, K=320, bn=0, extra=False),       # interior tiles, lean epilogue
+    dict(B=2, HW=1024, N=320, K=320, bn=256, extra=True),      # edge tile in N (320 = 256 + 64), residual + row bias
+    dict(B=4, HW=64, N=1280, K=640, bn=0, extra=True),         # 8x8 maps: a 128-row tile spans two images
+    dict(B=1, HW=4096, N=640, K=128, bn=160, extra=False),
+    dict(B=3, HW=96, N=64, K=64, bn=64, extra=False),          # M = 288: ragged last tile, whole 32-row segments
+])
+def test_gemm_groupnorm_statistics_in_epilogue(cuda, cfg):
+    """desc.gn_partial: the producer half of the fused conv + GroupNorm (ldm ResBlock): per-(32-row segment, channel)
+    records written by the epilogue, merged by odise_groupnorm_finalize_seg_f32 == torch group statistics of the output."""
+    from odise_b200 import lib, ops
+    B, HW, N, K = cfg["B"], cfg["HW"], cfg["N"], cfg["K"]
+    M, G, eps = B * HW, 32, 1e-5
+    g = torch.Generator().manual_seed(N + K + HW)
+    a, b = torch.randn(M, K, generator=g).to(cuda), torch.randn(N, K, generator=g).to(cuda)
+    bias = (torch.randn(N, generator=g) * 30).to(cuda)         # |mean| >> std inside some groups: the shifted sums must hold
+    kw = {}
+    if cfg["extra"]:
+        kw = dict(residual=torch.randn(M, N, generator=g).to(cuda), rowbias=torch.randn(B, N, generator=g).to(cuda),
+                  rows_per_group=HW)
+    out = torch.empty(M, N, device=cuda)
+    st = lib.GnStats(M, N, cuda)
+    lib.gemm(lib.split(a), lib.split(b), bias=bias, out=out, force_bn=cfg["bn"], gn=st, **kw)
+    assert not st.missing
+    gamma, beta = torch.ones(N, device=cuda), torch.zeros(N, device=cuda)
+    y_f, _ = ops.group_norm(out, B, HW, gamma, beta, eps, want_f32=True, want_planes=False, stats=st)
+    y_s, _ = ops.group_norm(out, B, HW, gamma, beta, eps, want_f32=True, want_planes=False)
+    torch.cuda.synchronize()
+    mean, rstd = _gn_ref(out.cpu(), B, HW, G, eps)
+    want = ((out.cpu().double().view(B, HW, G, -1) - mean.view(B, 1, G, 1)) * rstd.view(B, 1, G, 1)).view(M, N)
+    assert _rel(y_f.cpu(), want) < 2e-5 and _rel(y_s.cpu(), want) < 2e-5
+    assert _rel(y_f, y_s) < 1e-5
+
+
+def test_groupnorm_statistics_of_a_concat_and_fallbacks(cuda):
+    """Two producers write disjoint column ranges of one buffer (UNet skip concat, ldm.py:485) and of its records; a
+    split-K producer marks the records missing and group_norm falls back to the stand-alone pass."""
+    from odise_b200 import lib, ops
+    B, HW, C1, C2, K = 2, 256, 640, 320, 256
+    M = B * HW
+    g = torch.Generator().manual_seed(9)
+    a = torch.randn(M, K, generator=g).to(cuda)
+    w1, w2 = torch.randn(C1, K, generator=g).to(cuda), torch.randn(C2, K, generator=g).to(cuda)
+    buf = torch.empty(M, C1 + C2, device=cuda)
+    st = lib.GnStats(M, C1 + C2, cuda)
+    lib.gemm(lib.split(a), lib.split(w1), out=buf[:, :C1], gn=st.cols(0, C1))
+    lib.gemm(lib.split(a), lib.split(w2), out=buf[:, C1:], gn=st.cols(C1, C2))
+    gamma, beta = torch.randn(C1 + C2, generator=g).to(cuda), torch.randn(C1 + C2, generator=g).to(cuda)
+    y_f, _ = ops.group_norm(buf, B, HW, gamma, beta, 1e-6, want_f32=True, want_planes=False, stats=st)
+    want = torch.nn.functional.group_norm(buf.view(B, HW, -1).permute(0, 2, 1).double(), 32, gamma.double(), beta.double(), 1e-6)
+    assert _rel(y_f.view(B, HW, -1).permute(0, 2, 1), want) < 2e-5
+    # a column-slice consumer (the next block reads only the right half)
+    y_r, _ = ops.group_norm(buf[:, C1:], B, HW, gamma[C1:].contiguous(), beta[C1:].contiguous(), 1e-6, want_f32=True,
+                            want_planes=False, stats=st.cols(C1, C2))
+    want_r = torch.nn.functional.group_norm(buf[:, C1:].reshape(B, HW, -1).permute(0, 2, 1).double(), 32, gamma[C1:].double(),
+                                            beta[C1:].double(), 1e-6)
+    assert _rel(y_r.view(B, HW, -1).permute(0, 2, 1), want_r) < 2e-5
+    st2 = lib.GnStats(M, C2, cuda)
+    out2 = torch.empty(M, C2, device=cuda)
+    lib.gemm(lib.split(a), lib.split(w2), out=out2, gn=st2, split_k=2, workspace=lib.workspace(2 * M * C2 * 4, cuda))
+    assert st2.missing
+    y2, _ = ops.group_norm(out2, B, HW, gamma[:C2].contiguous(), beta[:C2].contiguous(), 1e-6, want_f32=True,
+                           want_planes=False, stats=st2)
+    want2 = torch.nn.functional.group_norm(out2.view(B, HW, -1).permute(0, 2, 1).double(), 32, gamma[:C2].double(),
+                                           beta[:C2].double(), 1e-6)
+    assert _rel(y2.view(B, HW, -1).permute(0, 2, 1), want2) < 2e-5
+    assert lib.GnStats(100, 64, cuda).missing                     # ragged rows: no records
