@@ -162,7 +162,11 @@ class BackboneEngine:
             _, a1 = ops.group_norm(t1, B, th * tw, self.F[n + "conv1.g"], self.F[n + "conv1.b"], 1e-5, ACT_RELU, lo=self.lo,
                                    stats=s1)
             t2, s2 = ops.empty(M, 128, self.dev), lib.GnStats(M, 128, self.dev)
-            lib.gemm(a1, self.W[n + "c2"], M=M, N=128, nmma=self.nmma, conv=(128, th, tw), out=t2, gn=s2)
+            if lib.conv_ok(th, tw):
+                lib.gemm(a1, self.W[n + "c2"], M=M, N=128, nmma=self.nmma, conv=(128, th, tw), out=t2, gn=s2)
+            else:     # map widths the implicit-GEMM boxes cannot tile (e.g. 12 = 384 / 32): materialised im2col
+                lib.gemm(ops.im2col3x3_split(a1.float(), B, th, tw, lo=self.lo)[0], self.W[n + "c2"], nmma=self.nmma, out=t2,
+                         gn=s2)
             _, a2 = ops.group_norm(t2, B, th * tw, self.F[n + "conv2.g"], self.F[n + "conv2.b"], 1e-5, ACT_RELU, lo=self.lo,
                                    stats=s2)
             t3, s3 = ops.empty(M, 512, self.dev), lib.GnStats(M, 512, self.dev)

@@ -162,7 +162,8 @@ class HeadEngine:
             starts.append(starts[-1] + h * w)
         pos = [pos_sine(h, w) for h, w in shapes]
         g = dict(S=S, starts=starts)
-        g["pd_pos"] = torch.cat([p + self.pd_level_embed[i][None] for i, p in enumerate(pos)], 0).to(dev)
+        if len(shapes) <= self.pd_level_embed.shape[0]:       # the pixel decoder's own levels (absent for decoder-only use)
+            g["pd_pos"] = torch.cat([p + self.pd_level_embed[i][None] for i, p in enumerate(pos)], 0).to(dev)
         g["dec_kpos"] = torch.cat([p + self.dec_level_embed[i][None] for i, p in enumerate(pos)], 0).to(dev)
         g["dec_lvl"] = torch.cat([self.dec_level_embed[i][None].expand(h * w, -1) for i, (h, w) in enumerate(shapes)], 0).contiguous().to(dev)
         g["ref"] = ref_points(shapes)[None].expand(B, -1, -1, -1).contiguous().to(dev)

@@ -191,10 +191,16 @@ class UNetEngine:
         M = B * T
         if HS is not None:
             Cp = HEADS * HS
-            if a == "attn1":
+            if a == "attn1" and kv_src is xq:
                 qk = Planes.empty(M, 2 * Cp, self.dev, lo=self.lo)
                 self._gemm(xq, t + a + ".qk", out_planes=qk)
                 qP, kP = qk.col_slice(0, Cp), qk.col_slice(Cp, Cp)
+            elif a == "attn1":           # keys / values from the row-padded copy of the tokens (T % 8 != 0)
+                wqk = self.W[t + a + ".qk"]
+                qP = Planes.empty(M, Cp, self.dev, lo=self.lo)
+                lib.gemm(xq, wqk.row_slice(0, Cp), nmma=self.nmma, out_planes=qP)
+                kP = Planes.empty(B * TkS, Cp, self.dev, lo=self.lo)
+                lib.gemm(kv_src, wqk.row_slice(Cp, Cp), nmma=self.nmma, out_planes=kP)
             else:
                 qP = Planes.empty(M, Cp, self.dev, lo=self.lo)
                 self._gemm(xq, t + a + ".q", out_planes=qP)
@@ -235,8 +241,17 @@ class UNetEngine:
         _, xn = ops.group_norm(x, B, T, self.F[q + "norm.g"], self.F[q + "norm.b"], 1e-6, ACT_NONE, lo=self.lo, stats=xs)
         h = ops.empty(M, ch, self.dev)
         self._gemm(xn, q + "proj_in", q + "proj_in.b", out=h)
-        _, n1 = ops.layer_norm(h, self.F[t + "norm1.g"], self.F[t + "norm1.b"], lo=self.lo)
-        o1 = self._attention(t, "attn1", n1, n1, B, T, T, ch)
+        if T % 8 == 0:
+            _, n1 = ops.layer_norm(h, self.F[t + "norm1.g"], self.F[t + "norm1.b"], lo=self.lo)
+            o1 = self._attention(t, "attn1", n1, n1, B, T, T, ch)
+        else:
+            # token counts that are not a multiple of 8 (6 x 6 = 36 at a 48 x 48 latent): the key / value planes carry
+            # TkS = ceil8(T) rows per image (zero rows, masked as keys) so the attention kernel's TMA box starts stay aligned
+            TkS = (T + 7) // 8 * 8
+            y1, n1 = ops.layer_norm(h, self.F[t + "norm1.g"], self.F[t + "norm1.b"], lo=self.lo, want_f32=True)
+            kvp = torch.zeros(B, TkS * ch, dtype=torch.float32, device=self.dev)
+            ops.copy2d(y1.view(B, T * ch), kvp[:, :T * ch])
+            o1 = self._attention(t, "attn1", n1, ops.split(kvp.view(B * TkS, ch), lo=self.lo), B, T, T, ch, TkS=TkS)
         h2 = ops.empty(M, ch, self.dev)
         self._gemm(o1, t + "attn1.out", t + "attn1.out.b", residual=h, out=h2)
         _, n2 = ops.layer_norm(h2, self.F[t + "norm2.g"], self.F[t + "norm2.b"], lo=self.lo)

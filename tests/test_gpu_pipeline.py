@@ -229,8 +229,8 @@ def test_full_size_batch4_1024_paste(cuda, world):
         assert _rel(got[k][2:3], w_) < 1e-3, (k, _rel(got[k][2:3], w_))
     one = eng.backbone.forward(1, 1024, 1024, images_u8=imgs[1:2].to(cuda))
     torch.cuda.synchronize()
-    for k, (t, h, w) in one.items():
-        assert _rel(got[k][1:2], _nchw(t, h, w)) < 1e-5, k
+    for k, (t, h, w) in one.items():           # same arithmetic up to the tile / split-K choices that depend on the batch rows
+        assert _rel(got[k][1:2], _nchw(t, h, w)) < 1e-4, k
 
 
 @torch.no_grad()
