@@ -42,6 +42,24 @@ if which in ("conv", "vaeconv"):
     ms = timeit(fn)
     fl = 2.0 * B * H * H * Co * 9 * C
     print(f"{which}: {ms*1000:.1f} us, {fl/ms/1e9:.1f} TFLOP/s algorithmic (bf16x3), {3*fl/ms/1e9:.1f} MMA-TFLOP/s")
+elif which == "convgn":
+    # the same ResBlock conv with the GroupNorm records of its output written by the epilogue (desc.gn_partial),
+    # followed by the record merge + apply + SiLU + split of the consumer (no statistics pass over the activation)
+    B, H, C, Co = 16, 64, 320, 320
+    x = lib.split(torch.randn(B * H * H, C, device=dev))
+    w = lib.split(torch.randn(Co, 9 * C, device=dev) * 0.02)
+    bias, emb = torch.randn(Co, device=dev), torch.randn(B, Co, device=dev)
+    res, out = torch.randn(B * H * H, Co, device=dev), torch.empty(B * H * H, Co, device=dev)
+    st = lib.GnStats(B * H * H, Co, dev)
+    ga, be = torch.randn(Co, device=dev), torch.randn(Co, device=dev)
+    f1 = lambda: lib.gemm(x, w, M=B * H * H, N=Co, conv=(C, H, H), bias=bias, rowbias=emb, rows_per_group=H * H,
+                          residual=res, out=out, gn=st)
+    f0 = lambda: lib.gemm(x, w, M=B * H * H, N=Co, conv=(C, H, H), bias=bias, rowbias=emb, rows_per_group=H * H,
+                          residual=res, out=out)
+    g1 = lambda: ops.group_norm(out, B, H * H, ga, be, 1e-5, act=2, stats=st)
+    g0 = lambda: ops.group_norm(out, B, H * H, ga, be, 1e-5, act=2)
+    print(f"convgn: conv {timeit(f0)*1000:.1f} us -> with records {timeit(f1)*1000:.1f} us; gn(stats pass + apply) "
+          f"{timeit(g0)*1000:.1f} us -> gn(record merge + apply) {timeit(g1)*1000:.1f} us")
 elif which == "gnapply":
     B, HW, C = 16, 4096, 320
     x = torch.randn(B * HW, C, device=dev)
