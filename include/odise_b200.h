@@ -97,6 +97,8 @@ typedef struct odise_gemm_desc {
                                         {0,1,2} * gn_plane_stride + n], seg = (z*M + m) / 32.  Needs M % 32 == 0, split_k <= 1.
                                         Merged per (image, group) by odise_groupnorm_finalize_seg_f32. */
   long long gn_seg_stride; long long gn_plane_stride;
+  int out_planes_fp16;               /* 1: out_hi / out_lo are written as fp16 (hi = fp16(v), lo = fp16(v - hi)) instead of
+                                        bf16: the V^T operand of odise_attention_tc in the bf16x3 mode */
 } odise_gemm_desc;
 int odise_gemm_bf16(const odise_gemm_desc* desc, void* stream);
 /* optional per-launch timing of odise_gemm_bf16 (CUDA events on the launch stream; not for use under graph capture):
@@ -111,6 +113,9 @@ int odise_profile_end(long long* launches, double* total_ms, double* total_flops
 /* fp32 -> (hi, lo); rows x cols with leading dims (elements). out_lo may be NULL. */
 int odise_split_f32(const float* x, long long ldx, void* hi, void* lo, long long ldo, long long rows, int cols,
                     void* stream);
+/* the same split into an fp16 pair (V^T of odise_attention_tc when it does not come out of a GEMM epilogue) */
+int odise_split_f16_f32(const float* x, long long ldx, void* hi, void* lo, long long ldo, long long rows, int cols,
+                        void* stream);
 /* GroupNorm statistics over NHWC x[B, HW, C] (pixel stride ldx): mean/rstd [B, G].
  * (torch.nn.GroupNorm in ldm ResBlock / SpatialTransformer / d2 BottleneckBlock / M2F input_proj) */
 int odise_groupnorm_stats_f32(const float* x, long long ldx, float* mean, float* rstd, int B, int HW, int C, int G,
@@ -220,7 +225,10 @@ int odise_nhwc_to_nchw_f32(const float* src, long long lds, float* dst, int B, i
  * GEMM writes it directly by swapping its operands).  tk_stride >= Tk is the per-image row count of the key /
  * value planes (multiple of 8: TMA box starts must be 16-byte aligned); keys t >= Tk are masked out.  d % 8 == 0 and
  * d <= 80, or d == 160 (other head sizes: odise_gemm_bf16 + odise_softmax_split_f32, e.g. the VAE mid block's d = 512).
- * out fp32 and/or (hi, lo) planes, UNPADDED [B*Tq, heads*d] with row stride ldo.
+ * nmma = 3: q, k are bf16 (hi, lo) planes, vt is an **fp16** (hi, lo) pair (odise_gemm_desc.out_planes_fp16 /
+ * odise_split_f16_f32): S = Q K^T runs hi*hi + hi*lo + lo*hi, the probabilities are rounded once to fp16 and
+ * O = P16 V_hi + P16 V_lo (tcgen05 kind::f16 needs A and B of one 16-bit type).  nmma = 1: bf16 hi planes only.
+ * out fp32 and/or (hi, lo) bf16 planes, UNPADDED [B*Tq, heads*d] with row stride ldo.
  * mask_bits / row_any (optional, from odise_attn_mask_bits_f32): the Mask2Former decoder's masked cross-attention
  * (d = 32) on the same tensor-core kernel — key k of row (b, t) is dropped when its bit is 0 and row_any != 0. */
 int odise_attention_tc(const void* q_hi, const void* q_lo, long long ldq, const void* k_hi, const void* k_lo,

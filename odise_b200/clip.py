@@ -47,7 +47,7 @@ class _ResBlocks:
             _, y = ops.layer_norm(h, self.F[n + "ln_1.g"], self.F[n + "ln_1.b"], lo=self.lo)
             qk = Planes.empty(M, 2 * Wd, dev, lo=self.lo)
             self._gemm(y, n + "qk", out_planes=qk)
-            vt = Planes.empty(Wd, M, dev, lo=self.lo)
+            vt = Planes.empty(Wd, M, dev, lo=self.lo, f16=self.lo)
             lib.gemm(self.W[n + "v"], y, nmma=self.nmma, bias_m=self.F[n + "v.b"], out_planes=vt)
             _, o = ops.attention_tc(qk.col_slice(0, Wd), qk.col_slice(Wd, Wd), vt, B, self.heads, d, TS, Tk, d ** -0.5,
                                     self.nmma, tk_stride=TS, mask_bits=bits, row_any=row_any)

@@ -11,7 +11,7 @@
 // Operands are head-padded planes: head h occupies columns [h*HS, h*HS + DP) of q / k and rows of v^T with
 // HS = 64 (d=40, DP=48) or 128 (d=80, DP=80); pad columns are zeros (produced by zero weight rows in the
 // projection GEMM).  bf16x3: S = Q K^T uses hi*hi + hi*lo + lo*hi (the logits are exponentiated); O = P V uses
-// P16 * V_hi + P16 * V_lo with P rounded once to fp16 (p in [0, 1]: 2^-12 relative, random sign, averaged over the keys;
+// P16 * V_hi + P16 * V_lo with V^T given as fp16 (hi, lo) planes (odise_gemm_desc.out_planes_fp16) and P rounded once to fp16 (p in [0, 1]: 2^-12 relative, random sign, averaged over the keys;
 // measured 9e-5 on the UNet taps by tools/precision_budget.py, bar 1e-3) — one F2FP per pair of probabilities instead of
 // the six-instruction (hi, lo) bf16 split, half the shared-memory stores, two PV MMAs instead of three.
 #include "ptx.cuh"
@@ -153,7 +153,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__
     if (lane == 0) {
       // ---------------------------------------------------------------- MMA issuer
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64);
-      constexpr uint32_t idesc_o = (NMMA == 3) ? umma_idesc_f16a_bf16b(128, DP) : umma_idesc_bf16(128, DP);
+      constexpr uint32_t idesc_o = (NMMA == 3) ? umma_idesc_f16(128, DP) : umma_idesc_bf16(128, DP);
       constexpr int KS = QK / 16;
       auto issue_s = [&](int j) {
         const int st = j & 1;                      // S buffer in TMEM

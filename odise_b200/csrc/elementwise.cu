@@ -928,6 +928,28 @@ extern "C" int odise_set_carveout_policy(int prefer_shared) {
   return (int)cudaDeviceSetCacheConfig(prefer_shared ? cudaFuncCachePreferShared : cudaFuncCachePreferNone);
 }
 
+__global__ void split_f16_kernel(const float* __restrict__ x, long long ldx, uint16_t* __restrict__ hi,
+                                 uint16_t* __restrict__ lo, long long ldo, long long rows, int cols) {
+  const long long total = rows * cols;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / cols;
+    const int c = (int)(i - r * cols);
+    uint16_t h, l;
+    split_f16(x[r * ldx + c], h, l);
+    hi[r * ldo + c] = h;
+    if (lo) lo[r * ldo + c] = l;
+  }
+}
+
+extern "C" int odise_split_f16_f32(const float* x, long long ldx, void* hi, void* lo, long long ldo, long long rows,
+                                   int cols, void* stream) {
+  if (!x || !hi || rows <= 0 || cols <= 0) return ODISE_ERR_ARG;
+  split_f16_kernel<<<grid_for(rows * cols, 256), 256, 0, STREAM(stream)>>>(x, ldx, reinterpret_cast<uint16_t*>(hi),
+                                                                        reinterpret_cast<uint16_t*>(lo), ldo, rows, cols);
+  count_launch(1);
+  return (int)cudaGetLastError();
+}
+
 extern "C" int odise_split_f32(const float* x, long long ldx, void* hi, void* lo, long long ldo, long long rows,
                                int cols, void* stream) {
   return odise_add_split_f32(x, ldx, nullptr, 0, 0, nullptr, 0, hi, lo, ldo, rows, cols, stream);

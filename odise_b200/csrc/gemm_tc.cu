@@ -48,6 +48,7 @@ struct GemmParams {
   int act;
   int geglu;   // N = 2*Nh with quad-interleaved (a, gate) columns: out[:, j] = a_j * gelu(g_j) -> planes [M, Nh]
   int vec_ok;  // all epilogue pointers / leading dims allow 16-byte vector access
+  int h16;     // (hi, lo) output planes as fp16 instead of bf16 (V^T operand of the attention kernel)
   float* partial;  // [splits][batch][M][N] when splits > 1
   // GroupNorm statistics of the OUTPUT, fused into the epilogue (the consumer's torch.nn.GroupNorm, ldm ResBlock
   // in_layers[0] / out_layers[0], call sites ldm.py:481-489): per (32-row segment, column) a record (shift, S1, S2) with
@@ -188,7 +189,10 @@ __device__ __forceinline__ void epilogue_quad(const GemmParams& p, int z, int m,
     __align__(8) __nv_bfloat16 h[4];
     __align__(8) __nv_bfloat16 l[4];
 #pragma unroll
-    for (int t = 0; t < 4; ++t) split_bf16(acc[t], h[t], l[t]);
+    for (int t = 0; t < 4; ++t) {
+      if (p.h16) split_f16(acc[t], *reinterpret_cast<uint16_t*>(&h[t]), *reinterpret_cast<uint16_t*>(&l[t]));
+      else split_bf16(acc[t], h[t], l[t]);
+    }
     if (vec) {
       *reinterpret_cast<uint2*>(dh) = *reinterpret_cast<const uint2*>(h);
       if (dl) *reinterpret_cast<uint2*>(dl) = *reinterpret_cast<const uint2*>(l);
@@ -483,7 +487,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
             if (has_res) { e[0] += r4[it].x; e[1] += r4[it].y; e[2] += r4[it].z; e[3] += r4[it].w; }
             if (has_gn) gn_acc_rows(gacc, e, it == 0, lane);
             if (to_f32) *reinterpret_cast<float4*>(p.D + oD[it] + c0) = make_float4(e[0], e[1], e[2], e[3]);
-            if (to_hi) {
+            if (to_hi && p.h16) {
+              // fp16 (hi, lo) planes: the V^T operand of the attention kernel's P V product
+              const __half2 h01 = __floats2half2_rn(e[0], e[1]), h23 = __floats2half2_rn(e[2], e[3]);
+              uint2 hv;
+              hv.x = *reinterpret_cast<const uint32_t*>(&h01);
+              hv.y = *reinterpret_cast<const uint32_t*>(&h23);
+              *reinterpret_cast<uint2*>(p.Dh + oH[it] + c0) = hv;
+              if (to_lo) {
+                const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+                const __half2 l01 = __floats2half2_rn(e[0] - f01.x, e[1] - f01.y);
+                const __half2 l23 = __floats2half2_rn(e[2] - f23.x, e[3] - f23.y);
+                uint2 lv;
+                lv.x = *reinterpret_cast<const uint32_t*>(&l01);
+                lv.y = *reinterpret_cast<const uint32_t*>(&l23);
+                *reinterpret_cast<uint2*>(p.Dl + oH[it] + c0) = lv;
+              }
+            } else if (to_hi) {
               // packed conversions: hi = bf16x2(e), lo = bf16x2(e - float(hi))  (same values as split_bf16)
               const __nv_bfloat162 h01 = __floats2bfloat162_rn(e[0], e[1]), h23 = __floats2bfloat162_rn(e[2], e[3]);
               uint2 hv;
@@ -724,6 +744,8 @@ extern "C" int odise_gemm_bf16(const odise_gemm_desc* d, void* stream_v) {
   p.ldh = d->ld_out_bf16; p.h_bs = d->out_bf16_batch_stride;
   p.act = d->act;
   p.geglu = d->geglu;
+  p.h16 = d->out_planes_fp16 ? 1 : 0;
+  if (p.h16 && (d->geglu || !d->out_hi)) return ODISE_ERR_UNSUPPORTED;
   if (d->gn_partial) {
     // whole 32-row segments, final values produced by this kernel (no split-K second pass, no GEGLU re-pairing)
     if (d->M % 32 || d->split_k > 1 || d->geglu || d->gn_seg_stride <= 0 || d->gn_plane_stride <= 0)

@@ -5,6 +5,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 
@@ -158,16 +159,25 @@ __device__ __forceinline__ uint32_t sw128_offset(uint32_t r, uint32_t chunk16) {
   return r * 128u + ((chunk16 ^ (r & 7u)) << 4);
 }
 
-// same with an fp16 A operand and a bf16 B operand (kind::f16 takes the two formats independently: a_format bits [7,10)
-// = 0 F16 / 1 BF16, b_format bits [10,13)): the attention kernel's P (fp16, one plane) x V (bf16 hi / lo planes)
-__host__ __device__ constexpr uint32_t umma_idesc_f16a_bf16b(uint32_t m, uint32_t n) {
-  return (1u << 4) | (0u << 7) | (1u << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
+// fp16 x fp16 -> fp32 (a_format bits [7,10) = 0, b_format bits [10,13) = 0).  kind::f16 wants A and B of the SAME 16-bit
+// type: a mixed fp16 x bf16 descriptor raises an illegal-instruction fault on B200 (found on hardware, round 2) — the
+// attention kernel's P (fp16, one plane) therefore multiplies V planes that the projection GEMM emits as fp16 (hi, lo).
+__host__ __device__ constexpr uint32_t umma_idesc_f16(uint32_t m, uint32_t n) {
+  return (1u << 4) | ((n >> 3) << 17) | ((m >> 4) << 24);
 }
 
 // fp32 -> (hi, lo) bf16 pair with hi + lo ~= x to ~16 mantissa bits (the "bf16x3" operand split)
 __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
   hi = __float2bfloat16_rn(x);
   lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+
+// the same split into an fp16 pair (11 + 11 mantissa bits; operands of the attention P V product)
+__device__ __forceinline__ void split_f16(float x, uint16_t& hi, uint16_t& lo) {
+  const __half h = __float2half_rn(x);
+  const __half l = __float2half_rn(x - __half2float(h));
+  hi = __half_as_ushort(h);
+  lo = __half_as_ushort(l);
 }
 
 }  // namespace ob

@@ -330,7 +330,7 @@ class HeadEngine:
             lib.gemm(kin_p.row_slice(starts[lvl], hw), self.W[f"dec.k{lvl}"], M=hw, N=nk * CP, K=256, nmma=self.nmma,
                      batch=B, a_bs=S * kin_p.ld, bias=self.F[f"dec.k{lvl}.b"], out_planes=k, outp_bs=hw * k.ld)
             # V^T [nk*CP, B*hw]: swapped operands, image z lands at column offset z*hw
-            vt = Planes.empty(nk * CP, B * hw, dev, lo=self.lo)
+            vt = Planes.empty(nk * CP, B * hw, dev, lo=self.lo, f16=self.lo)
             lib.gemm(self.W[f"dec.v{lvl}"], vin_p.row_slice(starts[lvl], hw), M=nk * CP, N=hw, K=256, nmma=self.nmma,
                      batch=B, b_bs=S * vin_p.ld, bias_m=self.F[f"dec.v{lvl}.b"], out_planes=vt, outp_bs=hw)
             K.append(k)

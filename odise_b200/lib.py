@@ -39,6 +39,7 @@ class GemmDesc(ctypes.Structure):
         ("conv_mode", c_int),
         ("geglu", c_int),
         ("gn_partial", c_void_p), ("gn_seg_stride", c_longlong), ("gn_plane_stride", c_longlong),
+        ("out_planes_fp16", c_int),
     ]
 
 
@@ -52,6 +53,7 @@ _SIGS = {
     "odise_profile_begin": [],
     "odise_profile_end": [c_void_p, c_void_p, c_void_p],
     "odise_split_f32": [c_void_p, c_longlong, c_void_p, c_void_p, c_longlong, c_longlong, c_int, c_void_p],
+    "odise_split_f16_f32": [c_void_p, c_longlong, c_void_p, c_void_p, c_longlong, c_longlong, c_int, c_void_p],
     "odise_groupnorm_stats_f32": [c_void_p, c_longlong, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float,
                                   c_void_p],
     "odise_groupnorm_apply_f32": [c_void_p, c_longlong, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
@@ -185,13 +187,14 @@ class PostprocessGeom(ctypes.Structure):
 class Planes:
     """(hi, lo) bf16 operand planes of a 2-D fp32 matrix [rows, cols] (row stride ld elements)."""
 
-    __slots__ = ("hi", "lo", "rows", "cols", "ld")
+    __slots__ = ("hi", "lo", "rows", "cols", "ld", "f16")
 
-    def __init__(self, hi, lo, rows, cols, ld):
+    def __init__(self, hi, lo, rows, cols, ld, f16=False):
         self.hi, self.lo, self.rows, self.cols, self.ld = hi, lo, rows, cols, ld
+        self.f16 = f16          # the 16-bit words are fp16, not bf16 (V^T operand of the attention kernel, bf16x3 mode)
 
     @staticmethod
-    def empty(rows, cols, device, lo=True, ld=None):
+    def empty(rows, cols, device, lo=True, ld=None, f16=False):
         ld = ld or ((cols + 7) // 8 * 8)
         hi = torch.empty(rows * ld, dtype=torch.bfloat16, device=device)
         lo_t = torch.empty(rows * ld, dtype=torch.bfloat16, device=device) if lo else None
@@ -199,22 +202,23 @@ class Planes:
             hi.zero_()
             if lo_t is not None:
                 lo_t.zero_()
-        return Planes(hi, lo_t, rows, cols, ld)
+        return Planes(hi, lo_t, rows, cols, ld, f16)
 
     def float(self):
-        h = self.hi.view(self.rows, self.ld)[:, : self.cols].float()
+        vw = (lambda t: t.view(torch.float16)) if self.f16 else (lambda t: t)
+        h = vw(self.hi).view(self.rows, self.ld)[:, : self.cols].float()
         if self.lo is not None:
-            h = h + self.lo.view(self.rows, self.ld)[:, : self.cols].float()
+            h = h + vw(self.lo).view(self.rows, self.ld)[:, : self.cols].float()
         return h
 
     def col_slice(self, c0, cols):
         """Planes viewing columns [c0, c0+cols) of every row (same ld); c0 % 8 == 0."""
         assert c0 % 8 == 0
-        return Planes(self.hi[c0:], None if self.lo is None else self.lo[c0:], self.rows, cols, self.ld)
+        return Planes(self.hi[c0:], None if self.lo is None else self.lo[c0:], self.rows, cols, self.ld, self.f16)
 
     def row_slice(self, r0, rows):
         return Planes(self.hi[r0 * self.ld:], None if self.lo is None else self.lo[r0 * self.ld:], rows, self.cols,
-                      self.ld)
+                      self.ld, self.f16)
 
 
 class GnStats:
@@ -251,16 +255,16 @@ class GnStats:
         return self.t.data_ptr() + 4 * self.col
 
 
-def split(x, out=None, lo=True):
-    """fp32 [rows, cols] (last dim contiguous) -> Planes."""
+def split(x, out=None, lo=True, f16=False):
+    """fp32 [rows, cols] (last dim contiguous) -> Planes (bf16 pair; f16=True: fp16 pair)."""
     _req(x, torch.float32, "x")
     x2 = x.reshape(-1, x.shape[-1])
     rows, cols = x2.shape
     assert x2.stride(1) == 1
     if out is None:
-        out = Planes.empty(rows, cols, x.device, lo=lo)
-    _check(load().odise_split_f32(_ptr(x2), x2.stride(0), _ptr(out.hi), _ptr(out.lo), out.ld, rows, cols, _stream()),
-           "odise_split_f32")
+        out = Planes.empty(rows, cols, x.device, lo=lo, f16=f16)
+    fn = load().odise_split_f16_f32 if out.f16 else load().odise_split_f32
+    _check(fn(_ptr(x2), x2.stride(0), _ptr(out.hi), _ptr(out.lo), out.ld, rows, cols, _stream()), "odise_split_f32")
     return out
 
 
@@ -324,6 +328,8 @@ def gemm(a, b, *, M=None, N=None, K=None, nmma=3, batch=1, a_bs=0, b_bs=0, conv=
     d.nmma = nmma
     if conv:
         d.conv3x3, d.conv_C, d.conv_H, d.conv_W = 1, conv[0], conv[1], conv[2]
+    if a.f16 or b.f16:
+        raise OdiseError("gemm: fp16 planes are attention-kernel operands (V^T), not GEMM inputs")
     d.a_hi, d.a_lo, d.lda, d.a_batch_stride = _ptr(a.hi), _ptr(a.lo), a.ld, a_bs
     d.b_hi, d.b_lo, d.ldb, d.b_batch_stride = _ptr(b.hi), _ptr(b.lo), b.ld, b_bs
     d.alpha = alpha
@@ -343,6 +349,7 @@ def gemm(a, b, *, M=None, N=None, K=None, nmma=3, batch=1, a_bs=0, b_bs=0, conv=
     if out_planes is not None:
         d.out_hi, d.out_lo, d.ld_out_bf16 = _ptr(out_planes.hi), _ptr(out_planes.lo), out_planes.ld
         d.out_bf16_batch_stride = outp_bs
+        d.out_planes_fp16 = 1 if out_planes.f16 else 0
     d.split_k = split_k
     if split_k > 1:
         need = split_k * batch * d.M * d.N * 4

@@ -148,6 +148,9 @@ def attention_tc(q, k, vt, B, heads, d, Tq, Tk, scale, nmma, want_f32=False, wan
     """q, k head-padded Planes; vt Planes [heads*HS, >= B*Tk]. Returns (fp32 | None, Planes | None) [B*Tq, heads*d]."""
     dev = q.hi.device
     C = heads * d
+    if vt.f16 != (nmma == 3):
+        raise lib.OdiseError("attention_tc: vt must be fp16 planes in the bf16x3 mode (Planes.empty(..., f16=True) / "
+                             "lib.split(..., f16=True)) and bf16 planes in the plain bf16 mode")
     out = empty(B * Tq, C, dev) if want_f32 else None
     p = Planes.empty(B * Tq, C, dev, lo=(nmma == 3)) if want_planes else None
     _check(load().odise_attention_tc(_ptr(q.hi), _ptr(q.lo), q.ld, _ptr(k.hi), _ptr(k.lo), k.ld, _ptr(vt.hi),

@@ -206,7 +206,7 @@ class UNetEngine:
                 self._gemm(xq, t + a + ".q", out_planes=qP)
                 kP = Planes.empty(B * TkS, Cp, self.dev, lo=self.lo)
                 self._gemm(kv_src, t + a + ".k", out_planes=kP)
-            vt = Planes.empty(Cp, B * TkS, self.dev, lo=self.lo)
+            vt = Planes.empty(Cp, B * TkS, self.dev, lo=self.lo, f16=self.lo)   # fp16 pair in the bf16x3 mode
             # V^T = Wv_pad @ X^T: the same K-major GEMM with the operands swapped
             lib.gemm(self.W[t + a + ".v"], kv_src, nmma=self.nmma, out_planes=vt)
             _, o = ops.attention_tc(qP, kP, vt, B, HEADS, d, T, Tk, scale, self.nmma, tk_stride=TkS)

@@ -32,7 +32,7 @@ def test_attention_tc(cuda, nmma, cfg):
     vt[:, :d, :, :Tk] = v.permute(2, 3, 0, 1)
     vt[:, :, :, Tk:] = 5.0
     qP, kP = lib.split(qp.view(B * Tq, heads * HS)), lib.split(kp.view(B * TkS, heads * HS))
-    vP = lib.split(vt.view(heads * HS, B * TkS))
+    vP = lib.split(vt.view(heads * HS, B * TkS), f16=nmma == 3)
     scale = d ** -0.5
     out, outp = ops.attention_tc(qP, kP, vP, B, heads, d, Tq, Tk, scale, nmma, want_f32=True, want_planes=True,
                                  tk_stride=TkS)
@@ -78,7 +78,7 @@ def test_masked_attention_tc_d32(cuda, nmma, cfg):
     vt = torch.zeros(heads, HS, B * Tk, device=cuda)
     vt[:, :d] = v.view(B * Tk, heads, d).permute(1, 2, 0)
     scale = d ** -0.5
-    out, _ = ops.attention_tc(lib.split(qp.view(B * Tq, -1)), lib.split(kp.view(B * Tk, -1)), lib.split(vt.view(heads * HS, -1)),
+    out, _ = ops.attention_tc(lib.split(qp.view(B * Tq, -1)), lib.split(kp.view(B * Tk, -1)), lib.split(vt.view(heads * HS, -1), f16=nmma == 3),
                               B, heads, d, Tq, Tk, scale, nmma, want_f32=True, want_planes=False, tk_stride=Tk,
                               mask_bits=bits, row_any=row_any)
     torch.cuda.synchronize()

@@ -73,7 +73,7 @@ elif which == "attn":
     HS = 64
     q = lib.split(torch.randn(B * T, heads * HS, device=dev))
     k = lib.split(torch.randn(B * T, heads * HS, device=dev))
-    vt = lib.split(torch.randn(heads * HS, B * T, device=dev))
+    vt = lib.split(torch.randn(heads * HS, B * T, device=dev), f16=True)
     fn = lambda: ops.attention_tc(q, k, vt, B, heads, d, T, T, d ** -0.5, 3)
     ms = timeit(fn, 5)
     fl = 4.0 * B * heads * T * T * d
@@ -118,7 +118,7 @@ elif which == "clipattn":
     # CLIP ViT-L/14-336 self-attention of 16 crops: 16 heads x d=64, 577 tokens (584 rows per image)
     B, heads, d, T, TS = 16, 16, 64, 577, 584
     qk = lib.split(torch.randn(B * TS, 2 * heads * d, device=dev))
-    vt = lib.split(torch.randn(heads * d, B * TS, device=dev))
+    vt = lib.split(torch.randn(heads * d, B * TS, device=dev), f16=True)
     fn = lambda: ops.attention_tc(qk.col_slice(0, heads * d), qk.col_slice(heads * d, heads * d), vt, B, heads, d, TS, T,
                                   d ** -0.5, 3, tk_stride=TS)
     ms = timeit(fn, 5)
