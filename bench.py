@@ -287,10 +287,11 @@ def run_c4(args, dev):
 
         reps = 20 if Lq == S else 200
         t_abi, t_fused = _time_ms(ours_abi, reps), _time_ms(ours_fused, reps)
-        # compulsory bytes: value once + loc / attn (3 floats per sample) + output, fp32
-        nbytes = 4.0 * N * (S * M * D + Lq * M * L * P * 3 + Lq * M * D)
         # what the gathers move through L1: 4 corners x 128 B per (query, head, sample)
         l1_bytes = 128.0 * 4 * N * Lq * M * L * P
+        # compulsory bytes: value once (at most what the samples can touch) + loc / attn (3 floats per
+        # sample) + output, fp32
+        nbytes = min(4.0 * N * S * M * D, l1_bytes) + 4.0 * N * (Lq * M * L * P * 3 + Lq * M * D)
         r = dict(Lq=Lq, compulsory_mb=nbytes / 1e6, ours_abi_us=1e3 * t_abi, ours_fused_us=1e3 * t_fused,
                  ours_abi_gbs=nbytes / t_abi / 1e6, ours_fused_gbs=nbytes / t_fused / 1e6,
                  frac_of_hbm_peak=nbytes / t_abi / 1e6 / pk["hbm"], gather_l1_tbs=l1_bytes / t_abi / 1e9)

@@ -19,3 +19,17 @@ def cuda():
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="session")
+def record():
+    """Parity numbers worth quoting are appended to gpurun_out/parity_numbers.txt when that directory
+    exists (GPU box runs); a no-op elsewhere."""
+    path = os.path.join(ROOT, "gpurun_out", "parity_numbers.txt")
+
+    def rec(line):
+        print(line)
+        if os.path.isdir(os.path.dirname(path)):
+            with open(path, "a") as f:
+                f.write(line + "\n")
+    return rec

@@ -1,5 +1,9 @@
 """GPU parity of the fused tcgen05 flash attention (odise_attention_tc) vs fp64 softmax attention.
-Shapes are the SD-v1 UNet ones: self-attention d=40 / d=80, cross-attention over 77 context tokens."""
+Shapes are the SD-v1 UNet ones: self-attention d=40 / d=80 / d=160, cross-attention over 77 context tokens.
+Tolerance in the bf16x3 mode: the probabilities enter the P V product rounded ONCE to fp16 (2^-12 relative per element,
+random sign -> ~1.5e-4 of the output scale on random data); the budget behind that choice is tools/precision_budget.py
+(5e-5 on the UNet taps, bar 1e-3).  S = Q K^T stays bf16x3 (2^-16)."""
+TOL3 = 3e-4
 import pytest
 import torch
 
@@ -39,7 +43,7 @@ def test_attention_tc(cuda, nmma, cfg):
     torch.cuda.synchronize()
     s = torch.einsum("bqhd,bkhd->bhqk", q.double(), k.double()) * scale
     ref = torch.einsum("bhqk,bkhd->bqhd", s.softmax(-1), v.double()).reshape(B * Tq, heads * d)
-    tol = 3e-5 if nmma == 3 else 3e-2
+    tol = TOL3 if nmma == 3 else 3e-2
     assert _rel(out, ref) < tol
     assert _rel(outp.float(), ref) < tol + 1e-2 * (nmma == 1)
 
@@ -87,4 +91,4 @@ def test_masked_attention_tc_d32(cuda, nmma, cfg):
     s = torch.einsum("bqhd,bkhd->bhqk", q.double(), k.double()) * scale
     s = s.masked_fill(am[:, None], float("-inf"))
     ref = torch.einsum("bhqk,bkhd->bqhd", s.softmax(-1), v.double()).reshape(B * Tq, heads * d)
-    assert _rel(out, ref) < (3e-5 if nmma == 3 else 3e-2)
+    assert _rel(out, ref) < (TOL3 if nmma == 3 else 3e-2)

@@ -169,7 +169,7 @@ UNCOND17 = lambda: torch.randn(1, 77, 768, generator=torch.Generator().manual_se
 
 
 @torch.no_grad()
-def test_c1_end_to_end_mask_logits_and_class_scores(cuda, world):
+def test_c1_end_to_end_mask_logits_and_class_scores(cuda, world, record):
     """BASELINE.json configs[0] / BASELINE.md §4 as stated: ONE 512 x 512 image, Q = 100, 20-class vocabulary; FINAL mask
     logits and FINAL class scores of the whole pipeline vs the composed oracle within 1e-3 (max |a-b| / max |b|, one global
     norm per tensor).  The three hard thresholds of the path (attention mask sigmoid < 0.5, odise.py:772; MaskPooling mask > 0,
@@ -205,14 +205,14 @@ def test_c1_end_to_end_mask_logits_and_class_scores(cuda, world):
     out = eng.step(1, 512, 512, images_u8=dimg)
     flips = [((h["pred_masks"].view_as(r).cpu() > 0) != (r > 0)).float().mean().item()
              for h, r in zip(out["aux"] + [dict(pred_masks=out["pred_masks"])], ref_masks)]
-    print(f"C1 end to end: final mask logits rel {e_mask:.2e}, category scores rel {e_cat:.2e}, merged class scores rel "
-          f"{e_cls:.2e}; un-forced sign flips per head {['%.1e' % f for f in flips]}")
+    record(f"C1 end to end (512^2, Q=100, 20 classes): final mask logits rel {e_mask:.2e}, category scores rel {e_cat:.2e}, "
+           f"merged class scores rel {e_cls:.2e}; un-forced sign flips per head {['%.1e' % f for f in flips]}")
     assert e_mask < 1e-3 and e_cat < 1e-3 and e_cls < 1e-3, (e_mask, e_cat, e_cls)
     assert max(flips) < 1e-2
 
 
 @torch.no_grad()
-def test_full_size_batch4_1024_paste(cuda, world):
+def test_full_size_batch4_1024_paste(cuda, world, record):
     """B = 4 x 1024^2 (BASELINE.json configs[1] shape): the real 4-crop paste with real VAE / CLIP / UNet taps.  The
     oracle runs ONE of the four images (4 crops on the host cores); the other three are checked against the engine's own
     single-image result (batch composition must not change an image's features)."""
@@ -224,6 +224,7 @@ def test_full_size_batch4_1024_paste(cuda, world):
     torch.cuda.synchronize()
     got = {k: _nchw(t, h, w) for k, (t, h, w) in got.items()}
     want = compose.slide_forward(sd, compose.load_modules(sd), imgs[2:3].float() / 255.0, UNCOND17())
+    record("B=4 x 1024^2 backbone vs oracle (image 2): " + ", ".join(f"{k} {_rel(got[k][2:3], w_):.2e}" for k, w_ in want.items()))
     for k, w_ in want.items():
         assert got[k].shape == (4, 512, 1024 // 2 ** int(k[1]), 1024 // 2 ** int(k[1]))
         assert _rel(got[k][2:3], w_) < 1e-3, (k, _rel(got[k][2:3], w_))
@@ -234,7 +235,7 @@ def test_full_size_batch4_1024_paste(cuda, world):
 
 
 @torch.no_grad()
-def test_1280_nine_overlapping_crops(cuda, world):
+def test_1280_nine_overlapping_crops(cuda, world, record):
     """1280 x 1280 (BASELINE.json configs[4]): 3 x 3 crops of 512 with stride 512 clamped to the border -> overlaps of 256
     pixels, paste-add + count + divide (feature_extractor.py:197-250)."""
     from odise_b200.backbone import BackboneEngine
@@ -246,13 +247,15 @@ def test_1280_nine_overlapping_crops(cuda, world):
     got = eng.backbone.forward(1, 1280, 1280, images_u8=img.to(cuda))
     torch.cuda.synchronize()
     want = compose.slide_forward(sd, compose.load_modules(sd), img.float() / 255.0, UNCOND17())
+    record("1280^2, 9 overlapping crops, backbone vs oracle: " + ", ".join(
+        f"{k} {_rel(_nchw(*got[k]), w_):.2e}" for k, w_ in want.items()))
     for k, w_ in want.items():
         t, h, w = got[k]
         assert _rel(_nchw(t, h, w), w_) < 1e-3, (k, _rel(_nchw(t, h, w), w_))
 
 
 @torch.no_grad()
-def test_short_side_below_512(cuda, world):
+def test_short_side_below_512(cuda, world, record):
     """A 384 x 640 image: two overlapping 384^2 crops, each bicubic-resized to 512^2 before the extractor
     (single_forward's T.Resize, feature_extractor.py:73-76,144) and brought back by the nearest resize of forward_features;
     then the whole engine runs on it (round 1 raised here)."""
@@ -262,6 +265,8 @@ def test_short_side_below_512(cuda, world):
     got = eng.backbone.forward(1, 384, 640, images_u8=img.to(cuda))
     torch.cuda.synchronize()
     want = compose.slide_forward(sd, compose.load_modules(sd), img.float() / 255.0, UNCOND17())
+    record("384 x 640 (two 384^2 crops resized to 512^2), backbone vs oracle: " + ", ".join(
+        f"{k} {_rel(_nchw(*got[k]), w_):.2e}" for k, w_ in want.items()))
     for k, w_ in want.items():
         t, h, w = got[k]
         assert (h, w) == tuple(w_.shape[-2:]) and _rel(_nchw(t, h, w), w_) < 1e-3, (k, _rel(_nchw(t, h, w), w_))
