@@ -57,6 +57,9 @@ struct GemmParams {
   // in fixed order (Chan's formula, double) -> no atomics, bit-reproducible, no second pass over the activation.
   float* gnp;
   long long gnp_seg, gnp_plane;
+  // 1: interior tiles leave through TMA stores (registers -> swizzled shared staging -> cp.async.bulk.tensor store issued by
+  // one lane; no per-thread global addressing, full-line writes); 2: the same for the (hi, lo) planes instead of fp32
+  int tma_out;
 };
 
 // 4 columns x the 4 rows a lane owns -> per-column (shift, S1, S2) of the warp's 32 rows; lanes 0..3 (rsub == 0) hold
@@ -214,7 +217,11 @@ struct GemmCfg {
   // quadrant and alternate 16-column chunks; BN=160/bf16x3 has no shared memory left for the second set
   static constexpr int NEPI = (BN == 160 && NMMA == 3) ? 4 : 8;
   static constexpr int THREADS = 64 + 32 * NEPI;
-  static constexpr int EPI_BYTES = NEPI * 32 * 16 * 4;  // per warp [32 rows x 16 fp32] staging (XOR swizzled)
+  // per warp [32 rows x 16 fp32] staging (XOR swizzled); doubled where shared memory allows so that the TMA store of
+  // chunk i can still be reading its buffer while chunk i + 1 is written
+  static constexpr int EPI_BUFS = (BN == 160 && NMMA == 3) ? 1 : 2;
+  static constexpr int EPI_PER_WARP = EPI_BUFS * 32 * 16 * 4;
+  static constexpr int EPI_BYTES = NEPI * EPI_PER_WARP;
   static constexpr int STAGES_RAW = (232448 - EPI_BYTES - 256) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr int ACC_STRIDE = (BN <= 64) ? 64 : (BN <= 128 ? 128 : 256);  // TMEM columns per accumulator
@@ -230,6 +237,7 @@ template <int BN, int NMMA, int EPI>
 __global__ void __launch_bounds__(GemmCfg<BN, NMMA>::THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
+               const __grid_constant__ CUtensorMap tmO0, const __grid_constant__ CUtensorMap tmO1,
                const GemmParams p) {
   using Cfg = GemmCfg<BN, NMMA>;
   extern __shared__ __align__(1024) uint8_t smem[];   // SWIZZLE_128B tiles need 1024-byte alignment
@@ -384,6 +392,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
     const int quad = warp & 3;  // TMEM lane quadrant this warp may touch
     int acc = 0;
     uint32_t accphase = 0;
+    uint32_t tma_cnt = 0;       // chunks this warp has sent through TMA stores (staging buffer parity / group accounting)
+    if (p.tma_out && lane == 0) {
+      tma_prefetch_desc(&tmO0);
+      if (p.tma_out == 2 && p.Dl) tma_prefetch_desc(&tmO1);
+    }
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int z = tile / tiles_per_z;
       int r = tile - z * tiles_per_z;
@@ -398,13 +411,116 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
       const bool has_k = kb0 < p.kblocks;  // a split with no k-blocks contributes zeros
       // TMEM -> registers (thread = row) -> XOR-swizzled shared staging -> coalesced epilogue: each warp-level
       // global access covers 8 rows x 64 contiguous bytes (full 32-byte sectors) instead of 32 rows x 16 bytes.
-      float* stg = epi_smem + (warp - 2) * (32 * 16);
+      float* stg = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(epi_smem) + (warp - 2) * Cfg::EPI_PER_WARP);
       const int m_base = mt * 128 + quad * 32;
       const int c_first = (Cfg::NEPI == 8 && warp >= 6) ? 16 : 0;
       const int c_step = (Cfg::NEPI == 8) ? 32 : 16;
       const int cq = lane & 3, rsub = lane >> 2;
       const bool interior = p.vec_ok && p.splits == 1 && (mt * 128 + 128 <= p.M) && (n0 + BN <= p.N);
-      if (interior) {
+      if (interior && EPI != 2 && p.tma_out) {
+        // ---- TMA-store epilogue: thread = output row (its TMEM lane), 16 consecutive columns per chunk
+        constexpr bool EXTRA = EPI == 1;
+        const long long m = m_base + lane;
+        const float* rbp = (EXTRA && p.rowbias)
+                               ? p.rowbias + (((long long)z * p.M + m) / p.rows_per_group) * p.rowbias_ld + n0 : nullptr;
+        const float bm = (EXTRA && p.bias_m) ? __ldg(p.bias_m + m) : 0.f;
+        const float* resp = (EXTRA && p.res) ? p.res + (long long)z * p.res_bs + m * p.ldres + n0 : nullptr;
+        const int act = p.act;
+        const float alpha = p.alpha;
+        const bool planes = p.tma_out == 2, to_lo = p.Dl != nullptr, h16 = p.h16 != 0;
+        uint8_t* wbase = reinterpret_cast<uint8_t*>(stg);
+#pragma unroll 1
+        for (int c0 = c_first; c0 < BN; c0 += c_step) {
+          uint32_t v[16];
+          tmem_ld16(t_row + c0, v);
+          float e[16];
+          float4 b4[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            b4[j] = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c0) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            e[4 * j + 0] = fmaf(__uint_as_float(v[4 * j + 0]), alpha, b4[j].x + bm);
+            e[4 * j + 1] = fmaf(__uint_as_float(v[4 * j + 1]), alpha, b4[j].y + bm);
+            e[4 * j + 2] = fmaf(__uint_as_float(v[4 * j + 2]), alpha, b4[j].z + bm);
+            e[4 * j + 3] = fmaf(__uint_as_float(v[4 * j + 3]), alpha, b4[j].w + bm);
+          }
+          if (EXTRA && rbp) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float4 rb = __ldg(reinterpret_cast<const float4*>(rbp + c0) + j);
+              e[4 * j] += rb.x; e[4 * j + 1] += rb.y; e[4 * j + 2] += rb.z; e[4 * j + 3] += rb.w;
+            }
+          }
+          if (act != ODISE_ACT_NONE) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) e[j] = apply_act(e[j], act);
+          }
+          if (EXTRA && resp) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float4 r4 = *(reinterpret_cast<const float4*>(resp + c0) + j);
+              e[4 * j] += r4.x; e[4 * j + 1] += r4.y; e[4 * j + 2] += r4.z; e[4 * j + 3] += r4.w;
+            }
+          }
+          // staging buffer: wait until the store that last used it has read it
+          const uint32_t sb = (Cfg::EPI_BUFS == 2) ? (tma_cnt & 1u) : 0u;
+          if (tma_cnt >= (uint32_t)Cfg::EPI_BUFS) {
+            if (lane == 0) tma_store_wait_read<Cfg::EPI_BUFS - 1>();
+            __syncwarp();
+          }
+          uint8_t* buf = wbase + sb * 2048;
+          if (!planes) {
+            // [32 rows][16 fp32] = 64-byte rows in the CU_TENSOR_MAP_SWIZZLE_64B pattern: 16-byte chunk ^= (row >> 1) & 3
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              *reinterpret_cast<float4*>(buf + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) =
+                  make_float4(e[4 * j], e[4 * j + 1], e[4 * j + 2], e[4 * j + 3]);
+          } else {
+            // hi plane at +0, lo plane at +1024: [32 rows][16 x 16 bit] = 32-byte rows, SWIZZLE_32B: chunk ^= (row >> 2) & 1
+            uint32_t hw[8], lw[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float a0 = e[2 * j], a1 = e[2 * j + 1];
+              if (h16) {
+                const __half2 h2 = __floats2half2_rn(a0, a1);
+                hw[j] = *reinterpret_cast<const uint32_t*>(&h2);
+                const float2 f = __half22float2(h2);
+                const __half2 l2 = __floats2half2_rn(a0 - f.x, a1 - f.y);
+                lw[j] = *reinterpret_cast<const uint32_t*>(&l2);
+              } else {
+                const __nv_bfloat162 h2 = __floats2bfloat162_rn(a0, a1);
+                hw[j] = *reinterpret_cast<const uint32_t*>(&h2);
+                const float2 f = __bfloat1622float2(h2);
+                const __nv_bfloat162 l2 = __floats2bfloat162_rn(a0 - f.x, a1 - f.y);
+                lw[j] = *reinterpret_cast<const uint32_t*>(&l2);
+              }
+            }
+            const uint32_t sw = (lane >> 2) & 1u;
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+              *reinterpret_cast<uint4*>(buf + lane * 32 + ((c ^ sw) << 4)) =
+                  make_uint4(hw[4 * c], hw[4 * c + 1], hw[4 * c + 2], hw[4 * c + 3]);
+              if (to_lo)
+                *reinterpret_cast<uint4*>(buf + 1024 + lane * 32 + ((c ^ sw) << 4)) =
+                    make_uint4(lw[4 * c], lw[4 * c + 1], lw[4 * c + 2], lw[4 * c + 3]);
+            }
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_3d(&tmO0, buf, n0 + c0, (int)(m_base), z);
+            if (planes && to_lo) tma_store_3d(&tmO1, buf + 1024, n0 + c0, (int)(m_base), z);
+            tma_store_commit();
+          }
+          ++tma_cnt;
+        }
+      } else if (interior) {
+        if (p.tma_out && tma_cnt) {   // (GEGLU never sets tma_out; kept for symmetry with the edge path below)
+          if (lane == 0) tma_store_wait_read<0>();
+          __syncwarp();
+        }
         // fast path: whole tile in range, vector accesses; per-row offsets hoisted out of the column loop
         constexpr bool EXTRA = EPI == 1, GEGLU = EPI == 2;
         long long oD[4], oR[4], oH[4];
@@ -525,6 +641,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
           __syncwarp();
         }
       } else {
+        if (p.tma_out && tma_cnt) {   // an edge tile reuses the staging buffer with plain stores: drain the TMA reads first
+          if (lane == 0) tma_store_wait_read<0>();
+          __syncwarp();
+        }
 #pragma unroll 1
         for (int c0 = c_first; c0 < BN; c0 += c_step) {
           uint32_t v[16];
@@ -591,6 +711,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
       mbar_arrive(&tempty[acc]);
       if (++acc == 2) { acc = 0; accphase ^= 1; }
     }
+    if (p.tma_out && lane == 0 && tma_cnt) tma_store_wait_read<0>();   // shared memory must outlive the stores' reads
   }
 
   tc_fence_before();
@@ -650,6 +771,23 @@ static int encode_map(CUtensorMap* tm, const void* base, int rank, const cuuint6
   return r == CUDA_SUCCESS ? ODISE_OK : ODISE_ERR_TENSORMAP;
 }
 
+// output tensor map of the TMA-store epilogue: {N, M, batch}, box {16 columns, 32 rows, 1}; fp32 rows of the box are 64 B
+// (SWIZZLE_64B), 16-bit plane rows 32 B (SWIZZLE_32B) — the staging writes in the kernel use the same XOR patterns
+static int encode_out_map(CUtensorMap* tm, void* base, bool f32, long long N, long long M, long long batch, long long ld,
+                          long long bs) {
+  auto enc = get_encode();
+  if (!enc) return ODISE_ERR_DRIVER;
+  const cuuint64_t es = f32 ? 4 : 2;
+  cuuint64_t dims[3] = {(cuuint64_t)N, (cuuint64_t)M, (cuuint64_t)batch};
+  cuuint64_t str[2] = {(cuuint64_t)ld * es, (cuuint64_t)(batch > 1 ? bs : M * ld) * es};
+  cuuint32_t box[3] = {16, 32, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(tm, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, base, dims, str, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, f32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B,
+                   CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? ODISE_OK : ODISE_ERR_TENSORMAP;
+}
+
 // ---- optional per-launch timing (bench.py roofline): CUDA events on the launch stream around every GEMM launch
 struct ProfRec { cudaEvent_t a, b; double flops; int M, N, K, batch, conv, bn, nmma, splits; };
 static std::vector<ProfRec> g_prof;
@@ -668,7 +806,7 @@ int num_sms() {
 
 template <int BN, int NMMA, int EPI>
 static int launch_cfg(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl,
-                      const GemmParams& p, cudaStream_t stream) {
+                      const CUtensorMap& o0, const CUtensorMap& o1, const GemmParams& p, cudaStream_t stream) {
   using Cfg = GemmCfg<BN, NMMA>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -679,7 +817,7 @@ static int launch_cfg(const CUtensorMap& ah, const CUtensorMap& al, const CUtens
   }
   const int total = p.tiles_m * p.tiles_n * p.splits * p.batch;
   const int grid = total < num_sms() ? total : num_sms();
-  gemm_tc_kernel<BN, NMMA, EPI><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(ah, al, bh, bl, p);
+  gemm_tc_kernel<BN, NMMA, EPI><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(ah, al, bh, bl, o0, o1, p);
   return (int)cudaGetLastError();
 }
 
@@ -860,10 +998,29 @@ extern "C" int odise_gemm_bf16(const odise_gemm_desc* d, void* stream_v) {
     cudaEventRecord(rec.a, stream);
   }
   const int epi = d->geglu ? 2 : ((d->residual || d->rowbias || d->bias_m) ? 1 : 0);
+  // TMA-store epilogue: one kind of output (fp32 OR planes), final values produced by this kernel, no fused GN records
+  // (those need the column-major view of the transposing epilogue).  ODISE_NO_TMA_STORE=1 keeps the round-1 epilogue (A/B).
+  CUtensorMap o0 = ah, o1 = ah;
+  {
+    static const bool off = getenv("ODISE_NO_TMA_STORE") != nullptr;
+    const bool one_kind = (d->out_f32 != nullptr) != (d->out_hi != nullptr);
+    if (!off && epi != 2 && p.vec_ok && p.splits == 1 && !p.gnp && one_kind) {
+      if (d->out_f32) {
+        rc = encode_out_map(&o0, d->out_f32, true, d->N, d->M, d->batch, d->ld_out, d->out_batch_stride);
+        if (!rc) p.tma_out = 1;
+      } else {
+        rc = encode_out_map(&o0, d->out_hi, false, d->N, d->M, d->batch, d->ld_out_bf16, d->out_bf16_batch_stride);
+        if (!rc && d->out_lo)
+          rc = encode_out_map(&o1, d->out_lo, false, d->N, d->M, d->batch, d->ld_out_bf16, d->out_bf16_batch_stride);
+        if (!rc) p.tma_out = 2;
+      }
+      if (rc) p.tma_out = 0;      // a shape the tensor map cannot express: the plain epilogue handles it
+    }
+  }
 #define ODISE_LAUNCH(BN_, NM_)                                                        \
-  rc = epi == 2   ? launch_cfg<BN_, NM_, 2>(ah, al, bh, bl, p, stream)                \
-       : epi == 1 ? launch_cfg<BN_, NM_, 1>(ah, al, bh, bl, p, stream)                \
-                  : launch_cfg<BN_, NM_, 0>(ah, al, bh, bl, p, stream)
+  rc = epi == 2   ? launch_cfg<BN_, NM_, 2>(ah, al, bh, bl, o0, o1, p, stream)        \
+       : epi == 1 ? launch_cfg<BN_, NM_, 1>(ah, al, bh, bl, o0, o1, p, stream)        \
+                  : launch_cfg<BN_, NM_, 0>(ah, al, bh, bl, o0, o1, p, stream)
   if (d->nmma == 3) {
     switch (BN) {
       case 64: ODISE_LAUNCH(64, 3); break;

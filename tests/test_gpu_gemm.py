@@ -246,3 +246,51 @@ def test_groupnorm_statistics_of_a_concat_and_fallbacks(cuda):
                                            beta[:C2].double(), 1e-6)
     assert _rel(y2.view(B, HW, -1).permute(0, 2, 1), want2) < 2e-5
     assert lib.GnStats(100, 64, cuda).missing                     # ragged rows: no records
+
+
+@pytest.mark.parametrize("kind", ["f32", "planes", "planes_hi_only", "planes_f16"])
+@pytest.mark.parametrize("cfg", [
+    dict(M=512, N=320, K=320, bn=0, batch=1, extra=False),       # interior tiles only
+    dict(M=1000, N=333 // 4 * 4 + 4, K=200, bn=128, batch=1, extra=True),   # ragged M and N: edge tiles take the plain path
+    dict(M=4096, N=640, K=128, bn=256, batch=1, extra=True),     # 640 = 2 x 256 + 128: interior + edge tile per row
+    dict(M=256, N=256, K=64, bn=64, batch=3, extra=False),       # batched (decoder-style), one k-block
+])
+def test_gemm_tma_store_epilogue(cuda, kind, cfg):
+    """One output kind (fp32 OR planes) leaves interior tiles through cp.async.bulk.tensor stores (SASS: UTMASTG): values must
+    equal the fp64 product to the GEMM tolerance, also when the output is a column slice of a wider buffer."""
+    from odise_b200 import lib
+    M, N, K, Bz = cfg["M"], cfg["N"], cfg["K"], cfg["batch"]
+    g = torch.Generator().manual_seed(M + N + K)
+    a = torch.randn(Bz, M, K, generator=g).to(cuda)
+    b = torch.randn(Bz, N, K, generator=g).to(cuda)
+    bias = torch.randn(N, generator=g).to(cuda)
+    kw = dict(bias=bias, act=2 if cfg["extra"] else 0, force_bn=cfg["bn"])
+    ref = torch.einsum("zmk,znk->zmn", a.double(), b.double()) + bias.double()
+    if cfg["extra"]:
+        ref = torch.nn.functional.silu(ref)
+        res = torch.randn(Bz, M, N, generator=g).to(cuda)
+        kw.update(residual=res, ld_res=N, res_bs=M * N)
+        ref = ref + res.double()
+    if Bz > 1:
+        kw.update(batch=Bz, a_bs=M * K, b_bs=N * K)
+    ap, bp = lib.split(a.view(Bz * M, K)), lib.split(b.view(Bz * N, K))
+    pad = 32                                       # outputs live in columns [pad, pad + N) of a wider buffer
+    if kind == "f32":
+        buf = torch.full((Bz, M, N + 2 * pad), 7.0, device=cuda)
+        lib.gemm(ap, bp, M=M, N=N, K=K, out=buf[:, :, pad:], ld_out=N + 2 * pad, out_bs=M * (N + 2 * pad), **kw)
+        torch.cuda.synchronize()
+        assert _rel(buf[:, :, pad:pad + N], ref) < 2e-5
+        assert (buf[:, :, :pad] == 7.0).all() and (buf[:, :, pad + N:] == 7.0).all()        # nothing outside the slice
+    else:
+        f16 = kind == "planes_f16"
+        P = lib.Planes.empty(Bz * M, N + 2 * pad, cuda, lo=kind != "planes_hi_only", f16=f16)
+        P.hi.fill_(0)
+        if P.lo is not None:
+            P.lo.fill_(0)
+        out = P.col_slice(pad, N)
+        lib.gemm(ap, bp, M=M, N=N, K=K, out_planes=out, outp_bs=M * P.ld, **kw)
+        torch.cuda.synchronize()
+        got = P.float().view(Bz, M, -1)
+        tol = 1e-4 if kind != "planes_hi_only" else 6e-3
+        assert _rel(got[:, :, pad:pad + N], ref) < tol
+        assert (got[:, :, :pad] == 0).all() and (got[:, :, pad + N:N + 2 * pad] == 0).all()
