@@ -315,6 +315,19 @@ int odise_instance_inference_f32(const float* probs, const float* logits, const 
                                  int Q, int K, int topk, int hs, int ws_, int H, int W,
                                  const odise_postprocess_geom* geom, void* stream);
 
+/* The three inference heads of CategoryODISE.forward (odise.py:326-370) from ONE resampling pass over the mask logits: the
+ * stand-alone entry points above each re-evaluate bilinear + sigmoid of every (pixel, query).  Output groups are optional
+ * (NULL = skip): semantic operand planes sem_hi / sem_lo [B*H*W, Qpad] (then run the semantic GEMM as before) | panoptic
+ * (arguments as odise_panoptic_inference_f32; pan_ws of odise_panoptic_ws_bytes) | instance (arguments as
+ * odise_instance_inference_f32; inst_ws of odise_postprocess_fused_ws_bytes; panoptic_filter = apply is_thing to `valid`). */
+long long odise_postprocess_fused_ws_bytes(int B, int Q, int H, int W);
+int odise_postprocess_fused_f32(const float* logits, void* sem_hi, void* sem_lo, int Qpad, const float* scores,
+                                const int32_t* labels, const int32_t* keep, const uint8_t* is_thing, int32_t* pan,
+                                int32_t* seg_info, int32_t* n_segments, void* pan_ws, double overlap_thr, const float* probs,
+                                float* inst_scores, int32_t* inst_classes, int32_t* inst_query, int32_t* inst_valid,
+                                uint8_t* inst_masks, void* inst_ws, int topk, int panoptic_filter, int B, int Q, int K,
+                                int hs, int ws_, int H, int W, const odise_postprocess_geom* geom, void* stream);
+
 /* MaskCLIP front-end (odise/modeling/meta_arch/clip.py:284-339) and the open-vocabulary merge (odise.py:1506-1536,
  * :300-323).
  * preprocess: whole image [N,3,H,W] (u8 0..255 or f32 in [0,1]) -> bilinear (align_corners=False) S x S, CLIP

@@ -339,6 +339,137 @@ __global__ void instance_finalize_kernel(const float* __restrict__ partial, cons
   scores[i] *= a / (c + 1e-6f);
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// ONE resampling pass for the three inference heads (round 2).  The stand-alone kernels above each re-evaluate the
+// bilinear upsample + sigmoid of every (pixel, query) — ~4e8 evaluations per 4 x 1024^2 batch, three times.  Here a warp
+// owns 32 consecutive pixels of one output row, each lane walks all Q queries of its pixel ONCE and feeds
+//   * semantic:  sigmoid -> (hi, lo) bf16 of 8 consecutive queries packed in registers -> one 16-byte store per plane
+//                into the pixel-major operand [pixel][Qpad] (the stand-alone kernel transposes through shared memory
+//                and issues 2-byte stores);
+//   * panoptic:  the per-pixel running argmax of score * sigmoid over kept queries lives in the lane's registers; the
+//                "sigmoid >= 0.5" pixel count of a query is one ballot + popc per (row segment, query);
+//   * instance:  sum(sigmoid * [logit > 0]) and the count per query: fixed-order butterfly per (row segment, query),
+//                accumulated in a per-warp shared array over the rows the block walks (deterministic), then combined
+//                over the 8 warps in fixed order -> partial [B, Q, chunks, 2] for instance_finalize_kernel; the binary
+//                masks leave as 32-byte row segments.
+// grid (ceil(W / 32), chunks, B), block 256 = 8 warps; the block walks rows [chunk * rpc, (chunk + 1) * rpc), 8 at a time.
+struct FusedPost {
+  const float* logits;       // [B, Q, hs, ws]
+  __nv_bfloat16* hi;         // semantic planes [B*H*W, Qpad] or null
+  __nv_bfloat16* lo;
+  const float* scores;       // panoptic: [B*Q] or null
+  const int32_t* keep;
+  int16_t* ids;              // [B*H*W]
+  uint8_t* fg;
+  int32_t *area, *orig, *inter;   // [B*Q] (zeroed by the caller)
+  float* partial;            // instance: [B, Q, chunks, 2] or null
+  uint8_t* masks;            // [B, Q, H, W] or null
+  int Q, Qpad, H, W, rows_per_chunk;
+};
+
+__global__ void __launch_bounds__(256)
+post_fused_kernel(const FusedPost a, const Sampler sp) {
+  extern __shared__ __align__(16) uint8_t fsm[];
+  const int Q = a.Q, Qpad = a.Qpad;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* inst = reinterpret_cast<float*>(fsm);                    // [8 warps][Q][2]
+  int32_t* cnt = reinterpret_cast<int32_t*>(inst + 8 * Q * 2);    // [3][Q]
+  const int b = blockIdx.z, chunk = blockIdx.y, ox = blockIdx.x * 32 + lane;
+  const bool sem = a.hi != nullptr, pan = a.scores != nullptr, ins = a.partial != nullptr;
+  for (int i = threadIdx.x; i < 8 * Q * 2; i += 256) inst[i] = 0.f;
+  for (int i = threadIdx.x; i < 3 * Q; i += 256) cnt[i] = 0;
+  __syncthreads();
+  const int hs = sp.hs, ws = sp.ws;
+  const long long npix = (long long)a.H * a.W;
+  const int y_begin = chunk * a.rows_per_chunk, y_end = min(a.H, y_begin + a.rows_per_chunk);
+  const bool xin = ox < a.W;
+  for (int y0r = y_begin; y0r < y_end; y0r += 8) {
+    const int oy = y0r + warp;
+    if (oy >= y_end) continue;                                    // warp-uniform
+    // pixel-dependent half of the bilinear sample (ATen area_pixel_compute_source_index, align_corners=False)
+    const float fy = fmaxf((oy + 0.5f) * sp.sy1 - 0.5f, 0.f), fx = fmaxf((ox + 0.5f) * sp.sx1 - 0.5f, 0.f);
+    const int sy0 = (int)fy, sx0 = min((int)fx, ws - 1);
+    const int sy1 = sy0 + (sy0 < hs - 1 ? 1 : 0), sx1 = sx0 + (sx0 < ws - 1 ? 1 : 0);
+    const float ly = fy - sy0, lx = fx - (int)fx, hy = 1.f - ly, hx = 1.f - lx;
+    const int o00 = sy0 * ws + sx0, o01 = sy0 * ws + sx1, o10 = sy1 * ws + sx0, o11 = sy1 * ws + sx1;
+    float best = -INFINITY;
+    int bq = -1;
+    bool bfg = false;
+    const float* srcb = a.logits + (long long)b * Q * hs * ws;
+    const long long pixel = (long long)b * npix + (long long)oy * a.W + ox;
+    for (int q0 = 0; q0 < Qpad; q0 += 8) {
+      // 8 queries per step: their (hi, lo) bf16 sigmoids leave as one 16-byte store per plane, pixel-major [pixel][Qpad]
+      uint32_t hw[4] = {0u, 0u, 0u, 0u}, lw[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int q = q0 + j;
+        if (q >= Q) break;                                        // warp-uniform (pad queries stay zero)
+        const float* src = srcb + (long long)q * hs * ws;
+        float lg;
+        if (!sp.two)
+          lg = hy * (hx * __ldg(src + o00) + lx * __ldg(src + o01)) + ly * (hx * __ldg(src + o10) + lx * __ldg(src + o11));
+        else
+          lg = sample(src, sp, oy, xin ? ox : 0);
+        const float s = 1.f / (1.f + expf(-lg));
+        if (sem) {
+          __nv_bfloat16 h, l;
+          split_bf16(s, h, l);
+          const uint32_t hb = __bfloat16_as_ushort(h), lb = __bfloat16_as_ushort(l);
+          hw[j >> 1] |= hb << ((j & 1) * 16);
+          lw[j >> 1] |= lb << ((j & 1) * 16);
+        }
+        if (pan && a.keep[b * Q + q]) {                          // warp-uniform
+          const bool f = s >= 0.5f;
+          const unsigned m = __ballot_sync(0xffffffffu, f && xin);
+          if (lane == 0 && m) atomicAdd(&cnt[Q + q], __popc(m));
+          const float pm = a.scores[b * Q + q] * s;
+          if (pm > best) { best = pm; bq = q; bfg = f; }         // argmax(0): first maximal kept query
+        }
+        if (ins) {
+          const bool on = lg > 0.f && xin;
+          float num = on ? s : 0.f;
+          const unsigned m = __ballot_sync(0xffffffffu, on);
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) num += __shfl_xor_sync(0xffffffffu, num, o);
+          if (lane == 0) { inst[(warp * Q + q) * 2] += num; inst[(warp * Q + q) * 2 + 1] += (float)__popc(m); }
+          if (a.masks && xin) a.masks[((long long)b * Q + q) * npix + (long long)oy * a.W + ox] = on ? 1 : 0;
+        }
+      }
+      if (sem && xin) {
+        *reinterpret_cast<uint4*>(a.hi + pixel * Qpad + q0) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+        if (a.lo) *reinterpret_cast<uint4*>(a.lo + pixel * Qpad + q0) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+      }
+    }
+    if (pan && xin) {
+      a.ids[pixel] = (int16_t)bq;
+      a.fg[pixel] = bfg ? 1 : 0;
+      if (bq >= 0) {
+        atomicAdd(&cnt[bq], 1);
+        if (bfg) atomicAdd(&cnt[2 * Q + bq], 1);
+      }
+    }
+  }
+  __syncthreads();
+  if (pan) {
+    for (int i = threadIdx.x; i < Q; i += 256) {
+      if (cnt[i]) atomicAdd(&a.area[b * Q + i], cnt[i]);
+      if (cnt[Q + i]) atomicAdd(&a.orig[b * Q + i], cnt[Q + i]);
+      if (cnt[2 * Q + i]) atomicAdd(&a.inter[b * Q + i], cnt[2 * Q + i]);
+    }
+  }
+  if (ins) {
+    // partial[b, q, chunk * gridDim.x + blockIdx.x, :] = sum over the 8 warps in fixed order
+    const int nparts = gridDim.y * gridDim.x, part = chunk * gridDim.x + blockIdx.x;
+    for (int q = threadIdx.x; q < Q; q += 256) {
+      float n0 = 0.f, d0 = 0.f;
+      for (int w = 0; w < 8; ++w) { n0 += inst[(w * Q + q) * 2]; d0 += inst[(w * Q + q) * 2 + 1]; }
+      float* o = a.partial + (((long long)b * Q + q) * nparts + part) * 2;
+      o[0] = n0; o[1] = d0;
+    }
+  }
+}
+
 }  // namespace ob
 
 using namespace ob;
@@ -435,5 +566,78 @@ extern "C" int odise_instance_inference_f32(const float* probs, const float* log
   const int n = B * topk;
   instance_finalize_kernel<<<(n + 255) / 256, 256, 0, st>>>(partial, query_index, scores, n, topk, Q, nchunks);
   count_launch(3);
+  return (int)cudaGetLastError();
+}
+
+// All three inference heads from ONE resampling pass (post_fused_kernel) + the small bookkeeping kernels.  Any of the
+// three groups of outputs may be absent (NULL): sem_hi | (pan, seg_info, n_segments, pan_ws) | (inst_scores, ...).
+static inline int fused_chunks(int H) { return H >= 128 ? 16 : 1; }
+extern "C" long long odise_postprocess_fused_ws_bytes(int B, int Q, int H, int W) {
+  const long long parts = (long long)fused_chunks(H) * ((W + 31) / 32);
+  return (long long)B * Q * parts * 2 * sizeof(float) + 256;
+}
+
+extern "C" int odise_postprocess_fused_f32(const float* logits, void* sem_hi, void* sem_lo, int Qpad,
+                                           const float* scores, const int32_t* labels, const int32_t* keep,
+                                           const uint8_t* is_thing, int32_t* pan, int32_t* seg_info, int32_t* n_segments,
+                                           void* pan_ws, double overlap_thr, const float* probs, float* inst_scores,
+                                           int32_t* inst_classes, int32_t* inst_query, int32_t* inst_valid,
+                                           uint8_t* inst_masks, void* inst_ws, int topk, int panoptic_filter, int B, int Q,
+                                           int K, int hs, int ws_, int H, int W, const odise_postprocess_geom* geom,
+                                           void* stream) {
+  if (!logits || B <= 0 || Q <= 0 || K <= 0 || hs <= 0 || ws_ <= 0 || H <= 0 || W <= 0 || geom_bad(geom)) return ODISE_ERR_ARG;
+  const bool sem = sem_hi != nullptr, panop = pan != nullptr, inst = inst_scores != nullptr;
+  if (!sem && !panop && !inst) return ODISE_ERR_ARG;
+  if (sem && (Qpad < Q || Qpad % 8)) return ODISE_ERR_ARG;
+  if (panop && (!scores || !labels || !keep || !is_thing || !seg_info || !n_segments || !pan_ws || Q > 32767 ||
+                K * 4 > 48 * 1024))
+    return ODISE_ERR_ARG;
+  if (inst && (!probs || !inst_classes || !inst_query || !inst_valid || !inst_ws || topk <= 0 || topk > 1024 ||
+               (long long)Q * K >= 0x7fffffffLL))
+    return ODISE_ERR_ARG;
+  cudaStream_t st = STREAM(stream);
+  const long long npix = (long long)B * H * W;
+  FusedPost a{};
+  a.logits = logits; a.Q = Q; a.Qpad = sem ? Qpad : (Q + 7) / 8 * 8; a.H = H; a.W = W;
+  const int chunks = fused_chunks(H);
+  a.rows_per_chunk = ((H + chunks - 1) / chunks + 7) / 8 * 8;
+  a.hi = reinterpret_cast<__nv_bfloat16*>(sem_hi); a.lo = reinterpret_cast<__nv_bfloat16*>(sem_lo);
+  int32_t* seg_of = nullptr;
+  if (panop) {
+    uint8_t* base = reinterpret_cast<uint8_t*>(pan_ws);
+    a.ids = reinterpret_cast<int16_t*>(base);
+    a.fg = base + (npix * 2 + 255) / 256 * 256;
+    int32_t* counters = reinterpret_cast<int32_t*>(a.fg + (npix + 255) / 256 * 256);
+    a.area = counters; a.orig = counters + B * Q; a.inter = counters + 2 * B * Q; seg_of = counters + 3 * B * Q;
+    a.scores = scores; a.keep = keep;
+    cudaError_t e = cudaMemsetAsync(counters, 0, sizeof(int32_t) * 3 * B * Q, st);
+    if (e != cudaSuccess) return (int)e;
+  }
+  int launches = 1;
+  if (inst) {
+    a.partial = reinterpret_cast<float*>(inst_ws); a.masks = inst_masks;
+    instance_topk_kernel<<<B, 1024, 0, st>>>(probs, panoptic_filter ? is_thing : nullptr, inst_scores, inst_classes,
+                                             inst_query, inst_valid, Q, K, topk);
+    ++launches;
+  }
+  dim3 grid((W + 31) / 32, (H + a.rows_per_chunk - 1) / a.rows_per_chunk, B);
+  const size_t smem = (size_t)8 * Q * 2 * sizeof(float) + (size_t)3 * Q * sizeof(int32_t);
+  if (smem > 48 * 1024) return ODISE_ERR_UNSUPPORTED;
+  post_fused_kernel<<<grid, 256, smem, st>>>(a, make_sampler(hs, ws_, H, W, geom));
+  if (panop) {
+    panoptic_assign_kernel<<<B, 32, K * sizeof(int32_t), st>>>(keep, labels, a.area, a.orig, a.inter, is_thing, seg_of,
+                                                            seg_info, n_segments, Q, K, overlap_thr);
+    int rb = (int)((npix + 255) / 256);
+    if (rb > 148 * 8) rb = 148 * 8;
+    panoptic_relabel_kernel<<<rb, 256, 0, st>>>(a.ids, a.fg, seg_of, pan, Q, (long long)H * W, B);
+    launches += 2;
+  }
+  if (inst) {
+    const int n = B * topk;
+    instance_finalize_kernel<<<(n + 255) / 256, 256, 0, st>>>(a.partial, inst_query, inst_scores, n, topk, Q,
+                                                              (int)(grid.x * grid.y));
+    ++launches;
+  }
+  count_launch(launches);
   return (int)cudaGetLastError();
 }

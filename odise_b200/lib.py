@@ -113,6 +113,8 @@ _SIGS = {
                                c_float, c_void_p],
     "odise_panoptic_inference_f32": [c_void_p] * 9 + [c_int] * 7 + [ctypes.c_double, c_void_p, c_void_p],
     "odise_instance_inference_f32": [c_void_p] * 9 + [c_int] * 8 + [c_void_p, c_void_p],
+    "odise_postprocess_fused_f32": [c_void_p, c_void_p, c_void_p, c_int] + [c_void_p] * 8 + [ctypes.c_double] + [c_void_p] * 7 +
+                                   [c_int] * 9 + [c_void_p, c_void_p],
     "odise_set_carveout_policy": [c_int],
     "odise_gather_rows_f32": [c_void_p, c_longlong, c_void_p, c_void_p, c_longlong, c_int, c_void_p, c_longlong, c_longlong,
                               c_int, c_void_p],
@@ -145,6 +147,8 @@ def load():
     lib.odise_panoptic_ws_bytes.argtypes = [c_int, c_int, c_int, c_int]
     lib.odise_instance_ws_bytes.restype = c_longlong
     lib.odise_instance_ws_bytes.argtypes = [c_int, c_int, c_int, c_int]
+    lib.odise_postprocess_fused_ws_bytes.restype = c_longlong
+    lib.odise_postprocess_fused_ws_bytes.argtypes = [c_int, c_int, c_int, c_int]
     lib.odise_mha_d32_ws_floats.argtypes = [c_int, c_int, c_int, c_int]
     for name, args in _SIGS.items():
         fn = getattr(lib, name)

@@ -52,10 +52,29 @@ class PostProcessor:
                                         K1, self.obj_thr, _stream()), "query_scores")
         out = {}
         pm = pred_masks.contiguous()
+        # ONE resampling pass over the mask logits feeds all requested heads (odise_postprocess_fused_f32)
+        sig = Planes.empty(B * H * W, Qp, dev, lo=self.lo, ld=Qp) if semantic else None
+        pan = seg_info = nseg = pws = None
+        if panoptic:
+            pan = torch.empty(B, H, W, dtype=torch.int32, device=dev)
+            seg_info = torch.zeros(B, Q, 3, dtype=torch.int32, device=dev)
+            nseg = torch.empty(B, dtype=torch.int32, device=dev)
+            pws = torch.empty(int(L.odise_panoptic_ws_bytes(B, Q, H, W)), dtype=torch.uint8, device=dev)
+        i_sc = i_cl = i_q = i_ok = qm = iws = None
+        if instance:
+            i_sc = torch.empty(B, topk, dtype=torch.float32, device=dev)
+            i_cl = torch.empty(B, topk, dtype=torch.int32, device=dev)
+            i_q = torch.empty(B, topk, dtype=torch.int32, device=dev)
+            i_ok = torch.empty(B, topk, dtype=torch.int32, device=dev)
+            qm = torch.empty(B, Q, H, W, dtype=torch.uint8, device=dev) if instance_masks else None
+            iws = torch.empty(int(L.odise_postprocess_fused_ws_bytes(B, Q, H, W)), dtype=torch.uint8, device=dev)
+        if semantic or panoptic or instance:
+          _check(L.odise_postprocess_fused_f32(
+              _ptr(pm), _ptr(sig.hi) if sig else None, _ptr(sig.lo) if sig else None, Qp, _ptr(scores), _ptr(labels),
+              _ptr(keep), _ptr(self.is_thing), _ptr(pan), _ptr(seg_info), _ptr(nseg), _ptr(pws), self.ov_thr, _ptr(probs),
+              _ptr(i_sc), _ptr(i_cl), _ptr(i_q), _ptr(i_ok), _ptr(qm), _ptr(iws), topk, 1 if panoptic_on else 0, B, Q, self.K,
+              hs, ws, H, W, geom, _stream()), "postprocess_fused")
         if semantic:
-            sig = Planes.empty(B * H * W, Qp, dev, lo=self.lo, ld=Qp)
-            _check(L.odise_upsample_sigmoid_split_f32(_ptr(pm), _ptr(sig.hi), _ptr(sig.lo), None, B, Q, Qp, hs, ws, H, W,
-                                                      geom, _stream()), "upsample_sigmoid")
             # sem[b] = P_b^T [K, Q] @ sig_b^T [Q, HW]: swapped-operand GEMM writes the reference's [K, H, W] layout
             ptp = ops.split(probs_t, lo=self.lo)
             sem = torch.empty(B, self.K, H * W, dtype=torch.float32, device=dev)
@@ -63,24 +82,8 @@ class PostProcessor:
                      out=sem, ld_out=H * W, out_bs=self.K * H * W)
             out["sem_seg"] = sem.view(B, self.K, H, W)
         if panoptic:
-            pan = torch.empty(B, H, W, dtype=torch.int32, device=dev)
-            seg_info = torch.zeros(B, Q, 3, dtype=torch.int32, device=dev)
-            nseg = torch.empty(B, dtype=torch.int32, device=dev)
-            wsb = torch.empty(int(L.odise_panoptic_ws_bytes(B, Q, H, W)), dtype=torch.uint8, device=dev)
-            _check(L.odise_panoptic_inference_f32(_ptr(pm), _ptr(scores), _ptr(labels), _ptr(keep), _ptr(self.is_thing),
-                                                  _ptr(pan), _ptr(seg_info), _ptr(nseg), _ptr(wsb), B, Q, self.K, hs, ws,
-                                                  H, W, self.ov_thr, geom, _stream()), "panoptic_inference")
             out.update(panoptic_seg=pan, seg_info=seg_info, n_segments=nseg)
         if instance:
-            i_sc = torch.empty(B, topk, dtype=torch.float32, device=dev)
-            i_cl = torch.empty(B, topk, dtype=torch.int32, device=dev)
-            i_q = torch.empty(B, topk, dtype=torch.int32, device=dev)
-            i_ok = torch.empty(B, topk, dtype=torch.int32, device=dev)
-            qm = torch.empty(B, Q, H, W, dtype=torch.uint8, device=dev) if instance_masks else None
-            wsb = torch.empty(int(L.odise_instance_ws_bytes(B, Q, H, W)), dtype=torch.uint8, device=dev)
-            _check(L.odise_instance_inference_f32(_ptr(probs), _ptr(pm), _ptr(self.is_thing) if panoptic_on else None,
-                                                  _ptr(i_sc), _ptr(i_cl), _ptr(i_q), _ptr(i_ok), _ptr(qm), _ptr(wsb), B, Q,
-                                                  self.K, topk, hs, ws, H, W, geom, _stream()), "instance_inference")
             out["instances"] = dict(scores=i_sc, pred_classes=i_cl, query_index=i_q, valid=i_ok, query_masks=qm)
         out.update(scores=scores.view(B, Q), labels=labels.view(B, Q), keep=keep.view(B, Q))
         return out

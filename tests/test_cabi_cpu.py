@@ -29,7 +29,7 @@ def test_every_declared_symbol_is_exported_and_bound(built):
     for n in names:
         assert hasattr(dll, n), f"{n} declared in the header but not exported"
     bound = set(lib._SIGS) | {"odise_version", "odise_launch_count", "odise_groupnorm_ws_floats", "odise_mha_d32_ws_floats", "odise_panoptic_ws_bytes",
-             "odise_instance_ws_bytes"}
+             "odise_instance_ws_bytes", "odise_postprocess_fused_ws_bytes"}
     assert set(names) <= bound, set(names) - bound
     assert lib.load().odise_version() == 100
 
