@@ -13,6 +13,11 @@
  * Operand convention for tensor-core GEMMs: fp32 values travel as a (hi, lo) pair of bf16 planes with
  * hi = bf16(x), lo = bf16(x - hi); "nmma = 3" issues hi*hi + hi*lo + lo*hi (fp32-grade, the parity mode),
  * "nmma = 1" uses the hi planes only (plain bf16).
+ * "nmma = 2" (ODISE_PLANES_F16Q8, round 2): hi = fp16(x); the second plane keeps the byte geometry of a 16-bit plane
+ * (2 bytes per element, same leading dimension, which must be a multiple of 64 elements with 128-byte aligned rows) but
+ * holds, per block of 64 consecutive k, 64 bytes e5m2(x * 2^-6) followed by 64 bytes e5m2((x - hi) * 2^6).  The GEMM
+ * issues hi*hi on kind::f16 and the two first-order cross terms on kind::f8f6f4 at twice the 16-bit rate: 8 MMA slots
+ * per 64-wide k-block instead of 12, ~2^-14 per product (UNet taps 1.1e-4 vs the fp32 oracle, bar 1e-3).
  */
 #ifndef ODISE_B200_H_
 #define ODISE_B200_H_
@@ -36,6 +41,18 @@ extern "C" {
 #define ODISE_ACT_SILU 2
 #define ODISE_ACT_GELU 3
 #define ODISE_ACT_QUICKGELU 4 /* x * sigmoid(1.702 x): open_clip QuickGELU (CLIP ViT MLP) */
+
+/* operand-plane formats (see the convention above) */
+#define ODISE_PLANES_BF16 0   /* (hi, lo) bf16 pair */
+#define ODISE_PLANES_F16 1    /* (hi, lo) fp16 pair: V^T of odise_attention_tc */
+#define ODISE_PLANES_F16Q8 2  /* fp16 hi + e5m2 correction bytes */
+/* Format of the (hi, lo) planes written by every producer entry point launched AFTER this call (odise_split_f32, the
+ * groupnorm / layernorm / GEGLU / add / act / upsample / im2col / patchify / softmax / l2-normalise passes, the plane outputs
+ * of odise_attention_tc, odise_mha_d32*, odise_msda_fused_f32 and the post-processing kernels): ODISE_PLANES_BF16 (default)
+ * or ODISE_PLANES_F16Q8.  A host-side launch parameter (process-global, not thread-safe), captured into CUDA graphs like
+ * any other kernel argument.  odise_gemm_bf16 takes its formats from the descriptor instead. */
+int odise_set_operand_format(int fmt);
+int odise_get_operand_format(void);
 
 int odise_version(void);
 /* number of kernels launched through this library since load (bench.py "gpu_launches") */
@@ -71,7 +88,7 @@ int odise_msda_fused_f32(const float* value, const int64_t* spatial_shapes, cons
  * All bf16 leading dimensions are multiples of 8 elements, fp32 ones multiples of 4; base pointers 16-byte aligned. */
 typedef struct odise_gemm_desc {
   int M, N, K, batch;
-  int nmma;     /* 1 = bf16, 3 = bf16x3 */
+  int nmma;     /* 1 = bf16, 3 = bf16x3 (bf16 pairs), 2 = fp16 + e5m2 corrections (both operands ODISE_PLANES_F16Q8) */
   int conv3x3;  /* 0 plain, 1 implicit 3x3 conv */
   int conv_C, conv_H, conv_W;
   const void* a_hi; const void* a_lo; long long lda; long long a_batch_stride; /* 0 = shared across batch */
@@ -97,8 +114,9 @@ typedef struct odise_gemm_desc {
                                         {0,1,2} * gn_plane_stride + n], seg = (z*M + m) / 32.  Needs M % 32 == 0, split_k <= 1.
                                         Merged per (image, group) by odise_groupnorm_finalize_seg_f32. */
   long long gn_seg_stride; long long gn_plane_stride;
-  int out_planes_fp16;               /* 1: out_hi / out_lo are written as fp16 (hi = fp16(v), lo = fp16(v - hi)) instead of
-                                        bf16: the V^T operand of odise_attention_tc in the bf16x3 mode */
+  int out_planes_fp16;               /* format of out_hi / out_lo: ODISE_PLANES_BF16 (0), ODISE_PLANES_F16 (1: hi = fp16(v),
+                                        lo = fp16(v - hi), the V^T operand of odise_attention_tc) or ODISE_PLANES_F16Q8 (2:
+                                        ld_out_bf16 % 64 == 0, rows 128-byte aligned) */
 } odise_gemm_desc;
 int odise_gemm_bf16(const odise_gemm_desc* desc, void* stream);
 /* optional per-launch timing of odise_gemm_bf16 (CUDA events on the launch stream; not for use under graph capture):

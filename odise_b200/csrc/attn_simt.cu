@@ -179,10 +179,7 @@ mha_d32_kernel(const float* __restrict__ q, long long ldq, const float* __restri
     const long long idx = ((long long)b * Tq + qi[t]) * ldo + h * 32 + lane;
     if (out) out[idx] = r;
     if (out_hi) {
-      __nv_bfloat16 hh, ll;
-      split_bf16(r, hh, ll);
-      out_hi[idx] = hh;
-      if (out_lo) out_lo[idx] = ll;
+      store_planes<1>(out_hi + idx, out_lo ? out_lo + idx : nullptr, &r);
     }
   }
 }
@@ -213,10 +210,7 @@ __global__ void mha_merge_kernel(const float* __restrict__ part, float* __restri
   const long long idx = ((long long)b * Tq + qd) * ldo + h * 32 + lane;
   if (out) out[idx] = r;
   if (out_hi) {
-    __nv_bfloat16 hh, ll;
-    split_bf16(r, hh, ll);
-    out_hi[idx] = hh;
-    if (out_lo) out_lo[idx] = ll;
+    store_planes<1>(out_hi + idx, out_lo ? out_lo + idx : nullptr, &r);
   }
 }
 
@@ -263,12 +257,12 @@ extern "C" int odise_mha_d32_ws_f32(const float* q, long long ldq, const float* 
   dim3 grid(qtiles * ks, heads, B);
   mha_d32_kernel<QPW><<<grid, 256, 0, st>>>(q, ldq, k, v, ldkv, bits, row_any, out,
                                             reinterpret_cast<__nv_bfloat16*>(out_hi),
-                                            reinterpret_cast<__nv_bfloat16*>(out_lo), ldo, Tq, Tk, heads, scale, ks, ws);
+                                            lo_arg(reinterpret_cast<__nv_bfloat16*>(out_lo)), ldo, Tq, Tk, heads, scale, ks, ws);
   int n = 1;
   if (ks > 1) {
     const long long warps = (long long)B * heads * Tq;
     mha_merge_kernel<<<(int)((warps + 7) / 8), 256, 0, st>>>(ws, out, reinterpret_cast<__nv_bfloat16*>(out_hi),
-                                                             reinterpret_cast<__nv_bfloat16*>(out_lo), ldo, B, Tq, heads,
+                                                             lo_arg(reinterpret_cast<__nv_bfloat16*>(out_lo)), ldo, B, Tq, heads,
                                                              ks);
     n = 2;
   }

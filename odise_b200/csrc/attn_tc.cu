@@ -327,12 +327,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__
 #pragma unroll
         for (int i = 0; i < DP; i += 8) {
           if (i < dpart) {
-            __align__(16) __nv_bfloat16 hi[8];
-            __align__(16) __nv_bfloat16 lo[8];
+            float ov[8];
 #pragma unroll
-            for (int t = 0; t < 8; ++t) split_bf16(acc[i + t] * inv, hi[t], lo[t]);
-            *reinterpret_cast<uint4*>(p.out_hi + o + i) = *reinterpret_cast<const uint4*>(hi);
-            if (p.out_lo) *reinterpret_cast<uint4*>(p.out_lo + o + i) = *reinterpret_cast<const uint4*>(lo);
+            for (int t = 0; t < 8; ++t) ov[t] = acc[i + t] * inv;
+            store_planes<8>(p.out_hi + o + i, p.out_lo ? p.out_lo + o + i : nullptr, ov);   // bf16 pair or F16Q8 (tagged lo)
           }
         }
       }
@@ -433,7 +431,8 @@ extern "C" int odise_attention_tc(const void* q_hi, const void* q_lo, long long 
   AttnParams p{};
   p.B = B; p.heads = heads; p.d = d; p.Tq = Tq; p.Tk = Tk; p.TkS = TkS;
   p.scale_log2 = scale * 1.4426950408889634f;
-  p.out = out; p.out_hi = reinterpret_cast<__nv_bfloat16*>(out_hi); p.out_lo = reinterpret_cast<__nv_bfloat16*>(out_lo);
+  p.out = out; p.out_hi = reinterpret_cast<__nv_bfloat16*>(out_hi); p.out_lo = lo_arg(reinterpret_cast<__nv_bfloat16*>(out_lo));
+  if (lo_is_q8(p.out_lo) && (ldo % 64 || (reinterpret_cast<uintptr_t>(out_lo) & 127))) return ODISE_ERR_ALIGN;
   p.ldo = ldo;
   p.bits = mask_bits; p.row_any = row_any;
   if (DP == 32) rc = nmma == 3 ? attn_launch<32, 3>(m, p, stream) : attn_launch<32, 1>(m, p, stream);

@@ -34,11 +34,8 @@ __device__ __forceinline__ float act_apply(float v, int act) {
 }
 
 __device__ __forceinline__ void store_split4(__nv_bfloat16* hi, __nv_bfloat16* lo, float4 v) {
-  __align__(8) __nv_bfloat16 h[4];
-  __align__(8) __nv_bfloat16 l[4];
-  split_bf16(v.x, h[0], l[0]); split_bf16(v.y, h[1], l[1]); split_bf16(v.z, h[2], l[2]); split_bf16(v.w, h[3], l[3]);
-  *reinterpret_cast<uint2*>(hi) = *reinterpret_cast<const uint2*>(h);
-  if (lo) *reinterpret_cast<uint2*>(lo) = *reinterpret_cast<const uint2*>(l);
+  const float e[4] = {v.x, v.y, v.z, v.w};
+  store_planes<4>(hi, lo, e);     // bf16 pair, or fp16 + e5m2 corrections when lo carries the F16Q8 tag (ptx.cuh)
 }
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -226,12 +223,7 @@ __global__ void gn_apply_kernel(const float* __restrict__ x, long long ldx, cons
 // 16-byte plane stores, two pixels in flight, <= 64 registers so that 4 x 256 threads stay resident per SM; the grid is
 // exactly one resident wave (grid-stride over pixel chunks).
 __device__ __forceinline__ void store_split8(__nv_bfloat16* hi, __nv_bfloat16* lo, const float* v) {
-  __align__(16) __nv_bfloat16 h[8];
-  __align__(16) __nv_bfloat16 l[8];
-#pragma unroll
-  for (int t = 0; t < 8; ++t) split_bf16(v[t], h[t], l[t]);
-  *reinterpret_cast<uint4*>(hi) = *reinterpret_cast<const uint4*>(h);
-  if (lo) *reinterpret_cast<uint4*>(lo) = *reinterpret_cast<const uint4*>(l);
+  store_planes<8>(hi, lo, v);
 }
 
 __global__ void __launch_bounds__(256, 4)
@@ -570,10 +562,7 @@ __global__ void im2col3x3_split_kernel(const float* __restrict__ x, long long ld
       const int iy = oy * stride + tap / 3 - pad_lo, ix = ox * stride + tap % 3 - pad_lo;
       if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = x[(((long long)b * H + iy) * W + ix) * ldx + c];
     }
-    __nv_bfloat16 h, l;
-    split_bf16(v, h, l);
-    hi[i] = h;
-    if (lo) lo[i] = l;
+    store_planes<1>(hi + i, lo ? lo + i : nullptr, &v);
   }
 }
 
@@ -647,10 +636,8 @@ __global__ void l2norm_split_kernel(const float* __restrict__ x, long long ldx, 
   // F.normalize: x / max(||x||_2, 1e-12)
   const float nrm = fmaxf(sqrtf(warp_sum(sq)), 1e-12f);
   for (int c = lane; c < cols; c += 32) {
-    __nv_bfloat16 h, l;
-    split_bf16(x[row * ldx + c] / nrm, h, l);
-    hi[row * ldo + c] = h;
-    if (lo) lo[row * ldo + c] = l;
+    const float v = x[row * ldx + c] / nrm;
+    store_planes<1>(hi + row * ldo + c, lo ? lo + row * ldo + c : nullptr, &v);
   }
 }
 
@@ -882,10 +869,7 @@ __global__ void patchify_split_kernel(const float* __restrict__ x, __nv_bfloat16
       const int c = k / (P * P), rem = k - c * P * P, ky = rem / P, kx = rem - ky * P;
       v = x[(((long long)b * S + gy * P + ky) * S + gx * P + kx) * 3 + c];
     }
-    __nv_bfloat16 h, l;
-    split_bf16(v, h, l);
-    hi[i] = h;
-    if (lo) lo[i] = l;
+    store_planes<1>(hi + i, lo ? lo + i : nullptr, &v);
   }
 }
 
@@ -906,10 +890,7 @@ __global__ void softmax_split_kernel(const float* __restrict__ x, long long ldx,
   sum = warp_sum(sum);
   for (int c = lane; c < cols_pad; c += 32) {
     const float v = c < cols ? expf(xr[c] * scale - mx) / sum : 0.f;
-    __nv_bfloat16 h, l;
-    split_bf16(v, h, l);
-    hi[row * ldo + c] = h;
-    if (lo) lo[row * ldo + c] = l;
+    store_planes<1>(hi + row * ldo + c, lo ? lo + row * ldo + c : nullptr, &v);
   }
 }
 
@@ -918,6 +899,23 @@ __global__ void softmax_split_kernel(const float* __restrict__ x, long long ldx,
 using namespace ob;
 #define STREAM(s) reinterpret_cast<cudaStream_t>(s)
 #define BF(p) reinterpret_cast<__nv_bfloat16*>(p)
+// second operand plane as the kernels receive it: tagged when odise_set_operand_format(ODISE_PLANES_F16Q8) is in effect
+#define BFL(p) ob::lo_arg(reinterpret_cast<__nv_bfloat16*>(p))
+// F16Q8 planes: rows on 128-byte boundaries (the kernels read an element's position in its 64-wide k-block off its address)
+#define Q8_CHECK(lo, ld)                                                                                     \
+  if ((lo) && ob::operand_format() == ODISE_PLANES_F16Q8 && (((ld) % 64) || (reinterpret_cast<uintptr_t>(lo) & 127))) \
+    return ODISE_ERR_ALIGN
+
+namespace ob {
+static int g_operand_format = ODISE_PLANES_BF16;
+int operand_format() { return g_operand_format; }
+}  // namespace ob
+extern "C" int odise_set_operand_format(int fmt) {
+  if (fmt != ODISE_PLANES_BF16 && fmt != ODISE_PLANES_F16Q8) return ODISE_ERR_ARG;
+  ob::g_operand_format = fmt;
+  return ODISE_OK;
+}
+extern "C" int odise_get_operand_format(void) { return ob::g_operand_format; }
 
 extern "C" int odise_version(void) { return 100; }
 extern "C" long long odise_launch_count(void) { return g_launches.load(); }
@@ -960,8 +958,9 @@ extern "C" int odise_add_split_f32(const float* a, long long lda, const float* b
                                    int cols, void* stream) {
   if (!a || rows <= 0 || cols <= 0 || (!y && !hi)) return ODISE_ERR_ARG;
   if (cols % 4 || lda % 4 || (b && ldb % 4) || (y && ldy % 4) || (hi && ldo % 4)) return ODISE_ERR_ALIGN;
+  Q8_CHECK(lo, ldo);
   add_split_kernel<<<grid_for(rows * (cols / 4), 256), 256, 0, STREAM(stream)>>>(a, lda, b, ldb, b_rows, y, ldy,
-                                                                               BF(hi), BF(lo), ldo, rows, cols / 4);
+                                                                               BF(hi), BFL(lo), ldo, rows, cols / 4);
   count_launch(1);
   return (int)cudaGetLastError();
 }
@@ -1005,7 +1004,8 @@ extern "C" int odise_groupnorm_apply_bs_f32(const float* x, long long ldx, long 
   if (!x || !mean || !rstd || !gamma || !beta || (!y && !hi) || C % G) return ODISE_ERR_ARG;
   if (C % 4 || ldx % 4 || x_bs % 4 || (y && (ldy % 4 || y_bs % 4)) || (hi && (ldo % 4 || o_bs % 4)))
     return ODISE_ERR_ALIGN;
-  int rc = launch_gn_apply(x, ldx, mean, rstd, gamma, beta, act, y, ldy, BF(hi), BF(lo), ldo, B, HW, C, G,
+  Q8_CHECK(lo, ldo);
+  int rc = launch_gn_apply(x, ldx, mean, rstd, gamma, beta, act, y, ldy, BF(hi), BFL(lo), ldo, B, HW, C, G,
                            x_bs ? x_bs : (long long)HW * ldx, y_bs ? y_bs : (long long)HW * ldy,
                            o_bs ? o_bs : (long long)HW * ldo, nullptr, 0, 0, STREAM(stream));
   if (rc) return rc;
@@ -1023,9 +1023,10 @@ extern "C" int odise_layernorm_f32(const float* x, long long ldx, const float* r
   const int wpb = 8;
   const int blocks = (int)((rows + wpb - 1) / wpb);
   const int nv = cols / 4;
+  Q8_CHECK(lo, ldo);
 #define LN_LAUNCH(MV)                                                                                              \
   layernorm_kernel<MV><<<blocks, wpb * 32, 0, STREAM(stream)>>>(x, ldx, res, ldres, gamma, beta, eps, y, ldy,       \
-                                                               post_add, ldpa, BF(hi), BF(lo), ldo, rows, cols)
+                                                               post_add, ldpa, BF(hi), BFL(lo), ldo, rows, cols)
   if (nv <= 64) LN_LAUNCH(2);
   else if (nv <= 128) LN_LAUNCH(4);
   else if (nv <= 320) LN_LAUNCH(10);
@@ -1039,7 +1040,8 @@ extern "C" int odise_geglu_f32(const float* x, long long ldx, void* hi, void* lo
                                int cols, void* stream) {
   if (!x || !hi || rows <= 0 || cols <= 0) return ODISE_ERR_ARG;
   if (cols % 4 || ldx % 4 || ldo % 4) return ODISE_ERR_ALIGN;
-  geglu_kernel<<<grid_for(rows * (cols / 4), 256), 256, 0, STREAM(stream)>>>(x, ldx, BF(hi), BF(lo), ldo, rows, cols);
+  Q8_CHECK(lo, ldo);
+  geglu_kernel<<<grid_for(rows * (cols / 4), 256), 256, 0, STREAM(stream)>>>(x, ldx, BF(hi), BFL(lo), ldo, rows, cols);
   count_launch(1);
   return (int)cudaGetLastError();
 }
@@ -1048,8 +1050,9 @@ extern "C" int odise_upsample2x_split_f32(const float* x, long long ldx, void* h
                                           int H, int W, int C, void* stream) {
   if (!x || !hi || B <= 0 || H <= 0 || W <= 0 || C <= 0) return ODISE_ERR_ARG;
   if (C % 4 || ldx % 4 || ldo % 4) return ODISE_ERR_ALIGN;
+  Q8_CHECK(lo, ldo);
   upsample2x_split_kernel<<<grid_for((long long)B * 4 * H * W * (C / 4), 256), 256, 0, STREAM(stream)>>>(
-      x, ldx, BF(hi), BF(lo), ldo, B, H, W, C);
+      x, ldx, BF(hi), BFL(lo), ldo, B, H, W, C);
   count_launch(1);
   return (int)cudaGetLastError();
 }
@@ -1059,8 +1062,9 @@ extern "C" int odise_im2col3x3_split_f32(const float* x, long long ldx, void* hi
   if (!x || !hi || B <= 0 || H <= 0 || W <= 0 || C <= 0 || stride <= 0 || Kpad < 9 * C || Kpad % 8)
     return ODISE_ERR_ARG;
   const int Ho = (H + pad_lo + pad_hi - 3) / stride + 1, Wo = (W + pad_lo + pad_hi - 3) / stride + 1;
+  Q8_CHECK(lo, Kpad);
   im2col3x3_split_kernel<<<grid_for((long long)B * Ho * Wo * Kpad, 256), 256, 0, STREAM(stream)>>>(
-      x, ldx, BF(hi), BF(lo), Kpad, B, H, W, C, stride, pad_lo, Ho, Wo);
+      x, ldx, BF(hi), BFL(lo), Kpad, B, H, W, C, stride, pad_lo, Ho, Wo);
   count_launch(1);
   return (int)cudaGetLastError();
 }
@@ -1105,7 +1109,8 @@ extern "C" int odise_nhwc_to_nchw_f32(const float* src, long long lds, float* ds
 extern "C" int odise_l2_normalize_split_f32(const float* x, long long ldx, void* hi, void* lo, long long ldo,
                                             long long rows, int cols, void* stream) {
   if (!x || !hi || rows <= 0 || cols <= 0) return ODISE_ERR_ARG;
-  l2norm_split_kernel<<<(int)((rows + 7) / 8), 256, 0, STREAM(stream)>>>(x, ldx, BF(hi), BF(lo), ldo, rows, cols);
+  Q8_CHECK(lo, ldo);
+  l2norm_split_kernel<<<(int)((rows + 7) / 8), 256, 0, STREAM(stream)>>>(x, ldx, BF(hi), BFL(lo), ldo, rows, cols);
   count_launch(1);
   return (int)cudaGetLastError();
 }
@@ -1146,7 +1151,8 @@ extern "C" int odise_pool_normalize_f32(const float* sums, const float* counts, 
 extern "C" int odise_softmax_split_f32(const float* x, long long ldx, void* hi, void* lo, long long ldo,
                                        long long rows, int cols, int cols_pad, float scale, void* stream) {
   if (!x || !hi || rows <= 0 || cols <= 0 || cols_pad < cols) return ODISE_ERR_ARG;
-  softmax_split_kernel<<<(int)((rows + 7) / 8), 256, 0, STREAM(stream)>>>(x, ldx, BF(hi), BF(lo), ldo, rows, cols,
+  Q8_CHECK(lo, ldo);
+  softmax_split_kernel<<<(int)((rows + 7) / 8), 256, 0, STREAM(stream)>>>(x, ldx, BF(hi), BFL(lo), ldo, rows, cols,
                                                                          cols_pad, scale);
   count_launch(1);
   return (int)cudaGetLastError();
@@ -1156,7 +1162,8 @@ extern "C" int odise_act_split_f32(const float* x, long long ldx, int act, void*
                                    long long rows, int cols, void* stream) {
   if (!x || !hi || rows <= 0 || cols <= 0) return ODISE_ERR_ARG;
   if (cols % 4 || ldx % 4 || ldo % 4) return ODISE_ERR_ALIGN;
-  act_split_kernel<<<grid_for(rows * (cols / 4), 256), 256, 0, STREAM(stream)>>>(x, ldx, act, BF(hi), BF(lo), ldo,
+  Q8_CHECK(lo, ldo);
+  act_split_kernel<<<grid_for(rows * (cols / 4), 256), 256, 0, STREAM(stream)>>>(x, ldx, act, BF(hi), BFL(lo), ldo,
                                                                                rows, cols / 4);
   count_launch(1);
   return (int)cudaGetLastError();
@@ -1169,7 +1176,8 @@ extern "C" int odise_groupnorm_apply_res_f32(const float* x, long long ldx, cons
                                              void* stream) {
   if (!x || !mean || !rstd || !gamma || !beta || (!y && !hi) || C % G) return ODISE_ERR_ARG;
   if (C % 4 || ldx % 4 || (y && ldy % 4) || (hi && ldo % 4) || (res && ldres % 4)) return ODISE_ERR_ALIGN;
-  int rc = launch_gn_apply(x, ldx, mean, rstd, gamma, beta, act, y, ldy, BF(hi), BF(lo), ldo, B, HW, C, G,
+  Q8_CHECK(lo, ldo);
+  int rc = launch_gn_apply(x, ldx, mean, rstd, gamma, beta, act, y, ldy, BF(hi), BFL(lo), ldo, B, HW, C, G,
                            (long long)HW * ldx, (long long)HW * ldy, (long long)HW * ldo, res, ldres, accumulate,
                            STREAM(stream));
   if (rc) return rc;
@@ -1288,7 +1296,8 @@ extern "C" int odise_crop_resize_bicubic(const void* img, int img_is_u8, float* 
 extern "C" int odise_patchify_split_f32(const float* x, void* hi, void* lo, int B, int S, int P, int Kpad, void* stream) {
   if (!x || !hi || B <= 0 || S <= 0 || P <= 0 || S % P || Kpad < 3 * P * P || Kpad % 8) return ODISE_ERR_ARG;
   const int G = S / P;
-  patchify_split_kernel<<<grid_for((long long)B * G * G * Kpad, 256), 256, 0, STREAM(stream)>>>(x, BF(hi), BF(lo), B, S,
+  Q8_CHECK(lo, Kpad);
+  patchify_split_kernel<<<grid_for((long long)B * G * G * Kpad, 256), 256, 0, STREAM(stream)>>>(x, BF(hi), BFL(lo), B, S,
                                                                                             P, Kpad);
   count_launch(1);
   return (int)cudaGetLastError();

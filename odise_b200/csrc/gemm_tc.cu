@@ -10,7 +10,10 @@
 //   (reference op: F.conv2d inside ldm ResBlock, call sites odise/modeling/meta_arch/ldm.py:481-489)
 // * precision: NMMA=1 plain bf16, NMMA=3 "bf16x3": operands carry a (hi, lo) bf16 pair per fp32 value and the
 //   kernel issues hi*hi + hi*lo + lo*hi into the same fp32 TMEM accumulator (~16 mantissa bits, the mode that
-//   meets the 1e-3 fp32 parity bar of BASELINE.json).
+//   meets the 1e-3 fp32 parity bar of BASELINE.json).  NMMA=2 "f16q8" (ptx.cuh, ODISE_PLANES_F16Q8):
+//   hi = fp16 plane, second plane = e5m2 bytes [x * 2^-6 | (x - hi) * 2^6] per 64-wide k-block; per k-block 4 kind::f16
+//   MMAs (hi*hi) + 4 kind::f8f6f4 MMAs (the two cross terms, K = 32 each, twice the MAC rate) into the same accumulator:
+//   8 instruction slots instead of 12, same shared-memory bytes, ~14 mantissa bits.
 // * persistent, warp-specialised: warp0 = TMA producer, warp1 = single-thread tcgen05.mma issuer, warps 2-5 =
 //   epilogue (tcgen05.ld -> bias / per-image row bias / residual / activation -> fp32 and/or (hi,lo) bf16 stores).
 //   Two TMEM accumulator stages let the epilogue of tile i overlap the main loop of tile i+1.
@@ -49,6 +52,7 @@ struct GemmParams {
   int geglu;   // N = 2*Nh with quad-interleaved (a, gate) columns: out[:, j] = a_j * gelu(g_j) -> planes [M, Nh]
   int vec_ok;  // all epilogue pointers / leading dims allow 16-byte vector access
   int h16;     // (hi, lo) output planes as fp16 instead of bf16 (V^T operand of the attention kernel)
+               // (F16Q8 output planes: Dl carries the q8 tag of ptx.cuh, store_planes() does the rest)
   float* partial;  // [splits][batch][M][N] when splits > 1
   // GroupNorm statistics of the OUTPUT, fused into the epilogue (the consumer's torch.nn.GroupNorm, ldm ResBlock
   // in_layers[0] / out_layers[0], call sites ldm.py:481-489): per (32-row segment, column) a record (shift, S1, S2) with
@@ -189,19 +193,24 @@ __device__ __forceinline__ void epilogue_quad(const GemmParams& p, int z, int m,
   if (p.Dh) {
     __nv_bfloat16* dh = p.Dh + (long long)z * p.h_bs + (long long)m * p.ldh + n;
     __nv_bfloat16* dl = p.Dl ? p.Dl + (long long)z * p.h_bs + (long long)m * p.ldh + n : nullptr;
-    __align__(8) __nv_bfloat16 h[4];
-    __align__(8) __nv_bfloat16 l[4];
+    if (p.h16) {
+      __align__(8) __nv_bfloat16 h[4];
+      __align__(8) __nv_bfloat16 l[4];
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      if (p.h16) split_f16(acc[t], *reinterpret_cast<uint16_t*>(&h[t]), *reinterpret_cast<uint16_t*>(&l[t]));
-      else split_bf16(acc[t], h[t], l[t]);
-    }
-    if (vec) {
-      *reinterpret_cast<uint2*>(dh) = *reinterpret_cast<const uint2*>(h);
-      if (dl) *reinterpret_cast<uint2*>(dl) = *reinterpret_cast<const uint2*>(l);
+      for (int t = 0; t < 4; ++t)
+        split_f16(acc[t], *reinterpret_cast<uint16_t*>(&h[t]), *reinterpret_cast<uint16_t*>(&l[t]));
+      if (vec) {
+        *reinterpret_cast<uint2*>(dh) = *reinterpret_cast<const uint2*>(h);
+        if (dl) *reinterpret_cast<uint2*>(dl) = *reinterpret_cast<const uint2*>(l);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) if (j < valid) { dh[j] = h[j]; if (dl) dl[j] = l[j]; }
+      }
+    } else if (vec) {
+      store_planes<4>(dh, dl, acc);
     } else {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) if (j < valid) { dh[j] = h[j]; if (dl) dl[j] = l[j]; }
+      for (int j = 0; j < 4; ++j) if (j < valid) store_planes<1>(dh + j, dl ? dl + j : nullptr, acc + j);
     }
   }
 }
@@ -211,15 +220,15 @@ struct GemmCfg {
   static constexpr int BM = 128, BK = 64;
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
-  static constexpr int PLANES = (NMMA == 3) ? 2 : 1;
+  static constexpr int PLANES = (NMMA == 1) ? 1 : 2;
   static constexpr int STAGE_BYTES = PLANES * (A_BYTES + B_BYTES);
   // epilogue warps: one warp per scheduler is latency bound (ncu: IPC 0.17/warp), so two warps share each TMEM lane
   // quadrant and alternate 16-column chunks; BN=160/bf16x3 has no shared memory left for the second set
-  static constexpr int NEPI = (BN == 160 && NMMA == 3) ? 4 : 8;
+  static constexpr int NEPI = (BN == 160 && NMMA != 1) ? 4 : 8;
   static constexpr int THREADS = 64 + 32 * NEPI;
   // per warp [32 rows x 16 fp32] staging (XOR swizzled); doubled where shared memory allows so that the TMA store of
   // chunk i can still be reading its buffer while chunk i + 1 is written
-  static constexpr int EPI_BUFS = (BN == 160 && NMMA == 3) ? 1 : 2;
+  static constexpr int EPI_BUFS = (BN == 160 && NMMA != 1) ? 1 : 2;
   static constexpr int EPI_PER_WARP = EPI_BUFS * 32 * 16 * 4;
   static constexpr int EPI_BYTES = NEPI * EPI_PER_WARP;
   static constexpr int STAGES_RAW = (232448 - EPI_BYTES - 256) / STAGE_BYTES;
@@ -259,7 +268,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
     }
     tma_prefetch_desc(&tmAh);
     tma_prefetch_desc(&tmBh);
-    if (NMMA == 3) {
+    if (NMMA != 1) {
       tma_prefetch_desc(&tmAl);
       tma_prefetch_desc(&tmBl);
     }
@@ -319,7 +328,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
             if (p.nseg == 1) {
               const int cx = w0 * p.cstride + kw - p.cpad, cy = h0 * p.cstride + kh - p.cpad;
               tma_load_4d(st, &tmAh, &full[stage], cc * 64, cx, cy, b0);
-              if (NMMA == 3) tma_load_4d(st + Cfg::A_BYTES, &tmAl, &full[stage], cc * 64, cx, cy, b0);
+              if (NMMA != 1) tma_load_4d(st + Cfg::A_BYTES, &tmAl, &full[stage], cc * 64, cx, cy, b0);
             } else {
               // widths that are neither a divisor nor a multiple of 128: raster-consecutive segments of
               // bw = gcd(W, 128) pixels never straddle an image row; each lands on its 8-row-aligned slice of the tile
@@ -331,18 +340,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
                 const int cx = wi * p.cstride + kw - p.cpad, cy = hi_ * p.cstride + kh - p.cpad;
                 uint8_t* sa = st + sg * p.bw * 128;
                 tma_load_4d(sa, &tmAh, &full[stage], cc * 64, cx, cy, bi);
-                if (NMMA == 3) tma_load_4d(sa + Cfg::A_BYTES, &tmAl, &full[stage], cc * 64, cx, cy, bi);
+                if (NMMA != 1) tma_load_4d(sa + Cfg::A_BYTES, &tmAl, &full[stage], cc * 64, cx, cy, bi);
               }
             }
           } else {
             const int za = p.a_batched ? z : 0;
             tma_load_3d(st, &tmAh, &full[stage], kb * 64, m0, za);
-            if (NMMA == 3) tma_load_3d(st + Cfg::A_BYTES, &tmAl, &full[stage], kb * 64, m0, za);
+            if (NMMA != 1) tma_load_3d(st + Cfg::A_BYTES, &tmAl, &full[stage], kb * 64, m0, za);
           }
           const int zb = p.b_batched ? z : 0;
           uint8_t* sb = st + Cfg::PLANES * Cfg::A_BYTES;
           tma_load_3d(sb, &tmBh, &full[stage], kb * 64, n0, zb);
-          if (NMMA == 3) tma_load_3d(sb + Cfg::B_BYTES, &tmBl, &full[stage], kb * 64, n0, zb);
+          if (NMMA != 1) tma_load_3d(sb + Cfg::B_BYTES, &tmBl, &full[stage], kb * 64, n0, zb);
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -350,7 +359,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
   } else if (warp == 1) {
     if (lane == 0) {
       // ------------------------------------------------------------ MMA issuer (one thread)
-      constexpr uint32_t idesc = umma_idesc_bf16(128, BN);
+      constexpr uint32_t idesc = NMMA == 2 ? umma_idesc_f16(128, BN) : umma_idesc_bf16(128, BN);
+      constexpr uint32_t idesc_q = umma_idesc_e5m2(128, BN);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -378,6 +388,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
               const uint64_t b_lo = umma_desc_sw128(sb + Cfg::B_BYTES + k * 32);
               umma_bf16(d_tmem, a_hi, b_lo, idesc, 1u);
               umma_bf16(d_tmem, a_lo, b_hi, idesc, 1u);
+            }
+          }
+          if (NMMA == 2) {
+            // cross terms on the 8-bit pipe: the second plane of a stage is [q_hi: 64 B | q_lo: 64 B] per row, i.e. 32-byte
+            // chunks 0,1 = q_hi(k 0..31 | 32..63), chunks 2,3 = q_lo;  A.q_hi * B.q_lo + A.q_lo * B.q_hi
+            const uint32_t a2 = sa + Cfg::A_BYTES, b2 = sb + Cfg::B_BYTES;
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+              umma_f8(d_tmem, umma_desc_sw128(a2 + k * 32), umma_desc_sw128(b2 + 64 + k * 32), idesc_q, 1u);
+              umma_f8(d_tmem, umma_desc_sw128(a2 + 64 + k * 32), umma_desc_sw128(b2 + k * 32), idesc_q, 1u);
             }
           }
           umma_commit(&empty[stage]);  // smem slot reusable once these MMAs retire
@@ -587,13 +607,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
               const float r1 = __shfl_xor_sync(0xffffffffu, odd ? e[1] : e[3], 1);
               const float a0 = odd ? r0 : e[0], a1 = odd ? r1 : e[1];
               const float g0 = odd ? e[2] : r0, g1 = odd ? e[3] : r1;
-              __nv_bfloat16 h0, l0, h1, l1;
-              split_bf16(a0 * gelu_erf_fast(g0), h0, l0);
-              split_bf16(a1 * gelu_erf_fast(g1), h1, l1);
+              const float gv[2] = {a0 * gelu_erf_fast(g0), a1 * gelu_erf_fast(g1)};
               const long long og = (long long)z * p.h_bs + (long long)(m_base + it * 8 + rsub) * p.ldh +
                                    ((n0 + c0) >> 1) + (cq >> 1) * 4 + (odd ? 2 : 0);
-              *reinterpret_cast<__nv_bfloat162*>(p.Dh + og) = __halves2bfloat162(h0, h1);
-              if (to_lo) *reinterpret_cast<__nv_bfloat162*>(p.Dl + og) = __halves2bfloat162(l0, l1);
+              store_planes<2>(p.Dh + og, to_lo ? p.Dl + og : nullptr, gv);
               continue;
             }
             if (act != ODISE_ACT_NONE) {
@@ -620,21 +637,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
                 *reinterpret_cast<uint2*>(p.Dl + oH[it] + c0) = lv;
               }
             } else if (to_hi) {
-              // packed conversions: hi = bf16x2(e), lo = bf16x2(e - float(hi))  (same values as split_bf16)
-              const __nv_bfloat162 h01 = __floats2bfloat162_rn(e[0], e[1]), h23 = __floats2bfloat162_rn(e[2], e[3]);
-              uint2 hv;
-              hv.x = *reinterpret_cast<const uint32_t*>(&h01);
-              hv.y = *reinterpret_cast<const uint32_t*>(&h23);
-              *reinterpret_cast<uint2*>(p.Dh + oH[it] + c0) = hv;
-              if (to_lo) {
-                const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
-                const __nv_bfloat162 l01 = __floats2bfloat162_rn(e[0] - f01.x, e[1] - f01.y);
-                const __nv_bfloat162 l23 = __floats2bfloat162_rn(e[2] - f23.x, e[3] - f23.y);
-                uint2 lv;
-                lv.x = *reinterpret_cast<const uint32_t*>(&l01);
-                lv.y = *reinterpret_cast<const uint32_t*>(&l23);
-                *reinterpret_cast<uint2*>(p.Dl + oH[it] + c0) = lv;
-              }
+              // bf16 pair (packed conversions, same values as split_bf16) or, when Dl carries the tag, fp16 + e5m2 bytes
+              store_planes<4>(p.Dh + oH[it] + c0, to_lo ? p.Dl + oH[it] + c0 : nullptr, e);
             }
           }
           if (has_gn) gn_acc_store(gacc, p, gn_seg, n0 + c0 + cq * 4, 4, lane);
@@ -675,13 +679,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
 #pragma unroll
                 for (int j = 0; j < 4; ++j) gt[j] = __shfl_xor_sync(0xffffffffu, e[j], 1);
                 if ((cq & 1) == 0 && m < p.M) {
-                  __align__(8) __nv_bfloat16 h[4];
-                  __align__(8) __nv_bfloat16 l[4];
+                  float gv[4];
 #pragma unroll
-                  for (int t = 0; t < 4; ++t) split_bf16(e[t] * gelu_erf_fast(gt[t]), h[t], l[t]);
+                  for (int t = 0; t < 4; ++t) gv[t] = e[t] * gelu_erf_fast(gt[t]);
                   const long long og = (long long)z * p.h_bs + (long long)m * p.ldh + ((n0 + c0) >> 1) + (cq >> 1) * 4;
-                  *reinterpret_cast<uint2*>(p.Dh + og) = *reinterpret_cast<const uint2*>(h);
-                  if (p.Dl) *reinterpret_cast<uint2*>(p.Dl + og) = *reinterpret_cast<const uint2*>(l);
+                  store_planes<4>(p.Dh + og, p.Dl ? p.Dl + og : nullptr, gv);
                 }
                 continue;
               }
@@ -864,8 +866,8 @@ using namespace ob;
 extern "C" int odise_gemm_bf16(const odise_gemm_desc* d, void* stream_v) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
   if (!d || !d->a_hi || !d->b_hi) return ODISE_ERR_ARG;
-  if (d->nmma != 1 && d->nmma != 3) return ODISE_ERR_ARG;
-  if (d->nmma == 3 && (!d->a_lo || !d->b_lo)) return ODISE_ERR_ARG;
+  if (d->nmma != 1 && d->nmma != 2 && d->nmma != 3) return ODISE_ERR_ARG;
+  if (d->nmma != 1 && (!d->a_lo || !d->b_lo)) return ODISE_ERR_ARG;
   if (d->M <= 0 || d->N <= 0 || d->K <= 0 || d->batch <= 0) return ODISE_ERR_ARG;
   if (!d->out_f32 && !d->out_hi) return ODISE_ERR_ARG;
 
@@ -882,8 +884,15 @@ extern "C" int odise_gemm_bf16(const odise_gemm_desc* d, void* stream_v) {
   p.ldh = d->ld_out_bf16; p.h_bs = d->out_bf16_batch_stride;
   p.act = d->act;
   p.geglu = d->geglu;
-  p.h16 = d->out_planes_fp16 ? 1 : 0;
+  p.h16 = d->out_planes_fp16 == ODISE_PLANES_F16 ? 1 : 0;
   if (p.h16 && (d->geglu || !d->out_hi)) return ODISE_ERR_UNSUPPORTED;
+  const bool oq8 = d->out_planes_fp16 == ODISE_PLANES_F16Q8 && d->out_hi;
+  if (d->out_planes_fp16 < 0 || d->out_planes_fp16 > 2) return ODISE_ERR_ARG;
+  if (oq8) {   // F16Q8 output planes: both planes, rows on 128-byte boundaries (store_planes reads k % 64 off the address)
+    if (!d->out_lo || d->ld_out_bf16 % 64 || d->out_bf16_batch_stride % 64 || (reinterpret_cast<uintptr_t>(d->out_lo) & 127))
+      return ODISE_ERR_ALIGN;
+    p.Dl = tag_q8(p.Dl);
+  }
   if (d->gn_partial) {
     // whole 32-row segments, final values produced by this kernel (no split-K second pass, no GEGLU re-pairing)
     if (d->M % 32 || d->split_k > 1 || d->geglu || d->gn_seg_stride <= 0 || d->gn_plane_stride <= 0)
@@ -945,7 +954,7 @@ extern "C" int odise_gemm_bf16(const odise_gemm_desc* d, void* stream_v) {
     cuuint32_t box[4] = {64, (cuuint32_t)(p.bw * p.cstride), (cuuint32_t)(p.bh * p.cstride), (cuuint32_t)p.bb};
     rc = encode_map(&ah, d->a_hi, 4, dims, str, box, p.cstride);
     if (rc) return rc;
-    rc = encode_map(&al, d->nmma == 3 ? d->a_lo : d->a_hi, 4, dims, str, box, p.cstride);
+    rc = encode_map(&al, d->nmma != 1 ? d->a_lo : d->a_hi, 4, dims, str, box, p.cstride);
     if (rc) return rc;
   } else {
     if (d->lda % 8 || d->a_batch_stride % 8) return ODISE_ERR_ALIGN;
@@ -955,7 +964,11 @@ extern "C" int odise_gemm_bf16(const odise_gemm_desc* d, void* stream_v) {
     cuuint32_t box[3] = {64, 128, 1};
     rc = encode_map(&ah, d->a_hi, 3, dims, str, box);
     if (rc) return rc;
-    rc = encode_map(&al, d->nmma == 3 ? d->a_lo : d->a_hi, 3, dims, str, box);
+    if (d->nmma == 2) {   // the q bytes of the last (partial) k-block occupy its whole 128-byte slot
+      dims[0] = (cuuint64_t)((d->K + 63) / 64 * 64);
+      if ((long long)dims[0] > d->lda) return ODISE_ERR_ALIGN;
+    }
+    rc = encode_map(&al, d->nmma != 1 ? d->a_lo : d->a_hi, 3, dims, str, box);
     if (rc) return rc;
   }
   const int BN = pick_bn(d->M, d->N, d->K, d->batch, d->force_bn, d->conv3x3 != 0);
@@ -967,7 +980,11 @@ extern "C" int odise_gemm_bf16(const odise_gemm_desc* d, void* stream_v) {
     cuuint32_t box[3] = {64, (cuuint32_t)BN, 1};
     rc = encode_map(&bh, d->b_hi, 3, dims, str, box);
     if (rc) return rc;
-    rc = encode_map(&bl, d->nmma == 3 ? d->b_lo : d->b_hi, 3, dims, str, box);
+    if (d->nmma == 2) {
+      dims[0] = (cuuint64_t)((d->K + 63) / 64 * 64);
+      if ((long long)dims[0] > d->ldb) return ODISE_ERR_ALIGN;
+    }
+    rc = encode_map(&bl, d->nmma != 1 ? d->b_lo : d->b_hi, 3, dims, str, box);
     if (rc) return rc;
   }
   if (d->geglu) {
@@ -1004,7 +1021,7 @@ extern "C" int odise_gemm_bf16(const odise_gemm_desc* d, void* stream_v) {
   {
     static const bool off = getenv("ODISE_NO_TMA_STORE") != nullptr;
     const bool one_kind = (d->out_f32 != nullptr) != (d->out_hi != nullptr);
-    if (!off && epi != 2 && p.vec_ok && p.splits == 1 && !p.gnp && one_kind) {
+    if (!off && epi != 2 && p.vec_ok && p.splits == 1 && !p.gnp && one_kind && !oq8) {
       if (d->out_f32) {
         rc = encode_out_map(&o0, d->out_f32, true, d->N, d->M, d->batch, d->ld_out, d->out_batch_stride);
         if (!rc) p.tma_out = 1;
@@ -1027,6 +1044,13 @@ extern "C" int odise_gemm_bf16(const odise_gemm_desc* d, void* stream_v) {
       case 128: ODISE_LAUNCH(128, 3); break;
       case 160: ODISE_LAUNCH(160, 3); break;
       default: ODISE_LAUNCH(256, 3); break;
+    }
+  } else if (d->nmma == 2) {
+    switch (BN) {
+      case 64: ODISE_LAUNCH(64, 2); break;
+      case 128: ODISE_LAUNCH(128, 2); break;
+      case 160: ODISE_LAUNCH(160, 2); break;
+      default: ODISE_LAUNCH(256, 2); break;
     }
   } else {
     switch (BN) {

@@ -103,12 +103,8 @@ msda_vec4_kernel(const float* __restrict__ value, const MsdaLevels lv, const flo
   const long long o = pair * D + c;
   if (out) *reinterpret_cast<float4*>(out + o) = acc;
   if (out_hi) {
-    __align__(8) __nv_bfloat16 h[4];
-    __align__(8) __nv_bfloat16 lo[4];
-    split_bf16(acc.x, h[0], lo[0]); split_bf16(acc.y, h[1], lo[1]);
-    split_bf16(acc.z, h[2], lo[2]); split_bf16(acc.w, h[3], lo[3]);
-    *reinterpret_cast<uint2*>(out_hi + o) = *reinterpret_cast<const uint2*>(h);
-    if (out_lo) *reinterpret_cast<uint2*>(out_lo + o) = *reinterpret_cast<const uint2*>(lo);
+    const float e[4] = {acc.x, acc.y, acc.z, acc.w};
+    store_planes<4>(out_hi + o, out_lo ? out_lo + o : nullptr, e);
   }
 }
 
@@ -247,12 +243,8 @@ msda_d32_kernel(const float* __restrict__ value, const MsdaLevels lv, const floa
   const long long o = pair * 32 + c;
   if (out) *reinterpret_cast<float4*>(out + o) = acc;
   if (out_hi) {
-    __align__(8) __nv_bfloat16 h[4];
-    __align__(8) __nv_bfloat16 lo[4];
-    split_bf16(acc.x, h[0], lo[0]); split_bf16(acc.y, h[1], lo[1]);
-    split_bf16(acc.z, h[2], lo[2]); split_bf16(acc.w, h[3], lo[3]);
-    *reinterpret_cast<uint2*>(out_hi + o) = *reinterpret_cast<const uint2*>(h);
-    if (out_lo) *reinterpret_cast<uint2*>(out_lo + o) = *reinterpret_cast<const uint2*>(lo);
+    const float e[4] = {acc.x, acc.y, acc.z, acc.w};
+    store_planes<4>(out_hi + o, out_lo ? out_lo + o : nullptr, e);
   }
 }
 
@@ -315,14 +307,14 @@ extern "C" int odise_msda_fused_f32(const float* value, const int64_t* spatial_s
   MsdaLevels lv{spatial_shapes, level_start};
   if (d32_ok(S, M, D, L, P)) {
     launch_d32<1>(value, lv, offs, logits, ref, out, reinterpret_cast<__nv_bfloat16*>(out_hi),
-                  reinterpret_cast<__nv_bfloat16*>(out_lo), N, S, M, L, Lq, P, stream);
+                  lo_arg(reinterpret_cast<__nv_bfloat16*>(out_lo)), N, S, M, L, Lq, P, stream);
   } else {
     const int lph = D / 4;
     const long long threads = (long long)N * Lq * M * lph;
     const int blocks = (int)((threads + 255) / 256);
     msda_vec4_kernel<1><<<blocks, 256, 0, stream>>>(value, lv, offs, logits, ref, out,
                                                     reinterpret_cast<__nv_bfloat16*>(out_hi),
-                                                    reinterpret_cast<__nv_bfloat16*>(out_lo), N, S, M, D, L, Lq, P, lph);
+                                                    lo_arg(reinterpret_cast<__nv_bfloat16*>(out_lo)), N, S, M, D, L, Lq, P, lph);
   }
   count_launch(1);
   return (int)cudaGetLastError();

@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
+#include <cuda_fp8.h>
 #include <stdint.h>
 #include <stdio.h>
 
@@ -187,12 +188,132 @@ __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bflo
   lo = __float2bfloat16_rn(x - __bfloat162float(hi));
 }
 
+// D[tmem] (+)= A[smem] * B[smem] on 8-bit float operands (kind::f8f6f4, K = 32 per instruction, fp32 accumulation into the
+// same TMEM accumulator the kind::f16 MMAs of a tile use): twice the MAC rate of the 16-bit kinds.  Operand tiles are the
+// same K-major SWIZZLE_128B layout with 128 one-byte elements per row, so the shared-memory descriptors are those of the
+// 16-bit path byte for byte; the instruction descriptor carries a/b format 1 = E5M2 (the bit pattern of umma_idesc_bf16).
+__device__ __forceinline__ void umma_f8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                        uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__host__ __device__ constexpr uint32_t umma_idesc_e5m2(uint32_t m, uint32_t n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
+}
+
 // the same split into an fp16 pair (11 + 11 mantissa bits; operands of the attention P V product)
 __device__ __forceinline__ void split_f16(float x, uint16_t& hi, uint16_t& lo) {
   const __half h = __float2half_rn(x);
   const __half l = __float2half_rn(x - __half2float(h));
   hi = __half_as_ushort(h);
   lo = __half_as_ushort(l);
+}
+
+// ------------------------------------------------------------------------------------------------ operand planes
+// Three formats of the (hi, lo) operand planes of an fp32 matrix [rows, K] (ODISE_PLANES_* in odise_b200.h):
+//   BF16  hi = bf16(x), lo = bf16(x - hi)                         -> bf16x3: hi*hi + hi*lo + lo*hi, 3 MMAs of kind::f16
+//   F16   the same with fp16 words (V^T of the attention kernel)
+//   F16Q8 hi = fp16(x);  the second plane has the SAME byte geometry (2 bytes per element, same row stride) but holds,
+//         per block of 64 consecutive k, 64 bytes q_hi[k] = e5m2(x * 2^-S) followed by 64 bytes
+//         q_lo[k] = e5m2((x - hi) * 2^S), S = kQ8Shift.  A GEMM in this format issues, per 64-wide k-block,
+//         4 x kind::f16 (A_hi * B_hi) + 4 x kind::f8f6f4 (A.q_hi * B.q_lo and A.q_lo * B.q_hi, the two first-order
+//         correction terms; the power-of-two scales cancel) = 8 MMA instruction slots instead of the 12 of bf16x3, into one
+//         fp32 TMEM accumulator.  Error per product ~2^-14 (e5m2 keeps 3 significant bits of a term that is itself 2^-12 of
+//         the product) vs 2^-16 for bf16x3; UNet taps 1.1e-4 vs 2e-5 against the fp32 oracle (tools/precision_budget.py),
+//         bar 1e-3.  Out-of-range values degrade gracefully: a saturated / flushed q byte only perturbs a 2^-12 term.
+// Rows of F16Q8 planes start on 128-byte boundaries (ld % 64 == 0, checked by the host), so the position of an element
+// inside its k-block can be read off its address; device code receives the second plane's pointer with bit 0 set as the
+// format tag (set by the launchers from odise_set_operand_format(), never part of the C ABI).
+constexpr int kQ8Shift = 6;
+constexpr float kQ8Down = 1.f / 64.f, kQ8Up = 64.f;   // 2^-S, 2^S
+
+__host__ __device__ __forceinline__ bool lo_is_q8(const void* lo) { return (reinterpret_cast<uintptr_t>(lo) & 1u) != 0; }
+template <typename T>
+__host__ __device__ __forceinline__ T* tag_q8(T* lo) {
+  return reinterpret_cast<T*>(reinterpret_cast<uintptr_t>(lo) | 1u);
+}
+// two floats -> two e5m2 bytes (first value in the low byte), round-to-nearest, saturating to +-57344
+__device__ __forceinline__ uint32_t e5m2x2(float a, float b) {
+  return (uint32_t)__nv_cvt_float2_to_fp8x2(make_float2(a, b), __NV_SATFINITE, __NV_E5M2);
+}
+__device__ __forceinline__ float clamp_f16(float x) { return fminf(fmaxf(x, -65504.f), 65504.f); }
+
+// N (1, 2, 4 or 8) consecutive columns starting at a column that is a multiple of N: `hi` / `lo` point AT the first element
+// (2-byte element units in both planes).  lo == nullptr: hi plane only (bf16).  Tagged lo: F16Q8.
+template <int N>
+__device__ __forceinline__ void store_planes(__nv_bfloat16* hi, __nv_bfloat16* lo, const float* v) {
+  static_assert(N == 1 || N == 2 || N == 4 || N == 8, "vector width");
+  if (lo_is_q8(lo)) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(lo) & ~static_cast<uintptr_t>(1);
+    uint8_t* q = reinterpret_cast<uint8_t*>(a - ((a >> 1) & 63u));   // block base + (column % 64)
+    if constexpr (N == 1) {
+      const __half h = __float2half_rn(clamp_f16(v[0]));
+      *reinterpret_cast<__half*>(hi) = h;
+      const uint32_t w = e5m2x2(v[0] * kQ8Down, (v[0] - __half2float(h)) * kQ8Up);
+      q[0] = (uint8_t)(w & 0xffu);
+      q[64] = (uint8_t)(w >> 8);
+    } else {
+      uint32_t hw[N / 2], qh[N / 2], ql[N / 2];
+#pragma unroll
+      for (int j = 0; j < N / 2; ++j) {
+        const __half2 h2 = __floats2half2_rn(clamp_f16(v[2 * j]), clamp_f16(v[2 * j + 1]));
+        hw[j] = *reinterpret_cast<const uint32_t*>(&h2);
+        const float2 f = __half22float2(h2);
+        qh[j] = e5m2x2(v[2 * j] * kQ8Down, v[2 * j + 1] * kQ8Down);
+        ql[j] = e5m2x2((v[2 * j] - f.x) * kQ8Up, (v[2 * j + 1] - f.y) * kQ8Up);
+      }
+      if constexpr (N == 2) {
+        *reinterpret_cast<uint32_t*>(hi) = hw[0];
+        *reinterpret_cast<uint16_t*>(q) = (uint16_t)qh[0];
+        *reinterpret_cast<uint16_t*>(q + 64) = (uint16_t)ql[0];
+      } else if constexpr (N == 4) {
+        *reinterpret_cast<uint2*>(hi) = make_uint2(hw[0], hw[1]);
+        *reinterpret_cast<uint32_t*>(q) = qh[0] | (qh[1] << 16);
+        *reinterpret_cast<uint32_t*>(q + 64) = ql[0] | (ql[1] << 16);
+      } else {
+        *reinterpret_cast<uint4*>(hi) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+        *reinterpret_cast<uint2*>(q) = make_uint2(qh[0] | (qh[1] << 16), qh[2] | (qh[3] << 16));
+        *reinterpret_cast<uint2*>(q + 64) = make_uint2(ql[0] | (ql[1] << 16), ql[2] | (ql[3] << 16));
+      }
+    }
+    return;
+  }
+  if constexpr (N == 1) {
+    __nv_bfloat16 h, l;
+    split_bf16(v[0], h, l);
+    *hi = h;
+    if (lo) *lo = l;
+  } else {
+    uint32_t hw[N / 2], lw[N / 2];
+#pragma unroll
+    for (int j = 0; j < N / 2; ++j) {   // packed conversions: same values as split_bf16
+      const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+      hw[j] = *reinterpret_cast<const uint32_t*>(&h2);
+      const float2 f = __bfloat1622float2(h2);
+      const __nv_bfloat162 l2 = __floats2bfloat162_rn(v[2 * j] - f.x, v[2 * j + 1] - f.y);
+      lw[j] = *reinterpret_cast<const uint32_t*>(&l2);
+    }
+    if constexpr (N == 2) {
+      *reinterpret_cast<uint32_t*>(hi) = hw[0];
+      if (lo) *reinterpret_cast<uint32_t*>(lo) = lw[0];
+    } else if constexpr (N == 4) {
+      *reinterpret_cast<uint2*>(hi) = make_uint2(hw[0], hw[1]);
+      if (lo) *reinterpret_cast<uint2*>(lo) = make_uint2(lw[0], lw[1]);
+    } else {
+      *reinterpret_cast<uint4*>(hi) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+      if (lo) *reinterpret_cast<uint4*>(lo) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+    }
+  }
+}
+
+// launch-time operand format of the planes written by the producer kernels (odise_set_operand_format)
+int operand_format();
+template <typename T>
+static inline T* lo_arg(T* lo) {
+  return (lo && operand_format() == 2) ? tag_q8(lo) : lo;
 }
 
 }  // namespace ob

@@ -116,6 +116,8 @@ _SIGS = {
     "odise_postprocess_fused_f32": [c_void_p, c_void_p, c_void_p, c_int] + [c_void_p] * 8 + [ctypes.c_double] + [c_void_p] * 7 +
                                    [c_int] * 9 + [c_void_p, c_void_p],
     "odise_set_carveout_policy": [c_int],
+    "odise_set_operand_format": [c_int],
+    "odise_get_operand_format": [],
     "odise_gather_rows_f32": [c_void_p, c_longlong, c_void_p, c_void_p, c_longlong, c_int, c_void_p, c_longlong, c_longlong,
                               c_int, c_void_p],
     "odise_maskclip_preprocess": [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
@@ -188,27 +190,52 @@ class PostprocessGeom(ctypes.Structure):
     _fields_ = [("pad_h", c_int), ("pad_w", c_int), ("img_h", c_int), ("img_w", c_int)]
 
 
+Q8 = "q8"          # value of the engines' `lo` switch in the F16Q8 operand mode (truthy: a second plane exists)
+Q8_SHIFT = 6       # kQ8Shift of csrc/ptx.cuh
+PLANES_BF16, PLANES_F16, PLANES_F16Q8 = 0, 1, 2
+
+
 class Planes:
-    """(hi, lo) bf16 operand planes of a 2-D fp32 matrix [rows, cols] (row stride ld elements)."""
+    """(hi, lo) operand planes of a 2-D fp32 matrix [rows, cols] (row stride ld elements of 2 bytes, both planes).
+    fmt: "bf16" = bf16 pair (lo may be None: plain bf16) | "f16" = fp16 pair (V^T of the attention kernel) | "q8" = fp16 hi +
+    e5m2 correction bytes [x * 2^-6 | (x - hi) * 2^6] per 64-wide k-block (ODISE_PLANES_F16Q8, include/odise_b200.h)."""
 
-    __slots__ = ("hi", "lo", "rows", "cols", "ld", "f16")
+    __slots__ = ("hi", "lo", "rows", "cols", "ld", "fmt")
 
-    def __init__(self, hi, lo, rows, cols, ld, f16=False):
+    def __init__(self, hi, lo, rows, cols, ld, f16=False, fmt=None):
         self.hi, self.lo, self.rows, self.cols, self.ld = hi, lo, rows, cols, ld
-        self.f16 = f16          # the 16-bit words are fp16, not bf16 (V^T operand of the attention kernel, bf16x3 mode)
+        self.fmt = fmt or ("f16" if f16 else "bf16")
+
+    @property
+    def f16(self):
+        return self.fmt == "f16"
+
+    @property
+    def code(self):
+        return {"bf16": PLANES_BF16, "f16": PLANES_F16, "q8": PLANES_F16Q8}[self.fmt]
 
     @staticmethod
     def empty(rows, cols, device, lo=True, ld=None, f16=False):
+        """lo: False = hi plane only | True = bf16 pair (fp16 pair with f16=True) | lib.Q8 = the F16Q8 format (rows padded to
+        whole 64-element k-blocks, pad bytes zero)."""
+        q8 = lo == Q8 and not f16
         ld = ld or ((cols + 7) // 8 * 8)
+        if q8:
+            ld = (ld + 63) // 64 * 64
         hi = torch.empty(rows * ld, dtype=torch.bfloat16, device=device)
         lo_t = torch.empty(rows * ld, dtype=torch.bfloat16, device=device) if lo else None
         if ld != cols:
             hi.zero_()
             if lo_t is not None:
                 lo_t.zero_()
-        return Planes(hi, lo_t, rows, cols, ld, f16)
+        return Planes(hi, lo_t, rows, cols, ld, fmt="q8" if q8 else ("f16" if f16 else "bf16"))
 
     def float(self):
+        if self.fmt == "q8":        # test helper: hi + the decoded low-order correction
+            h = self.hi.view(torch.float16).view(self.rows, self.ld)[:, : self.cols].float()
+            qb = self.lo.view(torch.uint8).view(self.rows, self.ld // 64, 2, 64)
+            ql = qb[:, :, 1, :].reshape(self.rows, self.ld)[:, : self.cols].contiguous().view(torch.float8_e5m2).float()
+            return h + ql * 2.0 ** -Q8_SHIFT
         vw = (lambda t: t.view(torch.float16)) if self.f16 else (lambda t: t)
         h = vw(self.hi).view(self.rows, self.ld)[:, : self.cols].float()
         if self.lo is not None:
@@ -216,13 +243,30 @@ class Planes:
         return h
 
     def col_slice(self, c0, cols):
-        """Planes viewing columns [c0, c0+cols) of every row (same ld); c0 % 8 == 0."""
-        assert c0 % 8 == 0
-        return Planes(self.hi[c0:], None if self.lo is None else self.lo[c0:], self.rows, cols, self.ld, self.f16)
+        """Planes viewing columns [c0, c0+cols) of every row (same ld); c0 % 8 == 0 (q8: whole 64-wide k-blocks)."""
+        assert c0 % (64 if self.fmt == "q8" else 8) == 0
+        return Planes(self.hi[c0:], None if self.lo is None else self.lo[c0:], self.rows, cols, self.ld, fmt=self.fmt)
 
     def row_slice(self, r0, rows):
         return Planes(self.hi[r0 * self.ld:], None if self.lo is None else self.lo[r0 * self.ld:], rows, self.cols,
-                      self.ld, self.f16)
+                      self.ld, fmt=self.fmt)
+
+
+_FMT_STATE = [PLANES_BF16]
+
+
+def pargs(p):
+    """(hi pointer, lo pointer, ld) of output planes for a producer entry point, and tell the library which format the
+    kernels launched next must write (odise_set_operand_format is a launch-time host parameter)."""
+    if p is None:
+        return None, None, 0
+    if p.fmt == "f16":
+        raise OdiseError("fp16-pair planes are written by odise_gemm_bf16 / odise_split_f16_f32 only")
+    code = p.code
+    if _FMT_STATE[0] != code:
+        _check(load().odise_set_operand_format(code), "odise_set_operand_format")
+        _FMT_STATE[0] = code
+    return _ptr(p.hi), _ptr(p.lo), p.ld
 
 
 class GnStats:
@@ -260,15 +304,21 @@ class GnStats:
 
 
 def split(x, out=None, lo=True, f16=False):
-    """fp32 [rows, cols] (last dim contiguous) -> Planes (bf16 pair; f16=True: fp16 pair)."""
+    """fp32 [rows, cols] (last dim contiguous) -> Planes (bf16 pair; f16=True: fp16 pair; lo=lib.Q8: F16Q8)."""
     _req(x, torch.float32, "x")
     x2 = x.reshape(-1, x.shape[-1])
     rows, cols = x2.shape
     assert x2.stride(1) == 1
     if out is None:
         out = Planes.empty(rows, cols, x.device, lo=lo, f16=f16)
-    fn = load().odise_split_f16_f32 if out.f16 else load().odise_split_f32
-    _check(fn(_ptr(x2), x2.stride(0), _ptr(out.hi), _ptr(out.lo), out.ld, rows, cols, _stream()), "odise_split_f32")
+    if out.f16:
+        _check(load().odise_split_f16_f32(_ptr(x2), x2.stride(0), _ptr(out.hi), _ptr(out.lo), out.ld, rows, cols, _stream()),
+               "odise_split_f16_f32")
+    else:
+        if out.fmt == "q8" and cols % 4:
+            raise OdiseError("split: F16Q8 planes need cols % 4 == 0")
+        hi, lo_p, ld = pargs(out)
+        _check(load().odise_split_f32(_ptr(x2), x2.stride(0), hi, lo_p, ld, rows, cols, _stream()), "odise_split_f32")
     return out
 
 
@@ -329,11 +379,19 @@ def gemm(a, b, *, M=None, N=None, K=None, nmma=3, batch=1, a_bs=0, b_bs=0, conv=
     d.N = N if N is not None else b.rows
     d.K = K if K is not None else (9 * conv[0] if conv else a.cols)
     d.batch = batch
-    d.nmma = nmma
     if conv:
         d.conv3x3, d.conv_C, d.conv_H, d.conv_W = 1, conv[0], conv[1], conv[2]
     if a.f16 or b.f16:
         raise OdiseError("gemm: fp16 planes are attention-kernel operands (V^T), not GEMM inputs")
+    if a.fmt != b.fmt:
+        raise OdiseError(f"gemm: operand formats differ ({a.fmt} x {b.fmt})")
+    if a.fmt == "q8":
+        if nmma == 1:
+            raise OdiseError("gemm: F16Q8 operands have no plain-bf16 mode")
+        nmma = 2               # fp16 hi*hi + e5m2 cross terms; the engines pass their own nmma (2) or the default 3
+    elif nmma == 2:
+        nmma = 3               # an engine in the F16Q8 mode calling with bf16-pair operands (attention / binary-mask GEMMs)
+    d.nmma = nmma
     d.a_hi, d.a_lo, d.lda, d.a_batch_stride = _ptr(a.hi), _ptr(a.lo), a.ld, a_bs
     d.b_hi, d.b_lo, d.ldb, d.b_batch_stride = _ptr(b.hi), _ptr(b.lo), b.ld, b_bs
     d.alpha = alpha
@@ -353,7 +411,7 @@ def gemm(a, b, *, M=None, N=None, K=None, nmma=3, batch=1, a_bs=0, b_bs=0, conv=
     if out_planes is not None:
         d.out_hi, d.out_lo, d.ld_out_bf16 = _ptr(out_planes.hi), _ptr(out_planes.lo), out_planes.ld
         d.out_bf16_batch_stride = outp_bs
-        d.out_planes_fp16 = 1 if out_planes.f16 else 0
+        d.out_planes_fp16 = out_planes.code
     d.split_k = split_k
     if split_k > 1:
         need = split_k * batch * d.M * d.N * 4

@@ -49,8 +49,7 @@ def group_norm(x, B, HW, gamma, beta, eps, act=ACT_NONE, G=32, want_f32=False, w
         ldy = y.stride(0)
     p = planes if planes is not None else (Planes.empty(B * HW, C, dev, lo=lo) if want_planes else None)
     _check(L.odise_groupnorm_apply_bs_f32(_ptr(x), ldx, x_bs, _ptr(mean), _ptr(rstd), _ptr(gamma), _ptr(beta), act,
-                                          _ptr(y), ldy or C, y_bs, _ptr(p.hi) if p else None,
-                                          _ptr(p.lo) if p else None, p.ld if p else 0, o_bs, B, HW, C, G, _stream()),
+                                          _ptr(y), ldy or C, y_bs, *lib.pargs(p), o_bs, B, HW, C, G, _stream()),
            "groupnorm_apply")
     return y, p
 
@@ -63,7 +62,7 @@ def layer_norm(x, gamma, beta, eps=1e-5, res=None, want_f32=False, want_planes=T
     _check(load().odise_layernorm_f32(_ptr(x), x.stride(0), _ptr(res), res.stride(0) if res is not None else 0,
                                       _ptr(gamma), _ptr(beta), eps, _ptr(y), cols, _ptr(post_add),
                                       post_add.stride(0) if post_add is not None else 0,
-                                      _ptr(p.hi) if p else None, _ptr(p.lo) if p else None, p.ld if p else 0, rows,
+                                      *lib.pargs(p), rows,
                                       cols, _stream()), "layernorm")
     return y, p
 
@@ -71,7 +70,7 @@ def layer_norm(x, gamma, beta, eps=1e-5, res=None, want_f32=False, want_planes=T
 def geglu(x, lo=True):
     rows, c2 = x.shape
     p = Planes.empty(rows, c2 // 2, x.device, lo=lo)
-    _check(load().odise_geglu_f32(_ptr(x), x.stride(0), _ptr(p.hi), _ptr(p.lo), p.ld, rows, c2 // 2, _stream()), "geglu")
+    _check(load().odise_geglu_f32(_ptr(x), x.stride(0), *lib.pargs(p), rows, c2 // 2, _stream()), "geglu")
     return p
 
 
@@ -80,15 +79,14 @@ def add_split(a, b=None, b_rows=0, want_f32=False, want_planes=True, lo=True):
     y = empty(rows, cols, a.device) if want_f32 else None
     p = Planes.empty(rows, cols, a.device, lo=lo) if want_planes else None
     _check(load().odise_add_split_f32(_ptr(a), a.stride(0), _ptr(b), b.stride(0) if b is not None else 0, b_rows,
-                                      _ptr(y), cols, _ptr(p.hi) if p else None, _ptr(p.lo) if p else None,
-                                      p.ld if p else 0, rows, cols, _stream()), "add_split")
+                                      _ptr(y), cols, *lib.pargs(p), rows, cols, _stream()), "add_split")
     return y, p
 
 
 def act_split(x, act, lo=True):
     rows, cols = x.shape
     p = Planes.empty(rows, cols, x.device, lo=lo)
-    _check(load().odise_act_split_f32(_ptr(x), x.stride(0), act, _ptr(p.hi), _ptr(p.lo), p.ld, rows, cols, _stream()),
+    _check(load().odise_act_split_f32(_ptr(x), x.stride(0), act, *lib.pargs(p), rows, cols, _stream()),
            "act_split")
     return p
 
@@ -96,7 +94,7 @@ def act_split(x, act, lo=True):
 def upsample2x_split(x, B, H, W, lo=True):
     C = x.shape[1]
     p = Planes.empty(B * 4 * H * W, C, x.device, lo=lo)
-    _check(load().odise_upsample2x_split_f32(_ptr(x), x.stride(0), _ptr(p.hi), _ptr(p.lo), p.ld, B, H, W, C, _stream()),
+    _check(load().odise_upsample2x_split_f32(_ptr(x), x.stride(0), *lib.pargs(p), B, H, W, C, _stream()),
            "upsample2x")
     return p
 
@@ -105,9 +103,10 @@ def im2col3x3_split(x, B, H, W, stride=1, pad_lo=1, pad_hi=1, lo=True):
     C = x.shape[1]
     Ho = (H + pad_lo + pad_hi - 3) // stride + 1
     Wo = (W + pad_lo + pad_hi - 3) // stride + 1
-    Kpad = (9 * C + 7) // 8 * 8
+    Kpad = (9 * C + 63) // 64 * 64 if lo == lib.Q8 else (9 * C + 7) // 8 * 8
     p = Planes.empty(B * Ho * Wo, Kpad, x.device, lo=lo, ld=Kpad)
-    _check(load().odise_im2col3x3_split_f32(_ptr(x), x.stride(0), _ptr(p.hi), _ptr(p.lo), Kpad, B, H, W, C, stride,
+    hi, lo_p, _ = lib.pargs(p)
+    _check(load().odise_im2col3x3_split_f32(_ptr(x), x.stride(0), hi, lo_p, Kpad, B, H, W, C, stride,
                                             pad_lo, pad_hi, _stream()), "im2col3x3")
     return p, Ho, Wo
 
@@ -144,25 +143,32 @@ def nhwc_to_nchw(x, B, H, W):
 
 
 def attention_tc(q, k, vt, B, heads, d, Tq, Tk, scale, nmma, want_f32=False, want_planes=True, tk_stride=None,
-                 mask_bits=None, row_any=None):
-    """q, k head-padded Planes; vt Planes [heads*HS, >= B*Tk]. Returns (fp32 | None, Planes | None) [B*Tq, heads*d]."""
+                 mask_bits=None, row_any=None, lo=None):
+    """q, k head-padded Planes (bf16 pair / plain bf16); vt Planes [heads*HS, >= B*Tk]. Returns (fp32 | None, Planes | None)
+    [B*Tq, heads*d].  nmma = 2 (an engine in the F16Q8 mode) runs the bf16x3 attention; `lo` = format of the output planes
+    (default: bf16 pair in the bf16x3 mode; lib.Q8 when the consumer GEMM runs F16Q8)."""
     dev = q.hi.device
     C = heads * d
+    if nmma == 2:
+        nmma = 3
+    if q.fmt != "bf16" or k.fmt != "bf16":
+        raise lib.OdiseError("attention_tc: q / k must be bf16 planes (the S = Q K^T product runs bf16x3)")
     if vt.f16 != (nmma == 3):
         raise lib.OdiseError("attention_tc: vt must be fp16 planes in the bf16x3 mode (Planes.empty(..., f16=True) / "
                              "lib.split(..., f16=True)) and bf16 planes in the plain bf16 mode")
     out = empty(B * Tq, C, dev) if want_f32 else None
-    p = Planes.empty(B * Tq, C, dev, lo=(nmma == 3)) if want_planes else None
+    p = Planes.empty(B * Tq, C, dev, lo=((nmma == 3) if lo is None else lo)) if want_planes else None
+    phi, plo, pld = lib.pargs(p)
     _check(load().odise_attention_tc(_ptr(q.hi), _ptr(q.lo), q.ld, _ptr(k.hi), _ptr(k.lo), k.ld, _ptr(vt.hi),
-                                     _ptr(vt.lo), vt.ld, vt.rows, _ptr(out), _ptr(p.hi) if p else None,
-                                     _ptr(p.lo) if p else None, p.ld if p else C, B, heads, d, Tq, Tk, tk_stride or Tk, scale, nmma,
+                                     _ptr(vt.lo), vt.ld, vt.rows, _ptr(out), phi,
+                                     plo, pld if p else C, B, heads, d, Tq, Tk, tk_stride or Tk, scale, nmma,
                                      _ptr(mask_bits), _ptr(row_any), _stream()), "attention_tc")
     return out, p
 
 
 def softmax_split(x, rows, cols, cols_pad, scale, lo=True):
     p = Planes.empty(rows, cols_pad, x.device, lo=lo, ld=cols_pad)
-    _check(load().odise_softmax_split_f32(_ptr(x), x.stride(0), _ptr(p.hi), _ptr(p.lo), p.ld, rows, cols, cols_pad,
+    _check(load().odise_softmax_split_f32(_ptr(x), x.stride(0), *lib.pargs(p), rows, cols, cols_pad,
                                           scale, _stream()), "softmax_split")
     return p
 
@@ -190,7 +196,7 @@ def msda_fused(value, spatial_shapes, level_start, ref, offs, logits, N, S, M, D
     out = empty(N * Lq, M * D, dev) if want_f32 else None
     p = Planes.empty(N * Lq, M * D, dev, lo=lo)
     _check(load().odise_msda_fused_f32(_ptr(value), _ptr(spatial_shapes), _ptr(level_start), _ptr(ref), _ptr(offs),
-                                       _ptr(logits), _ptr(out), _ptr(p.hi), _ptr(p.lo), N, S, M, D, L, Lq, P,
+                                       _ptr(logits), _ptr(out), *lib.pargs(p)[:2], N, S, M, D, L, Lq, P,
                                        _stream()), "msda_fused")
     return out, p
 
@@ -210,8 +216,8 @@ def mha_d32(q, ldq, k, v, ldkv, B, Tq, Tk, heads, scale, bits=None, row_any=None
     L = load()
     nws = int(L.odise_mha_d32_ws_floats(B, Tq, Tk, heads))
     ws = torch.empty(nws, dtype=torch.float32, device=q.device) if nws else None
-    _check(L.odise_mha_d32_ws_f32(_ptr(q), ldq, _ptr(k), _ptr(v), ldkv, _ptr(bits), _ptr(row_any), None, _ptr(p.hi),
-                                  _ptr(p.lo), p.ld, B, Tq, Tk, heads, scale, _ptr(ws), _stream()), "mha_d32")
+    _check(L.odise_mha_d32_ws_f32(_ptr(q), ldq, _ptr(k), _ptr(v), ldkv, _ptr(bits), _ptr(row_any), None, *lib.pargs(p),
+                                  B, Tq, Tk, heads, scale, _ptr(ws), _stream()), "mha_d32")
     return p
 
 
@@ -233,7 +239,7 @@ def pool_normalize(sums, counts, B, Q, C):
 def l2_normalize_split(x, lo=True):
     rows, cols = x.shape
     p = Planes.empty(rows, cols, x.device, lo=lo)
-    _check(load().odise_l2_normalize_split_f32(_ptr(x), x.stride(0), _ptr(p.hi), _ptr(p.lo), p.ld, rows, cols,
+    _check(load().odise_l2_normalize_split_f32(_ptr(x), x.stride(0), *lib.pargs(p), rows, cols,
                                                _stream()), "l2_normalize")
     return p
 
@@ -302,10 +308,11 @@ def crop_resize_bicubic(img, boxes_dev, n_crops, H, W, ch, cw, S=512):
 
 
 def patchify_split(x, B, S, P, lo=True):
-    Kpad = (3 * P * P + 7) // 8 * 8
+    Kpad = (3 * P * P + 63) // 64 * 64 if lo == lib.Q8 else (3 * P * P + 7) // 8 * 8
     G = S // P
     p = Planes.empty(B * G * G, Kpad, x.device, lo=lo, ld=Kpad)
-    _check(load().odise_patchify_split_f32(_ptr(x), _ptr(p.hi), _ptr(p.lo), B, S, P, Kpad, _stream()), "patchify")
+    hi, lo_p, _ = lib.pargs(p)
+    _check(load().odise_patchify_split_f32(_ptr(x), hi, lo_p, B, S, P, Kpad, _stream()), "patchify")
     return p
 
 

@@ -28,8 +28,9 @@ def _conv_w(w):
 class UNetEngine:
     def __init__(self, sd, device, nmma=3, prefix=spec.UNET_PREFIX):
         self.dev = torch.device(device)
-        self.nmma = nmma
-        self.lo = nmma == 3
+        self.nmma = nmma            # 3 = bf16x3 (bf16 pairs) | 2 = F16Q8 (fp16 + e5m2 cross terms, lib.Q8) | 1 = plain bf16
+        self.lo = lib.Q8 if nmma == 2 else (nmma == 3)
+        self.lb = bool(self.lo)     # attention operands (q, k: bf16 pair; V^T: fp16 pair) keep their formats in every mode
         self.p = prefix
         self.inp, self.mid, self.out = spec.unet_blocks()
         self.W = {}     # name -> Planes (GEMM weights)
@@ -192,25 +193,27 @@ class UNetEngine:
         if HS is not None:
             Cp = HEADS * HS
             if a == "attn1" and kv_src is xq:
-                qk = Planes.empty(M, 2 * Cp, self.dev, lo=self.lo)
+                qk = Planes.empty(M, 2 * Cp, self.dev, lo=self.lb)
                 self._gemm(xq, t + a + ".qk", out_planes=qk)
                 qP, kP = qk.col_slice(0, Cp), qk.col_slice(Cp, Cp)
             elif a == "attn1":           # keys / values from the row-padded copy of the tokens (T % 8 != 0)
                 wqk = self.W[t + a + ".qk"]
-                qP = Planes.empty(M, Cp, self.dev, lo=self.lo)
+                qP = Planes.empty(M, Cp, self.dev, lo=self.lb)
                 lib.gemm(xq, wqk.row_slice(0, Cp), nmma=self.nmma, out_planes=qP)
-                kP = Planes.empty(B * TkS, Cp, self.dev, lo=self.lo)
+                kP = Planes.empty(B * TkS, Cp, self.dev, lo=self.lb)
                 lib.gemm(kv_src, wqk.row_slice(Cp, Cp), nmma=self.nmma, out_planes=kP)
             else:
-                qP = Planes.empty(M, Cp, self.dev, lo=self.lo)
+                qP = Planes.empty(M, Cp, self.dev, lo=self.lb)
                 self._gemm(xq, t + a + ".q", out_planes=qP)
-                kP = Planes.empty(B * TkS, Cp, self.dev, lo=self.lo)
+                kP = Planes.empty(B * TkS, Cp, self.dev, lo=self.lb)
                 self._gemm(kv_src, t + a + ".k", out_planes=kP)
-            vt = Planes.empty(Cp, B * TkS, self.dev, lo=self.lo, f16=self.lo)   # fp16 pair in the bf16x3 mode
+            vt = Planes.empty(Cp, B * TkS, self.dev, lo=self.lb, f16=self.lb)   # fp16 pair in the bf16x3 mode
             # V^T = Wv_pad @ X^T: the same K-major GEMM with the operands swapped
             lib.gemm(self.W[t + a + ".v"], kv_src, nmma=self.nmma, out_planes=vt)
-            _, o = ops.attention_tc(qP, kP, vt, B, HEADS, d, T, Tk, scale, self.nmma, tk_stride=TkS)
+            _, o = ops.attention_tc(qP, kP, vt, B, HEADS, d, T, Tk, scale, self.nmma, tk_stride=TkS, lo=self.lo)
             return o
+        if self.nmma == 2:
+            raise lib.OdiseError("UNetEngine: the unfused attention path (head dims outside 40 / 80 / 160) has no F16Q8 mode")
         # head dim 160 (16x16 and 8x8 levels, < 2 % of the FLOPs): unfused S / softmax / PV through the GEMM
         src, Tkp = kv_src, TkS
         if a == "attn1":

@@ -61,6 +61,16 @@ def test_unet_taps_full_latent(cuda, unet_sd, oracle_unet):
     assert max(errs) < 1e-3, errs
 
 
+def test_unet_taps_f16q8_mode(cuda, unet_sd, oracle_unet, record):
+    """F16Q8 operand mode (nmma=2: fp16 hi*hi + the two cross terms on e5m2 MMAs, 8 MMA slots per k-block instead of 12):
+    ship rule = 3x margin to the 1e-3 bar (tools/precision_budget.py predicts 1.1e-4 for the scheme itself)."""
+    errs = _run(unet_sd, oracle_unet, cuda, B=1, hw=64, nmma=2)
+    record("UNet taps 64x64, F16Q8 mode (nmma=2) vs fp32 oracle: " + ", ".join(f"{e:.2e}" for e in errs))
+    assert max(errs) < 3.3e-4, errs
+    errs = _run(unet_sd, oracle_unet, cuda, B=2, hw=32, nmma=2)
+    assert max(errs) < 3.3e-4, errs
+
+
 def test_unet_taps_fast_mode_reported(cuda, unet_sd, oracle_unet):
     """plain bf16 (nmma=1) is NOT the parity mode; its error is recorded, only sanity-bounded."""
     errs = _run(unet_sd, oracle_unet, cuda, B=1, hw=32, nmma=1, with_cond=False)

@@ -12,14 +12,15 @@ mode = sys.argv[4] if len(sys.argv) > 4 else "f32"
 nmma = int(sys.argv[5]) if len(sys.argv) > 5 else 3
 bn = int(sys.argv[6]) if len(sys.argv) > 6 else 0
 dev = torch.device("cuda")
-a = lib.split(torch.randn(M, K, device=dev))
-b = lib.split(torch.randn(N, K, device=dev) * 0.05)
+lo = lib.Q8 if nmma == 2 else True          # nmma 2: F16Q8 operands (fp16 hi*hi + e5m2 cross terms)
+a = lib.split(torch.randn(M, K, device=dev), lo=lo)
+b = lib.split(torch.randn(N, K, device=dev) * 0.05, lo=lo)
 bias = torch.randn(N, device=dev)
 out = torch.empty(M, N, device=dev) if mode in ("f32", "both") else None
-outp = lib.Planes.empty(M, N, dev) if mode in ("planes", "both") else None
+outp = lib.Planes.empty(M, N, dev, lo=lo) if mode in ("planes", "both") else None
 kw = {}
 if mode == "geglu":
-    outp, kw = lib.Planes.empty(M, N // 2, dev), dict(geglu=True)
+    outp, kw = lib.Planes.empty(M, N // 2, dev, lo=lo), dict(geglu=True)
 for i in range(5):
     lib.gemm(a, b, nmma=nmma, bias=bias, out=out, out_planes=outp, force_bn=bn, **kw)
 torch.cuda.synchronize()

@@ -60,6 +60,17 @@ def contract(op, a, b, mode):
         # A rounded to 2 mantissa bits (e5m2), W_lo to 3 (e4m3); range / scaling not modelled -> an upper bound on the gain
         bh = q_fp16(b)
         return op(a, bh) + op(q_bits(a, 2), q_bits(b - bh, 3))
+    if mode.startswith("f16c8"):
+        # fp16 main product + BOTH cross terms on fp8 MMAs (kind::f8f6f4, twice the 16-bit rate) -> cost 2:
+        #   A_hi*W_hi [fp16]  +  e5m2(A * 2^-a) * e5m2(W_lo * 2^a)  +  e5m2(A_lo * 2^b) * e5m2(W * 2^-b)
+        # with the real e5m2 range / subnormals / saturation (torch.float8_e5m2) and global power-of-two scales (a, b)
+        t8 = torch.float8_e4m3fn if mode.endswith("e4") else torch.float8_e5m2
+        lim = 448.0 if mode.endswith("e4") else 57344.0
+        q8 = lambda x: x.clamp(-lim, lim).to(t8).float()
+        sa, sb = float(os.environ.get("PB_SA", 8)), float(os.environ.get("PB_SB", 4))
+        ah, bh = q_fp16(a), q_fp16(b)
+        al, bl = a - ah, b - bh
+        return op(ah, bh) + op(q8(a * 2.0 ** -sa), q8(bl * 2.0 ** sa)) + op(q8(al * 2.0 ** sb), q8(b * 2.0 ** -sb))
     raise ValueError(mode)
 
 
@@ -135,7 +146,7 @@ def main():
         return errs, time.time() - t0
 
     cost = {"fp32": None, "bf16x3": 3, "fp16x3": 3, "fp16x2": 2, "bf16x2": 2, "tf32": 2, "tf32t": 2, "bf16": 1, "fp16x2c8": 2.5,
-            "p16": 2.5}
+            "p16": 2.5, "f16c8": 2, "f16c8e4": 2}
     # MMA-FLOP share of the three classes in the minimal feature pass (profiles/r1*_gemm_shapes: convs ~ 62 %, linears /
     # 1x1 ~ 30 %, attention ~ 8 %) -> relative tensor time of a mix vs all-bf16x3
     share = {"conv3": 0.62, "lin": 0.30, "attn": 0.08}
