@@ -42,6 +42,9 @@ CONFIGS = {          # BASELINE.json `configs` (configs[0] is the CPU numerics c
 }
 
 
+NMMA = {"f16q8": 2, "bf16x3": 3, "bf16": 1}      # odise_gemm_desc.nmma of the operand mode
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -51,7 +54,11 @@ def parse():
     ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
     ap.add_argument("--batch", type=int, default=None, help="images per GPU per step (default: the config's)")
     ap.add_argument("--size", type=int, default=None)
-    ap.add_argument("--precision", default="bf16x3", choices=["bf16x3", "bf16"])
+    ap.add_argument("--precision", default="bf16x3", choices=["f16q8", "bf16x3", "bf16"],
+                    help="bf16x3: (hi, lo) bf16 pairs, 3 MMAs per k-step (2e-5 at the UNet taps).  f16q8: fp16 hi x hi + both "
+                         "cross terms on e5m2 MMAs at twice the rate = 2 MMA units per k-step (1e-4 at the taps, bar 1e-3); "
+                         "VAE / CLIP / UNet / projections run it, the head and the post-processing stay bf16x3.  bf16: plain "
+                         "(not a parity mode)")
     ap.add_argument("--vocab", default=None, choices=sorted(VOCABS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--hot-path-only", action="store_true",
@@ -312,7 +319,7 @@ def run_c4(args, dev):
     # (b) masked-attention decoder, Q = 256, 4 scales
     Q = 256
     sd = spec.synth_state_dict(spec.pixel_decoder_params() + spec.decoder_params(Q=Q, n_levels=L) + spec.category_head_params(), 1)
-    he = HeadEngine(sd, dev, nmma=3 if args.precision == "bf16x3" else 1, num_queries=Q)
+    he = HeadEngine(sd, dev, nmma=NMMA[args.precision], num_queries=Q)
     ms = [torch.randn(N, 256, h, w, generator=g).to(dev) for h, w in shapes]
     mfeat = torch.randn(N, 256, args.size // 4, args.size // 4, generator=g).to(dev)
     pd = he.pd_from_tensors(ms, mfeat)
@@ -375,7 +382,7 @@ def main():
     from odise_b200 import lib, spec
     from odise_b200.pipeline import ODISEEngine, full_param_list, gather_logits
     lib.load()
-    nmma = 3 if args.precision == "bf16x3" else 1
+    nmma = NMMA[args.precision]
     sd = spec.synth_state_dict(full_param_list(with_vae=args.full, with_clip=args.full), seed=0)
     eng = ODISEEngine(sd, dev, nmma=nmma, with_vae=args.full, with_clip=args.full, synthetic_uncond=True)
     del sd
@@ -458,7 +465,7 @@ def main():
         # projected 256-d bank; MaskCLIP's match clip.py:352-358 on the raw 768-d bank), CUDA events over 200 launches
         from odise_b200 import ops
         v = eng.head._vocab[eng.vocab_key]
-        me_p = ops.l2_normalize_split(torch.randn(B * eng.Q, 256, device=dev), lo=nmma == 3)
+        me_p = ops.l2_normalize_split(torch.randn(B * eng.Q, 256, device=dev), lo=nmma != 1)
         sims = ops.empty(B * eng.Q, v["Kp"], dev)
         t1 = _time_ms(lambda: lib.gemm(me_p, v["te_p"], nmma=nmma, alpha=eng.head.logit_scale, out=sims), 200)
         fl1 = 2.0 * B * eng.Q * v["Kp"] * 256
@@ -466,7 +473,7 @@ def main():
         extra["clip_match_gemm"] = {"category_head": {"M": B * eng.Q, "N": v["Kp"], "K": 256, "us": 1e3 * t1,
                                                       "tflops": fl1 / t1 / 1e9}}
         if cv is not None:
-            ce_p = ops.l2_normalize_split(torch.randn(B * eng.Q, 768, device=dev), lo=nmma == 3)
+            ce_p = ops.l2_normalize_split(torch.randn(B * eng.Q, 768, device=dev), lo=nmma != 1)
             sims2 = ops.empty(B * eng.Q, v["Kp"], dev)
             t2 = _time_ms(lambda: lib.gemm(ce_p, cv["te_p"], nmma=nmma, alpha=100.0, out=sims2), 200)
             extra["clip_match_gemm"]["maskclip_head"] = {"M": B * eng.Q, "N": v["Kp"], "K": 768, "us": 1e3 * t2,
@@ -523,7 +530,9 @@ def main():
                      "frac": achieved / pk["bf16_sustained"], "peak_source": pk["source"] + " sustained cuBLAS bf16",
                      "launches": int(n_gemm), "gemm_ms_per_step": gemm_ms, "algorithmic_tflop_per_step": gemm_flops / 1e12,
                      "mma_kind": "tcgen05.mma kind::f16 (bf16 in, fp32 TMEM accumulate)" +
-                                 (", 3 MMAs per k-step (bf16x3 split)" if nmma == 3 else ""),
+                                 (", 3 MMAs per k-step (bf16x3 split)" if nmma == 3 else "") +
+                                 (" for the head; VAE / CLIP / UNet / projections: kind::f16 (fp16 hi x hi) + kind::f8f6f4 "
+                                  "(e5m2 cross terms, K = 32) = 2 MMA units per k-step" if nmma == 2 else ""),
                      "tensor_pipe_equiv_frac": achieved * nmma / pk["bf16_sustained"],
                      "unet_frac_of_step": (UNET_TFLOP_PER_CROP * crops * B) / (gemm_flops / 1e12), "traffic": traffic,
                      "traffic_source": traffic_src,

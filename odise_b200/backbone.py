@@ -64,7 +64,7 @@ class BackboneEngine:
         vae: optional VAEEngine; without it the VAE taps / latent are synthetic.
         clip: optional ClipVisualEngine (§8f-2); without it the CLIP image embedding is a seeded synthetic tensor."""
         self.dev = torch.device(device)
-        self.nmma, self.lo = nmma, nmma == 3
+        self.nmma, self.lo = nmma, (lib.Q8 if nmma == 2 else nmma == 3)     # 2 = F16Q8 operand mode (lib.Q8)
         self.vae = vae
         self.clip = clip
         self._boxes = {}

@@ -18,7 +18,9 @@ class _ResBlocks:
     planes + the loop that runs them on a token matrix [B*TS, width] whose first Tk rows per image are the keys."""
 
     def __init__(self, sd, prefix, device, nmma, width, layers, heads):
-        self.dev, self.nmma, self.lo = torch.device(device), nmma, nmma == 3
+        # nmma: 3 = bf16x3 | 2 = F16Q8 operands for the linears (lib.Q8; the attention core keeps bf16x3 q / k, fp16 V^T) | 1
+        self.dev, self.nmma, self.lo = torch.device(device), nmma, (lib.Q8 if nmma == 2 else nmma == 3)
+        self.lb = bool(self.lo)
         self.width, self.layers, self.heads = width, layers, heads
         f = lambda t: t.to(self.dev, torch.float32).contiguous()
         pl = lambda w: lib.split(f(w), lo=self.lo)
@@ -45,12 +47,12 @@ class _ResBlocks:
         for i in range(self.layers):
             n = f"l{i}."
             _, y = ops.layer_norm(h, self.F[n + "ln_1.g"], self.F[n + "ln_1.b"], lo=self.lo)
-            qk = Planes.empty(M, 2 * Wd, dev, lo=self.lo)
+            qk = Planes.empty(M, 2 * Wd, dev, lo=self.lb)
             self._gemm(y, n + "qk", out_planes=qk)
-            vt = Planes.empty(Wd, M, dev, lo=self.lo, f16=self.lo)
+            vt = Planes.empty(Wd, M, dev, lo=self.lb, f16=self.lb)
             lib.gemm(self.W[n + "v"], y, nmma=self.nmma, bias_m=self.F[n + "v.b"], out_planes=vt)
             _, o = ops.attention_tc(qk.col_slice(0, Wd), qk.col_slice(Wd, Wd), vt, B, self.heads, d, TS, Tk, d ** -0.5,
-                                    self.nmma, tk_stride=TS, mask_bits=bits, row_any=row_any)
+                                    self.nmma, tk_stride=TS, mask_bits=bits, row_any=row_any, lo=self.lo)
             h2 = ops.empty(M, Wd, dev)
             self._gemm(o, n + "o", residual=h, out=h2)
             _, y2 = ops.layer_norm(h2, self.F[n + "ln_2.g"], self.F[n + "ln_2.b"], lo=self.lo)
@@ -64,7 +66,7 @@ class _ResBlocks:
 class ClipVisualEngine:
     def __init__(self, sd, device, nmma=3, prefix=spec.CLIP_PREFIX, width=1024, layers=24, heads=16, patch=14, image=336):
         self.dev = torch.device(device)
-        self.nmma, self.lo = nmma, nmma == 3
+        self.nmma, self.lo = nmma, (lib.Q8 if nmma == 2 else nmma == 3)
         self.width, self.layers, self.heads, self.patch, self.image = width, layers, heads, patch, image
         self.G = image // patch
         self.T = self.G * self.G + 1             # 577
@@ -152,7 +154,7 @@ class MaskClipHead:
 
     def __init__(self, visual, alpha=0.3, beta=0.7, logit_scale=100.0):
         self.visual, self.dev = visual, visual.dev
-        self.nmma, self.lo = visual.nmma, visual.lo
+        self.nmma, self.lo = visual.nmma, bool(visual.lo)     # the CLIP match itself (one small GEMM) stays bf16x3 in every mode
         self.alpha, self.beta = float(alpha), float(beta)
         self.logit_scale = float(min(logit_scale, 100.0))            # clamp(exp(clip.logit_scale), max=100), clip.py:247
         self._vocab = {}
@@ -198,6 +200,7 @@ class ClipTextEngine:
 
     def __init__(self, sd, device, nmma=3, prefix=spec.CLIP_TEXT_PREFIX, width=768, layers=12, heads=12, ctx=77, project=True):
         self.dev = torch.device(device)
+        nmma = 3 if nmma == 2 else nmma             # the text tower runs once per vocabulary: always the bf16x3 parity mode
         self.nmma, self.lo = nmma, nmma == 3
         self.width, self.ctx = width, ctx
         self.TS = (ctx + 7) // 8 * 8

@@ -447,7 +447,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
         const float* resp = (EXTRA && p.res) ? p.res + (long long)z * p.res_bs + m * p.ldres + n0 : nullptr;
         const int act = p.act;
         const float alpha = p.alpha;
-        const bool planes = p.tma_out == 2, to_lo = p.Dl != nullptr, h16 = p.h16 != 0;
+        const bool planes = p.tma_out == 2, to_lo = p.Dl != nullptr, h16 = p.h16 != 0, q8 = lo_is_q8(p.Dl);
         uint8_t* wbase = reinterpret_cast<uint8_t*>(stg);
 #pragma unroll 1
         for (int c0 = c_first; c0 < BN; c0 += c_step) {
@@ -503,7 +503,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const float a0 = e[2 * j], a1 = e[2 * j + 1];
-              if (h16) {
+              if (q8) {
+                // F16Q8: fp16 hi + e5m2 bytes; lw[0..3] = q_hi of the 16 columns, lw[4..7] = q_lo (two byte pairs per word)
+                const __half2 h2 = __floats2half2_rn(clamp_f16(a0), clamp_f16(a1));
+                hw[j] = *reinterpret_cast<const uint32_t*>(&h2);
+                const float2 f = __half22float2(h2);
+                const uint32_t qh = e5m2x2(a0 * kQ8Down, a1 * kQ8Down), ql = e5m2x2((a0 - f.x) * kQ8Up, (a1 - f.y) * kQ8Up);
+                if (j & 1) { lw[j >> 1] |= qh << 16; lw[4 + (j >> 1)] |= ql << 16; }
+                else { lw[j >> 1] = qh; lw[4 + (j >> 1)] = ql; }
+              } else if (h16) {
                 const __half2 h2 = __floats2half2_rn(a0, a1);
                 hw[j] = *reinterpret_cast<const uint32_t*>(&h2);
                 const float2 f = __half22float2(h2);
@@ -522,7 +530,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
             for (int c = 0; c < 2; ++c) {
               *reinterpret_cast<uint4*>(buf + lane * 32 + ((c ^ sw) << 4)) =
                   make_uint4(hw[4 * c], hw[4 * c + 1], hw[4 * c + 2], hw[4 * c + 3]);
-              if (to_lo)
+              if (q8)         // [32 rows][16 B] q_hi at +1024, q_lo at +1536, no swizzle (16-byte boxes)
+                *reinterpret_cast<uint4*>(buf + 1024 + c * 512 + lane * 16) =
+                    make_uint4(lw[4 * c], lw[4 * c + 1], lw[4 * c + 2], lw[4 * c + 3]);
+              else if (to_lo)
                 *reinterpret_cast<uint4*>(buf + 1024 + lane * 32 + ((c ^ sw) << 4)) =
                     make_uint4(lw[4 * c], lw[4 * c + 1], lw[4 * c + 2], lw[4 * c + 3]);
             }
@@ -531,7 +542,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
           __syncwarp();
           if (lane == 0) {
             tma_store_3d(&tmO0, buf, n0 + c0, (int)(m_base), z);
-            if (planes && to_lo) tma_store_3d(&tmO1, buf + 1024, n0 + c0, (int)(m_base), z);
+            if (planes && q8) {      // byte tensor map: column n sits at byte (n / 64) * 128 + n % 64 of its row, q_lo 64 further
+              const int n = n0 + c0, cb = ((n >> 6) << 7) + (n & 63);
+              tma_store_3d(&tmO1, buf + 1024, cb, (int)(m_base), z);
+              tma_store_3d(&tmO1, buf + 1536, cb + 64, (int)(m_base), z);
+            } else if (planes && to_lo) {
+              tma_store_3d(&tmO1, buf + 1024, n0 + c0, (int)(m_base), z);
+            }
             tma_store_commit();
           }
           ++tma_cnt;
@@ -775,6 +792,19 @@ static int encode_map(CUtensorMap* tm, const void* base, int rank, const cuuint6
 
 // output tensor map of the TMA-store epilogue: {N, M, batch}, box {16 columns, 32 rows, 1}; fp32 rows of the box are 64 B
 // (SWIZZLE_64B), 16-bit plane rows 32 B (SWIZZLE_32B) — the staging writes in the kernel use the same XOR patterns
+// second plane of F16Q8 output planes as bytes: {2 * ld bytes, M, batch}, box {16 bytes, 32 rows, 1}, no swizzle
+static int encode_q8_out_map(CUtensorMap* tm, void* base, long long M, long long batch, long long ld, long long bs) {
+  auto enc = get_encode();
+  if (!enc) return ODISE_ERR_DRIVER;
+  cuuint64_t dims[3] = {(cuuint64_t)ld * 2, (cuuint64_t)M, (cuuint64_t)batch};
+  cuuint64_t str[2] = {(cuuint64_t)ld * 2, (cuuint64_t)(batch > 1 ? bs : M * ld) * 2};
+  cuuint32_t box[3] = {16, 32, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, base, dims, str, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? ODISE_OK : ODISE_ERR_TENSORMAP;
+}
+
 static int encode_out_map(CUtensorMap* tm, void* base, bool f32, long long N, long long M, long long batch, long long ld,
                           long long bs) {
   auto enc = get_encode();
@@ -1021,13 +1051,15 @@ extern "C" int odise_gemm_bf16(const odise_gemm_desc* d, void* stream_v) {
   {
     static const bool off = getenv("ODISE_NO_TMA_STORE") != nullptr;
     const bool one_kind = (d->out_f32 != nullptr) != (d->out_hi != nullptr);
-    if (!off && epi != 2 && p.vec_ok && p.splits == 1 && !p.gnp && one_kind && !oq8) {
+    if (!off && epi != 2 && p.vec_ok && p.splits == 1 && !p.gnp && one_kind) {
       if (d->out_f32) {
         rc = encode_out_map(&o0, d->out_f32, true, d->N, d->M, d->batch, d->ld_out, d->out_batch_stride);
         if (!rc) p.tma_out = 1;
       } else {
         rc = encode_out_map(&o0, d->out_hi, false, d->N, d->M, d->batch, d->ld_out_bf16, d->out_bf16_batch_stride);
-        if (!rc && d->out_lo)
+        if (!rc && oq8)
+          rc = encode_q8_out_map(&o1, d->out_lo, d->M, d->batch, d->ld_out_bf16, d->out_bf16_batch_stride);
+        else if (!rc && d->out_lo)
           rc = encode_out_map(&o1, d->out_lo, false, d->N, d->M, d->batch, d->ld_out_bf16, d->out_bf16_batch_stride);
         if (!rc) p.tma_out = 2;
       }

@@ -14,6 +14,7 @@ class PostProcessor:
     def __init__(self, device, num_classes, thing_ids, object_mask_threshold=0.0, overlap_threshold=0.8, nmma=3):
         self.dev = torch.device(device)
         self.K = num_classes
+        nmma = 3 if nmma == 2 else nmma            # the semantic-inference GEMM (K = Q) keeps the bf16x3 planes in every mode
         self.nmma, self.lo = nmma, nmma == 3
         it = torch.zeros(num_classes, dtype=torch.uint8)
         it[list(thing_ids)] = 1

@@ -22,25 +22,28 @@ def _conv_w(w):
 class VAEEngine:
     def __init__(self, sd, device, nmma=3, prefix=spec.VAE_PREFIX):
         self.dev = torch.device(device)
-        self.nmma, self.lo = nmma, nmma == 3
+        # nmma: 3 = bf16x3 | 2 = F16Q8 (lib.Q8: fp16 + e5m2 cross terms) | 1 = plain bf16.  The two mid-block attentions
+        # (~2 % of the FLOPs; their batched S / P V GEMMs slice operands at token offsets) stay bf16x3 in the F16Q8 mode.
+        self.nmma, self.lo = nmma, (lib.Q8 if nmma == 2 else nmma == 3)
+        self.lb = bool(self.lo)
         self.W, self.F = {}, {}
         p = prefix
         g = lambda n: sd[p + n]
         f = lambda t: t.to(self.dev, torch.float32).contiguous()
 
-        def planes(w2d):
+        def planes(w2d, lo=None):
             w2d = f(w2d)
             if w2d.shape[1] % 8:
                 w2d = torch.nn.functional.pad(w2d, (0, 8 - w2d.shape[1] % 8))
-            return lib.split(w2d, lo=self.lo)
+            return lib.split(w2d, lo=self.lo if lo is None else lo)
 
         def conv(name, key):
             self.W[name] = planes(_conv_w(g(key + ".weight")))
             self.F[name + ".b"] = f(g(key + ".bias"))
 
-        def lin(name, key):
+        def lin(name, key, lo=None):
             w = g(key + ".weight")
-            self.W[name] = planes(w.reshape(w.shape[0], -1))
+            self.W[name] = planes(w.reshape(w.shape[0], -1), lo)
             self.F[name + ".b"] = f(g(key + ".bias"))
 
         def norm(name, key):
@@ -55,10 +58,10 @@ class VAEEngine:
         def attn(name, key):
             norm(name + "n", key + "norm")
             w = torch.cat([g(key + "q.weight"), g(key + "k.weight")], 0)
-            self.W[name + "qk"] = planes(w.reshape(w.shape[0], -1))
+            self.W[name + "qk"] = planes(w.reshape(w.shape[0], -1), self.lb)
             self.F[name + "qk.b"] = f(torch.cat([g(key + "q.bias"), g(key + "k.bias")], 0))
-            lin(name + "v", key + "v")
-            lin(name + "o", key + "proj_out")
+            lin(name + "v", key + "v", self.lb)
+            lin(name + "o", key + "proj_out", self.lb)
 
         ch, mult = 128, (1, 2, 4, 4)
         conv("e.conv_in", "encoder.conv_in")
@@ -87,8 +90,9 @@ class VAEEngine:
     def _gemm(self, a, name, **kw):
         return lib.gemm(a, self.W[name], nmma=self.nmma, bias=self.F.get(name + ".b"), **kw)
 
-    def _gn(self, x, B, HW, name, act, **kw):
-        return ops.group_norm(x, B, HW, self.F[name + ".g"], self.F[name + ".be"], 1e-6, act, lo=self.lo, **kw)
+    def _gn(self, x, B, HW, name, act, lo=None, **kw):
+        return ops.group_norm(x, B, HW, self.F[name + ".g"], self.F[name + ".be"], 1e-6, act,
+                              lo=self.lo if lo is None else lo, **kw)
 
     def _res(self, n, x, B, H, W, cin, cout, xs=None):
         """ldm ResnetBlock.  xs: GroupNorm records of x left by its producer's epilogue (lib.GnStats) or None;
@@ -113,16 +117,16 @@ class VAEEngine:
         """ldm AttnBlock: single head, d = C = 512, softmax(q k^T / sqrt(C)) v, 1x1 projections with bias."""
         T, C = H * W, 512
         M = B * T
-        _, xn = self._gn(x, B, T, n + "n", ACT_NONE, stats=xs)
-        qk = Planes.empty(M, 2 * C, self.dev, lo=self.lo)
+        _, xn = self._gn(x, B, T, n + "n", ACT_NONE, stats=xs, lo=self.lb)
+        qk = Planes.empty(M, 2 * C, self.dev, lo=self.lb)
         self._gemm(xn, n + "qk", out_planes=qk)
-        vt = Planes.empty(C, M, self.dev, lo=self.lo)
+        vt = Planes.empty(C, M, self.dev, lo=self.lb)
         lib.gemm(self.W[n + "v"], xn, nmma=self.nmma, bias_m=self.F[n + "v.b"], out_planes=vt)
         S = torch.empty(B, T, T, dtype=torch.float32, device=self.dev)
         lib.gemm(qk.col_slice(0, C), qk.col_slice(C, C), M=T, N=T, K=C, nmma=self.nmma, batch=B, a_bs=T * qk.ld,
                  b_bs=T * qk.ld, out=S, ld_out=T, out_bs=T * T)
-        P = ops.softmax_split(S.view(M, T), M, T, T, float(C) ** -0.5, lo=self.lo)
-        o = Planes.empty(M, C, self.dev, lo=self.lo)
+        P = ops.softmax_split(S.view(M, T), M, T, T, float(C) ** -0.5, lo=self.lb)
+        o = Planes.empty(M, C, self.dev, lo=self.lb)
         lib.gemm(P, vt, M=T, N=C, K=T, nmma=self.nmma, batch=B, a_bs=T * P.ld, b_bs=T, out_planes=o, outp_bs=T * o.ld)
         out = ops.empty(M, C, self.dev)
         os_ = lib.GnStats(M, C, self.dev)
