@@ -35,6 +35,11 @@ struct GemmParams {
   int nseg;                        // > 1: the 128 pixels of a tile are fetched as nseg row segments of bw pixels
   int cstride, cpad;               // conv stride (1 | 2) and low-side zero padding (0 | 1)
   int tiles_m, tiles_n, splits, kblocks;
+  // cl = 2: CTA pairs (cluster of 2 along M) work on the two M tiles {2i, 2i+1} of one n-tile in lock step; each CTA fetches
+  // half of the shared B tile and TMA-multicasts it to both -> one third fewer operand bytes through L2 / the crossbar per
+  // FLOP (ncu r2g: the K = 4608 GEMM delivers 7.25 GB at ~6 800 B/clk chip-wide = the L2 -> SM delivery ceiling, tensor pipe
+  // 65 % (bf16x3) / 48 % (F16Q8) active).  tiles_mp = M tiles per CTA of the cluster (= ceil(tiles_m / cl)).
+  int cl, tiles_mp;
   float alpha;
   const float* bias;
   const float* bias_m;  // per-row (m) bias, for swapped-operand (transposed-output) projections
@@ -274,7 +279,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
     }
     for (int s = 0; s < Cfg::STAGES; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], 1);
+      mbar_init(&empty[s], p.cl);      // one tcgen05.commit arrival per CTA that reads the stage
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull[s], 1);
@@ -288,11 +293,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
   }
   tc_fence_before();
   __syncthreads();
+  if (p.cl > 1) cluster_sync();        // the peer's barriers are initialised before any multicast / remote arrival
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const int crank = p.cl > 1 ? (int)cluster_ctarank() : 0;
 
-  const int tiles_per_z = p.tiles_m * p.tiles_n * p.splits;
+  // (pair mode: "tile" counts PAIRS of M tiles; both CTAs of a cluster walk the same sequence)
+  const int tiles_per_z = p.tiles_mp * p.tiles_n * p.splits;
   const int total_tiles = tiles_per_z * p.batch;
+  const int first_tile = (int)blockIdx.x / p.cl, tile_step = (int)gridDim.x / p.cl;
   const int kb_per_split = (p.kblocks + p.splits - 1) / p.splits;
 
   if (warp == 0) {
@@ -301,12 +310,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
       int stage = 0;
       uint32_t phase = 0;
       const int cpk = p.conv ? (p.C / 64) : 1;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
         const int z = tile / tiles_per_z;
         int r = tile - z * tiles_per_z;
-        const int sp = r / (p.tiles_m * p.tiles_n);
-        r -= sp * (p.tiles_m * p.tiles_n);
-        const int mt = r / p.tiles_n, nt = r - mt * p.tiles_n;
+        const int sp = r / (p.tiles_mp * p.tiles_n);
+        r -= sp * (p.tiles_mp * p.tiles_n);
+        const int mt = (r / p.tiles_n) * p.cl + crank, nt = r % p.tiles_n;
         const int m0 = mt * 128, n0 = nt * BN;
         const int kb0 = sp * kb_per_split;
         const int kb1 = min(p.kblocks, kb0 + kb_per_split);
@@ -350,8 +359,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
           }
           const int zb = p.b_batched ? z : 0;
           uint8_t* sb = st + Cfg::PLANES * Cfg::A_BYTES;
-          tma_load_3d(sb, &tmBh, &full[stage], kb * 64, n0, zb);
-          if (NMMA != 1) tma_load_3d(sb + Cfg::B_BYTES, &tmBl, &full[stage], kb * 64, n0, zb);
+          if (p.cl == 1) {
+            tma_load_3d(sb, &tmBh, &full[stage], kb * 64, n0, zb);
+            if (NMMA != 1) tma_load_3d(sb + Cfg::B_BYTES, &tmBl, &full[stage], kb * 64, n0, zb);
+          } else {
+            // this CTA's half of the B tile (rows [crank * BN/2, +BN/2), box = BN/2 rows), delivered to both CTAs of the pair
+            constexpr int HB = BN / 2;
+            uint8_t* sh = sb + crank * HB * 128;
+            tma_load_3d_mc(sh, &tmBh, &full[stage], kb * 64, n0 + crank * HB, zb, (uint16_t)3);
+            if (NMMA != 1) tma_load_3d_mc(sh + Cfg::B_BYTES, &tmBl, &full[stage], kb * 64, n0 + crank * HB, zb, (uint16_t)3);
+          }
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -365,9 +382,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
       uint32_t phase = 0;
       int acc = 0;
       uint32_t accphase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
         int r = tile % tiles_per_z;
-        const int sp = r / (p.tiles_m * p.tiles_n);
+        const int sp = r / (p.tiles_mp * p.tiles_n);
         const int kb0 = sp * kb_per_split;
         const int kb1 = min(p.kblocks, kb0 + kb_per_split);
         mbar_wait(&tempty[acc], accphase ^ 1);
@@ -400,7 +417,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
               umma_f8(d_tmem, umma_desc_sw128(a2 + 64 + k * 32), umma_desc_sw128(b2 + k * 32), idesc_q, 1u);
             }
           }
-          umma_commit(&empty[stage]);  // smem slot reusable once these MMAs retire
+          // smem slot reusable once these MMAs retire (pair mode: once the MMAs of BOTH CTAs have read their copy)
+          if (p.cl == 1) umma_commit(&empty[stage]);
+          else umma_commit_mc(&empty[stage], (uint16_t)3);
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
         umma_commit(&tfull[acc]);  // accumulator complete -> epilogue
@@ -417,12 +436,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
       tma_prefetch_desc(&tmO0);
       if (p.tma_out == 2 && p.Dl) tma_prefetch_desc(&tmO1);
     }
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
       const int z = tile / tiles_per_z;
       int r = tile - z * tiles_per_z;
-      const int sp = r / (p.tiles_m * p.tiles_n);
-      r -= sp * (p.tiles_m * p.tiles_n);
-      const int mt = r / p.tiles_n, nt = r - mt * p.tiles_n;
+      const int sp = r / (p.tiles_mp * p.tiles_n);
+      r -= sp * (p.tiles_mp * p.tiles_n);
+      const int mt = (r / p.tiles_n) * p.cl + crank, nt = r % p.tiles_n;
       const int n0 = nt * BN;
       mbar_wait(&tfull[acc], accphase);
       tc_fence_after();
@@ -735,6 +754,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
 
   tc_fence_before();
   __syncthreads();
+  if (p.cl > 1) cluster_sync();        // no CTA leaves while its peer can still multicast into it / arrive on its barriers
   if (warp == 1) {
     __syncwarp();
     tc_fence_after();
@@ -847,10 +867,36 @@ static int launch_cfg(const CUtensorMap& ah, const CUtensorMap& al, const CUtens
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
-  const int total = p.tiles_m * p.tiles_n * p.splits * p.batch;
-  const int grid = total < num_sms() ? total : num_sms();
-  gemm_tc_kernel<BN, NMMA, EPI><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(ah, al, bh, bl, o0, o1, p);
-  return (int)cudaGetLastError();
+  const int total = p.tiles_mp * p.tiles_n * p.splits * p.batch;       // tiles (cl = 1) or pairs of M tiles (cl = 2)
+  if (p.cl == 1) {
+    const int grid = total < num_sms() ? total : num_sms();
+    gemm_tc_kernel<BN, NMMA, EPI><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(ah, al, bh, bl, o0, o1, p);
+    return (int)cudaGetLastError();
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.blockDim = dim3(Cfg::THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  // a persistent grid must be ONE resident wave: pairs are placed inside a GPC, and a GPC with an odd number of usable SMs
+  // leaves one idle -> ask the driver how many 2-CTA clusters of this kernel can be co-resident
+  static int max_pairs = 0;
+  if (!max_pairs) {
+    cfg.gridDim = dim3(2 * (num_sms() / 2));
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, gemm_tc_kernel<BN, NMMA, EPI>, &cfg) != cudaSuccess || n <= 0) {
+      (void)cudaGetLastError();
+      n = num_sms() / 2 - 4;
+    }
+    max_pairs = n < num_sms() / 2 ? n : num_sms() / 2;
+    if (getenv("ODISE_VERBOSE")) fprintf(stderr, "odise_b200: gemm_tc<%d,%d,%d> co-resident CTA pairs: %d\n", BN, NMMA, EPI, max_pairs);
+  }
+  cfg.gridDim = dim3(2 * (total < max_pairs ? total : max_pairs));
+  return (int)cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, NMMA, EPI>, ah, al, bh, bl, o0, o1, p);
 }
 
 static int pick_bn(int M, int N, int K, int batch, int forced, bool conv) {
@@ -1002,12 +1048,22 @@ extern "C" int odise_gemm_bf16(const odise_gemm_desc* d, void* stream_v) {
     if (rc) return rc;
   }
   const int BN = pick_bn(d->M, d->N, d->K, d->batch, d->force_bn, d->conv3x3 != 0);
+  p.tiles_m = (d->M + 127) / 128;
+  {
+    // CTA pairs sharing the B tile by TMA multicast (GemmParams::cl): worth it when M tiles pair up without a large idle
+    // tail.  ODISE_GEMM_CLUSTER=0 disables (A/B switch), =2 forces pairs wherever there are at least two M tiles.
+    static const int mode = getenv("ODISE_GEMM_CLUSTER") ? atoi(getenv("ODISE_GEMM_CLUSTER")) : 1;
+    p.cl = 1;
+    if (mode == 2 && p.tiles_m >= 2) p.cl = 2;
+    else if (mode == 1 && p.tiles_m >= 2 && (p.tiles_m % 2 == 0 || p.tiles_m >= 16)) p.cl = 2;
+    p.tiles_mp = (p.tiles_m + p.cl - 1) / p.cl;
+  }
   {
     if (d->ldb % 8 || d->b_batch_stride % 8) return ODISE_ERR_ALIGN;
     const long long bs = d->b_batch_stride ? d->b_batch_stride : (long long)d->N * d->ldb;
     cuuint64_t dims[3] = {(cuuint64_t)d->K, (cuuint64_t)d->N, (cuuint64_t)(d->b_batch_stride ? d->batch : 1)};
     cuuint64_t str[2] = {(cuuint64_t)d->ldb * 2, (cuuint64_t)bs * 2};
-    cuuint32_t box[3] = {64, (cuuint32_t)BN, 1};
+    cuuint32_t box[3] = {64, (cuuint32_t)(BN / p.cl), 1};     // pair mode: each CTA fetches half of the B tile
     rc = encode_map(&bh, d->b_hi, 3, dims, str, box);
     if (rc) return rc;
     if (d->nmma == 2) {
@@ -1023,7 +1079,6 @@ extern "C" int odise_gemm_bf16(const odise_gemm_desc* d, void* stream_v) {
         !p.vec_ok || d->act != ODISE_ACT_NONE)
       return ODISE_ERR_UNSUPPORTED;
   }
-  p.tiles_m = (d->M + 127) / 128;
   p.tiles_n = (d->N + BN - 1) / BN;
   p.kblocks = (d->K + 63) / 64;
   p.splits = d->split_k > 1 ? d->split_k : 1;
