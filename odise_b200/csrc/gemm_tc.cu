@@ -220,11 +220,14 @@ __device__ __forceinline__ void epilogue_quad(const GemmParams& p, int z, int m,
   }
 }
 
-template <int BN, int NMMA>
+// SM2 = 1: the CTA pair runs cta_group::2 MMAs (M = 256 over the two CTAs' TMEM); each CTA keeps only ITS half of the B tile
+// (BN / 2 rows) in shared memory -> smaller stages (3 instead of 2 at BN = 256) and one third fewer operand bytes delivered
+// per FLOP.
+template <int BN, int NMMA, int SM2 = 0>
 struct GemmCfg {
   static constexpr int BM = 128, BK = 64;
   static constexpr int A_BYTES = BM * BK * 2;
-  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int B_BYTES = (SM2 ? BN / 2 : BN) * BK * 2;
   static constexpr int PLANES = (NMMA == 1) ? 1 : 2;
   static constexpr int STAGE_BYTES = PLANES * (A_BYTES + B_BYTES);
   // epilogue warps: one warp per scheduler is latency bound (ncu: IPC 0.17/warp), so two warps share each TMEM lane
@@ -240,20 +243,20 @@ struct GemmCfg {
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr int ACC_STRIDE = (BN <= 64) ? 64 : (BN <= 128 ? 128 : 256);  // TMEM columns per accumulator
   static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 256 /*barriers: 3 * STAGES + 4 of 8 B + TMEM slot*/;
 };
 
 // EPI selects the compiled epilogue of the interior fast path (the runtime flags it excludes are guaranteed off by the
 // host dispatch): 0 = lean (alpha, bias, activation -> fp32 and/or planes), 1 = + row bias / bias_m / residual,
 // 2 = fused GEGLU.  ncu on the K = 320 FF1 GEMM showed ~190 of the 354 instructions of a chunk iteration were runtime
 // flag tests, predicated-off adds and parameter re-loads; the lean variant drops them.
-template <int BN, int NMMA, int EPI>
-__global__ void __launch_bounds__(GemmCfg<BN, NMMA>::THREADS, 1)
+template <int BN, int NMMA, int EPI, int SM2>
+__global__ void __launch_bounds__(GemmCfg<BN, NMMA, SM2>::THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
                const __grid_constant__ CUtensorMap tmO0, const __grid_constant__ CUtensorMap tmO1,
                const GemmParams p) {
-  using Cfg = GemmCfg<BN, NMMA>;
+  using Cfg = GemmCfg<BN, NMMA, SM2>;
   extern __shared__ __align__(1024) uint8_t smem[];   // SWIZZLE_128B tiles need 1024-byte alignment
   float* epi_smem = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::EPI_BYTES);
@@ -261,7 +264,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
   uint64_t* empty = bars + Cfg::STAGES;        // [STAGES]
   uint64_t* tfull = bars + 2 * Cfg::STAGES;    // [2]
   uint64_t* tempty = bars + 2 * Cfg::STAGES + 2;  // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::STAGES + 4);
+  uint64_t* full2 = bars + 2 * Cfg::STAGES + 4;   // [STAGES]  SM2, leader CTA: "the peer's half of stage s has landed"
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * Cfg::STAGES + 4);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -279,17 +283,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
     }
     for (int s = 0; s < Cfg::STAGES; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], p.cl);      // one tcgen05.commit arrival per CTA that reads the stage
+      // multicast pairs: one tcgen05.commit arrival per CTA that reads the stage; SM2: the leader's (multicast) commit only
+      mbar_init(&empty[s], SM2 ? 1 : p.cl);
+      mbar_init(&full2[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull[s], 1);
-      mbar_init(&tempty[s], 32 * Cfg::NEPI);
+      mbar_init(&tempty[s], (SM2 ? 2 : 1) * 32 * Cfg::NEPI);   // SM2: the epilogue warps of BOTH CTAs release the pair's accumulator
     }
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
-    tmem_relinquish();
+    if (SM2) { tmem_alloc2(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish2(); }
+    else { tmem_alloc(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish(); }
   }
   tc_fence_before();
   __syncthreads();
@@ -359,7 +365,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
           }
           const int zb = p.b_batched ? z : 0;
           uint8_t* sb = st + Cfg::PLANES * Cfg::A_BYTES;
-          if (p.cl == 1) {
+          if (SM2) {
+            // 2-SM MMA: this CTA keeps rows [crank * BN/2, +BN/2) of the B tile only (tensor-map box = BN/2 rows)
+            tma_load_3d(sb, &tmBh, &full[stage], kb * 64, n0 + crank * (BN / 2), zb);
+            if (NMMA != 1) tma_load_3d(sb + Cfg::B_BYTES, &tmBl, &full[stage], kb * 64, n0 + crank * (BN / 2), zb);
+          } else if (p.cl == 1) {
             tma_load_3d(sb, &tmBh, &full[stage], kb * 64, n0, zb);
             if (NMMA != 1) tma_load_3d(sb + Cfg::B_BYTES, &tmBl, &full[stage], kb * 64, n0, zb);
           } else {
@@ -374,10 +384,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ------------------------------------------------------------ MMA issuer (one thread)
-      constexpr uint32_t idesc = NMMA == 2 ? umma_idesc_f16(128, BN) : umma_idesc_bf16(128, BN);
-      constexpr uint32_t idesc_q = umma_idesc_e5m2(128, BN);
+    if (lane == 0 && SM2 && crank == 1) {
+      // ------------------------------------------------------------ odd CTA of a 2-SM pair: no MMAs to issue; it tells the
+      // leader when ITS half of each stage has landed (the leader's MMAs read both CTAs' shared memory)
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
+        int r = tile % tiles_per_z;
+        const int sp = r / (p.tiles_mp * p.tiles_n);
+        const int kb0 = sp * kb_per_split;
+        const int kb1 = min(p.kblocks, kb0 + kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full[stage], phase);
+          mbar_arrive_remote(mapa_shared(&full2[stage], 0));
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    } else if (lane == 0) {
+      // ------------------------------------------------------------ MMA issuer (one thread; SM2: of the even CTA)
+      constexpr uint32_t MM = SM2 ? 256 : 128;
+      constexpr uint32_t idesc = NMMA == 2 ? umma_idesc_f16(MM, BN) : umma_idesc_bf16(MM, BN);
+      constexpr uint32_t idesc_q = umma_idesc_e5m2(MM, BN);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -387,11 +414,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
         const int sp = r / (p.tiles_mp * p.tiles_n);
         const int kb0 = sp * kb_per_split;
         const int kb1 = min(p.kblocks, kb0 + kb_per_split);
-        mbar_wait(&tempty[acc], accphase ^ 1);
+        if (SM2) mbar_wait_cluster(&tempty[acc], accphase ^ 1);
+        else mbar_wait(&tempty[acc], accphase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * Cfg::ACC_STRIDE;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full[stage], phase);
+          if (SM2) mbar_wait_cluster(&full2[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
           const uint32_t sb = sa + Cfg::PLANES * Cfg::A_BYTES;
@@ -399,12 +428,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
           for (int k = 0; k < 4; ++k) {
             const uint64_t a_hi = umma_desc_sw128(sa + k * 32);
             const uint64_t b_hi = umma_desc_sw128(sb + k * 32);
-            umma_bf16(d_tmem, a_hi, b_hi, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            const uint32_t accum = (kb > kb0 || k > 0) ? 1u : 0u;
+            if (SM2) umma2_f16(d_tmem, a_hi, b_hi, idesc, accum); else umma_bf16(d_tmem, a_hi, b_hi, idesc, accum);
             if (NMMA == 3) {
               const uint64_t a_lo = umma_desc_sw128(sa + Cfg::A_BYTES + k * 32);
               const uint64_t b_lo = umma_desc_sw128(sb + Cfg::B_BYTES + k * 32);
-              umma_bf16(d_tmem, a_hi, b_lo, idesc, 1u);
-              umma_bf16(d_tmem, a_lo, b_hi, idesc, 1u);
+              if (SM2) { umma2_f16(d_tmem, a_hi, b_lo, idesc, 1u); umma2_f16(d_tmem, a_lo, b_hi, idesc, 1u); }
+              else { umma_bf16(d_tmem, a_hi, b_lo, idesc, 1u); umma_bf16(d_tmem, a_lo, b_hi, idesc, 1u); }
             }
           }
           if (NMMA == 2) {
@@ -413,16 +443,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
             const uint32_t a2 = sa + Cfg::A_BYTES, b2 = sb + Cfg::B_BYTES;
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
-              umma_f8(d_tmem, umma_desc_sw128(a2 + k * 32), umma_desc_sw128(b2 + 64 + k * 32), idesc_q, 1u);
-              umma_f8(d_tmem, umma_desc_sw128(a2 + 64 + k * 32), umma_desc_sw128(b2 + k * 32), idesc_q, 1u);
+              const uint64_t ah = umma_desc_sw128(a2 + k * 32), bl = umma_desc_sw128(b2 + 64 + k * 32);
+              const uint64_t al = umma_desc_sw128(a2 + 64 + k * 32), bh = umma_desc_sw128(b2 + k * 32);
+              if (SM2) { umma2_f8(d_tmem, ah, bl, idesc_q, 1u); umma2_f8(d_tmem, al, bh, idesc_q, 1u); }
+              else { umma_f8(d_tmem, ah, bl, idesc_q, 1u); umma_f8(d_tmem, al, bh, idesc_q, 1u); }
             }
           }
           // smem slot reusable once these MMAs retire (pair mode: once the MMAs of BOTH CTAs have read their copy)
-          if (p.cl == 1) umma_commit(&empty[stage]);
+          if (SM2) umma2_commit_mc(&empty[stage], (uint16_t)3);
+          else if (p.cl == 1) umma_commit(&empty[stage]);
           else umma_commit_mc(&empty[stage], (uint16_t)3);
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tfull[acc]);  // accumulator complete -> epilogue
+        // accumulator complete -> epilogue (SM2: the epilogue warps of both CTAs, each on its own 128 rows)
+        if (SM2) umma2_commit_mc(&tfull[acc], (uint16_t)3);
+        else umma_commit(&tfull[acc]);
         if (++acc == 2) { acc = 0; accphase ^= 1; }
       }
     }
@@ -746,7 +781,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
         }
       }
       tc_fence_before();
-      mbar_arrive(&tempty[acc]);
+      if (SM2 && crank == 1) mbar_arrive_remote(mapa_shared(&tempty[acc], 0));   // the pair's accumulator belongs to the leader's MMA thread
+      else mbar_arrive(&tempty[acc]);
       if (++acc == 2) { acc = 0; accphase ^= 1; }
     }
     if (p.tma_out && lane == 0 && tma_cnt) tma_store_wait_read<0>();   // shared memory must outlive the stores' reads
@@ -758,7 +794,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
   if (warp == 1) {
     __syncwarp();
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    if (SM2) tmem_dealloc2(tmem_base, Cfg::TMEM_COLS);
+    else tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
 }
 
@@ -856,13 +893,13 @@ int num_sms() {
   return n;
 }
 
-template <int BN, int NMMA, int EPI>
+template <int BN, int NMMA, int EPI, int SM2>
 static int launch_cfg(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl,
                       const CUtensorMap& o0, const CUtensorMap& o1, const GemmParams& p, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN, NMMA>;
+  using Cfg = GemmCfg<BN, NMMA, SM2>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, NMMA, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, NMMA, EPI, SM2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
@@ -870,7 +907,7 @@ static int launch_cfg(const CUtensorMap& ah, const CUtensorMap& al, const CUtens
   const int total = p.tiles_mp * p.tiles_n * p.splits * p.batch;       // tiles (cl = 1) or pairs of M tiles (cl = 2)
   if (p.cl == 1) {
     const int grid = total < num_sms() ? total : num_sms();
-    gemm_tc_kernel<BN, NMMA, EPI><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(ah, al, bh, bl, o0, o1, p);
+    gemm_tc_kernel<BN, NMMA, EPI, SM2><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(ah, al, bh, bl, o0, o1, p);
     return (int)cudaGetLastError();
   }
   cudaLaunchConfig_t cfg{};
@@ -888,15 +925,15 @@ static int launch_cfg(const CUtensorMap& ah, const CUtensorMap& al, const CUtens
   if (!max_pairs) {
     cfg.gridDim = dim3(2 * (num_sms() / 2));
     int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, gemm_tc_kernel<BN, NMMA, EPI>, &cfg) != cudaSuccess || n <= 0) {
+    if (cudaOccupancyMaxActiveClusters(&n, gemm_tc_kernel<BN, NMMA, EPI, SM2>, &cfg) != cudaSuccess || n <= 0) {
       (void)cudaGetLastError();
       n = num_sms() / 2 - 4;
     }
     max_pairs = n < num_sms() / 2 ? n : num_sms() / 2;
-    if (getenv("ODISE_VERBOSE")) fprintf(stderr, "odise_b200: gemm_tc<%d,%d,%d> co-resident CTA pairs: %d\n", BN, NMMA, EPI, max_pairs);
+    if (getenv("ODISE_VERBOSE")) fprintf(stderr, "odise_b200: gemm_tc<%d,%d,%d,%d> co-resident CTA pairs: %d\n", BN, NMMA, EPI, SM2, max_pairs);
   }
   cfg.gridDim = dim3(2 * (total < max_pairs ? total : max_pairs));
-  return (int)cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, NMMA, EPI>, ah, al, bh, bl, o0, o1, p);
+  return (int)cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, NMMA, EPI, SM2>, ah, al, bh, bl, o0, o1, p);
 }
 
 static int pick_bn(int M, int N, int K, int batch, int forced, bool conv) {
@@ -1049,13 +1086,18 @@ extern "C" int odise_gemm_bf16(const odise_gemm_desc* d, void* stream_v) {
   }
   const int BN = pick_bn(d->M, d->N, d->K, d->batch, d->force_bn, d->conv3x3 != 0);
   p.tiles_m = (d->M + 127) / 128;
+  bool sm2 = false;
   {
     // CTA pairs sharing the B tile by TMA multicast (GemmParams::cl): worth it when M tiles pair up without a large idle
     // tail.  ODISE_GEMM_CLUSTER=0 disables (A/B switch), =2 forces pairs wherever there are at least two M tiles.
+    // ODISE_GEMM_CLUSTER: 0 = single CTAs | 1 (default) = 2-SM MMAs (cta_group::2, GemmCfg SM2) where M tiles pair up |
+    // 2 = 2-SM wherever there are two M tiles | 3 / 4 = the same two policies with 1-SM MMAs + multicast B (A/B switches)
     static const int mode = getenv("ODISE_GEMM_CLUSTER") ? atoi(getenv("ODISE_GEMM_CLUSTER")) : 1;
+    const bool pairable = p.tiles_m >= 2 && (p.tiles_m % 2 == 0 || p.tiles_m >= 16);
     p.cl = 1;
-    if (mode == 2 && p.tiles_m >= 2) p.cl = 2;
-    else if (mode == 1 && p.tiles_m >= 2 && (p.tiles_m % 2 == 0 || p.tiles_m >= 16)) p.cl = 2;
+    if ((mode == 2 || mode == 4) && p.tiles_m >= 2) p.cl = 2;
+    else if ((mode == 1 || mode == 3) && pairable) p.cl = 2;
+    sm2 = p.cl == 2 && (mode == 1 || mode == 2) && d->nmma != 1;
     p.tiles_mp = (p.tiles_m + p.cl - 1) / p.cl;
   }
   {
@@ -1121,10 +1163,15 @@ extern "C" int odise_gemm_bf16(const odise_gemm_desc* d, void* stream_v) {
       if (rc) p.tma_out = 0;      // a shape the tensor map cannot express: the plain epilogue handles it
     }
   }
+#define ODISE_LAUNCH_E(BN_, NM_, S_)                                                  \
+  rc = epi == 2   ? launch_cfg<BN_, NM_, 2, S_>(ah, al, bh, bl, o0, o1, p, stream)    \
+       : epi == 1 ? launch_cfg<BN_, NM_, 1, S_>(ah, al, bh, bl, o0, o1, p, stream)    \
+                  : launch_cfg<BN_, NM_, 0, S_>(ah, al, bh, bl, o0, o1, p, stream)
 #define ODISE_LAUNCH(BN_, NM_)                                                        \
-  rc = epi == 2   ? launch_cfg<BN_, NM_, 2>(ah, al, bh, bl, o0, o1, p, stream)        \
-       : epi == 1 ? launch_cfg<BN_, NM_, 1>(ah, al, bh, bl, o0, o1, p, stream)        \
-                  : launch_cfg<BN_, NM_, 0>(ah, al, bh, bl, o0, o1, p, stream)
+  do {                                                                                \
+    if (sm2 && NM_ != 1) { ODISE_LAUNCH_E(BN_, (NM_ == 1 ? 3 : NM_), 1); }            \
+    else { ODISE_LAUNCH_E(BN_, NM_, 0); }                                             \
+  } while (0)
   if (d->nmma == 3) {
     switch (BN) {
       case 64: ODISE_LAUNCH(64, 3); break;
@@ -1148,6 +1195,7 @@ extern "C" int odise_gemm_bf16(const odise_gemm_desc* d, void* stream_v) {
     }
   }
 #undef ODISE_LAUNCH
+#undef ODISE_LAUNCH_E
   if (rc) return rc;
   count_launch(p.splits > 1 ? 2 : 1);
   if (p.splits > 1) {
