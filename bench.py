@@ -54,7 +54,7 @@ def parse():
     ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
     ap.add_argument("--batch", type=int, default=None, help="images per GPU per step (default: the config's)")
     ap.add_argument("--size", type=int, default=None)
-    ap.add_argument("--precision", default="bf16x3", choices=["f16q8", "bf16x3", "bf16"],
+    ap.add_argument("--precision", default="f16q8", choices=["f16q8", "bf16x3", "bf16"],
                     help="bf16x3: (hi, lo) bf16 pairs, 3 MMAs per k-step (2e-5 at the UNet taps).  f16q8: fp16 hi x hi + both "
                          "cross terms on e5m2 MMAs at twice the rate = 2 MMA units per k-step (1e-4 at the taps, bar 1e-3); "
                          "VAE / CLIP / UNet / projections run it, the head and the post-processing stay bf16x3.  bf16: plain "

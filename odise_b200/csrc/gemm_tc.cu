@@ -878,7 +878,7 @@ static int encode_out_map(CUtensorMap* tm, void* base, bool f32, long long N, lo
 }
 
 // ---- optional per-launch timing (bench.py roofline): CUDA events on the launch stream around every GEMM launch
-struct ProfRec { cudaEvent_t a, b; double flops; int M, N, K, batch, conv, bn, nmma, splits; };
+struct ProfRec { cudaEvent_t a, b; double flops; int M, N, K, batch, conv, bn, nmma, splits, pair; };
 static std::vector<ProfRec> g_prof;
 static bool g_prof_on = false;
 
@@ -936,40 +936,42 @@ static int launch_cfg(const CUtensorMap& ah, const CUtensorMap& al, const CUtens
   return (int)cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, NMMA, EPI, SM2>, ah, al, bh, bl, o0, o1, p);
 }
 
-static int pick_bn(int M, int N, int K, int batch, int forced, bool conv) {
-  if (forced == 64 || forced == 128 || forced == 160 || forced == 256) return forced;
-  const int cands[4] = {256, 160, 128, 64};
+// Tile choice: output-tile width BN and whether CTA pairs run 2-SM MMAs (GemmCfg SM2; BN = 256 only: with 64 / 80-row B
+// halves the pair MMA runs at about half rate, tools/r2_gpu_batch7.sh).  Relative time per (output column x k) of a 128-row
+// tile, measured on B200 with tools/gemm_one.py at K >= 1024 (profiles/r2j_gemm_sm2_policy.txt):
+//                       BN = 256 pair   256    160    128    64
+//   F16Q8  (nmma 2)          0.92       1.12   0.95   1.00   1.45     (two 96 KB stages starve the single-CTA 256 tile)
+//   bf16x3 (nmma 3)          0.90       1.05   0.95   1.00   1.45
+//   bf16   (nmma 1)           -         0.90   0.95   1.00   1.45
+struct TileChoice { int bn; bool sm2; };
+static TileChoice pick_tile(int M, int N, int K, int batch, int forced, bool conv, int nmma, bool pair_ok) {
+  const int cands[5] = {256, 256, 160, 128, 64};                 // cands[0] = the pair variant
+  const double eff2[5] = {0.92, 1.12, 0.95, 1.0, 1.45}, eff3[5] = {0.90, 1.05, 0.95, 1.0, 1.45},
+               eff1[5] = {9.9, 0.90, 0.95, 1.0, 1.45};
+  const double* eff = nmma == 2 ? eff2 : (nmma == 3 ? eff3 : eff1);
+  const double epi_k[5] = {480.0, 480.0, 960.0, 480.0, 480.0};  // epilogue of a tile in units of MMA k (8 / 4 epilogue warps)
   const long long tm = (M + 127) / 128;
   double best = 1e30;
-  int best_bn = 128;
-  if (conv) {   // implicit convs (K >= 576) are MMA bound at every width: balance waves only
-    // 256-wide tiles move 25 % fewer operand bytes per FLOP from L2 into shared memory; on a power-capped board that is
-    // worth ~2.5 % of the whole step (A/B on one box: 172.6 vs 177.2 ms, SM clocks 1.68 vs 1.61 GHz).
-    // BN=64 is smem-bandwidth bound on the A re-read.
-    const double eff[4] = {0.95, 1.0, 1.0, 1.45};
-    for (int i = 0; i < 4; ++i) {
-      const int bn = cands[i];
-      const long long tiles = tm * ((N + bn - 1) / bn) * batch;
-      const long long waves = (tiles + num_sms() - 1) / num_sms();
-      const double cost = (double)waves * bn * eff[i] + 0.02 * bn;  // mild bias toward smaller tiles on ties
-      if (cost < best) { best = cost; best_bn = bn; }
-    }
-    return best_bn;
-  }
-  // plain GEMMs: per-tile time = max(MMA, epilogue) + fixed fill/drain.  Measured on B200 (tools/gemm_one.py): the
-  // epilogue of a 128-wide tile costs as much as K ~ 480 of MMA with 8 epilogue warps (BN 64/128/256) and K ~ 960 with
-  // the 4 warps of BN = 160; wider tiles re-read less of A (BN = 256 ~10 % faster than 128 at equal waves).
-  const double mma_eff[4] = {0.90, 0.95, 1.0, 1.45};
-  const double epi_k[4] = {480.0, 960.0, 480.0, 480.0};
-  for (int i = 0; i < 4; ++i) {
+  TileChoice c{128, false};
+  for (int i = 0; i < 5; ++i) {
     const int bn = cands[i];
-    const long long tiles = tm * ((N + bn - 1) / bn) * batch;
-    const long long waves = (tiles + num_sms() - 1) / num_sms();
-    const double mma = (double)bn * K * mma_eff[i], epi = (double)bn * epi_k[i];
-    const double cost = (double)waves * ((mma > epi ? mma : epi) + 20000.0);
-    if (cost < best) { best = cost; best_bn = bn; }
+    const bool sm2 = i == 0;
+    if (sm2 && !(pair_ok && nmma != 1 && K >= 1024)) continue;
+    if (forced && bn != forced) continue;
+    const long long tn = (N + bn - 1) / bn;
+    const long long units = sm2 ? ((tm + 1) / 2) * tn * batch : tm * tn * batch;
+    const long long slots = sm2 ? num_sms() / 2 : num_sms();
+    const long long waves = (units + slots - 1) / slots;
+    double cost;
+    if (conv) {          // implicit convs (K >= 576): main-loop bound at every width -> balance waves
+      cost = (double)waves * bn * eff[i] + 0.02 * bn;            // mild bias toward smaller tiles on ties
+    } else {             // plain GEMMs: per-tile time = max(main loop, epilogue) + fixed fill / drain
+      const double mma = (double)bn * K * eff[i], epi = (double)bn * epi_k[i];
+      cost = (double)waves * ((mma > epi ? mma : epi) + 20000.0);
+    }
+    if (cost < best) { best = cost; c = TileChoice{bn, sm2}; }
   }
-  return best_bn;
+  return c;
 }
 
 }  // namespace ob
@@ -1084,9 +1086,9 @@ extern "C" int odise_gemm_bf16(const odise_gemm_desc* d, void* stream_v) {
     rc = encode_map(&al, d->nmma != 1 ? d->a_lo : d->a_hi, 3, dims, str, box);
     if (rc) return rc;
   }
-  const int BN = pick_bn(d->M, d->N, d->K, d->batch, d->force_bn, d->conv3x3 != 0);
   p.tiles_m = (d->M + 127) / 128;
   bool sm2 = false;
+  int BN;
   {
     // CTA pairs sharing the B tile by TMA multicast (GemmParams::cl): worth it when M tiles pair up without a large idle
     // tail.  ODISE_GEMM_CLUSTER=0 disables (A/B switch), =2 forces pairs wherever there are at least two M tiles.
@@ -1094,10 +1096,18 @@ extern "C" int odise_gemm_bf16(const odise_gemm_desc* d, void* stream_v) {
     // 2 = 2-SM wherever there are two M tiles | 3 / 4 = the same two policies with 1-SM MMAs + multicast B (A/B switches)
     static const int mode = getenv("ODISE_GEMM_CLUSTER") ? atoi(getenv("ODISE_GEMM_CLUSTER")) : 1;
     const bool pairable = p.tiles_m >= 2 && (p.tiles_m % 2 == 0 || p.tiles_m >= 16);
+    const int fbn = (d->force_bn == 64 || d->force_bn == 128 || d->force_bn == 160 || d->force_bn == 256) ? d->force_bn : 0;
     p.cl = 1;
-    if ((mode == 2 || mode == 4) && p.tiles_m >= 2) p.cl = 2;
-    else if ((mode == 1 || mode == 3) && pairable) p.cl = 2;
-    sm2 = p.cl == 2 && (mode == 1 || mode == 2) && d->nmma != 1;
+    if (mode == 1) {                       // default: the measured cost model decides (pairs only at BN = 256, K >= 1024)
+      const TileChoice tc = pick_tile(d->M, d->N, d->K, d->batch, fbn, d->conv3x3 != 0, d->nmma, pairable);
+      BN = tc.bn; sm2 = tc.sm2;
+      if (sm2) p.cl = 2;
+    } else {
+      BN = pick_tile(d->M, d->N, d->K, d->batch, fbn, d->conv3x3 != 0, d->nmma, false).bn;
+      if ((mode == 2 || mode == 4) && p.tiles_m >= 2) p.cl = 2;
+      else if (mode == 3 && pairable) p.cl = 2;
+      sm2 = p.cl == 2 && mode == 2 && d->nmma != 1;
+    }
     p.tiles_mp = (p.tiles_m + p.cl - 1) / p.cl;
   }
   {
@@ -1138,7 +1148,7 @@ extern "C" int odise_gemm_bf16(const odise_gemm_desc* d, void* stream_v) {
     cudaEventCreate(&rec.b);
     rec.flops = 2.0 * d->M * d->N * (double)d->K * d->batch;
     rec.M = d->M; rec.N = d->N; rec.K = d->K; rec.batch = d->batch; rec.conv = d->conv3x3; rec.bn = BN;
-    rec.nmma = d->nmma; rec.splits = p.splits;
+    rec.nmma = d->nmma; rec.splits = p.splits; rec.pair = sm2 ? 2 : (p.cl == 2 ? 1 : 0);
     cudaEventRecord(rec.a, stream);
   }
   const int epi = d->geglu ? 2 : ((d->residual || d->rowbias || d->bias_m) ? 1 : 0);
@@ -1228,15 +1238,15 @@ extern "C" int odise_profile_end(long long* launches, double* total_ms, double* 
   double ms = 0, fl = 0;
   FILE* fcsv = nullptr;
   if (const char* path = getenv("ODISE_PROFILE_CSV")) fcsv = fopen(path, "a");
-  if (fcsv) fprintf(fcsv, "M,N,K,batch,conv,bn,nmma,splits,ms,tflops\n");
+  if (fcsv) fprintf(fcsv, "M,N,K,batch,conv,bn,nmma,splits,ms,tflops,pair\n");   // pair: 0 single CTAs, 1 multicast pairs, 2 2-SM MMAs
   for (auto& r : g_prof) {
     float t = 0;
     cudaEventElapsedTime(&t, r.a, r.b);
     ms += t;
     fl += r.flops;
     if (fcsv)
-      fprintf(fcsv, "%d,%d,%d,%d,%d,%d,%d,%d,%.4f,%.1f\n", r.M, r.N, r.K, r.batch, r.conv, r.bn, r.nmma, r.splits, t,
-              r.flops / (t * 1e9));
+      fprintf(fcsv, "%d,%d,%d,%d,%d,%d,%d,%d,%.4f,%.1f,%d\n", r.M, r.N, r.K, r.batch, r.conv, r.bn, r.nmma, r.splits, t,
+              r.flops / (t * 1e9), r.pair);
   }
   if (fcsv) fclose(fcsv);
   if (launches) *launches = (long long)g_prof.size();

@@ -13,12 +13,12 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=4)
 ap.add_argument("--size", type=int, default=1024)
 ap.add_argument("--iters", type=int, default=2)
-ap.add_argument("--precision", default="bf16x3")
+ap.add_argument("--precision", default="f16q8", choices=["f16q8", "bf16x3", "bf16"])
 ap.add_argument("--full", action="store_true", help="include the VAE (f-1) and CLIP image tower (f-2) stages")
 a = ap.parse_args()
 dev = torch.device("cuda:0")
 sd = spec.synth_state_dict(full_param_list(with_vae=a.full, with_clip=a.full), 0)
-eng = ODISEEngine(sd, dev, nmma=3 if a.precision == "bf16x3" else 1, synthetic_uncond=True, with_vae=a.full, with_clip=a.full)
+eng = ODISEEngine(sd, dev, nmma={"f16q8": 2, "bf16x3": 3, "bf16": 1}[a.precision], synthetic_uncond=True, with_vae=a.full, with_clip=a.full)
 eng.set_synthetic_vocabulary("ade150", 150, 403)
 n0 = lib.launch_count()
 for i in range(a.iters):
