@@ -22,6 +22,8 @@
 #include "launch_count.h"
 #include <cudaTypedefs.h>
 #include <mutex>
+#include <map>
+#include <cstring>
 #include <vector>
 #include <cstdlib>
 #include <cstdio>
@@ -1087,51 +1089,14 @@ extern "C" int odise_gemm_bf16(const odise_gemm_desc* d, void* stream_v) {
     if (rc) return rc;
   }
   p.tiles_m = (d->M + 127) / 128;
-  bool sm2 = false;
-  int BN;
-  {
-    // CTA pairs sharing the B tile by TMA multicast (GemmParams::cl): worth it when M tiles pair up without a large idle
-    // tail.  ODISE_GEMM_CLUSTER=0 disables (A/B switch), =2 forces pairs wherever there are at least two M tiles.
-    // ODISE_GEMM_CLUSTER: 0 = single CTAs | 1 (default) = 2-SM MMAs (cta_group::2, GemmCfg SM2) where M tiles pair up |
-    // 2 = 2-SM wherever there are two M tiles | 3 / 4 = the same two policies with 1-SM MMAs + multicast B (A/B switches)
-    static const int mode = getenv("ODISE_GEMM_CLUSTER") ? atoi(getenv("ODISE_GEMM_CLUSTER")) : 1;
-    const bool pairable = p.tiles_m >= 2 && (p.tiles_m % 2 == 0 || p.tiles_m >= 16);
-    const int fbn = (d->force_bn == 64 || d->force_bn == 128 || d->force_bn == 160 || d->force_bn == 256) ? d->force_bn : 0;
-    p.cl = 1;
-    if (mode == 1) {                       // default: the measured cost model decides (pairs only at BN = 256, K >= 1024)
-      const TileChoice tc = pick_tile(d->M, d->N, d->K, d->batch, fbn, d->conv3x3 != 0, d->nmma, pairable);
-      BN = tc.bn; sm2 = tc.sm2;
-      if (sm2) p.cl = 2;
-    } else {
-      BN = pick_tile(d->M, d->N, d->K, d->batch, fbn, d->conv3x3 != 0, d->nmma, false).bn;
-      if ((mode == 2 || mode == 4) && p.tiles_m >= 2) p.cl = 2;
-      else if (mode == 3 && pairable) p.cl = 2;
-      sm2 = p.cl == 2 && mode == 2 && d->nmma != 1;
-    }
-    p.tiles_mp = (p.tiles_m + p.cl - 1) / p.cl;
-  }
-  {
-    if (d->ldb % 8 || d->b_batch_stride % 8) return ODISE_ERR_ALIGN;
-    const long long bs = d->b_batch_stride ? d->b_batch_stride : (long long)d->N * d->ldb;
-    cuuint64_t dims[3] = {(cuuint64_t)d->K, (cuuint64_t)d->N, (cuuint64_t)(d->b_batch_stride ? d->batch : 1)};
-    cuuint64_t str[2] = {(cuuint64_t)d->ldb * 2, (cuuint64_t)bs * 2};
-    cuuint32_t box[3] = {64, (cuuint32_t)(BN / p.cl), 1};     // pair mode: each CTA fetches half of the B tile
-    rc = encode_map(&bh, d->b_hi, 3, dims, str, box);
-    if (rc) return rc;
-    if (d->nmma == 2) {
-      dims[0] = (cuuint64_t)((d->K + 63) / 64 * 64);
-      if ((long long)dims[0] > d->ldb) return ODISE_ERR_ALIGN;
-    }
-    rc = encode_map(&bl, d->nmma != 1 ? d->b_lo : d->b_hi, 3, dims, str, box);
-    if (rc) return rc;
-  }
+  if (d->ldb % 8 || d->b_batch_stride % 8) return ODISE_ERR_ALIGN;
+  if (d->nmma == 2 && (long long)((d->K + 63) / 64 * 64) > d->ldb) return ODISE_ERR_ALIGN;
   if (d->geglu) {
     // fused GEGLU: (a, gate) quads must share a 16-column chunk; 8-byte plane stores need the aligned path
     if (!d->out_hi || d->out_f32 || d->residual || d->rowbias || d->bias_m || d->split_k > 1 || d->N % 16 ||
         !p.vec_ok || d->act != ODISE_ACT_NONE)
       return ODISE_ERR_UNSUPPORTED;
   }
-  p.tiles_n = (d->N + BN - 1) / BN;
   p.kblocks = (d->K + 63) / 64;
   p.splits = d->split_k > 1 ? d->split_k : 1;
   if (p.splits > p.kblocks) p.splits = p.kblocks;
@@ -1140,16 +1105,6 @@ extern "C" int odise_gemm_bf16(const odise_gemm_desc* d, void* stream_v) {
         d->workspace_bytes < (long long)p.splits * d->batch * d->M * d->N * (long long)sizeof(float))
       return ODISE_ERR_WORKSPACE;
     p.partial = reinterpret_cast<float*>(d->workspace);
-  }
-
-  ProfRec rec{};
-  if (g_prof_on) {
-    cudaEventCreate(&rec.a);
-    cudaEventCreate(&rec.b);
-    rec.flops = 2.0 * d->M * d->N * (double)d->K * d->batch;
-    rec.M = d->M; rec.N = d->N; rec.K = d->K; rec.batch = d->batch; rec.conv = d->conv3x3; rec.bn = BN;
-    rec.nmma = d->nmma; rec.splits = p.splits; rec.pair = sm2 ? 2 : (p.cl == 2 ? 1 : 0);
-    cudaEventRecord(rec.a, stream);
   }
   const int epi = d->geglu ? 2 : ((d->residual || d->rowbias || d->bias_m) ? 1 : 0);
   // TMA-store epilogue: one kind of output (fp32 OR planes), final values produced by this kernel, no fused GN records
@@ -1173,48 +1128,147 @@ extern "C" int odise_gemm_bf16(const odise_gemm_desc* d, void* stream_v) {
       if (rc) p.tma_out = 0;      // a shape the tensor map cannot express: the plain epilogue handles it
     }
   }
+
+  // one launch with a given output-tile width / pairing: B tensor maps (box = bn rows, bn / 2 per CTA of a pair) + dispatch
+  auto launch_with = [&](int bn, int cl, bool s2) -> int {
+    p.cl = cl;
+    p.tiles_mp = (p.tiles_m + cl - 1) / cl;
+    p.tiles_n = (d->N + bn - 1) / bn;
+    const long long bs = d->b_batch_stride ? d->b_batch_stride : (long long)d->N * d->ldb;
+    cuuint64_t dims[3] = {(cuuint64_t)d->K, (cuuint64_t)d->N, (cuuint64_t)(d->b_batch_stride ? d->batch : 1)};
+    cuuint64_t str[2] = {(cuuint64_t)d->ldb * 2, (cuuint64_t)bs * 2};
+    cuuint32_t box[3] = {64, (cuuint32_t)(bn / cl), 1};     // pair modes: each CTA fetches half of the B tile
+    int r = encode_map(&bh, d->b_hi, 3, dims, str, box);
+    if (r) return r;
+    if (d->nmma == 2) dims[0] = (cuuint64_t)((d->K + 63) / 64 * 64);   // whole 64-blocks of q bytes
+    r = encode_map(&bl, d->nmma != 1 ? d->b_lo : d->b_hi, 3, dims, str, box);
+    if (r) return r;
 #define ODISE_LAUNCH_E(BN_, NM_, S_)                                                  \
-  rc = epi == 2   ? launch_cfg<BN_, NM_, 2, S_>(ah, al, bh, bl, o0, o1, p, stream)    \
-       : epi == 1 ? launch_cfg<BN_, NM_, 1, S_>(ah, al, bh, bl, o0, o1, p, stream)    \
-                  : launch_cfg<BN_, NM_, 0, S_>(ah, al, bh, bl, o0, o1, p, stream)
+  r = epi == 2   ? launch_cfg<BN_, NM_, 2, S_>(ah, al, bh, bl, o0, o1, p, stream)     \
+      : epi == 1 ? launch_cfg<BN_, NM_, 1, S_>(ah, al, bh, bl, o0, o1, p, stream)     \
+                 : launch_cfg<BN_, NM_, 0, S_>(ah, al, bh, bl, o0, o1, p, stream)
 #define ODISE_LAUNCH(BN_, NM_)                                                        \
   do {                                                                                \
-    if (sm2 && NM_ != 1) { ODISE_LAUNCH_E(BN_, (NM_ == 1 ? 3 : NM_), 1); }            \
+    if (s2 && NM_ != 1) { ODISE_LAUNCH_E(BN_, (NM_ == 1 ? 3 : NM_), 1); }             \
     else { ODISE_LAUNCH_E(BN_, NM_, 0); }                                             \
   } while (0)
-  if (d->nmma == 3) {
-    switch (BN) {
-      case 64: ODISE_LAUNCH(64, 3); break;
-      case 128: ODISE_LAUNCH(128, 3); break;
-      case 160: ODISE_LAUNCH(160, 3); break;
-      default: ODISE_LAUNCH(256, 3); break;
+    if (d->nmma == 3) {
+      switch (bn) {
+        case 64: ODISE_LAUNCH(64, 3); break;
+        case 128: ODISE_LAUNCH(128, 3); break;
+        case 160: ODISE_LAUNCH(160, 3); break;
+        default: ODISE_LAUNCH(256, 3); break;
+      }
+    } else if (d->nmma == 2) {
+      switch (bn) {
+        case 64: ODISE_LAUNCH(64, 2); break;
+        case 128: ODISE_LAUNCH(128, 2); break;
+        case 160: ODISE_LAUNCH(160, 2); break;
+        default: ODISE_LAUNCH(256, 2); break;
+      }
+    } else {
+      switch (bn) {
+        case 64: ODISE_LAUNCH(64, 1); break;
+        case 128: ODISE_LAUNCH(128, 1); break;
+        case 160: ODISE_LAUNCH(160, 1); break;
+        default: ODISE_LAUNCH(256, 1); break;
+      }
     }
-  } else if (d->nmma == 2) {
-    switch (BN) {
-      case 64: ODISE_LAUNCH(64, 2); break;
-      case 128: ODISE_LAUNCH(128, 2); break;
-      case 160: ODISE_LAUNCH(160, 2); break;
-      default: ODISE_LAUNCH(256, 2); break;
-    }
-  } else {
-    switch (BN) {
-      case 64: ODISE_LAUNCH(64, 1); break;
-      case 128: ODISE_LAUNCH(128, 1); break;
-      case 160: ODISE_LAUNCH(160, 1); break;
-      default: ODISE_LAUNCH(256, 1); break;
-    }
-  }
 #undef ODISE_LAUNCH
 #undef ODISE_LAUNCH_E
+    if (r) return r;
+    if (p.splits > 1) {
+      const long long total = (long long)p.batch * p.M * ((p.N + 3) / 4);
+      int blocks = (int)((total + 127) / 128);
+      if (blocks > 148 * 8) blocks = 148 * 8;
+      gemm_splitk_reduce_kernel<<<blocks, 128, 0, stream>>>(p);
+      r = (int)cudaGetLastError();
+    }
+    return r;
+  };
+
+  // ---- tile width / pairing.  ODISE_GEMM_CLUSTER: 1 (default) = measured choice: a per-shape autotune (every candidate is
+  // the same arithmetic in the same k order -> bit-identical results, so the choice is free) with the cost model
+  // pick_tile() as the fallback under stream capture; 0 = single CTAs; 2 = 2-SM MMAs wherever there are two M tiles;
+  // 3 / 4 = 1-SM MMAs + multicast B pairs (A/B switches).  ODISE_GEMM_AUTOTUNE=0: cost model only.
+  bool sm2 = false;
+  int BN, CL = 1;
+  {
+    static const int mode = getenv("ODISE_GEMM_CLUSTER") ? atoi(getenv("ODISE_GEMM_CLUSTER")) : 1;
+    static const bool tune = !(getenv("ODISE_GEMM_AUTOTUNE") && atoi(getenv("ODISE_GEMM_AUTOTUNE")) == 0);
+    const bool pairable = p.tiles_m >= 2 && (p.tiles_m % 2 == 0 || p.tiles_m >= 16);
+    const int fbn = (d->force_bn == 64 || d->force_bn == 128 || d->force_bn == 160 || d->force_bn == 256) ? d->force_bn : 0;
+    if (mode != 1) {
+      BN = pick_tile(d->M, d->N, d->K, d->batch, fbn, d->conv3x3 != 0, d->nmma, false).bn;
+      if ((mode == 2 || mode == 4) && p.tiles_m >= 2) CL = 2;
+      else if (mode == 3 && pairable) CL = 2;
+      sm2 = CL == 2 && mode == 2 && d->nmma != 1;
+    } else {
+      const TileChoice tc = pick_tile(d->M, d->N, d->K, d->batch, fbn, d->conv3x3 != 0, d->nmma, pairable);
+      BN = tc.bn; sm2 = tc.sm2;
+      struct Key {
+        int v[14];
+        bool operator<(const Key& o) const { return memcmp(v, o.v, sizeof(v)) < 0; }
+      };
+      static std::map<Key, TileChoice> cache;
+      static std::mutex mu;
+      const Key key{{d->M, d->N, d->K, d->batch, d->conv3x3 ? 1 + d->conv_mode : 0, d->conv_W, d->nmma, epi, p.splits,
+                    (d->out_f32 ? 1 : 0) | (d->out_hi ? 2 : 0) | (d->out_planes_fp16 << 2), p.gnp ? 1 : 0, d->act, p.tma_out,
+                    p.vec_ok}};
+      cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+      cudaStreamIsCapturing(stream, &cap);
+      std::lock_guard<std::mutex> lk(mu);
+      auto it = cache.find(key);
+      if (it != cache.end()) {
+        BN = it->second.bn; sm2 = it->second.sm2;
+      } else if (tune && !fbn && !g_prof_on && cap == cudaStreamCaptureStatusNone &&
+                 !(d->residual && (const void*)d->residual == (const void*)d->out_f32)) {
+        // candidates: the pair tile, then single CTAs from wide to narrow (64 only for narrow outputs)
+        const TileChoice cands[5] = {{256, true}, {256, false}, {160, false}, {128, false}, {64, false}};
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0);
+        cudaEventCreate(&e1);
+        float best = 1e30f;
+        TileChoice bc = tc;
+        for (int i = 0; i < 5; ++i) {
+          const TileChoice c = cands[i];
+          if (c.sm2 && !(pairable && d->nmma != 1)) continue;
+          if (c.bn == 64 && d->N > 96) continue;
+          if (c.bn > 128 && d->N <= 64) continue;
+          if (launch_with(c.bn, c.sm2 ? 2 : 1, c.sm2)) { (void)cudaGetLastError(); continue; }     // warm (attributes, L2)
+          cudaEventRecord(e0, stream);
+          int r2 = launch_with(c.bn, c.sm2 ? 2 : 1, c.sm2);
+          if (!r2) r2 = launch_with(c.bn, c.sm2 ? 2 : 1, c.sm2);
+          cudaEventRecord(e1, stream);
+          if (r2 || cudaEventSynchronize(e1) != cudaSuccess) { (void)cudaGetLastError(); continue; }
+          float ms = 0.f;
+          cudaEventElapsedTime(&ms, e0, e1);
+          if (ms < best) { best = ms; bc = c; }
+        }
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        cache[key] = bc;
+        BN = bc.bn; sm2 = bc.sm2;
+        if (getenv("ODISE_VERBOSE"))
+          fprintf(stderr, "odise_b200: gemm %d x %d x %d (batch %d, conv %d, nmma %d, epi %d): BN %d%s, %.1f us\n", d->M, d->N,
+                  d->K, d->batch, d->conv3x3, d->nmma, epi, BN, sm2 ? " pair (2-SM MMAs)" : "", best * 500.f);
+      }
+      if (sm2) CL = 2;
+    }
+  }
+
+  ProfRec rec{};
+  if (g_prof_on) {
+    cudaEventCreate(&rec.a);
+    cudaEventCreate(&rec.b);
+    rec.flops = 2.0 * d->M * d->N * (double)d->K * d->batch;
+    rec.M = d->M; rec.N = d->N; rec.K = d->K; rec.batch = d->batch; rec.conv = d->conv3x3; rec.bn = BN;
+    rec.nmma = d->nmma; rec.splits = p.splits; rec.pair = sm2 ? 2 : (CL == 2 ? 1 : 0);
+    cudaEventRecord(rec.a, stream);
+  }
+  rc = launch_with(BN, CL, sm2);
   if (rc) return rc;
   count_launch(p.splits > 1 ? 2 : 1);
-  if (p.splits > 1) {
-    const long long total = (long long)p.batch * p.M * ((p.N + 3) / 4);
-    int blocks = (int)((total + 127) / 128);
-    if (blocks > 148 * 8) blocks = 148 * 8;
-    gemm_splitk_reduce_kernel<<<blocks, 128, 0, stream>>>(p);
-    rc = (int)cudaGetLastError();
-  }
   if (g_prof_on) {
     cudaEventRecord(rec.b, stream);
     g_prof.push_back(rec);
