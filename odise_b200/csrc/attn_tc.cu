@@ -5,9 +5,13 @@
 // One CTA = 128 queries of one (image, head).  warp0: TMA producer; warp1: single-thread tcgen05.mma issuer;
 // warps 2-5: softmax, one thread per query row (= TMEM lane).  Per 64-key block j:
 //     S_j = Q K_j^T            (tcgen05, fp32 in TMEM, double buffered so S_{j+1} overlaps softmax of S_j)
-//     online softmax in registers (running max m, sum l), P_j -> ONE fp16 plane -> shared memory (SW128 K-major)
-//     O_j = P_j V_j            (tcgen05 into a double-buffered TMEM tile, NOT accumulated in TMEM)
-//     acc = acc * exp2(m_{j-1} - m_j) + O_j   in registers (consumed one block late so it overlaps the next softmax)
+//     online softmax in registers, P_j -> ONE fp16 plane -> shared memory (SW128 K-major)
+//     O += P_j V_j             (tcgen05, accumulated IN TMEM across the key blocks; round 2)
+// with LAZY rescaling: exponents are taken against a per-row reference maximum m_ref that only moves when a block's maximum
+// exceeds it by more than 2^8 (then O and l of that row are multiplied by 2^(m_ref_old - m_ref_new): tcgen05.ld -> mul ->
+// tcgen05.st by the warp that owns the rows, before it releases P_j).  Probabilities stay below 2^8 (fp16 holds them at full
+// relative precision), O / l is unchanged mathematically, and the per-block read-back of O (DP tcgen05.ld columns + DP FFMAs
+// per row and block, an o_full / o_empty round trip) of round 1 is gone: after the first blocks the reference rarely moves.
 // Operands are head-padded planes: head h occupies columns [h*HS, h*HS + DP) of q / k and rows of v^T with
 // HS = 64 (d=40, DP=48) or 128 (d=80, DP=80); pad columns are zeros (produced by zero weight rows in the
 // projection GEMM).  bf16x3: S = Q K^T uses hi*hi + hi*lo + lo*hi (the logits are exponentiated); O = P V uses
@@ -186,17 +190,17 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__
         const int st = j & 1;
         const uint32_t ph = (j >> 1) & 1;
         const int sv = j % Cfg::VSTAGES;
-        mbar_wait(p_full, j & 1);
+        mbar_wait(p_full, j & 1);           // P_j written AND (if the reference maximum moved) O rescaled by the softmax warps
         mbar_wait(&v_full[sv], (j / Cfg::VSTAGES) & 1);
-        mbar_wait(&o_empty[st], ph ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + 128 + st * Cfg::OSTRIDE;
+        (void)st; (void)ph;
+        const uint32_t d_tmem = tmem_base + 128;                 // ONE O tile, accumulated over all key blocks
         const uint32_t pp = smem_u32(sP), vv = smem_u32(sV + sv * Cfg::V_BYTES);
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
           const uint64_t ph_ = umma_desc_sw128(pp + ks * 32);
           const uint64_t vh = umma_desc_sw128(vv + ks * 32);
-          umma_bf16(d_tmem, ph_, vh, idesc_o, ks > 0 ? 1u : 0u);
+          umma_bf16(d_tmem, ph_, vh, idesc_o, (j > 0 || ks > 0) ? 1u : 0u);
           if (NMMA == 3) {
             const uint64_t vl = umma_desc_sw128(vv + Cfg::V_TILE + ks * 32);
             umma_bf16(d_tmem, ph_, vl, idesc_o, 1u);
@@ -204,7 +208,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__
         }
         umma_commit(&v_empty[sv]);
         umma_commit(p_empty);
-        umma_commit(&o_full[st]);
+        umma_commit(&o_full[0]);           // one phase per key block (the softmax warps wait on it only when they rescale)
       }
     }
   } else {
@@ -212,30 +216,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__
     const int quad = warp & 3;
     const int row = quad * 32 + lane;
     const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
-    float m = -INFINITY, l = 0.f, alpha_pending = 1.f;
+    float m = -INFINITY, l = 0.f;          // m: the row's REFERENCE maximum (lazy, see the header), l: running sum
+    constexpr float TAU = 8.f;             // the reference moves when a block maximum exceeds it by 2^TAU
     const int n_words = (p.Tk + 31) / 32;
     const uint32_t* mask_words = nullptr;
     if (p.bits && q0 + row < p.Tq && p.row_any[(long long)b * p.Tq + q0 + row] != 0)
       mask_words = p.bits + ((long long)b * p.Tq + q0 + row) * n_words;
-    float acc[DP];
-#pragma unroll
-    for (int i = 0; i < DP; ++i) acc[i] = 0.f;
-
-    auto consume_o = [&](int j, float alpha) {
-      const int st = j & 1;
-      mbar_wait(&o_full[st], (j >> 1) & 1);
-      tc_fence_after();
-#pragma unroll
-      for (int c0 = 0; c0 < DP; c0 += 16) {
-        uint32_t v[16];
-        tmem_ld16(t_lane + 128 + st * Cfg::OSTRIDE + c0, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 16; ++i) acc[c0 + i] = fmaf(acc[c0 + i], alpha, __uint_as_float(v[i]));
-      }
-      tc_fence_before();
-      mbar_arrive(&o_empty[st]);
-    };
+    const uint32_t t_o = t_lane + 128;
 
     for (int j = 0; j < nblk; ++j) {
       const int st = j & 1;
@@ -269,14 +256,36 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__
           if (!((w1 >> i) & 1u)) s[32 + i] = -INFINITY;
         }
       }
-      // running max on the raw scores (scale > 0), exponent as one FFMA + ex2: p = 2^(s*c - m*c)
-      float mx = m;
+      // block maximum of the raw scores (scale > 0): three-input max tree
+      float bm = fmaxf(s[0], s[1]);
 #pragma unroll
-      for (int i = 0; i < 64; ++i) mx = fmaxf(mx, s[i]);
+      for (int i = 2; i < 64; i += 2) bm = fmaxf(bm, fmaxf(s[i], s[i + 1]));
       const float c = p.scale_log2;
-      // guards: a row may have seen no attendable key yet (mx = -inf) -> p = 0, nothing to rescale
-      const float alpha = (m == -INFINITY) ? 0.f : fast_exp2((m - mx) * c);
-      const float mc = (mx == -INFINITY) ? 0.f : -mx * c;
+      // lazy reference: move it only when this block would push a probability above 2^TAU (or the row had none yet)
+      const bool move = (bm - m) * c > TAU || (m == -INFINITY && bm != -INFINITY);
+      float alpha = 1.f;
+      if (move) {
+        alpha = (m == -INFINITY) ? 0.f : fast_exp2((m - bm) * c);
+        m = bm;
+      }
+      if (j > 0 && __any_sync(0xffffffffu, move)) {
+        // rescale the rows of this warp in TMEM (lanes whose reference did not move multiply by 1): needs P V of block j - 1
+        mbar_wait(&o_full[0], (j - 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int c0 = 0; c0 < DP; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld16(t_o + c0, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+          tmem_st16(t_o + c0, v);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+      }
+      // guards: a row may have seen no attendable key yet (m = -inf) -> p = 0
+      const float mc = (m == -INFINITY) ? 0.f : -m * c;
       float sum = 0.f;
 #pragma unroll
       for (int i = 0; i < 64; ++i) {
@@ -284,7 +293,6 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__
         sum += s[i];
       }
       l = l * alpha + sum;
-      m = mx;
       // P_j -> shared memory (SW128 K-major [128 x 64]); wait until PV_{j-1} has finished reading the buffer
       mbar_wait(p_empty, (j & 1) ^ 1);
 #pragma unroll
@@ -306,10 +314,20 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__
       }
       fence_proxy_async();
       mbar_arrive(p_full);
-      if (j > 0) consume_o(j - 1, alpha_pending);
-      alpha_pending = alpha;
     }
-    consume_o(nblk - 1, alpha_pending);
+    // all key blocks accumulated: O of this row out of TMEM once
+    mbar_wait(&o_full[0], (nblk - 1) & 1);
+    tc_fence_after();
+    float acc[DP];
+#pragma unroll
+    for (int c0 = 0; c0 < DP; c0 += 16) {
+      uint32_t v[16];
+      tmem_ld16(t_o + c0, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 16; ++i) acc[c0 + i] = __uint_as_float(v[i]);
+    }
+    tc_fence_before();
 
     const int q = q0 + row;
     if (q < p.Tq) {

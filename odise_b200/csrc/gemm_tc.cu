@@ -1233,7 +1233,8 @@ extern "C" int odise_gemm_bf16(const odise_gemm_desc* d, void* stream_v) {
         for (int i = 0; i < 5; ++i) {
           const TileChoice c = cands[i];
           if (c.sm2 && !(pairable && d->nmma != 1)) continue;
-          if (c.bn == 64 && d->N > 96) continue;
+          // 64-wide tiles: narrow outputs, or problems too small to fill the SMs with wider ones (decoder linears)
+          if (c.bn == 64 && d->N > 96 && (long long)p.tiles_m * ((d->N + 127) / 128) * d->batch >= 2 * num_sms()) continue;
           if (c.bn > 128 && d->N <= 64) continue;
           if (launch_with(c.bn, c.sm2 ? 2 : 1, c.sm2)) { (void)cudaGetLastError(); continue; }     // warm (attributes, L2)
           cudaEventRecord(e0, stream);
