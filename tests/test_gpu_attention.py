@@ -3,7 +3,11 @@ Shapes are the SD-v1 UNet ones: self-attention d=40 / d=80 / d=160, cross-attent
 Tolerance in the bf16x3 mode: the probabilities enter the P V product rounded ONCE to fp16 (2^-12 relative per element,
 random sign -> ~1.5e-4 of the output scale on random data); the budget behind that choice is tools/precision_budget.py
 (5e-5 on the UNet taps, bar 1e-3).  S = Q K^T stays bf16x3 (2^-16)."""
-TOL3 = 3e-4
+# Expected size (round 2 note): each probability carries an independent relative rounding error of rms 2^-11 / sqrt(3) =
+# 2.8e-4; with n_eff = n / e effective keys for N(0, 1) scores the output error is 2.8e-4 |v| / sqrt(n_eff) rms, while the
+# outputs themselves are ~|v| / sqrt(n_eff): the max-error / max-output ratio this file measures is therefore ~2.8e-4
+# whatever n is, and one realisation lands anywhere in 1.5e-4 .. 4e-4.  The bound is 2x that expectation.
+TOL3 = 6e-4
 import pytest
 import torch
 
