@@ -260,7 +260,10 @@ class BackboneEngine:
                 crops = ops.image_crops(src, bx, B, sh, sw, net, net)
             if self.clip is not None:
                 with lib.nvtx("clip_image_tower"):
-                    clip_embed = self.clip.embed(src, bx, B, sh, sw, net, net)
+                    # maskclip_images (set by ODISEEngine.step): the images the MaskCLIP head will encode later in the step;
+                    # their image tokens share this pass, their keys / values are cached inside the CLIP engine
+                    clip_embed = self.clip.embed(src, bx, B, sh, sw, net, net,
+                                                 maskclip_images=getattr(self, "maskclip_images", None))
         elif short != self.in_size and vae_taps is None:
             net = self.in_size
         feats = self.extract(B, (net, net), vae_taps, crops, clip_embed, out_hw=(short, short))

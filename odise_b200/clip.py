@@ -40,10 +40,13 @@ class _ResBlocks:
     def _gemm(self, a, name, **kw):
         return lib.gemm(a, self.W[name], nmma=self.nmma, bias=self.F.get(name + ".b"), **kw)
 
-    def run(self, h, B, TS, Tk, bits=None, row_any=None):
+    def run(self, h, B, TS, Tk, bits=None, row_any=None, keep=None):
+        """keep = (first_image, n_images): also return, per layer, the K planes and V^T planes of those images' tokens
+        (views into the layer's projection outputs) — the keys / values a later run_queries() attends to."""
         dev, Wd = self.dev, self.width
         M = B * TS
         d = Wd // self.heads
+        cache = []
         for i in range(self.layers):
             n = f"l{i}."
             _, y = ops.layer_norm(h, self.F[n + "ln_1.g"], self.F[n + "ln_1.b"], lo=self.lo)
@@ -51,6 +54,8 @@ class _ResBlocks:
             self._gemm(y, n + "qk", out_planes=qk)
             vt = Planes.empty(Wd, M, dev, lo=self.lb, f16=self.lb)
             lib.gemm(self.W[n + "v"], y, nmma=self.nmma, bias_m=self.F[n + "v.b"], out_planes=vt)
+            if keep is not None:
+                cache.append((qk.col_slice(Wd, Wd).row_slice(keep[0] * TS, keep[1] * TS), vt.col_slice(keep[0] * TS, keep[1] * TS)))
             _, o = ops.attention_tc(qk.col_slice(0, Wd), qk.col_slice(Wd, Wd), vt, B, self.heads, d, TS, Tk, d ** -0.5,
                                     self.nmma, tk_stride=TS, mask_bits=bits, row_any=row_any, lo=self.lo)
             h2 = ops.empty(M, Wd, dev)
@@ -60,7 +65,32 @@ class _ResBlocks:
             self._gemm(y2, n + "fc", act=ACT_QUICKGELU, out_planes=u)
             h = ops.empty(M, Wd, dev)
             self._gemm(u, n + "pr", residual=h2, out=h)
-        return h
+        return (h, cache) if keep is not None else h
+
+    def run_queries(self, hq, cache, B, Q, TS, Tk, bits, row_any):
+        """Extra query tokens (MaskCLIP's mask tokens, clip.py:291-321) through the blocks: per layer they attend to the
+        cached keys / values of their image's first Tk tokens under their own key mask; nobody attends to THEM (the
+        reference masks the mask-token columns for every row), so only their q projection is needed and the image tokens'
+        stream — computed once by run(..., keep=...) — is untouched.  hq: fp32 [B*Q, width] (after ln_pre)."""
+        dev, Wd = self.dev, self.width
+        M = B * Q
+        d = Wd // self.heads
+        for i in range(self.layers):
+            n = f"l{i}."
+            kP, vt = cache[i]
+            _, y = ops.layer_norm(hq, self.F[n + "ln_1.g"], self.F[n + "ln_1.b"], lo=self.lo)
+            qP = Planes.empty(M, Wd, dev, lo=self.lb)
+            lib.gemm(y, self.W[n + "qk"].row_slice(0, Wd), nmma=self.nmma, bias=self.F[n + "qk.b"][:Wd], out_planes=qP)
+            _, o = ops.attention_tc(qP, kP, vt, B, self.heads, d, Q, Tk, d ** -0.5, self.nmma, tk_stride=TS,
+                                    mask_bits=bits, row_any=row_any, lo=self.lo)
+            h2 = ops.empty(M, Wd, dev)
+            self._gemm(o, n + "o", residual=hq, out=h2)
+            _, y2 = ops.layer_norm(h2, self.F[n + "ln_2.g"], self.F[n + "ln_2.b"], lo=self.lo)
+            u = Planes.empty(M, 4 * Wd, dev, lo=self.lo)
+            self._gemm(y2, n + "fc", act=ACT_QUICKGELU, out_planes=u)
+            hq = ops.empty(M, Wd, dev)
+            self._gemm(u, n + "pr", residual=h2, out=hq)
+        return hq
 
 
 class ClipVisualEngine:
@@ -90,39 +120,48 @@ class ClipVisualEngine:
         self.F["ln_post.g"], self.F["ln_post.b"] = f(g("ln_post.weight")), f(g("ln_post.bias"))
         self.W["proj"] = pl(g("proj").t())                                   # x @ proj == x @ (proj^T)^T
 
-    def _tokens(self, x, B, n_extra):
-        """normalised NHWC image [B*S*S, 3] -> pre-ln_pre token matrix [B*TS, width]: per image row 0 = class token,
-        rows 1..576 = patches (+ positional embedding), rows 577..577+n_extra-1 = mask tokens (copies of the class
-        row: ln_pre acts per row, so copying before it equals the reference's copy after it, clip.py:271-274)."""
-        dev, Wd, T = self.dev, self.width, self.T
-        TS = (T + n_extra + 7) // 8 * 8
-        patches = ops.patchify_split(x, B, self.image, self.patch, lo=self.lo)
+    def _tokens(self, parts):
+        """parts: [(normalised NHWC image batch [n*S*S, 3], n), ...] -> pre-ln_pre token matrix [B*TS, width] of all the
+        images in order: per image row 0 = class token, rows 1..576 = patches (+ positional embedding), zero pad rows."""
+        dev, Wd, T, TS = self.dev, self.width, self.T, self.TS
+        B = sum(n for _, n in parts)
         tok = torch.zeros(B * TS, Wd, dtype=torch.float32, device=dev)
-        lib.gemm(patches, self.W["conv1"], M=T - 1, N=Wd, K=patches.cols, nmma=self.nmma, batch=B,
-                 a_bs=(T - 1) * patches.ld, residual=self.F["pos_patches"], ld_res=Wd, res_bs=0,
-                 out=tok[1:], ld_out=Wd, out_bs=TS * Wd)
+        b0 = 0
+        for x, n in parts:
+            patches = ops.patchify_split(x, n, self.image, self.patch, lo=self.lo)
+            lib.gemm(patches, self.W["conv1"], M=T - 1, N=Wd, K=patches.cols, nmma=self.nmma, batch=n,
+                     a_bs=(T - 1) * patches.ld, residual=self.F["pos_patches"], ld_res=Wd, res_bs=0,
+                     out=tok[b0 * TS + 1:], ld_out=Wd, out_bs=TS * Wd)
+            b0 += n
         ops.copy2d(self.F["cls_row"].expand(B, Wd), tok.view(B, TS * Wd)[:, :Wd])
-        if n_extra:
-            # mask-token rows: broadcast the class row over [B, n_extra] rows in one strided copy per image block
-            src = self.F["cls_row"].expand(n_extra, Wd)
-            for b in range(B):
-                ops.copy2d(src, tok[b * TS + T: b * TS + T + n_extra])
-        return tok, TS
+        return tok, B
 
-    def _tower(self, tok, B, TS, bits=None, row_any=None):
+    def _tower(self, tok, B, keep=None):
         """ln_pre + the 24 residual attention blocks on [B*TS, width]; keys = the first 577 rows of every image."""
         h, _ = ops.layer_norm(tok, self.F["ln_pre.g"], self.F["ln_pre.b"], want_f32=True, want_planes=False, lo=self.lo)
-        return self.blocks.run(h, B, TS, self.T, bits, row_any)
+        return self.blocks.run(h, B, self.TS, self.T, keep=keep)
 
     @torch.no_grad()
-    def embed(self, img, boxes_dev, n_crops, H, W, ch, cw):
+    def embed(self, img, boxes_dev, n_crops, H, W, ch, cw, maskclip_images=None):
         """ClipAdapter.embed_image (clip.py:225-231) of every crop.
-        img: device uint8 / float32 [N, 3, H, W]; boxes [n_crops, 3] int32 -> image_embed fp32 [n_crops, 768]."""
-        B, Wd = n_crops, self.width
-        x = ops.clip_preprocess(img, boxes_dev, B, H, W, ch, cw, self.image)
-        tok, TS = self._tokens(x, B, 0)
-        h = self._tower(tok, B, TS)
-        cls = h.view(B, TS * Wd)[:, :Wd]                                       # token 0 of every image (strided rows)
+        img: device uint8 / float32 [N, 3, H, W]; boxes [n_crops, 3] int32 -> image_embed fp32 [n_crops, 768].
+        maskclip_images = (images [N, 3, Hi, Wi], N, Hi, Wi): the images MaskCLIP will look at later in the step.  Their
+        image-token stream does not depend on the masks (see _ResBlocks.run_queries), so it rides through the SAME GEMMs as
+        the crops (one batch of n_crops + N images) and its per-layer keys / values are kept for mask_embed()."""
+        B, Wd, TS = n_crops, self.width, self.TS
+        parts = [(ops.clip_preprocess(img, boxes_dev, B, H, W, ch, cw, self.image), B)]
+        keep = None
+        if maskclip_images is not None:
+            mi, Nm, Hm, Wm = maskclip_images
+            parts.append((ops.maskclip_preprocess(mi, Nm, Hm, Wm, self.image), Nm))
+            keep = (B, Nm)
+        tok, Ball = self._tokens(parts)
+        h = self._tower(tok, Ball, keep)
+        self._kv = None
+        if keep is not None:
+            h, cache = h
+            self._kv = (mi.data_ptr(), Nm, Hm, Wm, cache)
+        cls = h.view(Ball, TS * Wd)[:B, :Wd]                                   # token 0 of every crop (strided rows)
         _, c = ops.layer_norm(cls, self.F["ln_post.g"], self.F["ln_post.b"], lo=self.lo)
         out = ops.empty(B, self.W["proj"].rows, self.dev)
         lib.gemm(c, self.W["proj"], nmma=self.nmma, out=out)
@@ -133,17 +172,25 @@ class ClipVisualEngine:
         """MaskCLIP.get_mask_embed (clip.py:325-339): img [N,3,H,W] (u8 / f32 in [0,1]), mask logits [N,Q,hm,wm]
         -> fp32 [N*Q, 768].  The Q mask tokens are rows 577.. of each image's token block; their attention mask
         is 1 bit per (token, key) built straight from the low-resolution logits (odise_maskclip_bits_f32)."""
-        Wd, T = self.width, self.T
+        Wd, T, TS = self.width, self.T, self.TS
         Q, hm, wm = mask_logits.shape[1:]
-        x = ops.maskclip_preprocess(img, N, H, W, self.image)
-        tok, TS = self._tokens(x, N, Q)
-        bits, row_any = ops.maskclip_bits(mask_logits.contiguous(), N, Q, hm, wm, self.image, self.patch, TS, T)
-        h = self._tower(tok, N, TS, bits, row_any)
-        _, c = ops.layer_norm(h, self.F["ln_post.g"], self.F["ln_post.b"], lo=self.lo)
-        E = self.W["proj"].rows
-        out = ops.empty(N * Q, E, self.dev)
-        lib.gemm(c.row_slice(T, Q), self.W["proj"], M=Q, nmma=self.nmma, batch=N, a_bs=TS * c.ld, out=out, ld_out=E,
-                 out_bs=Q * E)
+        kv = getattr(self, "_kv", None)
+        if kv is not None and kv[:4] == (img.data_ptr(), N, H, W):
+            cache = kv[4]                       # image-token keys / values left by embed(..., maskclip_images=...)
+        else:                                   # stand-alone call: the image-token stream of these N images first
+            tok, _ = self._tokens([(ops.maskclip_preprocess(img, N, H, W, self.image), N)])
+            _, cache = self._tower(tok, N, keep=(0, N))
+        self._kv = None
+        # the mask tokens start as copies of the (ln_pre'd) class token (clip.py:271-274) and attend to the class token + the
+        # patches under their mask; 1 bit per (token, key)
+        bits, row_any = ops.maskclip_bits(mask_logits.contiguous(), N, Q, hm, wm, self.image, self.patch, Q, 0)
+        hq0 = ops.empty(N * Q, Wd, self.dev)
+        ops.copy2d(self.F["cls_row"].expand(N * Q, Wd), hq0)
+        hq, _ = ops.layer_norm(hq0, self.F["ln_pre.g"], self.F["ln_pre.b"], want_f32=True, want_planes=False, lo=self.lo)
+        hq = self.blocks.run_queries(hq, cache, N, Q, TS, T, bits, row_any)
+        _, c = ops.layer_norm(hq, self.F["ln_post.g"], self.F["ln_post.b"], lo=self.lo)
+        out = ops.empty(N * Q, self.W["proj"].rows, self.dev)
+        lib.gemm(c, self.W["proj"], nmma=self.nmma, out=out)
         return out
 
 

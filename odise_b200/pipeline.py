@@ -147,7 +147,14 @@ class ODISEEngine:
         padded only to its own maximum size, not to size_divisibility (odise.py:240-246)."""
         if images_u8 is None and (self.with_vae or self.with_clip):
             images_u8 = self._image_buffer(n_images, H, W)
-        feats = self.backbone.forward(n_images, H, W, vae_taps, images_u8)
+        ci = clip_images if clip_images is not None else images_u8
+        # MaskCLIP's image-token stream does not depend on the masks: it rides through the CLIP tower together with the crops
+        self.backbone.maskclip_images = ((ci, n_images, ci.shape[2], ci.shape[3])
+                                         if (self.clip_head is not None and self.vocab_key is not None and ci is not None) else None)
+        try:
+            feats = self.backbone.forward(n_images, H, W, vae_taps, images_u8)
+        finally:
+            self.backbone.maskclip_images = None
         out = self.head.forward(feats, n_images, vocab_key=self.vocab_key)
         h2, w2 = out["pd"]["mask_hw"]
         last = out["heads"][-1]
@@ -157,7 +164,6 @@ class ODISEEngine:
         if "pred_logits" in out:
             res["pred_logits"] = out["pred_logits"]
             if self.clip_head is not None:        # odise.py:292-323: MaskCLIP ensemble replaces the class scores
-                ci = clip_images if clip_images is not None else images_u8
                 with lib.nvtx("maskclip_ensemble"):
                     ch = self.clip_head.forward(self.vocab_key, ci, n_images, ci.shape[2], ci.shape[3], res["pred_masks"],
                                                 out["pred_logits"])

@@ -98,6 +98,21 @@ def test_step_graph_and_clip_head(cuda, world):
 
 
 @torch.no_grad()
+def test_maskclip_image_tokens_share_the_crop_pass(cuda, world):
+    """step() sends MaskCLIP's image tokens through the CLIP tower together with the crops and keeps their keys / values;
+    the mask tokens then run alone (nobody attends to them, clip.py:306).  Must equal the stand-alone MaskCLIP pass bit for
+    bit (same rows, same k order), for a batch of 2 images x 4 crops."""
+    eng = world["eng"]
+    img = torch.randint(0, 256, (2, 3, 1024, 1024), generator=torch.Generator().manual_seed(6), dtype=torch.uint8).to(cuda)
+    eng.use_vocabulary("v20")
+    a = eng.step(2, 1024, 1024, images_u8=img)
+    assert eng.clip_head.visual._kv is None                                   # consumed
+    alone = eng.clip_head.visual.mask_embed(img, a["pred_masks"].contiguous(), 2, 1024, 1024)
+    torch.cuda.synchronize()
+    assert torch.equal(a["clip_mask_embed"], alone)
+
+
+@torch.no_grad()
 def test_vocabulary_from_tokens(cuda, world):
     """tokenised prompts -> CLIP text bank on the device -> category + MaskCLIP vocabularies (odise.py:1281-1288)."""
     from odise_b200 import spec
