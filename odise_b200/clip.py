@@ -75,21 +75,28 @@ class _ResBlocks:
         dev, Wd = self.dev, self.width
         M = B * Q
         d = Wd // self.heads
+        # a few hundred rows: four M tiles, so a CTA's k loop is a serial chain of TMA round trips -> split K to spread it
+        # (K = 1024: 4 splits of 4 k-blocks; K = 4096: 8 splits), the reduce kernel applies the epilogue
+        sk1 = 4 if M <= 1024 and Wd >= 1024 else 1
+        sk4 = 8 if M <= 1024 and Wd >= 1024 else 1
+        ws = lib.workspace(max(sk1 * M * 4 * Wd, sk4 * M * Wd) * 4, dev) if sk1 > 1 else None
+        kw1 = dict(split_k=sk1, workspace=ws) if sk1 > 1 else {}
+        kw4 = dict(split_k=sk4, workspace=ws) if sk4 > 1 else {}
         for i in range(self.layers):
             n = f"l{i}."
             kP, vt = cache[i]
             _, y = ops.layer_norm(hq, self.F[n + "ln_1.g"], self.F[n + "ln_1.b"], lo=self.lo)
             qP = Planes.empty(M, Wd, dev, lo=self.lb)
-            lib.gemm(y, self.W[n + "qk"].row_slice(0, Wd), nmma=self.nmma, bias=self.F[n + "qk.b"][:Wd], out_planes=qP)
+            lib.gemm(y, self.W[n + "qk"].row_slice(0, Wd), nmma=self.nmma, bias=self.F[n + "qk.b"][:Wd], out_planes=qP, **kw1)
             _, o = ops.attention_tc(qP, kP, vt, B, self.heads, d, Q, Tk, d ** -0.5, self.nmma, tk_stride=TS,
                                     mask_bits=bits, row_any=row_any, lo=self.lo)
             h2 = ops.empty(M, Wd, dev)
-            self._gemm(o, n + "o", residual=hq, out=h2)
+            self._gemm(o, n + "o", residual=hq, out=h2, **kw1)
             _, y2 = ops.layer_norm(h2, self.F[n + "ln_2.g"], self.F[n + "ln_2.b"], lo=self.lo)
             u = Planes.empty(M, 4 * Wd, dev, lo=self.lo)
-            self._gemm(y2, n + "fc", act=ACT_QUICKGELU, out_planes=u)
+            self._gemm(y2, n + "fc", act=ACT_QUICKGELU, out_planes=u, **kw1)
             hq = ops.empty(M, Wd, dev)
-            self._gemm(u, n + "pr", residual=h2, out=hq)
+            self._gemm(u, n + "pr", residual=h2, out=hq, **kw4)
         return hq
 
 

@@ -8,6 +8,7 @@ One process per GPU; images shard over ranks with a single NCCL all-gather of th
 d2 evaluator gather).  A step at fixed (batch, H, W) is captured once into a CUDA graph and replayed.
 """
 import math
+import os
 
 import torch
 
@@ -149,8 +150,9 @@ class ODISEEngine:
             images_u8 = self._image_buffer(n_images, H, W)
         ci = clip_images if clip_images is not None else images_u8
         # MaskCLIP's image-token stream does not depend on the masks: it rides through the CLIP tower together with the crops
-        self.backbone.maskclip_images = ((ci, n_images, ci.shape[2], ci.shape[3])
-                                         if (self.clip_head is not None and self.vocab_key is not None and ci is not None) else None)
+        joint = self.clip_head is not None and self.vocab_key is not None and ci is not None and \
+            not os.environ.get("ODISE_NO_CLIP_JOINT")                       # A/B switch: stand-alone MaskCLIP pass
+        self.backbone.maskclip_images = (ci, n_images, ci.shape[2], ci.shape[3]) if joint else None
         try:
             feats = self.backbone.forward(n_images, H, W, vae_taps, images_u8)
         finally:
