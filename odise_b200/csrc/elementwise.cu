@@ -894,6 +894,46 @@ __global__ void softmax_split_kernel(const float* __restrict__ x, long long ldx,
   }
 }
 
+// Long rows (the KL-VAE mid-block attention: 4096 x 4096 scores per crop): the row is read from HBM ONCE into shared memory
+// (one warp per row, 8 rows per block), exponentials evaluated once, planes written 4 columns at a time — the three-pass kernel
+// above read the 1 GB score matrix three times and stored 2 bytes at a time (875 us per call, ncu launch list r2z).
+__global__ void __launch_bounds__(256)
+softmax_split_smem_kernel(const float* __restrict__ x, long long ldx, __nv_bfloat16* __restrict__ hi,
+                          __nv_bfloat16* __restrict__ lo, long long ldo, long long rows, int cols, int cols_pad,
+                          float scale) {
+  extern __shared__ __align__(16) float srow[];                 // [8 warps][cols_pad]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row = blockIdx.x * 8LL + warp;
+  if (row >= rows) return;
+  float* rb = srow + (size_t)warp * cols_pad;
+  const float* xr = x + row * ldx;
+  float mx = -INFINITY;
+#pragma unroll 8                                                   // 8 x 16 B per lane in flight (one block per SM: 128 KB of rows)
+  for (int c = lane * 4; c < cols; c += 128) {                  // cols % 4 == 0, ldx % 4 == 0 (checked by the launcher)
+    float4 v = __ldcs(reinterpret_cast<const float4*>(xr + c));  // streamed: the scores are read exactly once
+    v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
+    *reinterpret_cast<float4*>(rb + c) = v;
+    mx = fmaxf(fmaxf(mx, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
+  }
+  mx = warp_max(mx);
+  float sum = 0.f;
+  for (int c = lane * 4; c < cols; c += 128) {
+    float4 v = *reinterpret_cast<const float4*>(rb + c);
+    v.x = expf(v.x - mx); v.y = expf(v.y - mx); v.z = expf(v.z - mx); v.w = expf(v.w - mx);
+    *reinterpret_cast<float4*>(rb + c) = v;
+    sum += (v.x + v.y) + (v.z + v.w);
+  }
+  sum = warp_sum(sum);
+  for (int c = lane * 4; c < cols_pad; c += 128) {
+    float o[4] = {0.f, 0.f, 0.f, 0.f};
+    if (c < cols) {
+      const float4 v = *reinterpret_cast<const float4*>(rb + c);
+      o[0] = v.x / sum; o[1] = v.y / sum; o[2] = v.z / sum; o[3] = v.w / sum;
+    }
+    store_planes<4>(hi + row * ldo + c, lo ? lo + row * ldo + c : nullptr, o);
+  }
+}
+
 }  // namespace ob
 
 using namespace ob;
@@ -1152,8 +1192,23 @@ extern "C" int odise_softmax_split_f32(const float* x, long long ldx, void* hi, 
                                        long long rows, int cols, int cols_pad, float scale, void* stream) {
   if (!x || !hi || rows <= 0 || cols <= 0 || cols_pad < cols) return ODISE_ERR_ARG;
   Q8_CHECK(lo, ldo);
-  softmax_split_kernel<<<(int)((rows + 7) / 8), 256, 0, STREAM(stream)>>>(x, ldx, BF(hi), BFL(lo), ldo, rows, cols,
-                                                                         cols_pad, scale);
+  // rows that fit shared memory eight at a time and allow 16-byte accesses: one HBM read of the scores
+  const size_t smem = (size_t)8 * cols_pad * sizeof(float);
+  if (cols >= 512 && cols % 4 == 0 && cols_pad % 4 == 0 && ldx % 4 == 0 && ldo % 4 == 0 && smem <= 200 * 1024 &&
+      (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(hi) & 7) == 0 &&
+      (!lo || (reinterpret_cast<uintptr_t>(lo) & 7) == 0)) {
+    static size_t attr = 0;
+    if (smem > attr) {
+      cudaError_t e = cudaFuncSetAttribute(softmax_split_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return (int)e;
+      attr = smem;
+    }
+    softmax_split_smem_kernel<<<(int)((rows + 7) / 8), 256, smem, STREAM(stream)>>>(x, ldx, BF(hi), BFL(lo), ldo, rows, cols,
+                                                                                  cols_pad, scale);
+  } else {
+    softmax_split_kernel<<<(int)((rows + 7) / 8), 256, 0, STREAM(stream)>>>(x, ldx, BF(hi), BFL(lo), ldo, rows, cols,
+                                                                           cols_pad, scale);
+  }
   count_launch(1);
   return (int)cudaGetLastError();
 }

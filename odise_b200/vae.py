@@ -37,8 +37,8 @@ class VAEEngine:
                 w2d = torch.nn.functional.pad(w2d, (0, 8 - w2d.shape[1] % 8))
             return lib.split(w2d, lo=self.lo if lo is None else lo)
 
-        def conv(name, key):
-            self.W[name] = planes(_conv_w(g(key + ".weight")))
+        def conv(name, key, lo=None):
+            self.W[name] = planes(_conv_w(g(key + ".weight")), lo)
             self.F[name + ".b"] = f(g(key + ".bias"))
 
         def lin(name, key, lo=None):
@@ -64,7 +64,9 @@ class VAEEngine:
             lin(name + "o", key + "proj_out", self.lb)
 
         ch, mult = 128, (1, 2, 4, 4)
-        conv("e.conv_in", "encoder.conv_in")
+        # 3 -> 128 channels at 512^2: K = 27.  F16Q8 planes come in whole 64-wide k-blocks, the bf16 pair pads to 32 only: this
+        # one layer keeps the bf16 pair in every mode (half the im2col bytes over 4.2 M pixels, half the k-blocks)
+        conv("e.conv_in", "encoder.conv_in", self.lb)
         in_mult = (1,) + mult
         self.enc_blocks = []
         for i in range(4):
@@ -136,7 +138,7 @@ class VAEEngine:
     @torch.no_grad()
     def encode(self, img, B, H, W):
         """img: NHWC fp32 [B*H*W, 3], already (x - 0.5) / 0.5.  Returns dict(latent, enc5, enc7) of (tensor, h, w)."""
-        cols, _, _ = ops.im2col3x3_split(img, B, H, W, lo=self.lo)
+        cols, _, _ = ops.im2col3x3_split(img, B, H, W, lo=self.lb)
         h = ops.empty(B * H * W, 128, self.dev)
         hs = lib.GnStats(B * H * W, 128, self.dev)
         self._gemm(cols, "e.conv_in", out=h, gn=hs)

@@ -234,6 +234,13 @@ def test_q8_producers_match_the_bf16_pair(cuda):
     both(lambda lo: ops.geglu(torch.cat([x, x], 1).contiguous(), lo=lo))
     both(lambda lo: ops.l2_normalize_split(x, lo=lo))
     both(lambda lo: ops.softmax_split(x, rows, 300, cols, 0.3, lo=lo))
+    # long rows take the single-read shared-memory kernel (the KL-VAE 4096-key attention): against torch, both formats
+    xl = (torch.randn(40, 1024, generator=g) * 3).to(cuda)
+    want = torch.softmax(xl[:, :1000].double() * 0.3, -1)
+    for lo_ in (True, lib.Q8):
+        pl = ops.softmax_split(xl, 40, 1000, 1024, 0.3, lo=lo_)
+        assert _rel(pl.float()[:, :1000], want) < 2e-4 and pl.float()[:, 1000:].abs().max() == 0
+    both(lambda lo: ops.softmax_split(xl, 40, 1000, 1024, 0.3, lo=lo))
     both(lambda lo: ops.group_norm(x[:256].contiguous(), 2, 128, gam, bet, 1e-5, ops.ACT_SILU, lo=lo)[1])
     xs = torch.randn(2 * 8 * 8, 64, generator=g).to(cuda)
     both(lambda lo: ops.upsample2x_split(xs, 2, 8, 8, lo=lo))
