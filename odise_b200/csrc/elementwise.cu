@@ -396,51 +396,55 @@ __global__ void gn_finalize_kernel(const float* __restrict__ x, long long x_bs, 
   }
 }
 
-// merge of the (shift, S1, S2) records a GEMM epilogue wrote per (32-row segment, channel): one block per (image, group);
-// pass 1: mean of the segment means, pass 2: M2 = sum(M2_r + 32 (mean_r - mean)^2)  (Chan et al.), both in double with a
-// fixed reduction order (strided per-thread sums -> warp shuffles -> 8 warp partials) -> bit-reproducible
+// merge of the (shift, S1, S2) records a GEMM epilogue wrote per (32-row segment, channel): one block per (image, group),
+// ONE pass over the records: every record is a (n = 32, mean, M2) triple; a thread folds its strided share in fixed order with
+// Chan et al.'s pairwise update, the 32 lanes merge by a fixed xor butterfly, the 8 warps in index order — all in double,
+// bit-reproducible.  (Round 1/2a read the records twice: mean first, then M2 about it.)
+struct ChanAcc { double n, mu, m2; };
+__device__ __forceinline__ void chan_merge(ChanAcc& a, const ChanAcc& b) {
+  if (b.n == 0.0) return;
+  if (a.n == 0.0) { a = b; return; }
+  const double n = a.n + b.n, d = b.mu - a.mu;
+  a.mu += d * (b.n / n);
+  a.m2 += b.m2 + d * d * (a.n * b.n / n);
+  a.n = n;
+}
 __global__ void __launch_bounds__(256)
 gn_finalize_seg_kernel(const float* __restrict__ part, long long seg_stride, long long plane, float* __restrict__ mean,
                        float* __restrict__ rstd, int HW, int C, int G, float eps) {
-  __shared__ double red[8];
-  __shared__ double bc;
+  __shared__ ChanAcc red[8];
   const int b = blockIdx.x / G, g = blockIdx.x % G, cpg = C / G;
   const int nseg = HW >> 5;
   const int total = nseg * cpg;
   const float* base = part + (long long)b * nseg * seg_stride + g * cpg;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  auto block_sum = [&](double v) {
-    v = warp_sum_d(v);
-    __syncthreads();
-    if (lane == 0) red[warp] = v;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      double t = 0;
-      for (int w = 0; w < 8; ++w) t += red[w];
-      bc = t;
-    }
-    __syncthreads();
-    return bc;
-  };
-  double sm = 0;
-  for (int i = threadIdx.x; i < total; i += 256) {
-    const int sg = i / cpg, c = i - sg * cpg;
-    const float* r = base + (long long)sg * seg_stride + c;
-    sm += (double)r[0] + (double)r[plane] * (1.0 / 32.0);
-  }
-  const double mu = block_sum(sm) / (double)total;
-  double m2 = 0;
+  ChanAcc acc{0.0, 0.0, 0.0};
   for (int i = threadIdx.x; i < total; i += 256) {
     const int sg = i / cpg, c = i - sg * cpg;
     const float* r = base + (long long)sg * seg_stride + c;
     const double s1 = r[plane], s2 = r[2 * plane];
-    const double mr = (double)r[0] + s1 * (1.0 / 32.0);
-    m2 += (s2 - s1 * s1 * (1.0 / 32.0)) + 32.0 * (mr - mu) * (mr - mu);
+    ChanAcc rec{32.0, (double)r[0] + s1 * (1.0 / 32.0), s2 - s1 * s1 * (1.0 / 32.0)};
+    chan_merge(acc, rec);
   }
-  double var = block_sum(m2) / ((double)total * 32.0);
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    ChanAcc other;
+    other.n = __shfl_xor_sync(0xffffffffu, acc.n, o);
+    other.mu = __shfl_xor_sync(0xffffffffu, acc.mu, o);
+    other.m2 = __shfl_xor_sync(0xffffffffu, acc.m2, o);
+    // both partners must end with the same value: merge in (lower lane, higher lane) order on both sides
+    ChanAcc lo_ = (lane & o) ? other : acc, hi_ = (lane & o) ? acc : other;
+    chan_merge(lo_, hi_);
+    acc = lo_;
+  }
+  if (lane == 0) red[warp] = acc;
+  __syncthreads();
   if (threadIdx.x == 0) {
+    ChanAcc t = red[0];
+    for (int w = 1; w < 8; ++w) chan_merge(t, red[w]);
+    double var = t.m2 / t.n;
     if (var < 0) var = 0;
-    mean[blockIdx.x] = (float)mu;
+    mean[blockIdx.x] = (float)t.mu;
     rstd[blockIdx.x] = (float)(1.0 / sqrt(var + (double)eps));
   }
 }
