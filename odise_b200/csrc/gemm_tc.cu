@@ -505,10 +505,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
         const float alpha = p.alpha;
         const bool planes = p.tma_out == 2, to_lo = p.Dl != nullptr, h16 = p.h16 != 0, q8 = lo_is_q8(p.Dl);
         uint8_t* wbase = reinterpret_cast<uint8_t*>(stg);
+        // residual: each thread reads 64 contiguous bytes of ITS row per chunk, a full memory latency per chunk in this
+        // un-pipelined loop (K <= 640 GEMMs with a residual are epilogue bound) -> the next chunk's bytes are requested into L1
+        // one chunk ahead (a prefetch costs no registers; a register double buffer spilled, ptxas r2r)
+        if (EXTRA && resp) asm volatile("prefetch.global.L1 [%0];" ::"l"(resp + c_first));
 #pragma unroll 1
         for (int c0 = c_first; c0 < BN; c0 += c_step) {
           uint32_t v[16];
           tmem_ld16(t_row + c0, v);
+          if (EXTRA && resp && c0 + c_step < BN) asm volatile("prefetch.global.L1 [%0];" ::"l"(resp + c0 + c_step));
           float e[16];
           float4 b4[4];
 #pragma unroll
