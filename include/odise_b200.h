@@ -119,6 +119,10 @@ typedef struct odise_gemm_desc {
                                         ld_out_bf16 % 64 == 0, rows 128-byte aligned) */
 } odise_gemm_desc;
 int odise_gemm_bf16(const odise_gemm_desc* desc, void* stream);
+/* Host-only: the cost-model tile choice of odise_gemm_bf16 for a problem — output-tile width *bn (64 | 128 | 160 | 256) and
+ * *pair = 1 when CTA pairs run 2-SM MMAs (tcgen05 cta_group::2; BN = 256, K >= 1024, M tiles that pair up).  It is what the
+ * GEMM uses under CUDA-graph capture / with ODISE_GEMM_AUTOTUNE=0 and the first candidate of the one-time per-shape autotune. */
+int odise_gemm_tile_policy(int M, int N, int K, int batch, int conv3x3, int nmma, int* bn, int* pair);
 /* optional per-launch timing of odise_gemm_bf16 (CUDA events on the launch stream; not for use under graph capture):
  * begin() starts recording, end() synchronises and returns launch count, summed device ms and algorithmic FLOPs. */
 int odise_profile_begin(void);

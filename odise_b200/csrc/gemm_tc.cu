@@ -1282,6 +1282,18 @@ extern "C" int odise_gemm_bf16(const odise_gemm_desc* d, void* stream_v) {
   return rc;
 }
 
+// The cost-model choice of odise_gemm_bf16 for a problem (what it uses under stream capture / with ODISE_GEMM_AUTOTUNE=0, and
+// the starting point of the per-shape autotune): output-tile width and whether CTA pairs run 2-SM MMAs.  Host only.
+extern "C" int odise_gemm_tile_policy(int M, int N, int K, int batch, int conv3x3, int nmma, int* bn, int* pair) {
+  if (M <= 0 || N <= 0 || K <= 0 || batch <= 0 || !bn || !pair || nmma < 1 || nmma > 3) return ODISE_ERR_ARG;
+  const int tiles_m = (M + 127) / 128;
+  const bool pairable = tiles_m >= 2 && (tiles_m % 2 == 0 || tiles_m >= 16);
+  const TileChoice c = pick_tile(M, N, K, batch, 0, conv3x3 != 0, nmma, pairable);
+  *bn = c.bn;
+  *pair = c.sm2 ? 1 : 0;
+  return ODISE_OK;
+}
+
 extern "C" int odise_profile_begin(void) {
   for (auto& r : g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   g_prof.clear();

@@ -50,6 +50,7 @@ _SIGS = {
     "odise_msda_forward_f32": [c_void_p] * 6 + [c_int] * 7 + [c_void_p],
     "odise_msda_fused_f32": [c_void_p] * 9 + [c_int] * 7 + [c_void_p],
     "odise_gemm_bf16": [POINTER(GemmDesc), c_void_p],
+    "odise_gemm_tile_policy": [c_int] * 6 + [c_void_p, c_void_p],
     "odise_profile_begin": [],
     "odise_profile_end": [c_void_p, c_void_p, c_void_p],
     "odise_split_f32": [c_void_p, c_longlong, c_void_p, c_void_p, c_longlong, c_longlong, c_int, c_void_p],
@@ -429,6 +430,14 @@ def gemm(a, b, *, M=None, N=None, K=None, nmma=3, batch=1, a_bs=0, b_bs=0, conv=
     d.conv_mode = conv_mode
     _check(load().odise_gemm_bf16(ctypes.byref(d), _stream()), "odise_gemm_bf16")
     return out if out is not None else out_planes
+
+
+def gemm_tile_policy(M, N, K, batch=1, conv=False, nmma=2):
+    """(BN, pair) the GEMM's cost model picks for a problem (host only; include/odise_b200.h odise_gemm_tile_policy)."""
+    bn, pair = c_int(0), c_int(0)
+    _check(load().odise_gemm_tile_policy(M, N, K, batch, 1 if conv else 0, nmma, ctypes.byref(bn), ctypes.byref(pair)),
+           "odise_gemm_tile_policy")
+    return bn.value, bool(pair.value)
 
 
 def msda_forward(value, spatial_shapes, level_start_index, sampling_locations, attention_weights, im2col_step=128):
